@@ -1,0 +1,820 @@
+// ptb_api.cu — the C ABI of include/ptb200.h: tracer handle, scene export -> device buffers
+// (+ sphere BVH), ColorBuffer transfers, render dispatch, per-function parity entry points.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// (see __graft_entry__.build()).  There is deliberately no host fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptb200.h"
+#include "ptb_kernels.cuh"
+#include "ptb_wavefront.cuh"
+
+using namespace ptb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail(PTB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device buffers of one scene
+template <class R> struct SceneBuffers {
+    DScene<R> d{};
+    void* spheres = nullptr; void* sphere_material = nullptr; void* planes = nullptr; void* plane_material = nullptr;
+    void* materials = nullptr; void* lights = nullptr; void* bvh = nullptr; void* bvh_prim = nullptr;
+    size_t bytes = 0;
+    void release() {
+        for (void** p : {&spheres, &sphere_material, &planes, &plane_material, &materials, &lights, &bvh, &bvh_prim}) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+        }
+        bytes = 0;
+    }
+};
+
+// Host copy of the camera parameters (resize re-derives the basis because `ratio` depends on W/H).
+template <class R> struct CamParams { R origin[3], center[3], fov; };
+
+struct ptb_tracer {
+    ptb_config cfg{};
+    CamParams<float> c32{};
+    CamParams<double> c64{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int precision = 0;   // 0 none, 4 f32, 8 f64
+    SceneBuffers<float> s32;
+    SceneBuffers<double> s64;
+    uint32_t W = 0, H = 0;
+    void* accum = nullptr;          // device, W*H*4 reals
+    bool own_accum = false;
+    size_t accum_bytes = 0;
+    void* staging = nullptr;        // device, W*H*4 reals (mean image) or u8 frame
+    size_t staging_bytes = 0;
+    uint64_t frames = 0;
+    unsigned int* work_counter = nullptr;
+    DeviceCounters* counters = nullptr;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int sm_count = 0;
+    int fused_blocks_f32 = 0, fused_blocks_f64 = 0;
+    WavefrontState wf;
+};
+
+static size_t real_size(const ptb_tracer* t) { return (size_t)t->precision; }
+
+// ------------------------------------------------------------------------------------------------
+// BVH build over spheres (host, binned SAH, children stored adjacently)
+namespace {
+struct Box { float lo[3], hi[3]; };
+inline Box box_empty() { return Box{{3e38f, 3e38f, 3e38f}, {-3e38f, -3e38f, -3e38f}}; }
+inline void box_grow(Box& b, const Box& o) {
+    for (int k = 0; k < 3; ++k) { b.lo[k] = std::min(b.lo[k], o.lo[k]); b.hi[k] = std::max(b.hi[k], o.hi[k]); }
+}
+inline float box_area(const Box& b) {
+    float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+}
+struct BvhBuilder {
+    std::vector<Box> pbox;
+    std::vector<float> pcen;   // 3 per prim
+    std::vector<uint32_t> prim;
+    std::vector<BvhNode> nodes;
+    void build_node(uint32_t ni, uint32_t first, uint32_t count) {
+        Box nb = box_empty(), cb = box_empty();
+        for (uint32_t i = first; i < first + count; ++i) {
+            box_grow(nb, pbox[prim[i]]);
+            const float* c = &pcen[3 * prim[i]];
+            for (int k = 0; k < 3; ++k) { cb.lo[k] = std::min(cb.lo[k], c[k]); cb.hi[k] = std::max(cb.hi[k], c[k]); }
+        }
+        BvhNode& n = nodes[ni];
+        for (int k = 0; k < 3; ++k) { n.lo[k] = nb.lo[k]; n.hi[k] = nb.hi[k]; }
+        auto make_leaf = [&]() { nodes[ni].left_or_first = first; nodes[ni].count = count; };
+        if (count <= 2) { make_leaf(); return; }
+        constexpr int NB = 16;
+        float best_cost = 3e38f; int best_axis = -1, best_split = 0;
+        for (int ax = 0; ax < 3; ++ax) {
+            float ext = cb.hi[ax] - cb.lo[ax];
+            if (!(ext > 0.f)) continue;
+            Box bb[NB]; uint32_t bc[NB];
+            for (int b = 0; b < NB; ++b) { bb[b] = box_empty(); bc[b] = 0; }
+            float scale = NB / ext;
+            for (uint32_t i = first; i < first + count; ++i) {
+                int b = std::min(NB - 1, (int)((pcen[3 * prim[i] + ax] - cb.lo[ax]) * scale));
+                bc[b]++; box_grow(bb[b], pbox[prim[i]]);
+            }
+            float la[NB - 1], ra[NB - 1]; uint32_t lc[NB - 1], rc[NB - 1];
+            Box acc = box_empty(); uint32_t cnt = 0;
+            for (int b = 0; b < NB - 1; ++b) { box_grow(acc, bb[b]); cnt += bc[b]; la[b] = box_area(acc); lc[b] = cnt; }
+            acc = box_empty(); cnt = 0;
+            for (int b = NB - 1; b > 0; --b) { box_grow(acc, bb[b]); cnt += bc[b]; ra[b - 1] = box_area(acc); rc[b - 1] = cnt; }
+            for (int b = 0; b < NB - 1; ++b) {
+                if (lc[b] == 0 || rc[b] == 0) continue;
+                float cost = la[b] * lc[b] + ra[b] * rc[b];
+                if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = b; }
+            }
+        }
+        // no useful split for a small node: keep it as a leaf
+        if (count <= 4 && (best_axis < 0 || best_cost >= box_area(nb) * count)) { make_leaf(); return; }
+        uint32_t mid;
+        if (best_axis >= 0) {
+            float ext = cb.hi[best_axis] - cb.lo[best_axis];
+            float scale = NB / ext;
+            auto it = std::partition(prim.begin() + first, prim.begin() + first + count, [&](uint32_t p) {
+                int b = std::min(NB - 1, (int)((pcen[3 * p + best_axis] - cb.lo[best_axis]) * scale));
+                return b <= best_split;
+            });
+            mid = (uint32_t)(it - prim.begin());
+        } else {
+            mid = first + count / 2;   // all centroids coincide
+        }
+        if (mid == first || mid == first + count) mid = first + count / 2;
+        uint32_t left = (uint32_t)nodes.size();
+        nodes.push_back(BvhNode{});
+        nodes.push_back(BvhNode{});
+        nodes[ni].left_or_first = left;
+        nodes[ni].count = 0;
+        build_node(left, first, mid - first);
+        build_node(left + 1, mid, first + count - mid);
+    }
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// scene upload
+template <class R> struct PodTypes;
+template <> struct PodTypes<float> { using scene = ptb_scene_f32; using material = ptb_material_f32; };
+template <> struct PodTypes<double> { using scene = ptb_scene_f64; using material = ptb_material_f64; };
+
+template <class T> static cudaError_t upload_vec(void** dst, const std::vector<T>& v, cudaStream_t st, size_t& bytes) {
+    *dst = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(dst, n);
+    if (e != cudaSuccess) return e;
+    bytes += n;
+    if (!v.empty()) e = cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb, const typename PodTypes<R>::scene* sc) {
+    if (!t || !sc) return fail(PTB_E_INVALID, "null tracer or scene");
+    if ((sc->n_spheres && !sc->spheres) || (sc->n_planes && !sc->planes) || (sc->n_materials && !sc->materials) ||
+        (sc->n_lights && !sc->lights))
+        return fail(PTB_E_INVALID, "scene array pointer is NULL with a non-zero count");
+    if (sc->depth > 65535u) return fail(PTB_E_INVALID, "depth must fit u16 (scene.rs:28)");
+    for (uint32_t i = 0; i < sc->n_spheres; ++i)
+        if (sc->spheres[i].material >= sc->n_materials) return fail(PTB_E_INVALID, "sphere %u: material index out of range", i);
+    for (uint32_t i = 0; i < sc->n_planes; ++i)
+        if (sc->planes[i].material >= sc->n_materials) return fail(PTB_E_INVALID, "plane %u: material index out of range", i);
+    CU(cudaSetDevice(t->device));
+
+    bool patch = false;
+    for (uint32_t i = 0; i < sc->n_materials; ++i)
+        if ((sc->materials[i].set_mask & PTB_MAT_ALL) != PTB_MAT_ALL) patch = true;
+    const uint32_t thr = t->cfg.bvh_threshold ? t->cfg.bvh_threshold : 64u;
+    bool use_bvh = !(sc->flags & PTB_SCENE_NO_BVH) && sc->n_spheres > 0 && (sc->n_spheres >= thr || (sc->flags & PTB_SCENE_FORCE_BVH));
+    if (patch && use_bvh) return fail(PTB_E_INVALID, "BVH scenes need PTB_MAT_ALL on every material (order-independent)");
+    if (patch && sc->n_spheres + sc->n_planes > 64u)
+        return fail(PTB_E_INVALID, "partial material masks support at most 64 primitives");
+
+    std::vector<DSphere<R>> spheres(sc->n_spheres);
+    std::vector<uint32_t> smat(sc->n_spheres);
+    for (uint32_t i = 0; i < sc->n_spheres; ++i) {
+        spheres[i] = DSphere<R>{sc->spheres[i].center[0], sc->spheres[i].center[1], sc->spheres[i].center[2], sc->spheres[i].radius};
+        smat[i] = sc->spheres[i].material;
+    }
+    std::vector<DPlane<R>> planes(sc->n_planes);
+    std::vector<uint32_t> pmat(sc->n_planes);
+    for (uint32_t i = 0; i < sc->n_planes; ++i) {
+        const auto& p = sc->planes[i];
+        planes[i] = DPlane<R>{p.point[0], p.point[1], p.point[2], p.normal[0], p.normal[1], p.normal[2]};
+        pmat[i] = p.material;
+    }
+    std::vector<DMaterial<R>> mats(sc->n_materials);
+    for (uint32_t i = 0; i < sc->n_materials; ++i) {
+        const auto& m = sc->materials[i];
+        DMaterial<R>& o = mats[i];
+        const uint32_t k = m.set_mask;
+        // Material::new() defaults (material.rs:82-114) for everything this material does not assign
+        for (int c = 0; c < 3; ++c) { o.rgb[c] = (k & PTB_MAT_RGB) ? m.rgb[c] : R(1.5); o.emission[c] = (k & PTB_MAT_EMISSION) ? m.emission[c] : R(0); }
+        o.anisotropic = (k & PTB_MAT_ANISOTROPIC) ? m.anisotropic : R(0);
+        o.metallic = (k & PTB_MAT_METALLIC) ? m.metallic : R(0);
+        o.roughness = (k & PTB_MAT_ROUGHNESS) ? m.roughness : R(0.5);
+        o.subsurface = (k & PTB_MAT_SUBSURFACE) ? m.subsurface : R(0);
+        o.specular_tint = (k & PTB_MAT_SPECULAR_TINT) ? m.specular_tint : R(0);
+        o.sheen = (k & PTB_MAT_SHEEN) ? m.sheen : R(0);
+        o.sheen_tint = (k & PTB_MAT_SHEEN_TINT) ? m.sheen_tint : R(0);
+        o.clearcoat = (k & PTB_MAT_CLEARCOAT) ? m.clearcoat : R(0);
+        o.clearcoat_gloss = (k & PTB_MAT_CLEARCOAT_GLOSS) ? m.clearcoat_gloss : R(0);
+        o.spec_trans = (k & PTB_MAT_SPEC_TRANS) ? m.spec_trans : R(0);
+        o.ior = (k & PTB_MAT_IOR) ? m.ior : R(1.45);
+        o.set_mask = k & PTB_MAT_ALL;
+        o.albedo_kind = m.albedo_kind;
+        o.checker_a = m.checker_a; o.checker_b = m.checker_b; o.checker_scale = m.checker_scale; o.checker_offset = m.checker_offset;
+    }
+    std::vector<DLight<R>> lights(sc->n_lights);
+    const R PI_R = Const<R>::PI;
+    for (uint32_t i = 0; i < sc->n_lights; ++i) {
+        const auto& l = sc->lights[i];
+        DLight<R>& o = lights[i];
+        o.px = l.position[0]; o.py = l.position[1]; o.pz = l.position[2]; o.radius = l.radius;
+        o.ex = l.emission[0]; o.ey = l.emission[1]; o.ez = l.emission[2];
+        o.area = R(4) * PI_R * l.radius * l.radius;   // light.rs:22
+        o.type = l.type; o.pad[0] = o.pad[1] = o.pad[2] = 0;
+    }
+
+    // BVH
+    std::vector<BvhNode> nodes;
+    std::vector<uint32_t> prim;
+    if (use_bvh) {
+        BvhBuilder b;
+        b.pbox.resize(sc->n_spheres); b.pcen.resize(3 * (size_t)sc->n_spheres); b.prim.resize(sc->n_spheres);
+        for (uint32_t i = 0; i < sc->n_spheres; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                double c = (double)sc->spheres[i].center[k], r = std::fabs((double)sc->spheres[i].radius);
+                // outward-rounded f32 bounds with a small relative pad
+                float lo = (float)(c - r), hi = (float)(c + r);
+                lo = std::nextafterf(lo - std::fabs(lo) * 1e-6f, -3e38f);
+                hi = std::nextafterf(hi + std::fabs(hi) * 1e-6f, 3e38f);
+                b.pbox[i].lo[k] = lo; b.pbox[i].hi[k] = hi; b.pcen[3 * (size_t)i + k] = (float)c;
+            }
+            b.prim[i] = i;
+        }
+        b.nodes.reserve(2 * (size_t)sc->n_spheres);
+        b.nodes.push_back(BvhNode{});
+        b.build_node(0, 0, sc->n_spheres);
+        nodes.swap(b.nodes);
+        prim.swap(b.prim);
+    }
+
+    sb.release();
+    CU(upload_vec(&sb.spheres, spheres, t->stream, sb.bytes));
+    CU(upload_vec(&sb.sphere_material, smat, t->stream, sb.bytes));
+    CU(upload_vec(&sb.planes, planes, t->stream, sb.bytes));
+    CU(upload_vec(&sb.plane_material, pmat, t->stream, sb.bytes));
+    CU(upload_vec(&sb.materials, mats, t->stream, sb.bytes));
+    CU(upload_vec(&sb.lights, lights, t->stream, sb.bytes));
+    CU(upload_vec(&sb.bvh, nodes, t->stream, sb.bytes));
+    CU(upload_vec(&sb.bvh_prim, prim, t->stream, sb.bytes));
+    CU(cudaStreamSynchronize(t->stream));   // host vectors go out of scope
+
+    DScene<R>& d = sb.d;
+    d.n_spheres = sc->n_spheres; d.n_planes = sc->n_planes; d.n_materials = sc->n_materials; d.n_lights = sc->n_lights;
+    d.spheres = (const DSphere<R>*)sb.spheres; d.sphere_material = (const uint32_t*)sb.sphere_material;
+    d.planes = (const DPlane<R>*)sb.planes; d.plane_material = (const uint32_t*)sb.plane_material;
+    d.materials = (const DMaterial<R>*)sb.materials; d.lights = (const DLight<R>*)sb.lights;
+    d.bvh = use_bvh ? (const BvhNode*)sb.bvh : nullptr; d.bvh_prim = (const uint32_t*)sb.bvh_prim;
+    d.use_bvh = use_bvh; d.patch_materials = patch;
+    d.depth = sc->depth; d.flags = sc->flags; d.eps = sc->eps;
+    d.n_lights_f = (R)sc->n_lights;
+
+    // the camera basis is derived by derive_camera() once the frame size is known
+    for (int k = 0; k < 3; ++k) d.cam_origin[k] = sc->camera.origin[k];
+    d.bg_kind = sc->background.kind;
+    for (int k = 0; k < 3; ++k) { d.bg_a[k] = sc->background.colour_a[k]; d.bg_b[k] = sc->background.colour_b[k]; }
+    d.bg_scale = sc->background.scale; d.bg_gamma = sc->background.gamma;
+    return PTB_OK;
+}
+
+// camera/pinhole.rs:38-61, loop-invariant part, evaluated in R with the reference's operation
+// order (x86-64 host code built without -mfma, so nothing is contracted).
+template <class R> static void derive_camera(DScene<R>& d, const CamParams<R>& c, uint32_t W, uint32_t H) {
+    R width = (R)W, height = (R)H;
+    R ratio = width / height;
+    R half_width = std::tan((c.fov * (Const<R>::PI / R(180))) * R(0.5));
+    R half_height = half_width / ratio;
+    R o[3] = {c.origin[0], c.origin[1], c.origin[2]};
+    R wv[3] = {o[0] - c.center[0], o[1] - c.center[1], o[2] - c.center[2]};
+    R len = std::sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+    R w[3] = {wv[0] / len, wv[1] / len, wv[2] / len};
+    const R up[3] = {0, 1, 0};
+    R u[3] = {up[1] * w[2] - up[2] * w[1], up[2] * w[0] - up[0] * w[2], up[0] * w[1] - up[1] * w[0]};
+    R v[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};
+    for (int k = 0; k < 3; ++k) {
+        R lower_left = ((o[k] - u[k] * half_width) - v[k] * half_height) - w[k];
+        d.cam_base[k] = lower_left - o[k];
+        d.cam_horizontal[k] = u[k] * (half_width * R(2));
+        d.cam_vertical[k] = v[k] * (half_height * R(2));
+        d.cam_origin[k] = o[k];
+    }
+}
+
+static void refresh_camera(ptb_tracer* t) {
+    if (!t->W || !t->H) return;
+    if (t->precision == 4) derive_camera(t->s32.d, t->c32, t->W, t->H);
+    if (t->precision == 8) derive_camera(t->s64.d, t->c64, t->W, t->H);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ptb_abi_version(void) { return PTB_ABI_VERSION; }
+const char* ptb_last_error(void) { return g_err.c_str(); }
+int ptb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ptb_create(const ptb_config* cfg, ptb_tracer** out) {
+    if (!out) return fail(PTB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = ptb_device_count();
+    if (n <= 0) return fail(PTB_E_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    ptb_config c{};
+    if (cfg) c = *cfg;
+    if (c.device < 0 || c.device >= n) return fail(PTB_E_NO_DEVICE, "device %d out of range (have %d)", c.device, n);
+    if (c.integrator > PTB_INTEGRATOR_WAVEFRONT) return fail(PTB_E_INVALID, "unknown integrator %u", c.integrator);
+    CU(cudaSetDevice(c.device));
+    ptb_tracer* t = new ptb_tracer();
+    t->cfg = c;
+    t->device = c.device;
+    cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete t; return fail(PTB_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    t->own_stream = true;
+    cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, c.device);
+    cudaMalloc((void**)&t->work_counter, sizeof(unsigned int));
+    cudaMalloc((void**)&t->counters, sizeof(DeviceCounters));
+    cudaMemset(t->counters, 0, sizeof(DeviceCounters));
+    cudaEventCreate(&t->ev0);
+    cudaEventCreate(&t->ev1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { ptb_destroy(t); return fail(PTB_E_CUDA, "tracer setup: %s", cudaGetErrorString(e)); }
+    *out = t;
+    return PTB_OK;
+}
+
+void ptb_destroy(ptb_tracer* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    t->s32.release();
+    t->s64.release();
+    t->wf.release();
+    if (t->own_accum && t->accum) cudaFree(t->accum);
+    if (t->staging) cudaFree(t->staging);
+    if (t->work_counter) cudaFree(t->work_counter);
+    if (t->counters) cudaFree(t->counters);
+    if (t->ev0) cudaEventDestroy(t->ev0);
+    if (t->ev1) cudaEventDestroy(t->ev1);
+    if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+int ptb_set_stream(ptb_tracer* t, void* cuda_stream) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+    t->stream = (cudaStream_t)cuda_stream;
+    t->own_stream = false;
+    return PTB_OK;
+}
+
+int ptb_set_scene_f32(ptb_tracer* t, const ptb_scene_f32* sc) {
+    if (!t || !sc) return fail(PTB_E_INVALID, "null tracer or scene");
+    int r = set_scene_impl<float>(t, t->s32, sc);
+    if (r != PTB_OK) return r;
+    t->s64.release();
+    t->precision = 4;
+    CamParams<float>& c = t->c32;
+    for (int k = 0; k < 3; ++k) { c.origin[k] = sc->camera.origin[k]; c.center[k] = sc->camera.center[k]; }
+    c.fov = sc->camera.fov;
+    refresh_camera(t);
+    return PTB_OK;
+}
+int ptb_set_scene_f64(ptb_tracer* t, const ptb_scene_f64* sc) {
+    if (!t || !sc) return fail(PTB_E_INVALID, "null tracer or scene");
+    int r = set_scene_impl<double>(t, t->s64, sc);
+    if (r != PTB_OK) return r;
+    t->s32.release();
+    t->precision = 8;
+    CamParams<double>& c = t->c64;
+    for (int k = 0; k < 3; ++k) { c.origin[k] = sc->camera.origin[k]; c.center[k] = sc->camera.center[k]; }
+    c.fov = sc->camera.fov;
+    refresh_camera(t);
+    return PTB_OK;
+}
+
+static int need_scene(ptb_tracer* t, int precision) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    if (t->precision == 0) return fail(PTB_E_NO_SCENE, "no scene set (ptb_set_scene_f32/_f64)");
+    if (precision && t->precision != precision) return fail(PTB_E_PRECISION, "tracer holds an f%d scene", t->precision * 8);
+    return PTB_OK;
+}
+
+static int ensure_staging(ptb_tracer* t, size_t bytes) {
+    if (t->staging_bytes >= bytes) return PTB_OK;
+    if (t->staging) cudaFree(t->staging);
+    t->staging = nullptr; t->staging_bytes = 0;
+    CU(cudaMalloc(&t->staging, bytes));
+    t->staging_bytes = bytes;
+    return PTB_OK;
+}
+
+int ptb_clear(ptb_tracer* t) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    CU(cudaSetDevice(t->device));
+    CU(cudaMemsetAsync(t->accum, 0, t->accum_bytes, t->stream));
+    t->frames = 0;
+    return PTB_OK;
+}
+
+int ptb_resize(ptb_tracer* t, uint32_t width, uint32_t height) {
+    int r = need_scene(t, 0);
+    if (r) return r;
+    if (!width || !height || (uint64_t)width * height > (1ull << 31)) return fail(PTB_E_INVALID, "bad frame size %ux%u", width, height);
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    if (t->own_accum && t->accum) cudaFree(t->accum);
+    t->accum = nullptr; t->own_accum = false;
+    t->accum_bytes = (size_t)width * height * 4 * real_size(t);
+    CU(cudaMalloc(&t->accum, t->accum_bytes));
+    t->own_accum = true;
+    t->W = width; t->H = height;
+    refresh_camera(t);
+    return ptb_clear(t);
+}
+
+int ptb_bind_accumulator(ptb_tracer* t, void* device_ptr, uint32_t width, uint32_t height) {
+    int r = need_scene(t, 0);
+    if (r) return r;
+    if (!device_ptr) return ptb_resize(t, width, height);
+    if (!width || !height) return fail(PTB_E_INVALID, "bad frame size");
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    if (t->own_accum && t->accum) cudaFree(t->accum);
+    t->accum = device_ptr; t->own_accum = false;
+    t->accum_bytes = (size_t)width * height * 4 * real_size(t);
+    t->W = width; t->H = height;
+    t->frames = 0;
+    refresh_camera(t);
+    return PTB_OK;
+}
+
+}  // extern "C"
+template <class R> static int upload_impl(ptb_tracer* t, const R* pixels, uint64_t frames) {
+    if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    CU(cudaSetDevice(t->device));
+    int r = ensure_staging(t, t->accum_bytes);
+    if (r) return r;
+    CU(cudaMemcpyAsync(t->staging, pixels, t->accum_bytes, cudaMemcpyHostToDevice, t->stream));
+    using V4 = typename Vec4T<R>::type;
+    uint32_t n = t->W * t->H;
+    k_unresolve<R><<<(n + 255) / 256, 256, 0, t->stream>>>((const V4*)t->staging, (V4*)t->accum, (R)frames, n);
+    t->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(t->stream));
+    t->frames = frames;
+    return PTB_OK;
+}
+extern "C" {
+int ptb_upload_f32(ptb_tracer* t, const float* px, uint64_t frames) { int r = need_scene(t, 4); return r ? r : upload_impl<float>(t, px, frames); }
+int ptb_upload_f64(ptb_tracer* t, const double* px, uint64_t frames) { int r = need_scene(t, 8); return r ? r : upload_impl<double>(t, px, frames); }
+
+}  // extern "C"
+template <class R> static int download_impl(ptb_tracer* t, R* pixels) {
+    if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    CU(cudaSetDevice(t->device));
+    int r = ensure_staging(t, t->accum_bytes);
+    if (r) return r;
+    using V4 = typename Vec4T<R>::type;
+    uint32_t n = t->W * t->H;
+    k_resolve<R><<<(n + 255) / 256, 256, 0, t->stream>>>((const V4*)t->accum, (V4*)t->staging, n);
+    t->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pixels, t->staging, t->accum_bytes, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    return PTB_OK;
+}
+extern "C" {
+int ptb_download_f32(ptb_tracer* t, float* px) { int r = need_scene(t, 4); return r ? r : download_impl<float>(t, px); }
+int ptb_download_f64(ptb_tracer* t, double* px) { int r = need_scene(t, 8); return r ? r : download_impl<double>(t, px); }
+
+int ptb_frames(ptb_tracer* t, uint64_t* frames) {
+    if (!t || !frames) return fail(PTB_E_INVALID, "null argument");
+    *frames = t->frames;
+    return PTB_OK;
+}
+
+}  // extern "C"
+template <class R> static int render_fused(ptb_tracer* t, DScene<R>& d, uint32_t spp, uint64_t sample_base) {
+    RenderArgs a{};
+    a.accum = t->accum; a.W = t->W; a.H = t->H; a.spp = spp; a.sample_base = sample_base; a.seed = t->cfg.seed;
+    a.rr_start = t->cfg.rr_start;
+    a.tiles_x = (t->W + 15u) / 16u;
+    a.n_items = a.tiles_x * ((t->H + 15u) / 16u) * 256u;
+    a.work_counter = t->work_counter;
+    a.counters = t->counters;
+    int& blocks = sizeof(R) == 4 ? t->fused_blocks_f32 : t->fused_blocks_f64;
+    const bool count = t->cfg.collect_counters != 0;
+    if (blocks == 0) {
+        int per_sm = 0;
+        if (count) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_fused<R, true>, FUSED_THREADS, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_fused<R, false>, FUSED_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        blocks = per_sm * t->sm_count;
+    }
+    uint32_t max_useful = (a.n_items + FUSED_THREADS - 1) / FUSED_THREADS;
+    int grid = std::max(1, std::min<int>(blocks, (int)max_useful));
+    CU(cudaMemsetAsync(t->work_counter, 0, sizeof(unsigned int), t->stream));
+    CU(cudaEventRecord(t->ev0, t->stream));
+    if (count) k_render_fused<R, true><<<grid, FUSED_THREADS, 0, t->stream>>>(d, a);
+    else k_render_fused<R, false><<<grid, FUSED_THREADS, 0, t->stream>>>(d, a);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(t->ev1, t->stream));
+    t->timed = true;
+    t->launches++;
+    return PTB_OK;
+}
+
+extern "C" {
+int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
+    int r = need_scene(t, 0);
+    if (r) return r;
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    if (spp == 0) return PTB_OK;
+    CU(cudaSetDevice(t->device));
+    uint32_t integ = t->cfg.integrator == PTB_INTEGRATOR_AUTO ? PTB_INTEGRATOR_FUSED : t->cfg.integrator;
+    if (integ == PTB_INTEGRATOR_WAVEFRONT) {
+        if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the wavefront integrator is built for f32 only");
+        r = wavefront_render(t->wf, t->s32.d, t->accum, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters, t->ev0, t->ev1,
+                             &t->launches, g_err);
+        if (r) return r;
+        t->timed = true;
+    } else {
+        r = t->precision == 4 ? render_fused<float>(t, t->s32.d, spp, sample_base) : render_fused<double>(t, t->s64.d, spp, sample_base);
+        if (r) return r;
+    }
+    t->frames += spp;
+    return PTB_OK;
+}
+
+int ptb_synchronize(ptb_tracer* t) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    return PTB_OK;
+}
+
+}  // extern "C"
+template <class R> static int render_frame_impl(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t frames_before, R* pixels) {
+    if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
+    int r;
+    if (w != t->W || h != t->H || !t->accum) { if ((r = ptb_resize(t, w, h))) return r; }
+    if (frames_before == 0) { if ((r = ptb_clear(t))) return r; }
+    else if (frames_before != t->frames) { if ((r = upload_impl<R>(t, pixels, frames_before))) return r; }
+    if ((r = ptb_render(t, 1, frames_before))) return r;
+    return download_impl<R>(t, pixels);
+}
+extern "C" {
+int ptb_render_frame_f32(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, float* px) { int r = need_scene(t, 4); return r ? r : render_frame_impl<float>(t, w, h, fb, px); }
+int ptb_render_frame_f64(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, double* px) { int r = need_scene(t, 8); return r ? r : render_frame_impl<double>(t, w, h, fb, px); }
+
+int ptb_convert_to_u8(ptb_tracer* t, uint8_t* rgba8) {
+    int r = need_scene(t, 0);
+    if (r) return r;
+    if (!rgba8) return fail(PTB_E_INVALID, "rgba8 is NULL");
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    CU(cudaSetDevice(t->device));
+    uint32_t n = t->W * t->H;
+    if ((r = ensure_staging(t, (size_t)n * 4))) return r;
+    if (t->precision == 4) k_convert_u8<float><<<(n + 255) / 256, 256, 0, t->stream>>>((const float4*)t->accum, (uchar4*)t->staging, n, 1);
+    else k_convert_u8<double><<<(n + 255) / 256, 256, 0, t->stream>>>((const double4*)t->accum, (uchar4*)t->staging, n, 1);
+    t->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rgba8, t->staging, (size_t)n * 4, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    return PTB_OK;
+}
+
+int ptb_convert_to_u8_at(ptb_tracer* t, uint8_t* frame, uint32_t x, uint32_t y, uint32_t fw, uint32_t fh) {
+    int r = need_scene(t, 0);
+    if (r) return r;
+    if (!frame || !fw || !fh) return fail(PTB_E_INVALID, "bad frame");
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    CU(cudaSetDevice(t->device));
+    size_t bytes = (size_t)fw * fh * 4;
+    if ((r = ensure_staging(t, bytes))) return r;
+    CU(cudaMemcpyAsync(t->staging, frame, bytes, cudaMemcpyHostToDevice, t->stream));
+    uint32_t n = fw * fh;
+    if (t->precision == 4) k_convert_u8_at<float><<<(n + 255) / 256, 256, 0, t->stream>>>((const float4*)t->accum, t->W, t->H, (uchar4*)t->staging, x, y, fw, fh);
+    else k_convert_u8_at<double><<<(n + 255) / 256, 256, 0, t->stream>>>((const double4*)t->accum, t->W, t->H, (uchar4*)t->staging, x, y, fw, fh);
+    t->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(frame, t->staging, bytes, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    return PTB_OK;
+}
+
+int ptb_get_counters(ptb_tracer* t, ptb_counters* out) {
+    if (!t || !out) return fail(PTB_E_INVALID, "null argument");
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    static_assert(sizeof(DeviceCounters) == sizeof(ptb_counters), "counter layouts must match");
+    CU(cudaMemcpy(out, t->counters, sizeof(ptb_counters), cudaMemcpyDeviceToHost));
+    return PTB_OK;
+}
+int ptb_reset_counters(ptb_tracer* t) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    CU(cudaSetDevice(t->device));
+    CU(cudaMemsetAsync(t->counters, 0, sizeof(DeviceCounters), t->stream));
+    return PTB_OK;
+}
+int ptb_launch_count(ptb_tracer* t, uint64_t* launches) {
+    if (!t || !launches) return fail(PTB_E_INVALID, "null argument");
+    *launches = t->launches;
+    return PTB_OK;
+}
+int ptb_last_render_ms(ptb_tracer* t, float* ms) {
+    if (!t || !ms) return fail(PTB_E_INVALID, "null argument");
+    if (!t->timed) return fail(PTB_E_INVALID, "no render has been issued");
+    CU(cudaSetDevice(t->device));
+    CU(cudaEventSynchronize(t->ev1));
+    CU(cudaEventElapsedTime(ms, t->ev0, t->ev1));
+    return PTB_OK;
+}
+
+}  // extern "C"
+// ---- per-function parity entry points ----------------------------------------------------------
+namespace {
+struct Dev {   // device scratch holder for the test entry points
+    std::vector<void*> ptrs;
+    cudaStream_t st;
+    explicit Dev(cudaStream_t s) : st(s) {}
+    ~Dev() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> T* in(const T* host, size_t n) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        if (n) cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, st);
+        return (T*)d;
+    }
+    template <class T> T* out(size_t n) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(d);
+        cudaMemsetAsync(d, 0, std::max<size_t>(n, 1) * sizeof(T), st);
+        return (T*)d;
+    }
+    template <class T> void back(T* host, const T* dev, size_t n) {
+        if (n) cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, st);
+    }
+};
+inline unsigned grid_for(size_t n) { return (unsigned)std::max<size_t>(1, (n + 127) / 128); }
+}  // namespace
+
+extern "C" {
+#define TEST_BEGIN(need_sc)                                  \
+    int r_ = (need_sc) ? need_scene(t, 4) : (t ? PTB_OK : fail(PTB_E_INVALID, "null tracer")); \
+    if (r_) return r_;                                       \
+    CU(cudaSetDevice(t->device));                            \
+    Dev dv(t->stream);
+#define TEST_END()                           \
+    t->launches++;                           \
+    CU(cudaGetLastError());                  \
+    CU(cudaStreamSynchronize(t->stream));    \
+    return PTB_OK;
+
+int ptb_test_sphere_hit_f32(ptb_tracer* t, size_t n, const float* o, const float* d, const float* c, const float* r, float* t_out) {
+    TEST_BEGIN(false)
+    auto *po = dv.in(o, 3 * n), *pd = dv.in(d, 3 * n), *pc = dv.in(c, 3 * n), *pr = dv.in(r, n);
+    auto* pt = dv.out<float>(n);
+    k_test_sphere_hit<float><<<grid_for(n), 128, 0, t->stream>>>(n, po, pd, pc, pr, pt);
+    dv.back(t_out, pt, n);
+    TEST_END()
+}
+int ptb_test_plane_hit_f32(ptb_tracer* t, size_t n, const float* o, const float* d, const float* p, const float* nn, float* t_out) {
+    TEST_BEGIN(false)
+    auto *po = dv.in(o, 3 * n), *pd = dv.in(d, 3 * n), *pp = dv.in(p, 3 * n), *pn = dv.in(nn, 3 * n);
+    auto* pt = dv.out<float>(n);
+    k_test_plane_hit<float><<<grid_for(n), 128, 0, t->stream>>>(n, po, pd, pp, pn, pt);
+    dv.back(t_out, pt, n);
+    TEST_END()
+}
+int ptb_test_gen_ray_f32(ptb_tracer* t, size_t n, const float* p2, const float* off2, float w, float h, float* o_out, float* d_out) {
+    TEST_BEGIN(true)
+    DScene<float> sc = t->s32.d;
+    derive_camera(sc, t->c32, (uint32_t)w, (uint32_t)h);
+    auto *pp = dv.in(p2, 2 * n), *pf = dv.in(off2, 2 * n);
+    auto *po = dv.out<float>(3 * n), *pd = dv.out<float>(3 * n);
+    k_test_gen_ray<float><<<grid_for(n), 128, 0, t->stream>>>(sc, n, pp, pf, w, h, po, pd);
+    dv.back(o_out, po, 3 * n); dv.back(d_out, pd, 3 * n);
+    TEST_END()
+}
+int ptb_test_closest_hit_f32(ptb_tracer* t, size_t n, const float* o, const float* d, const float* hd_in, uint32_t* hit, uint32_t* em,
+                             float* hd_out, float* nrm, uint32_t* mat, float* lpdf, float* lem) {
+    TEST_BEGIN(true)
+    auto *po = dv.in(o, 3 * n), *pd = dv.in(d, 3 * n), *ph = dv.in(hd_in, n);
+    auto *qh = dv.out<uint32_t>(n), *qe = dv.out<uint32_t>(n), *qm = dv.out<uint32_t>(n);
+    auto *qd = dv.out<float>(n), *qn = dv.out<float>(3 * n), *qp = dv.out<float>(n), *ql = dv.out<float>(3 * n);
+    k_test_closest_hit<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, po, pd, ph, qh, qe, qd, qn, qm, qp, ql);
+    dv.back(hit, qh, n); dv.back(em, qe, n); dv.back(mat, qm, n); dv.back(hd_out, qd, n); dv.back(nrm, qn, 3 * n);
+    dv.back(lpdf, qp, n); dv.back(lem, ql, 3 * n);
+    TEST_END()
+}
+int ptb_test_any_hit_f32(ptb_tracer* t, size_t n, const float* o, const float* d, const float* md, uint32_t* hit) {
+    TEST_BEGIN(true)
+    auto *po = dv.in(o, 3 * n), *pd = dv.in(d, 3 * n), *pm = dv.in(md, n);
+    auto* qh = dv.out<uint32_t>(n);
+    k_test_any_hit<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, po, pd, pm, qh);
+    dv.back(hit, qh, n);
+    TEST_END()
+}
+int ptb_test_background_f32(ptb_tracer* t, size_t n, const float* d, float* rgb) {
+    TEST_BEGIN(true)
+    auto* pd = dv.in(d, 3 * n);
+    auto* q = dv.out<float>(3 * n);
+    k_test_background<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, pd, q);
+    dv.back(rgb, q, 3 * n);
+    TEST_END()
+}
+int ptb_test_sample_light_f32(ptb_tracer* t, size_t n, uint32_t li, const float* pos, const float* r1, const float* r2, float* nrm, float* em,
+                              float* dir, float* dist, float* pdf) {
+    TEST_BEGIN(true)
+    if (li >= t->s32.d.n_lights) return fail(PTB_E_INVALID, "light index out of range");
+    auto *pp = dv.in(pos, 3 * n), *p1 = dv.in(r1, n), *p2 = dv.in(r2, n);
+    auto *qn = dv.out<float>(3 * n), *qe = dv.out<float>(3 * n), *qd = dv.out<float>(3 * n), *qs = dv.out<float>(n), *qp = dv.out<float>(n);
+    k_test_sample_light<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, li, pp, p1, p2, qn, qe, qd, qs, qp);
+    dv.back(nrm, qn, 3 * n); dv.back(em, qe, 3 * n); dv.back(dir, qd, 3 * n); dv.back(dist, qs, n); dv.back(pdf, qp, n);
+    TEST_END()
+}
+int ptb_test_finalize_f32(ptb_tracer* t, size_t n, uint32_t mi, const float* o, const float* d, const float* hd, const float* nrm, float* rough,
+                          float* ccr, float* ax, float* ay, float* eta, float* ffn, float* fhp) {
+    TEST_BEGIN(true)
+    if (mi >= t->s32.d.n_materials) return fail(PTB_E_INVALID, "material index out of range");
+    auto *po = dv.in(o, 3 * n), *pd = dv.in(d, 3 * n), *ph = dv.in(hd, n), *pn = dv.in(nrm, 3 * n);
+    auto *q1 = dv.out<float>(n), *q2 = dv.out<float>(n), *q3 = dv.out<float>(n), *q4 = dv.out<float>(n), *q5 = dv.out<float>(n);
+    auto *q6 = dv.out<float>(3 * n), *q7 = dv.out<float>(3 * n);
+    k_test_finalize<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, mi, po, pd, ph, pn, q1, q2, q3, q4, q5, q6, q7);
+    dv.back(rough, q1, n); dv.back(ccr, q2, n); dv.back(ax, q3, n); dv.back(ay, q4, n); dv.back(eta, q5, n);
+    dv.back(ffn, q6, 3 * n); dv.back(fhp, q7, 3 * n);
+    TEST_END()
+}
+int ptb_test_disney_eval_f32(ptb_tracer* t, size_t n, uint32_t mi, const float* eta, const float* v, const float* nrm, const float* l,
+                             float* f_out, float* pdf_out) {
+    TEST_BEGIN(true)
+    if (mi >= t->s32.d.n_materials) return fail(PTB_E_INVALID, "material index out of range");
+    auto *pe = dv.in(eta, n), *pv = dv.in(v, 3 * n), *pn = dv.in(nrm, 3 * n), *pl = dv.in(l, 3 * n);
+    auto *qf = dv.out<float>(3 * n), *qp = dv.out<float>(n);
+    k_test_disney_eval<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, mi, pe, pv, pn, pl, qf, qp);
+    dv.back(f_out, qf, 3 * n); dv.back(pdf_out, qp, n);
+    TEST_END()
+}
+int ptb_test_disney_sample_f32(ptb_tracer* t, size_t n, uint32_t mi, const float* eta, const float* v, const float* nrm, const float* lprev,
+                               const float* r1, const float* r2, const float* coin, uint32_t* lobe, float* l_out, float* f_out, float* pdf_out) {
+    TEST_BEGIN(true)
+    if (mi >= t->s32.d.n_materials) return fail(PTB_E_INVALID, "material index out of range");
+    auto *pe = dv.in(eta, n), *pv = dv.in(v, 3 * n), *pn = dv.in(nrm, 3 * n), *pl = dv.in(lprev, 3 * n);
+    auto *p1 = dv.in(r1, n), *p2 = dv.in(r2, n), *p3 = dv.in(coin, n);
+    auto* ql = dv.out<uint32_t>(n);
+    auto *qd = dv.out<float>(3 * n), *qf = dv.out<float>(3 * n), *qp = dv.out<float>(n);
+    k_test_disney_sample<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, mi, pe, pv, pn, pl, p1, p2, p3, ql, qd, qf, qp);
+    dv.back(lobe, ql, n); dv.back(l_out, qd, 3 * n); dv.back(f_out, qf, 3 * n); dv.back(pdf_out, qp, n);
+    TEST_END()
+}
+int ptb_test_rng_f32(ptb_tracer* t, size_t n, const uint32_t* pixel, const uint64_t* sample, uint32_t bounce, float* out8) {
+    TEST_BEGIN(false)
+    auto* pp = dv.in(pixel, n);
+    auto* ps = dv.in((const unsigned long long*)sample, n);
+    auto* q = dv.out<float>(8 * n);
+    k_test_rng<float><<<grid_for(n), 128, 0, t->stream>>>(n, pp, ps, bounce, t->cfg.seed, q);
+    dv.back(out8, q, 8 * n);
+    TEST_END()
+}
+int ptb_test_convert_to_u8_f32(ptb_tracer* t, size_t n_pixels, const float* rgba, uint8_t* out) {
+    TEST_BEGIN(false)
+    auto* pi = dv.in(rgba, 4 * n_pixels);
+    auto* q = dv.out<uint8_t>(4 * n_pixels);
+    k_convert_u8<float><<<(unsigned)std::max<size_t>(1, (n_pixels + 255) / 256), 256, 0, t->stream>>>((const float4*)pi, (uchar4*)q, (uint32_t)n_pixels, 0);
+    dv.back(out, q, 4 * n_pixels);
+    TEST_END()
+}
+
+}  // extern "C"

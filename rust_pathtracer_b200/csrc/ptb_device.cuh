@@ -1,0 +1,1011 @@
+// ptb_device.cuh — device-side building blocks of the B200 path-tracing loop (sm_100a).
+//
+// Everything here is __device__ code templated on the scalar type R (float | double), the device
+// counterpart of the reference's `type F` switch (rust-pathtracer/src/lib.rs:5-6).  The functions
+// are shared by the fused persistent integrator, the wavefront stage kernels and the per-function
+// parity entry points, so what the tests measure is what the integrators run.
+//
+// Reference citations are relative to /root/reference/.  The code is NOT a transliteration:
+// loop-invariant camera terms are hoisted to the host, the shading frame / specular colours are
+// computed once per bounce and shared between next-event estimation and BSDF sampling, hit
+// attributes are computed once for the winning primitive, and materials are resolved after the
+// intersection loop from an "accepted primitive" bitmask.  All of these are value-preserving with
+// respect to the reference's arithmetic (same operations on the same operands), up to FMA
+// contraction and CUDA libm rounding, which the 1e-5 parity tests bound.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ptb200.h"
+
+namespace ptb {
+
+// ------------------------------------------------------------------------------------------------
+// scalar math wrappers
+#define PTB_DEV __device__ __forceinline__
+#define PTB_HD __host__ __device__ __forceinline__
+
+PTB_DEV float m_sqrt(float x) { return sqrtf(x); }
+PTB_DEV double m_sqrt(double x) { return sqrt(x); }
+PTB_DEV float m_abs(float x) { return fabsf(x); }
+PTB_DEV double m_abs(double x) { return fabs(x); }
+PTB_DEV float m_max(float a, float b) { return fmaxf(a, b); }   // f32::max: NaN-ignoring
+PTB_DEV double m_max(double a, double b) { return fmax(a, b); }
+PTB_DEV float m_pow(float a, float b) { return powf(a, b); }
+PTB_DEV double m_pow(double a, double b) { return pow(a, b); }
+PTB_DEV float m_log2(float a) { return log2f(a); }
+PTB_DEV double m_log2(double a) { return log2(a); }
+PTB_DEV float m_floor(float a) { return floorf(a); }
+PTB_DEV double m_floor(double a) { return floor(a); }
+PTB_DEV float m_fmod(float a, float b) { return fmodf(a, b); }
+PTB_DEV double m_fmod(double a, double b) { return fmod(a, b); }
+PTB_DEV void m_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+PTB_DEV void m_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+template <class R> PTB_DEV R m_clamp(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); }  // f32::clamp
+
+template <class R> struct Const;
+template <> struct Const<float> {
+    static constexpr float PI = 3.14159265358979323846f;
+    static constexpr float INV_PI = 1.0f / 3.14159265358979323846f;      // lib.rs:9, evaluated in F
+    static constexpr float TWO_PI = 3.14159265358979323846f * 2.0f;      // lib.rs:10
+    static constexpr float MAXV = 3.402823466e+38f;
+};
+template <> struct Const<double> {
+    static constexpr double PI = 3.14159265358979323846;
+    static constexpr double INV_PI = 1.0 / 3.14159265358979323846;
+    static constexpr double TWO_PI = 3.14159265358979323846 * 2.0;
+    static constexpr double MAXV = 1.7976931348623157e+308;
+};
+
+// ------------------------------------------------------------------------------------------------
+// F3 (fx.rs:209-515)
+template <class R> struct V3 {
+    R x, y, z;
+    PTB_HD V3() {}
+    PTB_HD V3(R a, R b, R c) : x(a), y(b), z(c) {}
+};
+template <class R> PTB_HD V3<R> operator+(V3<R> a, V3<R> b) { return V3<R>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <class R> PTB_HD V3<R> operator-(V3<R> a, V3<R> b) { return V3<R>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <class R> PTB_HD V3<R> operator*(V3<R> a, V3<R> b) { return V3<R>(a.x * b.x, a.y * b.y, a.z * b.z); }
+template <class R> PTB_HD V3<R> operator*(R s, V3<R> a) { return V3<R>(s * a.x, s * a.y, s * a.z); }
+template <class R> PTB_HD V3<R> operator-(V3<R> a) { return V3<R>(-a.x, -a.y, -a.z); }
+template <class R> PTB_HD R dot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class R> PTB_HD V3<R> cross(V3<R> a, V3<R> b) {
+    return V3<R>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template <class R> PTB_DEV R length(V3<R> a) { return m_sqrt(dot(a, a)); }
+template <class R> PTB_DEV V3<R> div_s(V3<R> a, R s) { return V3<R>(a.x / s, a.y / s, a.z / s); }
+template <class R> PTB_DEV V3<R> normalize(V3<R> a) { return div_s(a, length(a)); }     // fx.rs:306-313
+template <class R> PTB_DEV V3<R> mix3(V3<R> a, V3<R> b, R v) {                          // math.rs:33-39
+    R w = R(1) - v;
+    return V3<R>(w * a.x + b.x * v, w * a.y + b.y * v, w * a.z + b.z * v);
+}
+template <class R> PTB_DEV R mix1(R a, R b, R v) { return (R(1) - v) * a + b * v; }     // tracer.rs:228-231
+
+// ------------------------------------------------------------------------------------------------
+// Counter RNG: Philox4x32-10, key = (pixel, sample lo), ctr = (block, sample hi, seed lo, seed hi).
+// Slot layout in SURVEY.md §8d / oracle/pt_oracle.hpp.  Bit-exact with the oracle by construction
+// (integer arithmetic only; the uint->float conversions are exact).
+struct Philox4 { uint32_t v[4]; };
+PTB_DEV Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += W0;
+        k1 += W1;
+    }
+    Philox4 o;
+    o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+    return o;
+}
+
+template <class R> struct Rng;
+// f32: two blocks per bounce, four 24-bit draws each
+template <> struct Rng<float> {
+    uint32_t pixel, s_lo, s_hi, seed_lo, seed_hi;
+    PTB_DEV Rng(uint32_t p, uint64_t sample, uint64_t seed)
+        : pixel(p), s_lo((uint32_t)sample), s_hi((uint32_t)(sample >> 32)), seed_lo((uint32_t)seed), seed_hi((uint32_t)(seed >> 32)) {}
+    PTB_DEV static float u(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+    // slots 4*half .. 4*half+3 of `bounce`
+    PTB_DEV void block(uint32_t bounce, uint32_t half, float out[4]) const {
+        Philox4 p = philox4x32_10(bounce * 2u + half, s_hi, seed_lo, seed_hi, pixel, s_lo);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[i] = u(p.v[i]);
+    }
+    // all 8 slots of a bounce
+    PTB_DEV void draws(uint32_t bounce, float out[8]) const {
+        block(bounce, 0, out);
+        block(bounce, 1, out + 4);
+    }
+};
+// f64: four blocks per bounce, two 53-bit draws each
+template <> struct Rng<double> {
+    uint32_t pixel, s_lo, s_hi, seed_lo, seed_hi;
+    PTB_DEV Rng(uint32_t p, uint64_t sample, uint64_t seed)
+        : pixel(p), s_lo((uint32_t)sample), s_hi((uint32_t)(sample >> 32)), seed_lo((uint32_t)seed), seed_hi((uint32_t)(seed >> 32)) {}
+    PTB_DEV static double u(uint32_t w0, uint32_t w1) {
+        uint64_t bits = (((uint64_t)w0 << 32) | w1) >> 11;
+        return (double)bits * (1.0 / 9007199254740992.0);
+    }
+    PTB_DEV void block(uint32_t bounce, uint32_t half, double out[4]) const {
+#pragma unroll
+        for (uint32_t q = 0; q < 2; ++q) {
+            Philox4 p = philox4x32_10(bounce * 4u + half * 2u + q, s_hi, seed_lo, seed_hi, pixel, s_lo);
+            out[q * 2 + 0] = u(p.v[0], p.v[1]);
+            out[q * 2 + 1] = u(p.v[2], p.v[3]);
+        }
+    }
+    PTB_DEV void draws(uint32_t bounce, double out[8]) const {
+        block(bounce, 0, out);
+        block(bounce, 1, out + 4);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Device scene (what ptb_set_scene_* builds from the POD export)
+template <class R> struct DMaterial {
+    // resolved values: Material::new() defaults (material.rs:82-114) patched by this material
+    R rgb[3], emission[3];
+    R anisotropic, metallic, roughness, subsurface, specular_tint, sheen, sheen_tint, clearcoat, clearcoat_gloss, spec_trans, ior;
+    uint32_t set_mask, albedo_kind;
+    R checker_a, checker_b, checker_scale, checker_offset;
+};
+template <class R> struct DSphere { R cx, cy, cz, r; };                 // float4 for f32
+template <class R> struct DPlane { R px, py, pz, nx, ny, nz; };
+template <class R> struct DLight { R px, py, pz, radius, ex, ey, ez, area; uint32_t type, pad[3]; };
+
+// 32-byte BVH node over spheres (f32 bounds even for the f64 build; bounds are conservative).
+struct BvhNode {
+    float lo[3]; uint32_t left_or_first;   // inner: left child index (right = left + 1); leaf: first prim
+    float hi[3]; uint32_t count;           // 0 = inner, >0 = leaf prim count
+};
+
+constexpr int PTB_SMEM_MAX_SPHERES = 64;
+constexpr int PTB_SMEM_MAX_PLANES = 8;
+constexpr int PTB_SMEM_MAX_MATERIALS = 64;
+constexpr int PTB_SMEM_MAX_LIGHTS = 64;
+
+template <class R> struct DScene {
+    uint32_t n_spheres, n_planes, n_materials, n_lights;
+    const DSphere<R>* spheres;          // global memory (HBM), SoA-of-float4
+    const uint32_t* sphere_material;
+    const DPlane<R>* planes;
+    const uint32_t* plane_material;
+    const DMaterial<R>* materials;
+    const DLight<R>* lights;
+    const BvhNode* bvh;                 // NULL when the scene is small
+    const uint32_t* bvh_prim;           // sphere indices in leaf order
+    uint32_t use_bvh;
+    uint32_t patch_materials;           // 1 if any set_mask != PTB_MAT_ALL (order-dependent patching)
+    uint32_t depth, flags;
+    R eps;
+    // camera/pinhole.rs:38-61 with the loop-invariant part hoisted (host, same op order, in R)
+    R cam_origin[3], cam_base[3] /* lower_left - origin */, cam_horizontal[3], cam_vertical[3];
+    // background
+    uint32_t bg_kind;
+    R bg_a[3], bg_b[3], bg_scale, bg_gamma;
+    R n_lights_f;                       // number_of_lights() as F (tracer.rs:138,214)
+};
+
+// Scene arrays as the kernels read them: shared-memory copies for small scenes.
+template <class R> struct SceneView {
+    const DSphere<R>* spheres;
+    const uint32_t* sphere_material;
+    const DPlane<R>* planes;
+    const uint32_t* plane_material;
+    const DMaterial<R>* materials;
+    const DLight<R>* lights;
+};
+
+template <class R> struct SceneSmem {
+    DSphere<R> spheres[PTB_SMEM_MAX_SPHERES];
+    uint32_t sphere_material[PTB_SMEM_MAX_SPHERES];
+    DPlane<R> planes[PTB_SMEM_MAX_PLANES];
+    uint32_t plane_material[PTB_SMEM_MAX_PLANES];
+    DMaterial<R> materials[PTB_SMEM_MAX_MATERIALS];
+    DLight<R> lights[PTB_SMEM_MAX_LIGHTS];
+};
+
+template <class R> PTB_DEV bool scene_fits_smem(const DScene<R>& s) {
+    return s.n_spheres <= PTB_SMEM_MAX_SPHERES && s.n_planes <= PTB_SMEM_MAX_PLANES && s.n_materials <= PTB_SMEM_MAX_MATERIALS &&
+           s.n_lights <= PTB_SMEM_MAX_LIGHTS;
+}
+
+// Cooperative copy of the (small) scene arrays into shared memory; call from all threads of the CTA.
+template <class R> __device__ inline SceneView<R> stage_scene(const DScene<R>& s, SceneSmem<R>* sm) {
+    SceneView<R> v;
+    const bool small = scene_fits_smem(s);
+    // lights / planes / materials are always small enough or stay in global memory together
+    if (small) {
+        const int tid = threadIdx.x, nt = blockDim.x;
+        auto copy_words = [&](void* dst, const void* src, uint32_t bytes) {
+            uint32_t* d = (uint32_t*)dst;
+            const uint32_t* q = (const uint32_t*)src;
+            for (uint32_t i = tid; i < bytes / 4u; i += nt) d[i] = q[i];
+        };
+        copy_words(sm->spheres, s.spheres, s.n_spheres * sizeof(DSphere<R>));
+        copy_words(sm->sphere_material, s.sphere_material, s.n_spheres * sizeof(uint32_t));
+        copy_words(sm->planes, s.planes, s.n_planes * sizeof(DPlane<R>));
+        copy_words(sm->plane_material, s.plane_material, s.n_planes * sizeof(uint32_t));
+        copy_words(sm->materials, s.materials, s.n_materials * sizeof(DMaterial<R>));
+        copy_words(sm->lights, s.lights, s.n_lights * sizeof(DLight<R>));
+        __syncthreads();
+        v.spheres = sm->spheres; v.sphere_material = sm->sphere_material;
+        v.planes = sm->planes; v.plane_material = sm->plane_material;
+        v.materials = sm->materials; v.lights = sm->lights;
+    } else {
+        v.spheres = s.spheres; v.sphere_material = s.sphere_material;
+        v.planes = s.planes; v.plane_material = s.plane_material;
+        v.materials = s.materials; v.lights = s.lights;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Material in registers (material.rs:48-78 + derived fields of finalize, material.rs:117-131)
+template <class R> struct Mat {
+    V3<R> rgb, emission;
+    R anisotropic, metallic, roughness, subsurface, specular_tint, sheen, sheen_tint, clearcoat, clearcoat_gloss, spec_trans, ior;
+    R clearcoat_roughness, ax, ay;
+};
+
+template <class R> PTB_DEV void mat_defaults(Mat<R>& m) {    // material.rs:82-114
+    m.rgb = V3<R>(R(1.5), R(1.5), R(1.5));
+    m.emission = V3<R>(0, 0, 0);
+    m.anisotropic = 0; m.metallic = 0; m.roughness = R(0.5); m.subsurface = 0; m.specular_tint = 0;
+    m.sheen = 0; m.sheen_tint = 0; m.clearcoat = 0; m.clearcoat_gloss = 0; m.spec_trans = 0; m.ior = R(1.45);
+    m.clearcoat_roughness = 0; m.ax = 0; m.ay = 0;
+}
+
+// analytical.rs:107-111
+template <class R> PTB_DEV R checker(R x, R y, R a, R b) {
+    R x1 = m_fmod(m_floor(x), R(2));
+    R y1 = m_fmod(m_floor(y), R(2));
+    return (m_fmod(x1 + y1, R(2)) < R(1)) ? a : b;
+}
+
+template <class R> PTB_DEV V3<R> material_rgb(const DMaterial<R>& dm, V3<R> rd) {
+    if (dm.albedo_kind == PTB_ALBEDO_CHECKER_DIR_RATIO) {   // analytical.rs:113-115 (quirk A.7)
+        R c = checker(rd.x / rd.y * dm.checker_scale + dm.checker_offset, rd.z / rd.y * dm.checker_scale + dm.checker_offset,
+                      dm.checker_a, dm.checker_b);
+        return V3<R>(c, c, c);
+    }
+    return V3<R>(dm.rgb[0], dm.rgb[1], dm.rgb[2]);
+}
+
+// first accepted primitive: defaults patched by dm == dm's resolved values
+template <class R> PTB_DEV void mat_load(Mat<R>& m, const DMaterial<R>& dm, V3<R> rd) {
+    m.rgb = (dm.set_mask & PTB_MAT_RGB) ? material_rgb(dm, rd) : V3<R>(dm.rgb[0], dm.rgb[1], dm.rgb[2]);
+    m.emission = V3<R>(dm.emission[0], dm.emission[1], dm.emission[2]);
+    m.anisotropic = dm.anisotropic; m.metallic = dm.metallic; m.roughness = dm.roughness; m.subsurface = dm.subsurface;
+    m.specular_tint = dm.specular_tint; m.sheen = dm.sheen; m.sheen_tint = dm.sheen_tint; m.clearcoat = dm.clearcoat;
+    m.clearcoat_gloss = dm.clearcoat_gloss; m.spec_trans = dm.spec_trans; m.ior = dm.ior;
+}
+// later accepted primitives assign only their masked fields (see PTB_MAT_* in ptb200.h)
+template <class R> PTB_DEV void mat_patch(Mat<R>& m, const DMaterial<R>& dm, V3<R> rd) {
+    const uint32_t k = dm.set_mask;
+    if (k & PTB_MAT_RGB) m.rgb = material_rgb(dm, rd);
+    if (k & PTB_MAT_EMISSION) m.emission = V3<R>(dm.emission[0], dm.emission[1], dm.emission[2]);
+    if (k & PTB_MAT_ANISOTROPIC) m.anisotropic = dm.anisotropic;
+    if (k & PTB_MAT_METALLIC) m.metallic = dm.metallic;
+    if (k & PTB_MAT_ROUGHNESS) m.roughness = dm.roughness;
+    if (k & PTB_MAT_SUBSURFACE) m.subsurface = dm.subsurface;
+    if (k & PTB_MAT_SPECULAR_TINT) m.specular_tint = dm.specular_tint;
+    if (k & PTB_MAT_SHEEN) m.sheen = dm.sheen;
+    if (k & PTB_MAT_SHEEN_TINT) m.sheen_tint = dm.sheen_tint;
+    if (k & PTB_MAT_CLEARCOAT) m.clearcoat = dm.clearcoat;
+    if (k & PTB_MAT_CLEARCOAT_GLOSS) m.clearcoat_gloss = dm.clearcoat_gloss;
+    if (k & PTB_MAT_SPEC_TRANS) m.spec_trans = dm.spec_trans;
+    if (k & PTB_MAT_IOR) m.ior = dm.ior;
+}
+// material.rs:117-131
+template <class R> PTB_DEV void mat_finalize(Mat<R>& m) {
+    m.roughness = m_max(m.roughness, R(0.01));
+    m.clearcoat_roughness = mix1(R(0.1), R(0.001), m.clearcoat_gloss);
+    R aspect = m_sqrt(R(1) - m.anisotropic * R(0.9));
+    m.ax = m_max(m.roughness / aspect, R(0.001));
+    m.ay = m_max(m.roughness * aspect, R(0.001));
+}
+
+// ------------------------------------------------------------------------------------------------
+// intersections
+// analytical.rs:166-190 / scene.rs:39-63.  Returns t >= 0 or -1 for None.  The cancelling
+// expression d2 = l.l - tca^2 is evaluated without FMA contraction so that near-tangent rays take
+// the same branch as the reference's separately rounded products far more often.
+PTB_DEV float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+PTB_DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+PTB_DEV float add_rn(float a, float b) { return __fadd_rn(a, b); }
+PTB_DEV double add_rn(double a, double b) { return __dadd_rn(a, b); }
+PTB_DEV float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+PTB_DEV double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+template <class R> PTB_DEV R dot_rn(V3<R> a, V3<R> b) {
+    return add_rn(add_rn(mul_rn(a.x, b.x), mul_rn(a.y, b.y)), mul_rn(a.z, b.z));
+}
+
+template <class R> PTB_DEV R isect_sphere(V3<R> o, V3<R> d, V3<R> c, R radius) {
+    V3<R> l = c - o;
+    R tca = dot_rn(l, d);
+    R d2 = sub_rn(dot_rn(l, l), mul_rn(tca, tca));
+    R radius2 = radius * radius;
+    if (d2 > radius2) return R(-1);
+    R thc = m_sqrt(radius2 - d2);
+    R t0 = tca - thc, t1 = tca + thc;
+    if (t0 > t1) { R tmp = t0; t0 = t1; t1 = tmp; }
+    if (t0 < R(0)) {
+        t0 = t1;
+        if (t0 < R(0)) return R(-1);
+    }
+    return t0;
+}
+// analytical.rs:193-204 generalised to (point, normal)
+template <class R> PTB_DEV R isect_plane(V3<R> o, V3<R> d, V3<R> p, V3<R> n) {
+    R denom = dot_rn(n, d);
+    if (m_abs(denom) > R(0.0001)) {
+        R t = dot_rn(p - o, n) / denom;
+        if (t >= R(0)) return t;
+    }
+    return R(-1);
+}
+
+// camera/pinhole.rs:38-61 (invariants hoisted into DScene by the host); p = film position,
+// off = jitter, inv_w/inv_h = pixel_size
+template <class R> PTB_DEV void gen_ray(const DScene<R>& s, R px, R py, R offx, R offy, R inv_w, R inv_h, V3<R>& o, V3<R>& d) {
+    R a = inv_w * offx + px;
+    R b = inv_h * offy + py;
+    V3<R> rd(s.cam_base[0], s.cam_base[1], s.cam_base[2]);
+    rd = rd + V3<R>(s.cam_horizontal[0] * a, s.cam_horizontal[1] * a, s.cam_horizontal[2] * a);
+    rd = rd + V3<R>(s.cam_vertical[0] * b, s.cam_vertical[1] * b, s.cam_vertical[2] * b);
+    o = V3<R>(s.cam_origin[0], s.cam_origin[1], s.cam_origin[2]);
+    d = normalize(rd);
+}
+
+// film coordinates of tracer.rs:34-46 for pixel x of memory row `row` (0 = top)
+template <class R> PTB_DEV void film_coords(uint32_t x, uint32_t row, uint32_t W, uint32_t H, R& px, R& py) {
+    // j counts rows from the LAST memory row (par_rchunks_exact_mut): j = H-1-row; y = H - j
+    R hf = (R)H;
+    R y = hf - (R)(H - 1u - row);
+    R yy = y / hf;
+    px = (R)x / (R)W;
+    py = R(1) - yy;
+}
+
+// Scene::background, analytical.rs:28-32
+template <class R> PTB_DEV V3<R> background(const DScene<R>& s, V3<R> d) {
+    V3<R> a(s.bg_a[0], s.bg_a[1], s.bg_a[2]);
+    if (s.bg_kind == PTB_BG_GRADIENT_Y) {
+        R t = R(0.5) * (d.y + R(1));
+        V3<R> b(s.bg_b[0], s.bg_b[1], s.bg_b[2]);
+        V3<R> c = (R(1) - t) * a + t * b;
+        return V3<R>(m_pow(c.x, s.bg_gamma) * s.bg_scale, m_pow(c.y, s.bg_gamma) * s.bg_scale, m_pow(c.z, s.bg_gamma) * s.bg_scale);
+    }
+    return a;
+}
+
+// Result of Scene::closest_hit (analytical.rs:36-127 + scene.rs:36-86)
+template <class R> struct HitRec {
+    bool hit, is_emitter;
+    R hit_dist;            // state.hit_dist after the call (stale value kept when nothing was hit, A.1)
+    V3<R> normal;          // geometry normal of the closest geometric hit (valid if geom)
+    bool geom;             // a sphere/plane was accepted this call
+    uint32_t material;     // material index of the final geometric hit, 0xffffffff if none
+    R light_pdf;           // light_sample.pdf   (valid if is_emitter)
+    V3<R> light_emission;  // light_sample.emission
+};
+
+// BVH traversal (closest): returns best sphere index or -1, updates best_t.
+template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
+    int best = -1;
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float idx = 1.0f / (float)d.x, idy = 1.0f / (float)d.y, idz = 1.0f / (float)d.z;
+    uint32_t stack[48];
+    int sp = 0;
+    uint32_t node = 0;
+    while (true) {
+        const BvhNode nd = s.bvh[node];
+        // slab test, inflated by a relative margin so that f32 rounding can never cull a true hit
+        float tx0 = (nd.lo[0] - ox) * idx, tx1 = (nd.hi[0] - ox) * idx;
+        float ty0 = (nd.lo[1] - oy) * idy, ty1 = (nd.hi[1] - oy) * idy;
+        float tz0 = (nd.lo[2] - oz) * idz, tz1 = (nd.hi[2] - oz) * idz;
+        float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+        float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+        bool overlap = tn * 0.9999f <= tf * 1.0001f && (float)best_t >= tn * 0.9999f;
+        if (overlap) {
+            if (nd.count == 0) {
+                stack[sp++] = nd.left_or_first + 1;
+                node = nd.left_or_first;
+                continue;
+            }
+            for (uint32_t i = 0; i < nd.count; ++i) {
+                uint32_t si = s.bvh_prim[nd.left_or_first + i];
+                DSphere<R> sp_ = s.spheres[si];
+                R t = isect_sphere(o, d, V3<R>(sp_.cx, sp_.cy, sp_.cz), sp_.r);
+                // reference order: ascending index, strict `d < dist` => lowest index wins ties
+                if (t >= R(0) && (t < best_t || (t == best_t && (int)si < best))) { best_t = t; best = (int)si; }
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return best;
+}
+template <class R> PTB_DEV bool bvh_any(const DScene<R>& s, V3<R> o, V3<R> d, R max_dist, bool ignore_max) {
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float idx = 1.0f / (float)d.x, idy = 1.0f / (float)d.y, idz = 1.0f / (float)d.z;
+    const float tmax = ignore_max ? 3.0e38f : (float)max_dist;
+    uint32_t stack[48];
+    int sp = 0;
+    uint32_t node = 0;
+    while (true) {
+        const BvhNode nd = s.bvh[node];
+        float tx0 = (nd.lo[0] - ox) * idx, tx1 = (nd.hi[0] - ox) * idx;
+        float ty0 = (nd.lo[1] - oy) * idy, ty1 = (nd.hi[1] - oy) * idy;
+        float tz0 = (nd.lo[2] - oz) * idz, tz1 = (nd.hi[2] - oz) * idz;
+        float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+        float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+        bool overlap = tn * 0.9999f <= tf * 1.0001f && tmax >= tn * 0.9999f;
+        if (overlap) {
+            if (nd.count == 0) {
+                stack[sp++] = nd.left_or_first + 1;
+                node = nd.left_or_first;
+                continue;
+            }
+            for (uint32_t i = 0; i < nd.count; ++i) {
+                DSphere<R> sp_ = s.spheres[s.bvh_prim[nd.left_or_first + i]];
+                R t = isect_sphere(o, d, V3<R>(sp_.cx, sp_.cy, sp_.cz), sp_.r);
+                if (t >= R(0) && (ignore_max || t < max_dist)) return true;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return false;
+}
+
+// Scene::closest_hit for the exported scene.  `hit_dist_in` is State::hit_dist carried across
+// bounces (A.1).  Fills `mat` (un-finalized) when geometry was accepted.
+template <class R>
+PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, Mat<R>& mat) {
+    HitRec<R> h;
+    h.hit = false; h.is_emitter = false; h.geom = false; h.hit_dist = hit_dist_in; h.material = 0xffffffffu;
+    h.light_pdf = 0; h.light_emission = V3<R>(0, 0, 0); h.normal = V3<R>(0, 0, 0);
+    R dist = Const<R>::MAXV;
+    int best = -1;                 // < n_spheres: sphere; else plane (best - n_spheres)
+    uint64_t accepted = 0;         // bit i set: primitive i was "closest so far" when tested (patching scenes only)
+    if (s.use_bvh) {
+        best = bvh_closest(s, o, d, dist);
+    } else {
+        for (uint32_t i = 0; i < s.n_spheres; ++i) {
+            DSphere<R> sp = sv.spheres[i];
+            R t = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
+            if (t >= R(0) && (i == 0 || t < dist)) {   // analytical.rs:43 (unconditional), :74 (d < dist)
+                dist = t; best = (int)i; accepted |= (1ull << (i & 63u));
+            }
+        }
+    }
+    for (uint32_t i = 0; i < s.n_planes; ++i) {
+        DPlane<R> pl = sv.planes[i];
+        R t = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
+        if (t >= R(0) && t < dist) {                   // analytical.rs:101-103
+            dist = t; best = (int)(s.n_spheres + i); accepted |= (1ull << ((s.n_spheres + i) & 63u));
+        }
+    }
+    if (best >= 0) {
+        h.hit = true; h.geom = true; h.hit_dist = dist;
+        uint32_t mi;
+        if ((uint32_t)best < s.n_spheres) {
+            DSphere<R> sp = s.use_bvh ? s.spheres[best] : sv.spheres[best];
+            V3<R> c(sp.cx, sp.cy, sp.cz);
+            V3<R> hp = o + dist * d;                   // analytical.rs:45-46
+            h.normal = normalize(hp - c);
+            mi = s.use_bvh ? s.sphere_material[best] : sv.sphere_material[best];
+        } else {
+            DPlane<R> pl = sv.planes[best - s.n_spheres];
+            h.normal = V3<R>(pl.nx, pl.ny, pl.nz);     // analytical.rs:105
+            mi = sv.plane_material[best - s.n_spheres];
+        }
+        h.material = mi;
+        if (!s.patch_materials) {
+            mat_load(mat, sv.materials[mi], d);
+        } else {
+            // replay the reference's assignment order over the accepted primitives
+            bool first = true;
+            while (accepted) {
+                int i = __ffsll((long long)accepted) - 1;
+                accepted &= accepted - 1;
+                uint32_t m = (uint32_t)i < s.n_spheres ? sv.sphere_material[i] : sv.plane_material[i - s.n_spheres];
+                if (first) { mat_load(mat, sv.materials[m], d); first = false; }
+                else mat_patch(mat, sv.materials[m], d);
+            }
+        }
+    }
+    // Scene::sample_lights, scene.rs:36-86 — starts from the possibly stale state.hit_dist
+    R ldist = h.hit_dist;
+    int lbest = -1;
+    for (uint32_t i = 0; i < s.n_lights; ++i) {
+        DLight<R> L = sv.lights[i];
+        if (L.type != PTB_LIGHT_SPHERICAL) continue;
+        R t = isect_sphere(o, d, V3<R>(L.px, L.py, L.pz), L.radius);
+        if (t >= R(0) && t < ldist) { ldist = t; lbest = (int)i; }
+    }
+    if (lbest >= 0) {
+        DLight<R> L = sv.lights[lbest];
+        V3<R> hp = o + ldist * d;
+        R cos_theta = dot(-d, normalize(hp - V3<R>(L.px, L.py, L.pz)));
+        h.light_pdf = (ldist * ldist) / (L.area * cos_theta * R(0.5));       // scene.rs:75
+        h.light_emission = V3<R>(L.ex, L.ey, L.ez);
+        h.is_emitter = true;
+        h.hit_dist = ldist;
+        h.hit = true;
+    }
+    return h;
+}
+
+// Scene::any_hit, analytical.rs:130-145 (+ max_dist unless the scene flag says the impl ignores it)
+template <class R> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+    const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
+    if (s.use_bvh) {
+        if (bvh_any(s, o, d, max_dist, ignore)) return true;
+    } else {
+        for (uint32_t i = 0; i < s.n_spheres; ++i) {
+            DSphere<R> sp = sv.spheres[i];
+            R t = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
+            if (t >= R(0) && (ignore || t < max_dist)) return true;
+        }
+    }
+    for (uint32_t i = 0; i < s.n_planes; ++i) {
+        DPlane<R> pl = sv.planes[i];
+        R t = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
+        if (t >= R(0) && (ignore || t < max_dist)) return true;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Disney BSDF terms (tracer.rs:222-439)
+template <class R> PTB_DEV R power_heuristic(R a, R b) { R t = a * a; return t / (b * b + t); }   // tracer.rs:223-226
+template <class R> PTB_DEV R luminance(V3<R> c) { return R(0.212671) * c.x + R(0.715160) * c.y + R(0.072169) * c.z; }
+template <class R> PTB_DEV R schlick_fresnel(R u) {                                                // tracer.rs:288-292
+    R m = m_clamp(R(1) - u, R(0), R(1));
+    R m2 = m * m;
+    return m2 * m2 * m;
+}
+template <class R> PTB_DEV R dielectric_fresnel(R cos_theta_i, R eta) {                            // tracer.rs:308-322
+    R sin_theta_tsq = eta * eta * (R(1) - cos_theta_i * cos_theta_i);
+    if (sin_theta_tsq > R(1)) return R(1);
+    R cos_theta_t = m_sqrt(m_max(R(1) - sin_theta_tsq, R(0)));
+    R rs = (eta * cos_theta_t - cos_theta_i) / (eta * cos_theta_t + cos_theta_i);
+    R rp = (eta * cos_theta_i - cos_theta_t) / (eta * cos_theta_i + cos_theta_t);
+    return R(0.5) * (rs * rs + rp * rp);
+}
+template <class R> PTB_DEV R gtr1(R ndoth, R a) {                                                  // tracer.rs:233-240 (log2: A.3)
+    if (a >= R(1)) return Const<R>::INV_PI;
+    R a2 = a * a;
+    R t = R(1) + (a2 - R(1)) * ndoth * ndoth;
+    return (a2 - R(1)) / (Const<R>::PI * m_log2(a2) * t);
+}
+template <class R> PTB_DEV R smithg(R ndotv, R alphag) {                                           // tracer.rs:276-280
+    R a = alphag * alphag;
+    R b = ndotv * ndotv;
+    return (R(2) * ndotv) / (ndotv + m_sqrt(a + b - a * b));
+}
+template <class R> PTB_DEV R gtr2aniso(R ndoth, R hdotx, R hdoty, R ax, R ay) {                    // tracer.rs:294-299
+    R a = hdotx / ax;
+    R b = hdoty / ay;
+    R c = a * a + b * b + ndoth * ndoth;
+    return R(1) / (Const<R>::PI * ax * ay * c * c);
+}
+template <class R> PTB_DEV R smithganiso(R ndotv, R vdotx, R vdoty, R ax, R ay) {                  // tracer.rs:301-306
+    R a = vdotx * ax;
+    R b = vdoty * ay;
+    R c = ndotv;
+    return (R(2) * ndotv) / (ndotv + m_sqrt(a * a + b * b + c * c));
+}
+template <class R> PTB_DEV R disney_fresnel(const Mat<R>& m, R eta, R ldoth, R vdoth) {            // tracer.rs:435-439
+    R metallic_fresnel = schlick_fresnel(ldoth);
+    R dielectric = dielectric_fresnel(m_abs(vdoth), eta);
+    return mix1(dielectric, metallic_fresnel, m.metallic);
+}
+// tracer.rs:449-454 (identical copies at 184-189 and 559-564)
+template <class R> PTB_DEV void onb(V3<R> n, V3<R>& t, V3<R>& b) {
+    V3<R> up = m_abs(n.z) < R(0.999) ? V3<R>(0, 0, 1) : V3<R>(1, 0, 0);
+    t = normalize(cross(up, n));
+    b = cross(n, t);
+}
+
+// samplers, tracer.rs:242-274, 324-333
+template <class R> PTB_DEV V3<R> cosine_sample_hemisphere(R r1, R r2) {
+    R r = m_sqrt(r1);
+    R phi = Const<R>::TWO_PI * r2;
+    R s, c;
+    m_sincos(phi, &s, &c);
+    R x = r * c, y = r * s;
+    return V3<R>(x, y, m_sqrt(m_max(R(0), R(1) - x * x - y * y)));
+}
+template <class R> PTB_DEV V3<R> sample_gtr1(R rgh, R r1) {                      // r2 unused: quirk A.4
+    R a = m_max(R(0.001), rgh);
+    R a2 = a * a;
+    R phi = r1 * Const<R>::TWO_PI;
+    R cos_theta = m_sqrt((R(1) - m_pow(a2, R(1) - r1)) / (R(1) - a2));
+    R sin_theta = m_clamp(m_sqrt(R(1) - (cos_theta * cos_theta)), R(0), R(1));
+    R sp, cp;
+    m_sincos(phi, &sp, &cp);
+    return V3<R>(sin_theta * cp, sin_theta * sp, cos_theta);
+}
+template <class R> PTB_DEV V3<R> sample_ggxvndf(V3<R> v, R ax, R ay, R r1, R r2) {
+    V3<R> vh = normalize(V3<R>(ax * v.x, ay * v.y, v.z));
+    R lensq = vh.x * vh.x + vh.y * vh.y;
+    V3<R> t_1;
+    if (lensq > R(0)) { R il = R(1) / m_sqrt(lensq); t_1 = V3<R>(-vh.y * il, vh.x * il, R(0) * il); }
+    else t_1 = V3<R>(1, 0, 0);
+    V3<R> t_2 = cross(vh, t_1);
+    R r = m_sqrt(r1);
+    R phi = R(2) * Const<R>::PI * r2;
+    R s_, c_;
+    m_sincos(phi, &s_, &c_);
+    R t1 = r * c_;
+    R t2 = r * s_;
+    R s = R(0.5) * (R(1) + vh.z);
+    t2 = (R(1) - s) * m_sqrt(R(1) - t1 * t1) + s * t2;
+    V3<R> nh = t1 * t_1 + t2 * t_2 + m_sqrt(m_max(R(0), R(1) - t1 * t1 - t2 * t2)) * vh;
+    return normalize(V3<R>(ax * nh.x, ay * nh.y, m_max(R(0), nh.z)));
+}
+
+// Per-bounce shading context: everything disney_eval (tracer.rs:555-600) and disney_sample
+// (tracer.rs:441-493) both derive from (material, eta, n, v).  The reference recomputes it in each
+// call; computing it once is value-identical.
+template <class R> struct ShadeCtx {
+    V3<R> t, b, n;       // onb(n)
+    V3<R> v;             // to_local(v_world)
+    V3<R> spec_col, sheen_col;
+    R eta;
+};
+template <class R> PTB_DEV V3<R> to_local(const ShadeCtx<R>& c, V3<R> w) { return V3<R>(dot(w, c.t), dot(w, c.b), dot(w, c.n)); }
+template <class R> PTB_DEV V3<R> to_world(const ShadeCtx<R>& c, V3<R> l) { return l.x * c.t + l.y * c.b + l.z * c.n; }
+
+template <class R> PTB_DEV void shade_ctx_init(ShadeCtx<R>& c, const Mat<R>& m, R eta, V3<R> n, V3<R> v_world) {
+    c.n = n;
+    onb(n, c.t, c.b);
+    c.v = to_local(c, v_world);
+    c.eta = eta;
+    // get_spec_color, tracer.rs:335-341
+    R lum = luminance(m.rgb);
+    V3<R> ctint = lum > R(0) ? div_s(m.rgb, lum) : V3<R>(1, 1, 1);
+    R f0 = (R(1) - eta) / (R(1) + eta);
+    c.spec_col = mix3((f0 * f0) * mix3(V3<R>(1, 1, 1), ctint, m.specular_tint), m.rgb, m.metallic);
+    c.sheen_col = mix3(V3<R>(1, 1, 1), ctint, m.sheen_tint);
+}
+
+// tracer.rs:421-433
+template <class R>
+PTB_DEV void lobe_probabilities(const Mat<R>& m, V3<R> spec_col, R approx_fresnel, R& wd, R& wr, R& wt, R& wc) {
+    R lum = luminance(m.rgb);
+    wd = lum * (R(1) - m.metallic) * (R(1) - m.spec_trans);
+    wr = luminance(mix3(spec_col, V3<R>(1, 1, 1), approx_fresnel));
+    wt = (R(1) - approx_fresnel) * (R(1) - m.metallic) * m.spec_trans * lum;
+    wc = R(0.25) * m.clearcoat * (R(1) - m.metallic);
+    R total = wd + wr + wt + wc;
+    wd /= total; wr /= total; wt /= total; wc /= total;
+}
+
+// lobe evaluations in the local frame, tracer.rs:343-419
+template <class R> PTB_DEV V3<R> eval_diffuse(const Mat<R>& m, V3<R> c_sheen, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
+    pdf = 0;
+    if (l.z <= R(0)) return V3<R>(0, 0, 0);
+    R ldh = dot(l, h);
+    R fl = schlick_fresnel(l.z);
+    R fv = schlick_fresnel(v.z);
+    R fh = schlick_fresnel(ldh);
+    R fd90 = R(0.5) + R(2) * ldh * ldh * m.roughness;
+    R fd = mix1(R(1), fd90, fl) * mix1(R(1), fd90, fv);
+    R fss90 = ldh * ldh * m.roughness;
+    R fss = mix1(R(1), fss90, fl) * mix1(R(1), fss90, fv);
+    R ss = R(1.25) * (fss * (R(1) / (l.z + v.z) - R(0.5)) + R(0.5));
+    V3<R> fsheen = (fh * m.sheen) * c_sheen;
+    pdf = l.z * Const<R>::INV_PI;
+    return ((R(1) - m.metallic) * (R(1) - m.spec_trans)) * ((Const<R>::INV_PI * mix1(fd, ss, m.subsurface)) * m.rgb + fsheen);
+}
+template <class R> PTB_DEV V3<R> eval_spec_reflection(const Mat<R>& m, R eta, V3<R> spec_col, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
+    pdf = 0;
+    if (l.z <= R(0)) return V3<R>(0, 0, 0);
+    R fm = disney_fresnel(m, eta, dot(l, h), dot(v, h));
+    V3<R> f = mix3(spec_col, V3<R>(1, 1, 1), fm);
+    R d = gtr2aniso(h.z, h.x, h.y, m.ax, m.ay);
+    R g1 = smithganiso(m_abs(v.z), v.x, v.y, m.ax, m.ay);
+    R g2 = g1 * smithganiso(m_abs(l.z), l.x, l.y, m.ax, m.ay);
+    pdf = g1 * d / (R(4) * v.z);
+    return div_s((d * g2) * f, R(4) * l.z * v.z);
+}
+template <class R> PTB_DEV V3<R> eval_spec_refraction(const Mat<R>& m, R eta, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
+    pdf = 0;
+    if (l.z >= R(0)) return V3<R>(0, 0, 0);
+    R vdh = dot(v, h), ldh = dot(l, h);
+    R f = dielectric_fresnel(m_abs(vdh), eta);
+    R d = gtr2aniso(h.z, h.x, h.y, m.ax, m.ay);
+    R g1 = smithganiso(m_abs(v.z), v.x, v.y, m.ax, m.ay);
+    R g2 = g1 * smithganiso(m_abs(l.z), l.x, l.y, m.ax, m.ay);
+    R denom = ldh + vdh * eta;
+    denom *= denom;
+    R eta2 = eta * eta;
+    R jacobian = m_abs(ldh) / denom;
+    pdf = g1 * m_max(R(0), vdh) * d * jacobian / v.z;
+    R s = (R(1) - m.metallic) * m.spec_trans * (R(1) - f) * d * g2 * m_abs(vdh) * jacobian * eta2 / m_abs(l.z * v.z);
+    return s * V3<R>(m_pow(m.rgb.x, R(0.5)), m_pow(m.rgb.y, R(0.5)), m_pow(m.rgb.z, R(0.5)));
+}
+template <class R> PTB_DEV V3<R> eval_clearcoat(const Mat<R>& m, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
+    pdf = 0;
+    if (l.z <= R(0)) return V3<R>(0, 0, 0);
+    R vdh = dot(v, h);
+    R fh = dielectric_fresnel(vdh, R(1) / R(1.5));
+    R f = mix1(R(0.04), R(1), fh);
+    R d = gtr1(h.z, m.clearcoat_roughness);
+    R g = smithg(l.z, R(0.25)) * smithg(v.z, R(0.25));
+    R jacobian = R(1) / (R(4) * vdh);
+    pdf = d * h.z * jacobian;
+    R s = m.clearcoat * f * d * g / (R(4) * l.z * v.z);
+    return s * V3<R>(R(0.25), R(0.25), R(0.25));
+}
+
+// Tracer::disney_eval, tracer.rs:555-626 (returns |l.z| * f)
+template <class R> PTB_DEV V3<R> disney_eval(const Mat<R>& m, const ShadeCtx<R>& c, V3<R> l_world, R& bsdf_pdf) {
+    bsdf_pdf = 0;
+    V3<R> f(0, 0, 0);
+    const V3<R> v = c.v;
+    const V3<R> l = to_local(c, l_world);
+    V3<R> h = l.z > R(0) ? normalize(l + v) : normalize(l + c.eta * v);
+    if (h.z < R(0)) h = -h;
+    R wd, wr, wt, wc;
+    R fresnel = disney_fresnel(m, c.eta, dot(l, h), dot(v, h));
+    lobe_probabilities(m, c.spec_col, fresnel, wd, wr, wt, wc);
+    R pdf;
+    if (wd > R(0) && l.z > R(0)) { f = f + eval_diffuse(m, c.sheen_col, v, l, h, pdf); bsdf_pdf += pdf * wd; }
+    if (wr > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_spec_reflection(m, c.eta, c.spec_col, v, l, h, pdf); bsdf_pdf += pdf * wr; }
+    if (wt > R(0) && l.z < R(0)) { f = f + eval_spec_refraction(m, c.eta, v, l, h, pdf); bsdf_pdf += pdf * wt; }
+    if (wc > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_clearcoat(m, v, l, h, pdf); bsdf_pdf += pdf * wc; }
+    return m_abs(l.z) * f;
+}
+
+// lobe ids
+enum { LOBE_DIFFUSE = 0, LOBE_CLEARCOAT = 1, LOBE_REFLECT = 2, LOBE_REFRACT = 3 };
+
+// Lobe selection of disney_sample, tracer.rs:488-523: CDF order diffuse, clearcoat, specular.
+// Returns the lobe class (DIFFUSE / CLEARCOAT / REFLECT meaning "specular, coin not yet tossed"),
+// rescales r1 as the reference does and returns the lobe weights.
+template <class R> struct LobePick { int lobe; R r1; R wd, wr, wt, wc; };
+template <class R> PTB_DEV LobePick<R> pick_lobe(const Mat<R>& m, const ShadeCtx<R>& c, R r1) {
+    LobePick<R> p;
+    R approx_fresnel = disney_fresnel(m, c.eta, c.v.z, c.v.z);
+    lobe_probabilities(m, c.spec_col, approx_fresnel, p.wd, p.wr, p.wt, p.wc);
+    R cdf0 = p.wd;
+    R cdf1 = cdf0 + p.wc;
+    if (r1 < cdf0) { p.lobe = LOBE_DIFFUSE; p.r1 = r1 / cdf0; }
+    else if (r1 < cdf1) { p.lobe = LOBE_CLEARCOAT; p.r1 = (r1 - cdf0) / (cdf1 - cdf0); }
+    else { p.lobe = LOBE_REFLECT; p.r1 = (r1 - cdf1) / (R(1) - cdf1); }
+    return p;
+}
+
+template <class R> PTB_DEV V3<R> reflect(V3<R> i, V3<R> n) {                        // tracer.rs:464-466
+    R d = dot(n, i);
+    return V3<R>(i.x - R(2) * n.x * d, i.y - R(2) * n.y * d, i.z - R(2) * n.z * d);
+}
+template <class R> PTB_DEV V3<R> refract(V3<R> i, V3<R> n, R eta) {                 // tracer.rs:468-475
+    R ndi = dot(n, i);
+    R k = R(1) - eta * eta * (R(1) - ndi * ndi);
+    if (k < R(0)) return V3<R>(0, 0, 0);
+    return eta * i - (eta * ndi + m_sqrt(k)) * n;
+}
+
+// The three lobe samplers of disney_sample (tracer.rs:501-549).  Each returns f (local-frame lobe
+// value, NOT yet times |n.l|), writes l (local) and pdf (already times the lobe weight).
+template <class R> PTB_DEV V3<R> sample_lobe_diffuse(const Mat<R>& m, const ShadeCtx<R>& c, const LobePick<R>& p, R r2, V3<R>& l, R& pdf) {
+    l = cosine_sample_hemisphere(p.r1, r2);
+    V3<R> h = normalize(l + c.v);
+    V3<R> f = eval_diffuse(m, c.sheen_col, c.v, l, h, pdf);
+    pdf *= p.wd;
+    return f;
+}
+template <class R> PTB_DEV V3<R> sample_lobe_clearcoat(const Mat<R>& m, const ShadeCtx<R>& c, const LobePick<R>& p, V3<R>& l, R& pdf) {
+    V3<R> h = sample_gtr1(m.clearcoat_roughness, p.r1);
+    if (h.z < R(0)) h = -h;
+    l = normalize(reflect(-c.v, h));
+    V3<R> f = eval_clearcoat(m, c.v, l, h, pdf);
+    pdf *= p.wc;
+    return f;
+}
+// specular lobe: `l_prev_world` is the stale `l` the reference reads at tracer.rs:531 (quirk A.5)
+template <class R>
+PTB_DEV V3<R> sample_lobe_specular(const Mat<R>& m, const ShadeCtx<R>& c, const LobePick<R>& p, R r2, R coin, V3<R> l_prev_world,
+                                   V3<R>& l, R& pdf, int& lobe) {
+    V3<R> h = sample_ggxvndf(c.v, m.ax, m.ay, p.r1, r2);
+    if (h.z < R(0)) h = -h;
+    R fresnel = disney_fresnel(m, c.eta, dot(l_prev_world, h), dot(c.v, h));
+    R ff = R(1) - ((R(1) - fresnel) * m.spec_trans * (R(1) - m.metallic));
+    V3<R> f;
+    if (coin < ff) {
+        l = normalize(reflect(-c.v, h));
+        f = eval_spec_reflection(m, c.eta, c.spec_col, c.v, l, h, pdf);
+        pdf *= ff;
+        lobe = LOBE_REFLECT;
+    } else {
+        l = normalize(refract(-c.v, h, c.eta));
+        f = eval_spec_refraction(m, c.eta, c.v, l, h, pdf);
+        pdf *= R(1) - ff;
+        lobe = LOBE_REFRACT;
+    }
+    pdf *= p.wr + p.wt;
+    return f;
+}
+
+// Tracer::disney_sample, tracer.rs:441-553: returns |n.l| * f, writes l (world), pdf, lobe.
+template <class R>
+PTB_DEV V3<R> disney_sample(const Mat<R>& m, const ShadeCtx<R>& c, R r1, R r2, R coin, V3<R> l_prev_world, V3<R>& l_world, R& pdf,
+                            int& lobe) {
+    LobePick<R> p = pick_lobe(m, c, r1);
+    V3<R> l, f;
+    lobe = p.lobe;
+    if (p.lobe == LOBE_DIFFUSE) f = sample_lobe_diffuse(m, c, p, r2, l, pdf);
+    else if (p.lobe == LOBE_CLEARCOAT) f = sample_lobe_clearcoat(m, c, p, l, pdf);
+    else f = sample_lobe_specular(m, c, p, r2, coin, l_prev_world, l, pdf, lobe);
+    l_world = to_world(c, l);
+    return m_abs(dot(c.n, l_world)) * f;
+}
+
+// Tracer::sample_light, tracer.rs:173-220
+template <class R> struct LightSample { V3<R> normal, emission, direction; R dist, pdf; };
+template <class R> PTB_DEV LightSample<R> sample_light(const DLight<R>& L, R n_lights_f, V3<R> scatter_pos, R r1, R r2) {
+    LightSample<R> ls;
+    V3<R> lp(L.px, L.py, L.pz);
+    V3<R> c2s = scatter_pos - lp;
+    R dist_c = length(c2s);
+    R rr = m_sqrt(m_max(R(0), R(1) - r1 * r1));           // uniform_sample_hemisphere, tracer.rs:178-182
+    R phi = Const<R>::TWO_PI * r2;
+    R s, c;
+    m_sincos(phi, &s, &c);
+    V3<R> sd(rr * c, rr * s, r1);
+    c2s = div_s(c2s, dist_c);
+    V3<R> t, b;
+    onb(c2s, t, b);
+    V3<R> dir = sd.x * t + sd.y * b + sd.z * c2s;
+    V3<R> surf = lp + L.radius * dir;
+    ls.direction = surf - scatter_pos;
+    ls.dist = length(ls.direction);
+    R dist_sq = ls.dist * ls.dist;
+    ls.direction = div_s(ls.direction, ls.dist);
+    ls.normal = normalize(surf - lp);
+    ls.emission = n_lights_f * V3<R>(L.ex, L.ey, L.ez);
+    ls.pdf = dist_sq / (L.area * R(0.5) * m_abs(dot(ls.normal, ls.direction)));
+    return ls;
+}
+
+// State::finalize, globals.rs:50-62
+template <class R> PTB_DEV void state_finalize(V3<R> o, V3<R> d, R hit_dist, V3<R> normal, Mat<R>& m, V3<R>& fhp, V3<R>& ffn, R& eta) {
+    fhp = o + hit_dist * d;
+    R nd = dot(normal, d);
+    ffn = nd <= R(0) ? normal : -normal;
+    mat_finalize(m);
+    eta = nd < R(0) ? R(1) / m.ior : m.ior;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One path: the body of the per-pixel loop, tracer.rs:51-103.
+template <class R> struct PathState {
+    V3<R> o, d;             // ray (ray.rs)
+    V3<R> thr, rad;         // throughput, radiance (tracer.rs:51-52)
+    R hit_dist;             // State::hit_dist, carried across bounces (A.1)
+    R prev_pdf;             // scatter_sample.pdf of the previous bounce (0 on the first)
+    uint32_t bounce;
+};
+
+struct PathCounters {   // per-thread event counts (only when collect_counters)
+    uint32_t closest_hit, any_hit, shade, nee_contrib, eval_calls, lobe[4], end_sky, end_emitter, end_pdf, end_depth, end_rr;
+};
+
+template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, uint32_t x, uint32_t row, uint32_t W, uint32_t H,
+                                           R inv_w, R inv_h, R j0, R j1) {
+    R px, py;
+    film_coords<R>(x, row, W, H, px, py);
+    gen_ray(s, px, py, j0, j1, inv_w, inv_h, p.o, p.d);
+    p.thr = V3<R>(1, 1, 1);
+    p.rad = V3<R>(0, 0, 0);
+    p.hit_dist = R(-1);        // globals.rs:28
+    p.prev_pdf = 0;
+    p.bounce = 0;
+}
+
+// Runs ONE bounce; returns true while the path continues.  `u` holds the 8 slot draws of this
+// bounce (slots 2..7 are used here).  COUNT enables event counters.
+template <class R, bool COUNT>
+PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, uint32_t rr_start, PathCounters* pc) {
+    if (rr_start != 0 && p.bounce >= rr_start && p.bounce > 0) {
+        // Russian roulette EXTENSION (the reference has none, quirk A.12); off in every parity run.
+        // Survival probability from the throughput (GLSL-PathTracer's rule), decided by slot 0 of
+        // this bounce, which is free after bounce 0 (slots 0,1 are the camera jitter).
+        R q = m_max(p.thr.x, m_max(p.thr.y, p.thr.z)) + R(0.001);
+        q = q > R(0.95) ? R(0.95) : q;
+        if (u[0] >= q) {
+            if (COUNT) pc->end_rr++;
+            return false;
+        }
+        p.thr = (R(1) / q) * p.thr;
+    }
+    Mat<R> mat;
+    if (COUNT) pc->closest_hit++;
+    HitRec<R> h = closest_hit(s, sv, p.o, p.d, p.hit_dist, mat);
+    p.hit_dist = h.hit_dist;
+    if (!h.hit) {                                               // tracer.rs:66-69
+        V3<R> bg = background(s, p.d);
+        p.rad = p.rad + bg * p.thr;
+        if (COUNT) pc->end_sky++;
+        return false;
+    }
+    if (!h.geom) mat_defaults(mat);                             // tracer.rs:63: only a light was hit
+    if (h.is_emitter) {                                         // tracer.rs:72-87
+        // finalize() would run first but none of its outputs reach the radiance; emission of the
+        // geometry material (if any) is still added (tracer.rs:74)
+        p.rad = p.rad + mat.emission * p.thr;
+        R w = power_heuristic(p.prev_pdf, h.light_pdf);         // `state.depth > 0` is always true (A.2)
+        p.rad = p.rad + (w * h.light_emission) * p.thr;
+        if (COUNT) pc->end_emitter++;
+        return false;
+    }
+    V3<R> fhp, ffn;
+    R eta;
+    state_finalize(p.o, p.d, h.hit_dist, h.normal, mat, fhp, ffn, eta);
+    p.rad = p.rad + mat.emission * p.thr;                       // tracer.rs:74
+    if (COUNT) pc->shade++;
+
+    ShadeCtx<R> c;
+    shade_ctx_init(c, mat, eta, ffn, -p.d);
+
+    // direct_light, tracer.rs:126-170
+    if (s.n_lights > 0) {
+        uint32_t li = (uint32_t)(u[2] * s.n_lights_f);          // tracer.rs:137-139
+        V3<R> scatter_pos = fhp + s.eps * ffn;
+        LightSample<R> ls = sample_light(sv.lights[li], s.n_lights_f, scatter_pos, u[3], u[4]);
+        if (sv.lights[li].type == PTB_LIGHT_SPHERICAL && dot(ls.direction, ls.normal) < R(0)) {
+            if (COUNT) pc->any_hit++;
+            bool shadow = any_hit(s, sv, scatter_pos, ls.direction, ls.dist - s.eps);
+            if (!shadow) {
+                R bpdf;
+                if (COUNT) pc->eval_calls++;
+                V3<R> f = disney_eval(mat, c, ls.direction, bpdf);
+                R w = R(1);
+                if (sv.lights[li].area > R(0)) w = power_heuristic(ls.pdf, bpdf);
+                if (bpdf > R(0)) {
+                    V3<R> ld = (w * ls.emission) * div_s(f, ls.pdf);
+                    p.rad = p.rad + ld * p.thr;
+                    if (COUNT) pc->nee_contrib++;
+                }
+            }
+        }
+    }
+
+    // disney_sample, tracer.rs:92-97; stale `l` = previous sampled direction = current ray dir (A.5)
+    V3<R> l_prev = p.bounce == 0 ? V3<R>(0, 0, 0) : p.d;
+    V3<R> l;
+    R pdf;
+    int lobe;
+    V3<R> f = disney_sample(mat, c, u[5], u[6], u[7], l_prev, l, pdf, lobe);
+    if (COUNT) pc->lobe[lobe]++;
+    if (!(pdf > R(0))) {
+        if (COUNT) pc->end_pdf++;
+        return false;
+    }
+    p.thr = p.thr * div_s(f, pdf);
+    p.prev_pdf = pdf;
+    p.d = l;                                                    // tracer.rs:100-101
+    p.o = fhp + s.eps * l;
+    p.bounce++;
+    if (p.bounce >= s.depth) {
+        if (COUNT) pc->end_depth++;
+        return false;
+    }
+    return true;
+}
+
+}  // namespace ptb

@@ -1,0 +1,463 @@
+"""Host-side mirror of `rust_pathtracer::prelude::*` (rust-pathtracer/src/lib.rs:24-48) above the
+C ABI of include/ptb200.h.
+
+Same names, argument meaning and behaviour as the reference crate, with the one API addition the
+device path needs: `Scene.device_export()`.  A GPU cannot call back into host
+scene code, so `Tracer.new(scene)` FAILS for a scene that does not export itself — there is no CPU
+render path in this package.
+
+    scene  = AnalyticalScene.new()
+    buffer = ColorBuffer.new(800, 600)
+    pt     = Tracer.new(scene)
+    pt.render(buffer)                 # one more sample per pixel, running mean in buffer.pixels
+    buffer.convert_to_u8(frame)       # frame: bytearray / np.uint8 array of w*h*4
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+
+# lib.rs:5-6 — the scalar switch.  "f32" (the reference's setting at this commit) or "f64".
+F = "f32"
+I = np.int32
+
+_NP = {"f32": np.float32, "f64": np.float64}
+
+
+class F3:
+    """fx.rs:209-515 (value type; only what scene descriptions need)."""
+    __slots__ = ("x", "y", "z")
+
+    def __init__(self, x=0.0, y=0.0, z=0.0):
+        self.x, self.y, self.z = float(x), float(y), float(z)
+
+    @staticmethod
+    def new(x, y, z):
+        return F3(x, y, z)
+
+    @staticmethod
+    def new_x(v):
+        return F3(v, v, v)
+
+    @staticmethod
+    def zeros():
+        return F3(0.0, 0.0, 0.0)
+
+    def __iter__(self):
+        return iter((self.x, self.y, self.z))
+
+    def __repr__(self):
+        return f"F3({self.x}, {self.y}, {self.z})"
+
+
+def _f3(v) -> F3:
+    return v if isinstance(v, F3) else F3(*v)
+
+
+@dataclass
+class Material:
+    """material.rs:48-114 — defaults are Material::new()'s (rgb 1.5!, roughness 0.5, ior 1.45).
+
+    `set_mask` lists which fields the owning primitive's closest_hit branch assigns
+    (see PTB_MAT_* in include/ptb200.h); `None` = derive from the fields passed to the constructor
+    via `Material.assigning(...)`, PTB_MAT_ALL when built directly.
+    """
+    rgb: F3 = field(default_factory=lambda: F3(1.5, 1.5, 1.5))
+    emission: F3 = field(default_factory=F3.zeros)
+    anisotropic: float = 0.0
+    metallic: float = 0.0
+    roughness: float = 0.5
+    subsurface: float = 0.0
+    specular_tint: float = 0.0
+    sheen: float = 0.0
+    sheen_tint: float = 0.0
+    clearcoat: float = 0.0
+    clearcoat_gloss: float = 0.0
+    spec_trans: float = 0.0
+    ior: float = 1.45
+    set_mask: int = _abi.PTB_MAT_ALL
+    albedo_kind: int = _abi.PTB_ALBEDO_CONSTANT
+    checker_a: float = 0.25
+    checker_b: float = 0.1
+    checker_scale: float = 0.5
+    checker_offset: float = 100.0
+
+    _MASKS = {"rgb": _abi.PTB_MAT_RGB, "emission": _abi.PTB_MAT_EMISSION, "anisotropic": _abi.PTB_MAT_ANISOTROPIC,
+              "metallic": _abi.PTB_MAT_METALLIC, "roughness": _abi.PTB_MAT_ROUGHNESS, "subsurface": _abi.PTB_MAT_SUBSURFACE,
+              "specular_tint": _abi.PTB_MAT_SPECULAR_TINT, "sheen": _abi.PTB_MAT_SHEEN, "sheen_tint": _abi.PTB_MAT_SHEEN_TINT,
+              "clearcoat": _abi.PTB_MAT_CLEARCOAT, "clearcoat_gloss": _abi.PTB_MAT_CLEARCOAT_GLOSS,
+              "spec_trans": _abi.PTB_MAT_SPEC_TRANS, "ior": _abi.PTB_MAT_IOR}
+
+    @staticmethod
+    def new() -> "Material":
+        return Material()
+
+    @staticmethod
+    def assigning(**fields) -> "Material":
+        """A material that assigns exactly the given fields on top of Material::new(), the way a
+        closest_hit branch of the reference does (analytical.rs:56-58, 82-85, 115-116)."""
+        mask = 0
+        kw = {}
+        for k, v in fields.items():
+            if k in Material._MASKS:
+                mask |= Material._MASKS[k]
+                kw[k] = _f3(v) if k in ("rgb", "emission") else float(v)
+            else:
+                kw[k] = v
+        if kw.get("albedo_kind", _abi.PTB_ALBEDO_CONSTANT) != _abi.PTB_ALBEDO_CONSTANT:
+            mask |= _abi.PTB_MAT_RGB
+        return Material(set_mask=mask, **kw)
+
+
+@dataclass
+class Light:
+    """globals.rs:76-84"""
+    light_type: int
+    position: F3
+    emission: F3
+    radius: float
+    area: float
+
+
+class AnalyticalLight:
+    """light.rs:5-28"""
+
+    def __init__(self, light: Light):
+        self.light = light
+
+    @staticmethod
+    def spherical(position, radius: float, emission) -> "AnalyticalLight":
+        import math
+        return AnalyticalLight(Light(_abi.PTB_LIGHT_SPHERICAL, _f3(position), _f3(emission), float(radius),
+                                     4.0 * math.pi * radius * radius))
+
+
+class Camera3D:
+    """camera/mod.rs:7-18"""
+
+    def set(self, origin, center):
+        raise NotImplementedError
+
+    def set_fov(self, fov: float):
+        raise NotImplementedError
+
+
+class Pinhole(Camera3D):
+    """camera/pinhole.rs:5-36 — origin (0,0,3), centre 0, fov 80 degrees (horizontal)."""
+
+    def __init__(self):
+        self.origin = F3(0.0, 0.0, 3.0)
+        self.center = F3(0.0, 0.0, 0.0)
+        self.fov = 80.0
+
+    @staticmethod
+    def new() -> "Pinhole":
+        return Pinhole()
+
+    def set(self, origin, center):
+        self.origin, self.center = _f3(origin), _f3(center)
+
+    def set_fov(self, fov: float):
+        self.fov = float(fov)
+
+
+@dataclass
+class Sphere:
+    center: F3
+    radius: float
+    material: int
+
+
+@dataclass
+class Plane:
+    point: F3
+    normal: F3
+    material: int
+
+
+@dataclass
+class Background:
+    kind: int = _abi.PTB_BG_GRADIENT_Y
+    colour_a: F3 = field(default_factory=lambda: F3(1.0, 1.0, 1.0))
+    colour_b: F3 = field(default_factory=lambda: F3(0.5, 0.7, 1.0))
+    scale: float = 0.5
+    gamma: float = 2.2
+
+
+@dataclass
+class DeviceScene:
+    """What `Scene.device_export()` returns: the scene as data (ptb_scene_f32 / _f64)."""
+    spheres: List[Sphere] = field(default_factory=list)
+    planes: List[Plane] = field(default_factory=list)
+    materials: List[Material] = field(default_factory=list)
+    lights: List[AnalyticalLight] = field(default_factory=list)
+    camera: Pinhole = field(default_factory=Pinhole)
+    background: Background = field(default_factory=Background)
+    depth: int = 4          # Scene::recursion_depth, scene.rs:28-30
+    flags: int = 0
+    eps: float = 0.005      # tracer.rs:16
+
+    def to_c(self, precision: str = "f32"):
+        """Build the POD struct; returns (scene_struct, keepalive)."""
+        T = _abi.TYPES[precision]
+        real = _abi.REAL[precision]
+
+        def v3(v):
+            return (real * 3)(*tuple(_f3(v)))
+
+        sph = (T["Sphere"] * max(1, len(self.spheres)))()
+        for i, s in enumerate(self.spheres):
+            sph[i].center = v3(s.center); sph[i].radius = s.radius; sph[i].material = s.material
+        pl = (T["Plane"] * max(1, len(self.planes)))()
+        for i, p in enumerate(self.planes):
+            pl[i].point = v3(p.point); pl[i].normal = v3(p.normal); pl[i].material = p.material
+        mats = (T["Material"] * max(1, len(self.materials)))()
+        for i, m in enumerate(self.materials):
+            d = mats[i]
+            d.rgb = v3(m.rgb); d.emission = v3(m.emission)
+            for k in ("anisotropic", "metallic", "roughness", "subsurface", "specular_tint", "sheen", "sheen_tint", "clearcoat",
+                      "clearcoat_gloss", "spec_trans", "ior", "checker_a", "checker_b", "checker_scale", "checker_offset"):
+                setattr(d, k, getattr(m, k))
+            d.set_mask = m.set_mask; d.albedo_kind = m.albedo_kind
+        li = (T["Light"] * max(1, len(self.lights)))()
+        for i, l in enumerate(self.lights):
+            li[i].position = v3(l.light.position); li[i].radius = l.light.radius
+            li[i].emission = v3(l.light.emission); li[i].type = l.light.light_type
+        sc = T["Scene"]()
+        sc.n_spheres, sc.n_planes, sc.n_materials, sc.n_lights = len(self.spheres), len(self.planes), len(self.materials), len(self.lights)
+        sc.spheres = C.cast(sph, C.POINTER(T["Sphere"])); sc.planes = C.cast(pl, C.POINTER(T["Plane"]))
+        sc.materials = C.cast(mats, C.POINTER(T["Material"])); sc.lights = C.cast(li, C.POINTER(T["Light"]))
+        sc.camera.origin = v3(self.camera.origin); sc.camera.center = v3(self.camera.center); sc.camera.fov = self.camera.fov
+        sc.background.kind = self.background.kind
+        sc.background.colour_a = v3(self.background.colour_a); sc.background.colour_b = v3(self.background.colour_b)
+        sc.background.scale = self.background.scale; sc.background.gamma = self.background.gamma
+        sc.depth, sc.flags, sc.eps = self.depth, self.flags, self.eps
+        return sc, (sph, pl, mats, li)
+
+
+class Scene:
+    """scene.rs:5-90 — the plug-in trait.  The per-ray callbacks (`closest_hit`, `any_hit`,
+    `background`) are host code the device cannot call; a scene instead describes itself once
+    through `device_export()`."""
+
+    @classmethod
+    def new(cls):
+        return cls()
+
+    def camera(self) -> Camera3D:
+        raise NotImplementedError
+
+    def number_of_lights(self) -> int:
+        raise NotImplementedError
+
+    def light_at(self, index: int) -> AnalyticalLight:
+        raise NotImplementedError
+
+    def recursion_depth(self) -> int:     # scene.rs:28-30
+        return 4
+
+    def device_export(self) -> Optional[DeviceScene]:
+        """NEW trait method (default None => Tracer.new() fails: no CPU fallback)."""
+        return None
+
+    def as_any(self):                     # scene.rs:88
+        return self
+
+
+class ColorBuffer:
+    """buffer.rs:6-102 — `pixels` is the running MEAN, RGBA interleaved, row 0 = top."""
+
+    def __init__(self, width: int, height: int, precision: str = None):
+        self.precision = precision or F
+        self.width, self.height = int(width), int(height)
+        self.pixels = np.zeros(self.width * self.height * 4, dtype=_NP[self.precision])
+        self.frames = 0
+        self._tracer = None       # tracer whose device image mirrors (pixels, frames)
+
+    @staticmethod
+    def new(width: int, height: int, precision: str = None) -> "ColorBuffer":
+        return ColorBuffer(width, height, precision)
+
+    def at(self, x: int, y: int):                                   # buffer.rs:29-32
+        i = y * self.width * 4 + x * 4
+        return [self.pixels[i], self.pixels[i + 1], self.pixels[i + 2], self.pixels[i + 3]]
+
+    def _device_current(self) -> bool:
+        t = self._tracer
+        return t is not None and t._alive() and t._device_frames() == self.frames and t._size == (self.width, self.height)
+
+    def convert_to_u8(self, frame) -> None:                         # buffer.rs:55-64
+        """Gamma-encode into `frame` (w*h*4 bytes).  Runs on the device: from the resident image
+        when this buffer was last written by a tracer, otherwise after uploading `pixels`."""
+        out = np.frombuffer(frame, dtype=np.uint8) if not isinstance(frame, np.ndarray) else frame
+        assert out.size >= self.width * self.height * 4
+        if self._tracer is None or not self._tracer._alive():
+            raise RuntimeError("ColorBuffer.convert_to_u8 runs on the device: render into the buffer with a Tracer first")
+        if not self._device_current():
+            self._tracer._upload(self)
+        self._tracer._convert_to_u8(out)
+
+    def to_u8_vec(self) -> np.ndarray:                              # buffer.rs:37-52
+        out = np.zeros(self.width * self.height * 4, dtype=np.uint8)
+        self.convert_to_u8(out)
+        return out
+
+    def convert_to_u8_at(self, frame, at: Sequence[int]) -> None:   # buffer.rs:67-102
+        out = np.frombuffer(frame, dtype=np.uint8) if not isinstance(frame, np.ndarray) else frame
+        if self._tracer is None or not self._tracer._alive():
+            raise RuntimeError("ColorBuffer.convert_to_u8_at runs on the device: render into the buffer with a Tracer first")
+        if not self._device_current():
+            self._tracer._upload(self)
+        self._tracer._convert_to_u8_at(out, at)
+
+
+class Tracer:
+    """tracer.rs:5-19, 22-123, 629-631."""
+
+    def __init__(self, scene: Scene, device: int = 0, precision: str = None, integrator: int = _abi.PTB_INTEGRATOR_AUTO,
+                 seed: int = 0, collect_counters: bool = False, rr_start: int = 0, wave_paths: int = 0, bvh_threshold: int = 0):
+        self.eps = 0.005
+        self._scene = scene
+        self.precision = precision or F
+        self._lib = _abi.load()
+        export = scene.device_export()
+        if export is None:
+            raise RuntimeError("scene does not implement device_export(); the B200 tracer has no CPU fallback")
+        cfg = _abi.Config(device=device, integrator=integrator, seed=seed, rr_start=rr_start, wave_paths=wave_paths,
+                          bvh_threshold=bvh_threshold, collect_counters=1 if collect_counters else 0)
+        h = C.c_void_p()
+        _abi.check(self._lib.ptb_create(C.byref(cfg), C.byref(h)))
+        self._ptr = h
+        self._size = (0, 0)
+        self.sync_scene()
+
+    @staticmethod
+    def new(scene: Scene, **kw) -> "Tracer":
+        return Tracer(scene, **kw)
+
+    def scene(self) -> Scene:                                       # tracer.rs:629-631
+        """Mutable access to the scene; call `sync_scene()` after editing it."""
+        return self._scene
+
+    def sync_scene(self) -> None:
+        """Re-export the scene to the device (the reference re-reads the scene every ray)."""
+        export = self._scene.device_export()
+        sc, keep = export.to_c(self.precision)
+        fn = self._lib.ptb_set_scene_f32 if self.precision == "f32" else self._lib.ptb_set_scene_f64
+        _abi.check(fn(self._handle(), C.byref(sc)))
+        self.scene_bytes = C.sizeof(sc) + sum(C.sizeof(k) for k in keep)
+        self.eps = export.eps
+
+    # -- internals ------------------------------------------------------------------------------
+    def _handle(self):
+        if self._ptr is None:
+            raise RuntimeError("tracer destroyed")
+        return self._ptr
+
+    def _alive(self) -> bool:
+        return self._ptr is not None
+
+    def _device_frames(self) -> int:
+        f = C.c_uint64()
+        _abi.check(self._lib.ptb_frames(self._handle(), C.byref(f)))
+        return f.value
+
+    def _ensure_size(self, buffer: ColorBuffer):
+        if self._size != (buffer.width, buffer.height):
+            _abi.check(self._lib.ptb_resize(self._handle(), buffer.width, buffer.height))
+            self._size = (buffer.width, buffer.height)
+
+    def _upload(self, buffer: ColorBuffer):
+        self._ensure_size(buffer)
+        fn = self._lib.ptb_upload_f32 if self.precision == "f32" else self._lib.ptb_upload_f64
+        _abi.check(fn(self._handle(), buffer.pixels.ctypes.data, buffer.frames))
+        buffer._tracer = self
+
+    def _convert_to_u8(self, out: np.ndarray):
+        _abi.check(self._lib.ptb_convert_to_u8(self._handle(), out.ctypes.data))
+
+    def _convert_to_u8_at(self, out: np.ndarray, at):
+        _abi.check(self._lib.ptb_convert_to_u8_at(self._handle(), out.ctypes.data, at[0], at[1], at[2], at[3]))
+
+    # -- the hot path ---------------------------------------------------------------------------
+    def render(self, buffer: ColorBuffer) -> None:
+        """tracer.rs:22-123: one more sample per pixel accumulated into buffer.pixels (running
+        mean), buffer.frames += 1.  `buffer.frames = 0` restarts the accumulation, as in the
+        reference."""
+        assert buffer.precision == self.precision
+        fn = self._lib.ptb_render_frame_f32 if self.precision == "f32" else self._lib.ptb_render_frame_f64
+        _abi.check(fn(self._handle(), buffer.width, buffer.height, buffer.frames, buffer.pixels.ctypes.data))
+        self._size = (buffer.width, buffer.height)
+        buffer.frames += 1
+        buffer._tracer = self
+
+    def render_spp(self, buffer: ColorBuffer, spp: int, download: bool = True) -> None:
+        """Extension: `spp` samples per pixel in one device pass (the reference needs `spp` calls).
+        Equivalent to calling render() spp times up to f32 summation order."""
+        assert buffer.precision == self.precision
+        self._ensure_size(buffer)
+        if buffer.frames == 0:
+            _abi.check(self._lib.ptb_clear(self._handle()))
+        elif self._device_frames() != buffer.frames or buffer._tracer is not self:
+            self._upload(buffer)
+        _abi.check(self._lib.ptb_render(self._handle(), spp, buffer.frames))
+        buffer.frames += spp
+        buffer._tracer = self
+        if download:
+            self.download(buffer)
+
+    def download(self, buffer: ColorBuffer) -> None:
+        fn = self._lib.ptb_download_f32 if self.precision == "f32" else self._lib.ptb_download_f64
+        _abi.check(fn(self._handle(), buffer.pixels.ctypes.data))
+
+    def synchronize(self) -> None:
+        _abi.check(self._lib.ptb_synchronize(self._handle()))
+
+    # -- instrumentation ------------------------------------------------------------------------
+    def counters(self) -> dict:
+        c = _abi.Counters()
+        _abi.check(self._lib.ptb_get_counters(self._handle(), C.byref(c)))
+        return c.as_dict()
+
+    def reset_counters(self) -> None:
+        _abi.check(self._lib.ptb_reset_counters(self._handle()))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _abi.check(self._lib.ptb_launch_count(self._handle(), C.byref(n)))
+        return n.value
+
+    def last_render_ms(self) -> float:
+        ms = C.c_float()
+        _abi.check(self._lib.ptb_last_render_ms(self._handle(), C.byref(ms)))
+        return ms.value
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _abi.check(self._lib.ptb_set_stream(self._handle(), C.c_void_p(cuda_stream)))
+
+    def bind_accumulator(self, device_ptr: int, width: int, height: int) -> None:
+        _abi.check(self._lib.ptb_bind_accumulator(self._handle(), C.c_void_p(device_ptr), width, height))
+        self._size = (width, height)
+
+    def render_samples(self, spp: int, sample_base: int) -> None:
+        """Raw ptb_render: add samples [sample_base, sample_base+spp) to the device accumulators."""
+        _abi.check(self._lib.ptb_render(self._handle(), spp, sample_base))
+
+    def clear(self) -> None:
+        _abi.check(self._lib.ptb_clear(self._handle()))
+
+    def close(self) -> None:
+        if getattr(self, "_ptr", None) is not None:
+            self._lib.ptb_destroy(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

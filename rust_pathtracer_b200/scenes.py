@@ -1,0 +1,157 @@
+"""Scenes for the device path.
+
+`AnalyticalScene` is the data form of the reference's only Scene impl
+(renderer/src/analytical.rs, constants in SURVEY.md Appendix E).  `sphere_field_scene` and
+`divergence_stress_scene` are the synthetic configs 4 and 5 of BASELINE.json,
+generated with a seeded splitmix64 so the oracle and the device are fed identical data.
+"""
+from __future__ import annotations
+
+import math
+
+from . import _abi
+from .prelude import (AnalyticalLight, Background, DeviceScene, F3, Material, Pinhole, Plane, Scene, Sphere)
+
+
+class AnalyticalScene(Scene):
+    """renderer/src/analytical.rs:4-159 as data."""
+
+    def __init__(self):
+        em = 3.0
+        self.lights = [AnalyticalLight.spherical(F3(3.0, 2.0, 2.0), 1.0, F3(em, em, em))]   # analytical.rs:15-16
+        self.pinhole = Pinhole.new()                                                          # analytical.rs:20
+
+    def camera(self):
+        return self.pinhole
+
+    def number_of_lights(self):
+        return len(self.lights)
+
+    def light_at(self, index):
+        return self.lights[index]
+
+    def device_export(self) -> DeviceScene:
+        mats = [
+            # analytical.rs:56-58 — metal sphere assigns rgb, roughness, metallic
+            Material.assigning(rgb=(1.0, 1.0, 1.0), roughness=0.05, metallic=1.0),
+            # analytical.rs:82-85 — orange clearcoat sphere assigns rgb, clearcoat, clearcoat_gloss, roughness
+            Material.assigning(rgb=(1.0, 0.186, 0.0), clearcoat=1.0, clearcoat_gloss=1.0, roughness=0.1),
+            # analytical.rs:107-116 — plane assigns rgb (direction-ratio checker) and roughness
+            Material.assigning(albedo_kind=_abi.PTB_ALBEDO_CHECKER_DIR_RATIO, checker_a=0.25, checker_b=0.1, checker_scale=0.5,
+                               checker_offset=100.0, roughness=1.0),
+        ]
+        return DeviceScene(
+            spheres=[Sphere(F3(-1.1, 0.0, 0.0), 1.0, 0), Sphere(F3(1.1, 0.0, 0.0), 1.0, 1)],       # analytical.rs:41,70
+            planes=[Plane(F3(0.0, -1.0, 0.0), F3(0.0, 1.0, 0.0), 2)],                               # analytical.rs:193-198
+            materials=mats,
+            lights=list(self.lights),
+            camera=self.pinhole,
+            background=Background(_abi.PTB_BG_GRADIENT_Y, F3(1.0, 1.0, 1.0), F3(0.5, 0.7, 1.0), 0.5, 2.2),  # analytical.rs:28-32
+            depth=self.recursion_depth(),
+            flags=_abi.PTB_SCENE_ANYHIT_IGNORES_MAX_DIST,                                           # analytical.rs:130
+            eps=0.005,
+        )
+
+
+class _SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next(self) -> int:
+        self.s = (self.s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+    def u(self) -> float:
+        return (self.next() >> 11) * (1.0 / 9007199254740992.0)
+
+    def uniform(self, a, b) -> float:
+        return a + (b - a) * self.u()
+
+
+class ExportedScene(Scene):
+    """A Scene that simply carries a prepared DeviceScene."""
+
+    def __init__(self, export: DeviceScene):
+        self._export = export
+
+    def camera(self):
+        return self._export.camera
+
+    def number_of_lights(self):
+        return len(self._export.lights)
+
+    def light_at(self, index):
+        return self._export.lights[index]
+
+    def recursion_depth(self):
+        return self._export.depth
+
+    def device_export(self):
+        return self._export
+
+
+def _checker_plane_material():
+    m = Material()      # full mask: order-independent (required with the BVH)
+    m.albedo_kind = _abi.PTB_ALBEDO_CHECKER_DIR_RATIO
+    m.roughness = 1.0
+    return m
+
+
+def sphere_field_scene(n_spheres: int = 100_000, n_lights_side: int = 8, seed: int = 0xB200) -> ExportedScene:
+    """BASELINE.json config 4: procedural sphere field, mixed Disney materials
+    (metal / glass / clearcoat by id % 3), n_lights_side^2 spherical lights, sphere BVH."""
+    rng = _SplitMix64(seed)
+    spheres, mats = [], [_checker_plane_material()]
+    for i in range(n_spheres):
+        r = 0.05 * math.exp(rng.u() * math.log(0.6 / 0.05))            # log-uniform [0.05, 0.6]
+        x = rng.uniform(-60.0, 60.0)
+        z = rng.uniform(-120.0, 0.0)
+        y = -1.0 + r + rng.uniform(0.0, 6.0)
+        kind = i % 3
+        m = Material()
+        if kind == 0:      # metal
+            m.metallic = 1.0; m.roughness = rng.uniform(0.02, 0.4)
+            m.rgb = F3(rng.uniform(0.5, 1.0), rng.uniform(0.5, 1.0), rng.uniform(0.5, 1.0))
+        elif kind == 1:    # glass
+            m.spec_trans = 1.0; m.ior = 1.45; m.roughness = rng.uniform(0.01, 0.1); m.rgb = F3(1.0, 1.0, 1.0)
+        else:              # clearcoat
+            m.clearcoat = 1.0; m.clearcoat_gloss = rng.uniform(0.5, 1.0); m.roughness = rng.uniform(0.1, 0.6)
+            m.rgb = F3(rng.u(), rng.u(), rng.u())
+        mats.append(m)
+        spheres.append(Sphere(F3(x, y, z), r, len(mats) - 1))
+    lights = []
+    for gz in range(n_lights_side):
+        for gx in range(n_lights_side):
+            px = -52.5 + 105.0 * (gx / max(1, n_lights_side - 1)) if n_lights_side > 1 else 0.0
+            pz = -112.5 + 105.0 * (gz / max(1, n_lights_side - 1)) if n_lights_side > 1 else -60.0
+            lights.append(AnalyticalLight.spherical(F3(px, 10.0, pz), 0.5, F3(40.0, 40.0, 40.0)))
+    cam = Pinhole.new()
+    cam.set(F3(0.0, 4.0, 14.0), F3(0.0, 0.0, -40.0))
+    cam.set_fov(60.0)
+    return ExportedScene(DeviceScene(spheres=spheres, planes=[Plane(F3(0.0, -1.0, 0.0), F3(0.0, 1.0, 0.0), 0)], materials=mats,
+                                     lights=lights, camera=cam, depth=4, flags=0, eps=0.005))
+
+
+def divergence_stress_scene(side: int = 64, depth: int = 16, seed: int = 0xD1CE) -> ExportedScene:
+    """BASELINE.json config 5: side*side sphere grid, high roughness, half with transmission."""
+    rng = _SplitMix64(seed)
+    spheres, mats = [], [_checker_plane_material()]
+    for iz in range(side):
+        for ix in range(side):
+            m = Material()
+            m.roughness = rng.uniform(0.6, 1.0)
+            m.rgb = F3(rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.0), rng.uniform(0.3, 1.0))
+            if (ix + iz) % 2 == 0:
+                m.spec_trans = rng.uniform(0.5, 1.0)
+            mats.append(m)
+            spheres.append(Sphere(F3((ix - side / 2 + 0.5) * 1.2, -0.5, -iz * 1.2 - 2.0), 0.5, len(mats) - 1))
+    lights = [AnalyticalLight.spherical(F3(0.0, 12.0, -side * 0.6), 3.0, F3(20.0, 20.0, 20.0)),
+              AnalyticalLight.spherical(F3(-side * 0.5, 8.0, -4.0), 2.0, F3(15.0, 12.0, 9.0))]
+    cam = Pinhole.new()
+    cam.set(F3(0.0, 5.0, 6.0), F3(0.0, -0.5, -side * 0.5))
+    cam.set_fov(70.0)
+    return ExportedScene(DeviceScene(spheres=spheres, planes=[Plane(F3(0.0, -1.0, 0.0), F3(0.0, 1.0, 0.0), 0)], materials=mats,
+                                     lights=lights, camera=cam, depth=depth, flags=0, eps=0.005))
