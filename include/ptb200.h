@@ -185,6 +185,8 @@ typedef struct ptb_counters {
     uint64_t eval_calls;      /* disney_eval calls                                                */
     uint64_t lobe_diffuse, lobe_clearcoat, lobe_reflect, lobe_refract;
     uint64_t end_sky, end_emitter, end_pdf, end_depth, end_rr;
+    /* lobe evaluations, inside disney_eval and disney_sample together (tracer.rs:343-419) */
+    uint64_t ev_diffuse, ev_clearcoat, ev_reflect, ev_refract;
 } ptb_counters;
 
 typedef struct ptb_tracer ptb_tracer;

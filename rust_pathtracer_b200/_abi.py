@@ -72,7 +72,8 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "samples", "closest_hit", "any_hit", "shade", "nee_contrib", "eval_calls",
         "lobe_diffuse", "lobe_clearcoat", "lobe_reflect", "lobe_refract",
-        "end_sky", "end_emitter", "end_pdf", "end_depth", "end_rr")]
+        "end_sky", "end_emitter", "end_pdf", "end_depth", "end_rr",
+        "ev_diffuse", "ev_clearcoat", "ev_reflect", "ev_refract")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -84,7 +84,7 @@ template <class R> PTB_DEV R mix1(R a, R b, R v) { return (R(1) - v) * a + b * v
 
 // ------------------------------------------------------------------------------------------------
 // Counter RNG: Philox4x32-10, key = (pixel, sample lo), ctr = (block, sample hi, seed lo, seed hi).
-// Slot layout in SURVEY.md §8d / oracle/pt_oracle.hpp.  Bit-exact with the oracle by construction
+// Slot layout in SURVEY.md §8d.  Bit-exact with the CPU checker by construction
 // (integer arithmetic only; the uint->float conversions are exact).
 struct Philox4 { uint32_t v[4]; };
 PTB_DEV Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
@@ -751,8 +751,11 @@ template <class R> PTB_DEV V3<R> eval_clearcoat(const Mat<R>& m, V3<R> v, V3<R> 
     return s * V3<R>(R(0.25), R(0.25), R(0.25));
 }
 
+// lobe ids
+enum { LOBE_DIFFUSE = 0, LOBE_CLEARCOAT = 1, LOBE_REFLECT = 2, LOBE_REFRACT = 3 };
+
 // Tracer::disney_eval, tracer.rs:555-626 (returns |l.z| * f)
-template <class R> PTB_DEV V3<R> disney_eval(const Mat<R>& m, const ShadeCtx<R>& c, V3<R> l_world, R& bsdf_pdf) {
+template <class R> PTB_DEV V3<R> disney_eval(const Mat<R>& m, const ShadeCtx<R>& c, V3<R> l_world, R& bsdf_pdf, uint32_t* ev = nullptr) {
     bsdf_pdf = 0;
     V3<R> f(0, 0, 0);
     const V3<R> v = c.v;
@@ -763,15 +766,12 @@ template <class R> PTB_DEV V3<R> disney_eval(const Mat<R>& m, const ShadeCtx<R>&
     R fresnel = disney_fresnel(m, c.eta, dot(l, h), dot(v, h));
     lobe_probabilities(m, c.spec_col, fresnel, wd, wr, wt, wc);
     R pdf;
-    if (wd > R(0) && l.z > R(0)) { f = f + eval_diffuse(m, c.sheen_col, v, l, h, pdf); bsdf_pdf += pdf * wd; }
-    if (wr > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_spec_reflection(m, c.eta, c.spec_col, v, l, h, pdf); bsdf_pdf += pdf * wr; }
-    if (wt > R(0) && l.z < R(0)) { f = f + eval_spec_refraction(m, c.eta, v, l, h, pdf); bsdf_pdf += pdf * wt; }
-    if (wc > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_clearcoat(m, v, l, h, pdf); bsdf_pdf += pdf * wc; }
+    if (wd > R(0) && l.z > R(0)) { f = f + eval_diffuse(m, c.sheen_col, v, l, h, pdf); bsdf_pdf += pdf * wd; if (ev) ev[LOBE_DIFFUSE]++; }
+    if (wr > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_spec_reflection(m, c.eta, c.spec_col, v, l, h, pdf); bsdf_pdf += pdf * wr; if (ev) ev[LOBE_REFLECT]++; }
+    if (wt > R(0) && l.z < R(0)) { f = f + eval_spec_refraction(m, c.eta, v, l, h, pdf); bsdf_pdf += pdf * wt; if (ev) ev[LOBE_REFRACT]++; }
+    if (wc > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_clearcoat(m, v, l, h, pdf); bsdf_pdf += pdf * wc; if (ev) ev[LOBE_CLEARCOAT]++; }
     return m_abs(l.z) * f;
 }
-
-// lobe ids
-enum { LOBE_DIFFUSE = 0, LOBE_CLEARCOAT = 1, LOBE_REFLECT = 2, LOBE_REFRACT = 3 };
 
 // Lobe selection of disney_sample, tracer.rs:488-523: CDF order diffuse, clearcoat, specular.
 // Returns the lobe class (DIFFUSE / CLEARCOAT / REFLECT meaning "specular, coin not yet tossed"),
@@ -902,7 +902,7 @@ template <class R> struct PathState {
 };
 
 struct PathCounters {   // per-thread event counts (only when collect_counters)
-    uint32_t closest_hit, any_hit, shade, nee_contrib, eval_calls, lobe[4], end_sky, end_emitter, end_pdf, end_depth, end_rr;
+    uint32_t closest_hit, any_hit, shade, nee_contrib, eval_calls, lobe[4], end_sky, end_emitter, end_pdf, end_depth, end_rr, ev[4];
 };
 
 template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, uint32_t x, uint32_t row, uint32_t W, uint32_t H,
@@ -973,7 +973,7 @@ PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R
             if (!shadow) {
                 R bpdf;
                 if (COUNT) pc->eval_calls++;
-                V3<R> f = disney_eval(mat, c, ls.direction, bpdf);
+                V3<R> f = disney_eval(mat, c, ls.direction, bpdf, COUNT ? pc->ev : nullptr);
                 R w = R(1);
                 if (sv.lights[li].area > R(0)) w = power_heuristic(ls.pdf, bpdf);
                 if (bpdf > R(0)) {
@@ -991,7 +991,7 @@ PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R
     R pdf;
     int lobe;
     V3<R> f = disney_sample(mat, c, u[5], u[6], u[7], l_prev, l, pdf, lobe);
-    if (COUNT) pc->lobe[lobe]++;
+    if (COUNT) { pc->lobe[lobe]++; pc->ev[lobe]++; }
     if (!(pdf > R(0))) {
         if (COUNT) pc->end_pdf++;
         return false;

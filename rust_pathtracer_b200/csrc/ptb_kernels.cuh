@@ -13,7 +13,7 @@ PTB_DEV double4 mk4(double a, double b, double c, double d) { return make_double
 
 struct DeviceCounters {   // mirrors ptb_counters
     unsigned long long samples, closest_hit, any_hit, shade, nee_contrib, eval_calls, lobe[4], end_sky, end_emitter, end_pdf,
-        end_depth, end_rr;
+        end_depth, end_rr, ev[4];
 };
 
 struct RenderArgs {
@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_con
         pc.closest_hit = pc.any_hit = pc.shade = pc.nee_contrib = pc.eval_calls = 0;
         pc.lobe[0] = pc.lobe[1] = pc.lobe[2] = pc.lobe[3] = 0;
         pc.end_sky = pc.end_emitter = pc.end_pdf = pc.end_depth = pc.end_rr = 0;
+        pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
     }
     uint32_t n_samples = 0;
 
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_con
         atomicAdd(&c->nee_contrib, (unsigned long long)pc.nee_contrib);
         atomicAdd(&c->eval_calls, (unsigned long long)pc.eval_calls);
         for (int i = 0; i < 4; ++i) atomicAdd(&c->lobe[i], (unsigned long long)pc.lobe[i]);
+        for (int i = 0; i < 4; ++i) atomicAdd(&c->ev[i], (unsigned long long)pc.ev[i]);
         atomicAdd(&c->end_sky, (unsigned long long)pc.end_sky);
         atomicAdd(&c->end_emitter, (unsigned long long)pc.end_emitter);
         atomicAdd(&c->end_pdf, (unsigned long long)pc.end_pdf);

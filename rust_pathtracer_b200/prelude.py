@@ -272,16 +272,21 @@ class Scene:
 class ColorBuffer:
     """buffer.rs:6-102 — `pixels` is the running MEAN, RGBA interleaved, row 0 = top."""
 
-    def __init__(self, width: int, height: int, precision: str = None):
+    def __init__(self, width: int, height: int, precision: str = None, storage: np.ndarray = None):
         self.precision = precision or F
         self.width, self.height = int(width), int(height)
-        self.pixels = np.zeros(self.width * self.height * 4, dtype=_NP[self.precision])
+        if storage is not None:      # caller-provided (e.g. page-locked) memory for `pixels`
+            assert storage.dtype == _NP[self.precision] and storage.size == self.width * self.height * 4 and storage.flags.c_contiguous
+            self.pixels = storage.reshape(-1)
+            self.pixels[:] = 0
+        else:
+            self.pixels = np.zeros(self.width * self.height * 4, dtype=_NP[self.precision])
         self.frames = 0
         self._tracer = None       # tracer whose device image mirrors (pixels, frames)
 
     @staticmethod
-    def new(width: int, height: int, precision: str = None) -> "ColorBuffer":
-        return ColorBuffer(width, height, precision)
+    def new(width: int, height: int, precision: str = None, storage: np.ndarray = None) -> "ColorBuffer":
+        return ColorBuffer(width, height, precision, storage)
 
     def at(self, x: int, y: int):                                   # buffer.rs:29-32
         i = y * self.width * 4 + x * 4

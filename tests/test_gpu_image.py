@@ -1,0 +1,303 @@
+"""GPU parity at image level: the CUDA integrator (through the host mirror and the C ABI) against
+the CPU oracle, plus the drop-in semantics of Tracer::render / ColorBuffer.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §7):
+  * deterministic, shared counter RNG: >= 99 % of pixels within 1e-4 relative of the oracle
+    (outliers are paths that took a different branch at a silhouette / CDF edge);
+  * statistical, independent RNG streams: mean relative luminance error < 0.5 %, per-pixel RMSE
+    <= 1.2 x the Monte Carlo bound sqrt(var_a/N_a + var_b/N_b) estimated from batch means.
+"""
+import numpy as np
+import pytest
+
+from devfn import DeviceFns
+
+pytestmark = pytest.mark.gpu
+
+
+def pix_rel(a, b):
+    a = a.reshape(-1, 4)[:, :3].astype(np.float64); b = b.reshape(-1, 4)[:, :3].astype(np.float64)
+    return np.abs(a - b).max(1) / np.maximum(np.abs(b).max(1), 1e-3)
+
+
+def lum(img):
+    p = img.reshape(-1, 4).astype(np.float64)
+    return 0.212671 * p[:, 0] + 0.715160 * p[:, 1] + 0.072169 * p[:, 2]
+
+
+@pytest.fixture(scope="module")
+def scene(rp):
+    return rp.AnalyticalScene.new()
+
+
+@pytest.mark.parametrize("spp", [1, 4, 16])
+def test_image_deterministic_parity(rp, scene, oracle_demo, spp):
+    W, H = 200, 150
+    buf = rp.ColorBuffer.new(W, H)
+    pt = rp.Tracer.new(scene)
+    for _ in range(spp):
+        pt.render(buf)                                   # the drop-in call, 1 spp each, host pixels round trip
+    ref, frames, _, _ = oracle_demo.render(W, H, spp)
+    assert buf.frames == frames == spp
+    rel = pix_rel(buf.pixels, ref)
+    assert (rel < 1e-4).mean() >= 0.99, (rel < 1e-4).mean()
+    assert np.median(rel) < 1e-6
+    assert np.all(buf.pixels.reshape(-1, 4)[:, 3] == 1.0)
+    assert abs(lum(buf.pixels).mean() / lum(ref).mean() - 1) < 1e-4
+    pt.close()
+
+
+def test_batch_render_equals_repeated_render(rp, scene):
+    W, H, N = 128, 96, 8
+    pt = rp.Tracer.new(scene)
+    a = rp.ColorBuffer.new(W, H)
+    for _ in range(N):
+        pt.render(a)
+    b = rp.ColorBuffer.new(W, H)
+    pt.render_spp(b, N)
+    assert a.frames == b.frames == N
+    assert np.allclose(a.pixels, b.pixels, rtol=2e-6, atol=1e-7)     # same samples, different f32 summation order
+    # bit-reproducible run to run
+    c = rp.ColorBuffer.new(W, H)
+    pt.render_spp(c, N)
+    assert np.array_equal(b.pixels, c.pixels)
+    pt.close()
+
+
+def test_reset_and_resume_semantics(rp, scene, oracle_demo):
+    W, H = 96, 64
+    pt = rp.Tracer.new(scene)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render(buf); pt.render(buf); pt.render(buf)
+    three = buf.pixels.copy()
+    buf.frames = 0                                       # the reference's reset idiom
+    pt.render(buf)
+    one, _, _, _ = oracle_demo.render(W, H, 1)
+    assert buf.frames == 1 and (pix_rel(buf.pixels, one) < 1e-4).mean() > 0.99
+    # the app edits the public fields: a foreign image with frames = 1 is uploaded and averaged with sample #1
+    buf.pixels[:] = 0.25; buf.frames = 1
+    pt.render(buf)
+    second, _, _, _ = oracle_demo.render(W, H, 1, sample_base=1)
+    want = 0.5 * 0.25 + 0.5 * second.reshape(-1, 4)
+    want[:, 3] = 1.0
+    assert buf.frames == 2 and np.allclose(buf.pixels.reshape(-1, 4)[:, :3], want[:, :3], rtol=1e-4, atol=1e-6)
+    # resume a checkpointed (pixels, frames) pair on a NEW tracer: identical to never having stopped
+    pt2 = rp.Tracer.new(scene)
+    chk = rp.ColorBuffer.new(W, H)
+    pt2.render(chk); pt2.render(chk)
+    saved = (chk.pixels.copy(), chk.frames)
+    pt3 = rp.Tracer.new(scene)
+    res = rp.ColorBuffer.new(W, H); res.pixels[:] = saved[0]; res.frames = saved[1]
+    pt3.render(res)
+    assert res.frames == 3 and np.allclose(res.pixels, three, rtol=3e-6, atol=1e-7)
+    for t in (pt, pt2, pt3):
+        t.close()
+
+
+def test_sample_split_invariance(rp, scene):
+    """the multi-GPU decomposition: disjoint sample ranges summed == one range"""
+    W, H = 120, 80
+    pt = rp.Tracer.new(scene)
+    a = rp.ColorBuffer.new(W, H)
+    pt.render_spp(a, 8)
+    b = rp.ColorBuffer.new(W, H)
+    pt._ensure_size(b); pt.clear()
+    pt.render_samples(4, 4); pt.render_samples(3, 0); pt.render_samples(1, 3)      # out of order on purpose
+    pt.download(b)
+    assert np.allclose(a.pixels, b.pixels, rtol=2e-6, atol=1e-7)
+    pt.close()
+
+
+def test_statistical_parity_4096spp(rp, scene, po, demo_export):
+    W, H, K, B = 160, 90, 8, 512                        # 8 batches x 512 spp = 4096 spp per side
+    pt = rp.Tracer.new(scene, seed=0xC0FFEE)            # independent stream from the oracle's seed 0
+    gb, ob = [], []
+    osc = po.OracleScene(demo_export)
+    for k in range(K):
+        buf = rp.ColorBuffer.new(W, H)
+        pt._ensure_size(buf); pt.clear(); pt.render_samples(B, k * B); pt.download(buf)
+        gb.append(buf.pixels.reshape(-1, 4)[:, :3].astype(np.float64))
+        ref, _, _, _ = osc.render(W, H, B, sample_base=k * B)
+        ob.append(ref.reshape(-1, 4)[:, :3].astype(np.float64))
+    gb, ob = np.stack(gb), np.stack(ob)
+    gm, om = gb.mean(0), ob.mean(0)
+    w = np.array([0.212671, 0.715160, 0.072169])
+    lg, lo = gm @ w, om @ w
+    rel_lum = abs(lg.mean() / lo.mean() - 1)
+    assert rel_lum < 0.005, rel_lum                     # < 0.5 % mean relative luminance error
+    var = gb.var(0, ddof=1) / K + ob.var(0, ddof=1) / K
+    rmse = np.sqrt(((gm - om) ** 2).mean())
+    bound = np.sqrt(var.mean())
+    assert rmse <= 1.2 * bound, (rmse, bound)
+    assert rmse >= 0.5 * bound                           # and the streams really are independent
+    pt.close()
+
+
+def test_counters_match_oracle(rp, scene, oracle_demo):
+    W, H, S = 200, 150, 4
+    pt = rp.Tracer.new(scene, collect_counters=True)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render_spp(buf, S)
+    c = pt.counters()
+    _, _, _, o = oracle_demo.render(W, H, S, counters=True)
+    n = W * H * S
+    assert c["samples"] == o["samples"] == n
+    for k in ("closest_hit", "any_hit", "shade", "nee_contrib", "eval_calls", "lobe_diffuse", "lobe_clearcoat", "lobe_reflect",
+              "lobe_refract", "end_sky", "end_emitter", "end_pdf", "end_depth"):
+        assert abs(c[k] - o[k]) <= max(3, 2e-4 * n), (k, c[k], o[k])
+    assert c["end_sky"] + c["end_emitter"] + c["end_pdf"] + c["end_depth"] == n
+    # counting must not change the image
+    pt2 = rp.Tracer.new(scene)
+    b2 = rp.ColorBuffer.new(W, H)
+    pt2.render_spp(b2, S)
+    assert np.array_equal(buf.pixels, b2.pixels)
+    pt.close(); pt2.close()
+
+
+@pytest.mark.parametrize("wh", [(1, 1), (37, 19), (16, 16), (17, 33)])
+def test_odd_frame_sizes(rp, scene, oracle_demo, wh):
+    W, H = wh
+    pt = rp.Tracer.new(scene)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render_spp(buf, 3)
+    ref, _, _, _ = oracle_demo.render(W, H, 3)
+    assert np.all(buf.pixels.reshape(-1, 4)[:, 3] == 1.0)             # every pixel got its samples
+    assert (pix_rel(buf.pixels, ref) < 1e-4).mean() >= 0.97
+    pt.render_samples(0, 0)                                            # spp = 0 is a no-op
+    pt.close()
+
+
+def test_convert_to_u8_paths(rp, scene, po):
+    W, H = 96, 64
+    pt = rp.Tracer.new(scene)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render_spp(buf, 8)
+    frame = np.zeros(W * H * 4, np.uint8)
+    buf.convert_to_u8(frame)                                           # from the device-resident image
+    ref = po.convert_to_u8(buf.pixels)
+    d = np.abs(frame.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3
+    assert np.array_equal(buf.to_u8_vec(), frame)
+    buf.pixels[:] = np.linspace(0, 1.2, buf.pixels.size, dtype=np.float32)   # host edit -> upload path
+    frame2 = np.zeros(W * H * 4, np.uint8)
+    buf.convert_to_u8(frame2)
+    ref2 = po.convert_to_u8(buf.pixels)
+    # upload multiplies by `frames` and the kernel divides again: +-1 LSB where that rounding crosses an integer
+    d2 = np.abs(frame2.astype(np.int32) - ref2.astype(np.int32))
+    assert d2.max() <= 1 and (d2 != 0).mean() < 2e-3
+    # convert_to_u8_at: no gamma, strict bounds, rows counted from the bottom (buffer.rs:67-102)
+    fw, fh = 128, 100
+    big = np.full(fw * fh * 4, 9, np.uint8)
+    buf.convert_to_u8_at(big, (10, 7, fw, fh))
+    want = po.convert_to_u8_at(buf.pixels, W, H, np.full(fw * fh * 4, 9, np.uint8), 10, 7, fw, fh)
+    d3 = np.abs(big.astype(np.int32) - want.astype(np.int32))
+    assert d3.max() <= 1 and (d3 != 0).mean() < 2e-3 and (big != 9).sum() > 0
+    pt.close()
+
+
+def test_f64_switch(rp, scene, po, demo_export):
+    """the F = f64 instantiation (lib.rs:6) against the f64 oracle"""
+    W, H, S = 96, 64, 4
+    pt = rp.Tracer.new(scene, precision="f64")
+    buf = rp.ColorBuffer.new(W, H, "f64")
+    for _ in range(S):
+        pt.render(buf)
+    ref, _, _, _ = po.OracleScene(demo_export, "f64").render(W, H, S)
+    rel = pix_rel(buf.pixels, ref)
+    assert (rel < 1e-9).mean() >= 0.99 and np.median(rel) < 1e-13
+    # and f32 vs f64 agree statistically (different RNG grids, same distribution)
+    pt32 = rp.Tracer.new(scene)
+    b32 = rp.ColorBuffer.new(W, H)
+    pt32.render_spp(b32, 256)
+    b64 = rp.ColorBuffer.new(W, H, "f64")
+    pt.render_spp(b64, 256)
+    assert abs(lum(b32.pixels).mean() / lum(b64.pixels).mean() - 1) < 0.01
+    with pytest.raises(rp._abi.PtbError):
+        rp._abi.check(rp._abi.load().ptb_download_f32(pt._handle(), b32.pixels.ctypes.data))   # precision mismatch is an error
+    pt.close(); pt32.close()
+
+
+def _small_field(rp, n=1500, side=2):
+    return rp.sphere_field_scene(n_spheres=n, n_lights_side=side)
+
+
+def test_bvh_equals_bruteforce_and_oracle(rp, po):
+    sc = _small_field(rp)
+    export = sc.device_export()
+    W, H, S = 96, 54, 2
+    img = {}
+    for name, flags in (("bvh", rp._abi.PTB_SCENE_FORCE_BVH), ("brute", rp._abi.PTB_SCENE_NO_BVH)):
+        export.flags = flags
+        pt = rp.Tracer.new(sc)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        img[name] = buf.pixels.copy()
+        pt.close()
+    assert np.array_equal(img["bvh"], img["brute"])                    # same arithmetic per sphere, same tie rule
+    export.flags = 0
+    ref, _, _, _ = po.OracleScene(export).render(W, H, S)              # linear scan on the CPU
+    rel = pix_rel(img["bvh"], ref)
+    assert (rel < 1e-4).mean() >= 0.98, (rel < 1e-4).mean()
+    assert abs(lum(img["bvh"]).mean() / lum(ref).mean() - 1) < 2e-3
+
+
+def test_bvh_closest_hit_function_parity(rp, po):
+    sc = _small_field(rp, 3000, 3)
+    export = sc.device_export()
+    dev = DeviceFns(rp, export)
+    osc = po.OracleScene(export)
+    rng = np.random.default_rng(77)
+    n = 20000
+    o = np.stack([rng.uniform(-60, 60, n), rng.uniform(0, 8, n), rng.uniform(-120, 10, n)]).astype(np.float32)
+    d = rng.normal(size=(3, n)); d[1] = -np.abs(d[1]) * 0.3; d /= np.linalg.norm(d, axis=0); d = d.astype(np.float32)
+    hd = np.full(n, -1.0, np.float32)
+    ref, got = osc.closest_hit(o, d, hd), dev.closest_hit(o, d, hd)
+    same = (ref["hit"] == got["hit"]) & (ref["material"] == got["material"]) & (ref["is_emitter"] == got["is_emitter"])
+    assert (~same).sum() <= 5
+    m = same & (ref["hit"] == 1)
+    assert (ref["material"][m] > 0).sum() > 1000                       # plenty of sphere hits, not only the plane
+    assert np.abs(got["hit_dist"][m] - ref["hit_dist"][m]).max() < 1e-3
+    md = rng.uniform(0, 30, n).astype(np.float32)
+    assert (osc.any_hit(o, d, md) != dev.any_hit(o, d, md)).sum() <= 5
+    dev.close()
+
+
+def test_russian_roulette_is_unbiased(rp):
+    sc = rp.divergence_stress_scene(side=6, depth=16)
+    W, H, S = 128, 72, 512
+    means = []
+    for rr in (0, 3):
+        pt = rp.Tracer.new(sc, rr_start=rr, collect_counters=True)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        means.append(lum(buf.pixels).mean())
+        c = pt.counters()
+        assert (c["end_rr"] > 0) == (rr > 0)
+        pt.close()
+    assert abs(means[0] / means[1] - 1) < 0.02, means
+
+
+def test_degenerate_scenes(rp):
+    # no primitives, no lights: every path is sky after one closest_hit
+    e = rp.DeviceScene()
+    pt = rp.Tracer.new(rp.ExportedScene(e), collect_counters=True)
+    buf = rp.ColorBuffer.new(32, 16)
+    pt.render_spp(buf, 2)
+    c = pt.counters()
+    assert c["closest_hit"] == c["samples"] == c["end_sky"] == 32 * 16 * 2 and c["any_hit"] == 0
+    px = buf.pixels.reshape(-1, 4)
+    assert np.all(px[:, 2] == 0.5) and np.all(px[:, 3] == 1.0)         # blue channel of the gradient sky is 1^2.2 * 0.5
+    pt.close()
+    # depth 1: exactly one closest_hit per sample
+    e = rp.AnalyticalScene.new().device_export(); e.depth = 1
+    pt = rp.Tracer.new(rp.ExportedScene(e), collect_counters=True)
+    pt.render_spp(buf, 1)
+    c = pt.counters()
+    assert c["closest_hit"] == c["samples"]
+    pt.close()
+    # lights but no geometry, and a light in front of the camera: stale hit_dist = -1 hides it (A.1) -> pure sky
+    e = rp.DeviceScene(lights=[rp.AnalyticalLight.spherical((0, 0, 0), 1.0, (5, 5, 5))])
+    pt = rp.Tracer.new(rp.ExportedScene(e), collect_counters=True)
+    pt.render_spp(buf, 1)
+    assert pt.counters()["end_emitter"] == 0
+    pt.close()
