@@ -229,10 +229,11 @@ int  ptb_frames(ptb_tracer* t, uint64_t* frames);
  * give each rank a disjoint index range. */
 int  ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base);
 /* Drop-in for one `Tracer::render(&mut ColorBuffer)` call, tracer.rs:22-123: if frames_before
- * is 0 the accumulators are cleared, else if it differs from the device's frame count the host
- * pixels are uploaded first (the app may have edited the public fields); then ONE sample per
- * pixel is traced with sample index frames_before and the running mean is written back to
- * `pixels_rgba_inout`.  Synchronous. */
+ * is 0 the accumulators are cleared, otherwise the host pixels are uploaded first (they are the
+ * source of truth: `pixels` and `frames` are public fields the app may edit between calls);
+ * then ONE sample per pixel is traced with sample index frames_before and the running mean is
+ * written back to `pixels_rgba_inout`.  Synchronous.  Throughput-minded callers keep the image
+ * device-resident instead: ptb_render + ptb_download. */
 int  ptb_render_frame_f32(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,
                           float* pixels_rgba_inout);
 int  ptb_render_frame_f64(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,
@@ -246,6 +247,16 @@ int  ptb_convert_to_u8(ptb_tracer* t, uint8_t* rgba8);
  * memory holding the existing frame contents (pixels outside the rectangle are kept). */
 int  ptb_convert_to_u8_at(ptb_tracer* t, uint8_t* frame_rgba8, uint32_t x, uint32_t y,
                           uint32_t frame_w, uint32_t frame_h);
+
+/* The same two conversions applied to HOST pixels (w*h RGBA reals in, bytes out): what
+ * ColorBuffer::convert_to_u8 / convert_to_u8_at do to the public `pixels` field, whatever the
+ * app stored there (any alpha).  H2D + kernel + D2H. */
+int  ptb_convert_pixels_to_u8_f32(ptb_tracer* t, size_t n_pixels, const float* rgba, uint8_t* rgba8);
+int  ptb_convert_pixels_to_u8_f64(ptb_tracer* t, size_t n_pixels, const double* rgba, uint8_t* rgba8);
+int  ptb_convert_pixels_to_u8_at_f32(ptb_tracer* t, const float* rgba, uint32_t width, uint32_t height,
+                                     uint8_t* frame_rgba8, uint32_t x, uint32_t y, uint32_t frame_w, uint32_t frame_h);
+int  ptb_convert_pixels_to_u8_at_f64(ptb_tracer* t, const double* rgba, uint32_t width, uint32_t height,
+                                     uint8_t* frame_rgba8, uint32_t x, uint32_t y, uint32_t frame_w, uint32_t frame_h);
 
 int  ptb_get_counters(ptb_tracer* t, ptb_counters* out);
 int  ptb_reset_counters(ptb_tracer* t);
@@ -310,8 +321,6 @@ int  ptb_test_disney_sample_f32(ptb_tracer* t, size_t n, uint32_t material_index
  * slot values of `bounce` for n (pixel, sample) pairs: out[slot*n + i].  Bit-exact vs oracle. */
 int  ptb_test_rng_f32(ptb_tracer* t, size_t n, const uint32_t* pixel, const uint64_t* sample,
                       uint32_t bounce, float* out8);
-/* buffer.rs:55-64 on arbitrary floats (NaN, <0, >1 included): n RGBA pixels in, n*4 bytes out */
-int  ptb_test_convert_to_u8_f32(ptb_tracer* t, size_t n_pixels, const float* rgba, uint8_t* out);
 
 #ifdef __cplusplus
 }

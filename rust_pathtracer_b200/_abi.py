@@ -85,11 +85,12 @@ SYMBOLS = [
     "ptb_set_scene_f32", "ptb_set_scene_f64", "ptb_resize", "ptb_bind_accumulator", "ptb_clear",
     "ptb_upload_f32", "ptb_upload_f64", "ptb_download_f32", "ptb_download_f64", "ptb_frames",
     "ptb_render", "ptb_render_frame_f32", "ptb_render_frame_f64", "ptb_synchronize",
-    "ptb_convert_to_u8", "ptb_convert_to_u8_at", "ptb_get_counters", "ptb_reset_counters", "ptb_launch_count",
+    "ptb_convert_to_u8", "ptb_convert_to_u8_at", "ptb_convert_pixels_to_u8_f32", "ptb_convert_pixels_to_u8_f64",
+    "ptb_convert_pixels_to_u8_at_f32", "ptb_convert_pixels_to_u8_at_f64", "ptb_get_counters", "ptb_reset_counters", "ptb_launch_count",
     "ptb_last_render_ms",
     "ptb_test_sphere_hit_f32", "ptb_test_plane_hit_f32", "ptb_test_gen_ray_f32", "ptb_test_closest_hit_f32",
     "ptb_test_any_hit_f32", "ptb_test_background_f32", "ptb_test_sample_light_f32", "ptb_test_finalize_f32",
-    "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32", "ptb_test_convert_to_u8_f32",
+    "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32",
 ]
 
 LIB_NAME = "libptb200.so"
@@ -156,7 +157,9 @@ def load():
     lib.ptb_test_disney_eval_f32.argtypes = [vp, C.c_size_t, C.c_uint32] + [vp] * 6
     lib.ptb_test_disney_sample_f32.argtypes = [vp, C.c_size_t, C.c_uint32] + [vp] * 11
     lib.ptb_test_rng_f32.argtypes = [vp, C.c_size_t, vp, vp, C.c_uint32, vp]
-    lib.ptb_test_convert_to_u8_f32.argtypes = [vp, C.c_size_t, vp, vp]
+    for sfx in ("f32", "f64"):
+        getattr(lib, f"ptb_convert_pixels_to_u8_{sfx}").argtypes = [vp, C.c_size_t, vp, vp]
+        getattr(lib, f"ptb_convert_pixels_to_u8_at_{sfx}").argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp] + [C.c_uint32] * 4
     if lib.ptb_abi_version() != PTB_ABI_VERSION:
         raise RuntimeError("libptb200.so ABI version mismatch")
     _lib = lib

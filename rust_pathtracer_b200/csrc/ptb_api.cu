@@ -41,11 +41,10 @@ static int fail(int code, const char* fmt, ...) {
 // device buffers of one scene
 template <class R> struct SceneBuffers {
     DScene<R> d{};
-    void* spheres = nullptr; void* sphere_material = nullptr; void* planes = nullptr; void* plane_material = nullptr;
-    void* materials = nullptr; void* lights = nullptr; void* bvh = nullptr; void* bvh_prim = nullptr;
+    void* blob = nullptr; void* bvh = nullptr; void* bvh_prim = nullptr;
     size_t bytes = 0;
     void release() {
-        for (void** p : {&spheres, &sphere_material, &planes, &plane_material, &materials, &lights, &bvh, &bvh_prim}) {
+        for (void** p : {&blob, &bvh, &bvh_prim}) {
             if (*p) cudaFree(*p);
             *p = nullptr;
         }
@@ -270,22 +269,35 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         prim.swap(b.prim);
     }
 
+    // pack the arrays into one blob (16-byte aligned sections) so a CTA stages it with one loop
+    std::vector<unsigned char> blob;
+    auto append = [&](const void* src, size_t bytes) {
+        size_t off = (blob.size() + 15) & ~size_t(15);
+        blob.resize(off + bytes);
+        if (bytes) memcpy(blob.data() + off, src, bytes);
+        return (uint32_t)off;
+    };
+    DScene<R>& d = sb.d;
+    d.off_spheres = append(spheres.data(), spheres.size() * sizeof(DSphere<R>));
+    d.off_planes = append(planes.data(), planes.size() * sizeof(DPlane<R>));
+    d.off_materials = append(mats.data(), mats.size() * sizeof(DMaterial<R>));
+    d.off_lights = append(lights.data(), lights.size() * sizeof(DLight<R>));
+    d.off_sphere_material = append(smat.data(), smat.size() * sizeof(uint32_t));
+    d.off_plane_material = append(pmat.data(), pmat.size() * sizeof(uint32_t));
+    blob.resize((blob.size() + 15) & ~size_t(15));
+
     sb.release();
-    CU(upload_vec(&sb.spheres, spheres, t->stream, sb.bytes));
-    CU(upload_vec(&sb.sphere_material, smat, t->stream, sb.bytes));
-    CU(upload_vec(&sb.planes, planes, t->stream, sb.bytes));
-    CU(upload_vec(&sb.plane_material, pmat, t->stream, sb.bytes));
-    CU(upload_vec(&sb.materials, mats, t->stream, sb.bytes));
-    CU(upload_vec(&sb.lights, lights, t->stream, sb.bytes));
+    CU(upload_vec(&sb.blob, blob, t->stream, sb.bytes));
     CU(upload_vec(&sb.bvh, nodes, t->stream, sb.bytes));
     CU(upload_vec(&sb.bvh_prim, prim, t->stream, sb.bytes));
     CU(cudaStreamSynchronize(t->stream));   // host vectors go out of scope
 
-    DScene<R>& d = sb.d;
+    const char* base = (const char*)sb.blob;
+    d.blob = sb.blob; d.blob_bytes = (uint32_t)blob.size();
     d.n_spheres = sc->n_spheres; d.n_planes = sc->n_planes; d.n_materials = sc->n_materials; d.n_lights = sc->n_lights;
-    d.spheres = (const DSphere<R>*)sb.spheres; d.sphere_material = (const uint32_t*)sb.sphere_material;
-    d.planes = (const DPlane<R>*)sb.planes; d.plane_material = (const uint32_t*)sb.plane_material;
-    d.materials = (const DMaterial<R>*)sb.materials; d.lights = (const DLight<R>*)sb.lights;
+    d.spheres = (const DSphere<R>*)(base + d.off_spheres); d.sphere_material = (const uint32_t*)(base + d.off_sphere_material);
+    d.planes = (const DPlane<R>*)(base + d.off_planes); d.plane_material = (const uint32_t*)(base + d.off_plane_material);
+    d.materials = (const DMaterial<R>*)(base + d.off_materials); d.lights = (const DLight<R>*)(base + d.off_lights);
     d.bvh = use_bvh ? (const BvhNode*)sb.bvh : nullptr; d.bvh_prim = (const uint32_t*)sb.bvh_prim;
     d.use_bvh = use_bvh; d.patch_materials = patch;
     d.depth = sc->depth; d.flags = sc->flags; d.eps = sc->eps;
@@ -400,6 +412,7 @@ int ptb_set_scene_f32(ptb_tracer* t, const ptb_scene_f32* sc) {
     if (r != PTB_OK) return r;
     t->s64.release();
     t->precision = 4;
+    t->fused_blocks_f32 = t->fused_blocks_f64 = 0;
     CamParams<float>& c = t->c32;
     for (int k = 0; k < 3; ++k) { c.origin[k] = sc->camera.origin[k]; c.center[k] = sc->camera.center[k]; }
     c.fov = sc->camera.fov;
@@ -412,6 +425,7 @@ int ptb_set_scene_f64(ptb_tracer* t, const ptb_scene_f64* sc) {
     if (r != PTB_OK) return r;
     t->s32.release();
     t->precision = 8;
+    t->fused_blocks_f32 = t->fused_blocks_f64 = 0;
     CamParams<double>& c = t->c64;
     for (int k = 0; k < 3; ++k) { c.origin[k] = sc->camera.origin[k]; c.center[k] = sc->camera.center[k]; }
     c.fov = sc->camera.fov;
@@ -534,10 +548,12 @@ template <class R> static int render_fused(ptb_tracer* t, DScene<R>& d, uint32_t
     a.counters = t->counters;
     int& blocks = sizeof(R) == 4 ? t->fused_blocks_f32 : t->fused_blocks_f64;
     const bool count = t->cfg.collect_counters != 0;
+    void (*kern)(const DScene<R>, const RenderArgs) =
+        d.use_bvh ? (count ? k_render_fused<R, true, true> : k_render_fused<R, false, true>)
+                  : (count ? k_render_fused<R, true, false> : k_render_fused<R, false, false>);
     if (blocks == 0) {
         int per_sm = 0;
-        if (count) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_fused<R, true>, FUSED_THREADS, 0));
-        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_fused<R, false>, FUSED_THREADS, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         blocks = per_sm * t->sm_count;
     }
@@ -545,8 +561,7 @@ template <class R> static int render_fused(ptb_tracer* t, DScene<R>& d, uint32_t
     int grid = std::max(1, std::min<int>(blocks, (int)max_useful));
     CU(cudaMemsetAsync(t->work_counter, 0, sizeof(unsigned int), t->stream));
     CU(cudaEventRecord(t->ev0, t->stream));
-    if (count) k_render_fused<R, true><<<grid, FUSED_THREADS, 0, t->stream>>>(d, a);
-    else k_render_fused<R, false><<<grid, FUSED_THREADS, 0, t->stream>>>(d, a);
+    kern<<<grid, FUSED_THREADS, 0, t->stream>>>(d, a);
     CU(cudaGetLastError());
     CU(cudaEventRecord(t->ev1, t->stream));
     t->timed = true;
@@ -588,8 +603,10 @@ template <class R> static int render_frame_impl(ptb_tracer* t, uint32_t w, uint3
     if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
     int r;
     if (w != t->W || h != t->H || !t->accum) { if ((r = ptb_resize(t, w, h))) return r; }
+    // the host buffer is the source of truth, exactly as in the reference where `pixels` and `frames`
+    // are public fields the app may edit between calls
     if (frames_before == 0) { if ((r = ptb_clear(t))) return r; }
-    else if (frames_before != t->frames) { if ((r = upload_impl<R>(t, pixels, frames_before))) return r; }
+    else { if ((r = upload_impl<R>(t, pixels, frames_before))) return r; }
     if ((r = ptb_render(t, 1, frames_before))) return r;
     return download_impl<R>(t, pixels);
 }
@@ -624,14 +641,65 @@ int ptb_convert_to_u8_at(ptb_tracer* t, uint8_t* frame, uint32_t x, uint32_t y, 
     if ((r = ensure_staging(t, bytes))) return r;
     CU(cudaMemcpyAsync(t->staging, frame, bytes, cudaMemcpyHostToDevice, t->stream));
     uint32_t n = fw * fh;
-    if (t->precision == 4) k_convert_u8_at<float><<<(n + 255) / 256, 256, 0, t->stream>>>((const float4*)t->accum, t->W, t->H, (uchar4*)t->staging, x, y, fw, fh);
-    else k_convert_u8_at<double><<<(n + 255) / 256, 256, 0, t->stream>>>((const double4*)t->accum, t->W, t->H, (uchar4*)t->staging, x, y, fw, fh);
+    if (t->precision == 4) k_convert_u8_at<float><<<(n + 255) / 256, 256, 0, t->stream>>>((const float4*)t->accum, t->W, t->H, (uchar4*)t->staging, x, y, fw, fh, 1);
+    else k_convert_u8_at<double><<<(n + 255) / 256, 256, 0, t->stream>>>((const double4*)t->accum, t->W, t->H, (uchar4*)t->staging, x, y, fw, fh, 1);
     t->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(frame, t->staging, bytes, cudaMemcpyDeviceToHost, t->stream));
     CU(cudaStreamSynchronize(t->stream));
     return PTB_OK;
 }
+
+}  // extern "C"
+template <class R> static int convert_pixels_impl(ptb_tracer* t, size_t n, const R* rgba, uint8_t* out) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    if (!rgba || !out) return fail(PTB_E_INVALID, "null buffer");
+    if (n == 0) return PTB_OK;
+    if (n > (1ull << 31)) return fail(PTB_E_INVALID, "too many pixels");
+    CU(cudaSetDevice(t->device));
+    using V4 = typename Vec4T<R>::type;
+    void *din = nullptr, *dout = nullptr;
+    CU(cudaMalloc(&din, n * sizeof(V4)));
+    cudaError_t e = cudaMalloc(&dout, n * 4);
+    if (e != cudaSuccess) { cudaFree(din); return fail(PTB_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(din, rgba, n * sizeof(V4), cudaMemcpyHostToDevice, t->stream);
+    k_convert_u8<R><<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>((const V4*)din, (uchar4*)dout, (uint32_t)n, 0);
+    t->launches++;
+    cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, t->stream);
+    e = cudaStreamSynchronize(t->stream);
+    cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) return fail(PTB_E_CUDA, "convert_pixels: %s", cudaGetErrorString(e));
+    return PTB_OK;
+}
+template <class R>
+static int convert_pixels_at_impl(ptb_tracer* t, const R* rgba, uint32_t w, uint32_t h, uint8_t* frame, uint32_t x, uint32_t y, uint32_t fw,
+                                  uint32_t fh) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    if (!rgba || !frame || !w || !h || !fw || !fh) return fail(PTB_E_INVALID, "bad argument");
+    CU(cudaSetDevice(t->device));
+    using V4 = typename Vec4T<R>::type;
+    size_t nin = (size_t)w * h, nf = (size_t)fw * fh;
+    void *din = nullptr, *dfr = nullptr;
+    CU(cudaMalloc(&din, nin * sizeof(V4)));
+    cudaError_t e = cudaMalloc(&dfr, nf * 4);
+    if (e != cudaSuccess) { cudaFree(din); return fail(PTB_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(din, rgba, nin * sizeof(V4), cudaMemcpyHostToDevice, t->stream);
+    cudaMemcpyAsync(dfr, frame, nf * 4, cudaMemcpyHostToDevice, t->stream);
+    k_convert_u8_at<R><<<(unsigned)((nf + 255) / 256), 256, 0, t->stream>>>((const V4*)din, w, h, (uchar4*)dfr, x, y, fw, fh, 0);
+    t->launches++;
+    cudaMemcpyAsync(frame, dfr, nf * 4, cudaMemcpyDeviceToHost, t->stream);
+    e = cudaStreamSynchronize(t->stream);
+    cudaFree(din); cudaFree(dfr);
+    if (e != cudaSuccess) return fail(PTB_E_CUDA, "convert_pixels_at: %s", cudaGetErrorString(e));
+    return PTB_OK;
+}
+extern "C" {
+int ptb_convert_pixels_to_u8_f32(ptb_tracer* t, size_t n, const float* rgba, uint8_t* out) { return convert_pixels_impl<float>(t, n, rgba, out); }
+int ptb_convert_pixels_to_u8_f64(ptb_tracer* t, size_t n, const double* rgba, uint8_t* out) { return convert_pixels_impl<double>(t, n, rgba, out); }
+int ptb_convert_pixels_to_u8_at_f32(ptb_tracer* t, const float* rgba, uint32_t w, uint32_t h, uint8_t* frame, uint32_t x, uint32_t y, uint32_t fw,
+                                    uint32_t fh) { return convert_pixels_at_impl<float>(t, rgba, w, h, frame, x, y, fw, fh); }
+int ptb_convert_pixels_to_u8_at_f64(ptb_tracer* t, const double* rgba, uint32_t w, uint32_t h, uint8_t* frame, uint32_t x, uint32_t y, uint32_t fw,
+                                    uint32_t fh) { return convert_pixels_at_impl<double>(t, rgba, w, h, frame, x, y, fw, fh); }
 
 int ptb_get_counters(ptb_tracer* t, ptb_counters* out) {
     if (!t || !out) return fail(PTB_E_INVALID, "null argument");
@@ -808,13 +876,4 @@ int ptb_test_rng_f32(ptb_tracer* t, size_t n, const uint32_t* pixel, const uint6
     dv.back(out8, q, 8 * n);
     TEST_END()
 }
-int ptb_test_convert_to_u8_f32(ptb_tracer* t, size_t n_pixels, const float* rgba, uint8_t* out) {
-    TEST_BEGIN(false)
-    auto* pi = dv.in(rgba, 4 * n_pixels);
-    auto* q = dv.out<uint8_t>(4 * n_pixels);
-    k_convert_u8<float><<<(unsigned)std::max<size_t>(1, (n_pixels + 255) / 256), 256, 0, t->stream>>>((const float4*)pi, (uchar4*)q, (uint32_t)n_pixels, 0);
-    dv.back(out, q, 4 * n_pixels);
-    TEST_END()
-}
-
 }  // extern "C"

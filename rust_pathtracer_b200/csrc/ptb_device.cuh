@@ -31,7 +31,10 @@ PTB_DEV float m_abs(float x) { return fabsf(x); }
 PTB_DEV double m_abs(double x) { return fabs(x); }
 PTB_DEV float m_max(float a, float b) { return fmaxf(a, b); }   // f32::max: NaN-ignoring
 PTB_DEV double m_max(double a, double b) { return fmax(a, b); }
-PTB_DEV float m_pow(float a, float b) { return powf(a, b); }
+// powf as exp2(b*log2(a)): ~3 ulp for the |b*log2(a)| <= 20 this path produces, a fraction of the
+// size of powf's full special-case tree (the fused kernel is instruction-cache bound).
+// a == 0 -> 0, a < 0 -> NaN, a == 1 -> 1, as powf.
+PTB_DEV float m_pow(float a, float b) { return exp2f(b * log2f(a)); }
 PTB_DEV double m_pow(double a, double b) { return pow(a, b); }
 PTB_DEV float m_log2(float a) { return log2f(a); }
 PTB_DEV double m_log2(double a) { return log2(a); }
@@ -39,7 +42,26 @@ PTB_DEV float m_floor(float a) { return floorf(a); }
 PTB_DEV double m_floor(double a) { return floor(a); }
 PTB_DEV float m_fmod(float a, float b) { return fmodf(a, b); }
 PTB_DEV double m_fmod(double a, double b) { return fmod(a, b); }
-PTB_DEV void m_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+// IEEE division where a branch decision hangs on the last bit (checker cell, film coordinates)
+PTB_DEV float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+PTB_DEV double div_rn(double a, double b) { return a / b; }
+// sin/cos of an angle known to lie in [0, 2*pi] (every call site passes TWO_PI * u, u in [0,1)):
+// quadrant reduction with a three-term Cody-Waite pi/2 and the Cephes sinf/cosf minimax kernels on
+// [-pi/4, pi/4]; ~1 ulp, no large-argument slow path (sincosf's Payne-Hanek tail is dead code here).
+PTB_DEV void m_sincos(float x, float* s, float* c) {
+    float kf = rintf(x * 0.636619772f);
+    float r = fmaf(kf, -1.5703125f, x);
+    r = fmaf(kf, -4.837512969970703125e-4f, r);
+    r = fmaf(kf, -7.54978995489188216e-8f, r);
+    float z = r * r;
+    float sn = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, r, r);
+    float cs = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f) * z, z, fmaf(-0.5f, z, 1.0f));
+    int k = (int)kf;
+    float a = (k & 1) ? cs : sn;
+    float b = (k & 1) ? sn : cs;
+    *s = (k & 2) ? -a : a;
+    *c = ((k + 1) & 2) ? -b : b;
+}
 PTB_DEV void m_sincos(double a, double* s, double* c) { sincos(a, s, c); }
 template <class R> PTB_DEV R m_clamp(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); }  // f32::clamp
 
@@ -74,8 +96,15 @@ template <class R> PTB_HD V3<R> cross(V3<R> a, V3<R> b) {
     return V3<R>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 template <class R> PTB_DEV R length(V3<R> a) { return m_sqrt(dot(a, a)); }
-template <class R> PTB_DEV V3<R> div_s(V3<R> a, R s) { return V3<R>(a.x / s, a.y / s, a.z / s); }
-template <class R> PTB_DEV V3<R> normalize(V3<R> a) { return div_s(a, length(a)); }     // fx.rs:306-313
+// F3 / scalar and normalize (fx.rs:306-313: three divides by sqrt).  f32: one reciprocal (MUFU.RCP /
+// MUFU.RSQ, <= 2 ulp) and three multiplies — a handful of instructions instead of three division
+// sequences; f64 keeps IEEE division.
+PTB_DEV float m_rcp(float x) { return __fdividef(1.0f, x); }
+PTB_DEV double m_rcp(double x) { return 1.0 / x; }
+PTB_DEV V3<float> div_s(V3<float> a, float s) { float r = m_rcp(s); return V3<float>(a.x * r, a.y * r, a.z * r); }
+PTB_DEV V3<double> div_s(V3<double> a, double s) { return V3<double>(a.x / s, a.y / s, a.z / s); }
+PTB_DEV V3<float> normalize(V3<float> a) { float r = rsqrtf(dot(a, a)); return V3<float>(a.x * r, a.y * r, a.z * r); }
+PTB_DEV V3<double> normalize(V3<double> a) { return div_s(a, length(a)); }
 template <class R> PTB_DEV V3<R> mix3(V3<R> a, V3<R> b, R v) {                          // math.rs:33-39
     R w = R(1) - v;
     return V3<R>(w * a.x + b.x * v, w * a.y + b.y * v, w * a.z + b.z * v);
@@ -166,14 +195,11 @@ struct BvhNode {
     float hi[3]; uint32_t count;           // 0 = inner, >0 = leaf prim count
 };
 
-constexpr int PTB_SMEM_MAX_SPHERES = 64;
-constexpr int PTB_SMEM_MAX_PLANES = 8;
-constexpr int PTB_SMEM_MAX_MATERIALS = 64;
-constexpr int PTB_SMEM_MAX_LIGHTS = 64;
-
 template <class R> struct DScene {
     uint32_t n_spheres, n_planes, n_materials, n_lights;
-    const DSphere<R>* spheres;          // global memory (HBM), SoA-of-float4
+    const void* blob;                   // packed scene arrays in HBM (see stage_scene)
+    uint32_t blob_bytes, off_spheres, off_planes, off_materials, off_lights, off_sphere_material, off_plane_material;
+    const DSphere<R>* spheres;          // the same arrays, addressed directly (BVH leaves, parity kernels)
     const uint32_t* sphere_material;
     const DPlane<R>* planes;
     const uint32_t* plane_material;
@@ -193,7 +219,10 @@ template <class R> struct DScene {
     R n_lights_f;                       // number_of_lights() as F (tracer.rs:138,214)
 };
 
-// Scene arrays as the kernels read them: shared-memory copies for small scenes.
+// Scene arrays as the kernels read them.  Small scenes are staged in shared memory: the host packs
+// [spheres | planes | materials | lights | sphere_material | plane_material] into ONE blob
+// (DScene::blob, blob_bytes) and every CTA copies it with a single loop; larger scenes are read
+// from HBM through L1/L2.
 template <class R> struct SceneView {
     const DSphere<R>* spheres;
     const uint32_t* sphere_material;
@@ -203,47 +232,26 @@ template <class R> struct SceneView {
     const DLight<R>* lights;
 };
 
-template <class R> struct SceneSmem {
-    DSphere<R> spheres[PTB_SMEM_MAX_SPHERES];
-    uint32_t sphere_material[PTB_SMEM_MAX_SPHERES];
-    DPlane<R> planes[PTB_SMEM_MAX_PLANES];
-    uint32_t plane_material[PTB_SMEM_MAX_PLANES];
-    DMaterial<R> materials[PTB_SMEM_MAX_MATERIALS];
-    DLight<R> lights[PTB_SMEM_MAX_LIGHTS];
-};
+constexpr uint32_t PTB_SMEM_SCENE_BYTES = 12 * 1024;    // capacity of the shared-memory scene copy
 
-template <class R> PTB_DEV bool scene_fits_smem(const DScene<R>& s) {
-    return s.n_spheres <= PTB_SMEM_MAX_SPHERES && s.n_planes <= PTB_SMEM_MAX_PLANES && s.n_materials <= PTB_SMEM_MAX_MATERIALS &&
-           s.n_lights <= PTB_SMEM_MAX_LIGHTS;
-}
+template <class R> struct alignas(16) SceneSmem { uint32_t words[PTB_SMEM_SCENE_BYTES / 4]; };
 
-// Cooperative copy of the (small) scene arrays into shared memory; call from all threads of the CTA.
+// Cooperative copy of the (small) scene blob into shared memory; call from all threads of the CTA.
 template <class R> __device__ inline SceneView<R> stage_scene(const DScene<R>& s, SceneSmem<R>* sm) {
-    SceneView<R> v;
-    const bool small = scene_fits_smem(s);
-    // lights / planes / materials are always small enough or stay in global memory together
-    if (small) {
-        const int tid = threadIdx.x, nt = blockDim.x;
-        auto copy_words = [&](void* dst, const void* src, uint32_t bytes) {
-            uint32_t* d = (uint32_t*)dst;
-            const uint32_t* q = (const uint32_t*)src;
-            for (uint32_t i = tid; i < bytes / 4u; i += nt) d[i] = q[i];
-        };
-        copy_words(sm->spheres, s.spheres, s.n_spheres * sizeof(DSphere<R>));
-        copy_words(sm->sphere_material, s.sphere_material, s.n_spheres * sizeof(uint32_t));
-        copy_words(sm->planes, s.planes, s.n_planes * sizeof(DPlane<R>));
-        copy_words(sm->plane_material, s.plane_material, s.n_planes * sizeof(uint32_t));
-        copy_words(sm->materials, s.materials, s.n_materials * sizeof(DMaterial<R>));
-        copy_words(sm->lights, s.lights, s.n_lights * sizeof(DLight<R>));
+    const char* base = (const char*)s.blob;
+    if (s.blob_bytes <= PTB_SMEM_SCENE_BYTES) {
+        const uint32_t* src = (const uint32_t*)s.blob;
+        for (uint32_t i = threadIdx.x; i < s.blob_bytes / 4u; i += blockDim.x) sm->words[i] = src[i];
         __syncthreads();
-        v.spheres = sm->spheres; v.sphere_material = sm->sphere_material;
-        v.planes = sm->planes; v.plane_material = sm->plane_material;
-        v.materials = sm->materials; v.lights = sm->lights;
-    } else {
-        v.spheres = s.spheres; v.sphere_material = s.sphere_material;
-        v.planes = s.planes; v.plane_material = s.plane_material;
-        v.materials = s.materials; v.lights = s.lights;
+        base = (const char*)sm->words;
     }
+    SceneView<R> v;
+    v.spheres = (const DSphere<R>*)(base + s.off_spheres);
+    v.planes = (const DPlane<R>*)(base + s.off_planes);
+    v.materials = (const DMaterial<R>*)(base + s.off_materials);
+    v.lights = (const DLight<R>*)(base + s.off_lights);
+    v.sphere_material = (const uint32_t*)(base + s.off_sphere_material);
+    v.plane_material = (const uint32_t*)(base + s.off_plane_material);
     return v;
 }
 
@@ -264,15 +272,19 @@ template <class R> PTB_DEV void mat_defaults(Mat<R>& m) {    // material.rs:82-1
 }
 
 // analytical.rs:107-111
+// `v % 2.0` for an integer-valued v: v - 2*trunc(v/2) is exact in floating point and keeps the
+// dividend's sign like fmod (NaN/inf -> NaN), at a fraction of fmodf's code size.
+PTB_DEV float fmod2_int(float v) { return v - 2.0f * truncf(v * 0.5f); }
+PTB_DEV double fmod2_int(double v) { return v - 2.0 * trunc(v * 0.5); }
 template <class R> PTB_DEV R checker(R x, R y, R a, R b) {
-    R x1 = m_fmod(m_floor(x), R(2));
-    R y1 = m_fmod(m_floor(y), R(2));
-    return (m_fmod(x1 + y1, R(2)) < R(1)) ? a : b;
+    R x1 = fmod2_int(m_floor(x));
+    R y1 = fmod2_int(m_floor(y));
+    return (fmod2_int(x1 + y1) < R(1)) ? a : b;
 }
 
 template <class R> PTB_DEV V3<R> material_rgb(const DMaterial<R>& dm, V3<R> rd) {
     if (dm.albedo_kind == PTB_ALBEDO_CHECKER_DIR_RATIO) {   // analytical.rs:113-115 (quirk A.7)
-        R c = checker(rd.x / rd.y * dm.checker_scale + dm.checker_offset, rd.z / rd.y * dm.checker_scale + dm.checker_offset,
+        R c = checker(div_rn(rd.x, rd.y) * dm.checker_scale + dm.checker_offset, div_rn(rd.z, rd.y) * dm.checker_scale + dm.checker_offset,
                       dm.checker_a, dm.checker_b);
         return V3<R>(c, c, c);
     }
@@ -370,8 +382,8 @@ template <class R> PTB_DEV void film_coords(uint32_t x, uint32_t row, uint32_t W
     // j counts rows from the LAST memory row (par_rchunks_exact_mut): j = H-1-row; y = H - j
     R hf = (R)H;
     R y = hf - (R)(H - 1u - row);
-    R yy = y / hf;
-    px = (R)x / (R)W;
+    R yy = div_rn(y, hf);
+    px = div_rn((R)x, (R)W);
     py = R(1) - yy;
 }
 
@@ -469,7 +481,7 @@ template <class R> PTB_DEV bool bvh_any(const DScene<R>& s, V3<R> o, V3<R> d, R 
 
 // Scene::closest_hit for the exported scene.  `hit_dist_in` is State::hit_dist carried across
 // bounces (A.1).  Fills `mat` (un-finalized) when geometry was accepted.
-template <class R>
+template <class R, bool BVH>
 PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, Mat<R>& mat) {
     HitRec<R> h;
     h.hit = false; h.is_emitter = false; h.geom = false; h.hit_dist = hit_dist_in; h.material = 0xffffffffu;
@@ -477,9 +489,10 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
     R dist = Const<R>::MAXV;
     int best = -1;                 // < n_spheres: sphere; else plane (best - n_spheres)
     uint64_t accepted = 0;         // bit i set: primitive i was "closest so far" when tested (patching scenes only)
-    if (s.use_bvh) {
+    if (BVH) {
         best = bvh_closest(s, o, d, dist);
     } else {
+#pragma unroll 1
         for (uint32_t i = 0; i < s.n_spheres; ++i) {
             DSphere<R> sp = sv.spheres[i];
             R t = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
@@ -488,6 +501,7 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
             }
         }
     }
+#pragma unroll 1
     for (uint32_t i = 0; i < s.n_planes; ++i) {
         DPlane<R> pl = sv.planes[i];
         R t = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
@@ -499,22 +513,23 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
         h.hit = true; h.geom = true; h.hit_dist = dist;
         uint32_t mi;
         if ((uint32_t)best < s.n_spheres) {
-            DSphere<R> sp = s.use_bvh ? s.spheres[best] : sv.spheres[best];
+            DSphere<R> sp = BVH ? s.spheres[best] : sv.spheres[best];
             V3<R> c(sp.cx, sp.cy, sp.cz);
             V3<R> hp = o + dist * d;                   // analytical.rs:45-46
             h.normal = normalize(hp - c);
-            mi = s.use_bvh ? s.sphere_material[best] : sv.sphere_material[best];
+            mi = BVH ? s.sphere_material[best] : sv.sphere_material[best];
         } else {
             DPlane<R> pl = sv.planes[best - s.n_spheres];
             h.normal = V3<R>(pl.nx, pl.ny, pl.nz);     // analytical.rs:105
             mi = sv.plane_material[best - s.n_spheres];
         }
         h.material = mi;
-        if (!s.patch_materials) {
+        if (BVH || !s.patch_materials) {
             mat_load(mat, sv.materials[mi], d);
         } else {
             // replay the reference's assignment order over the accepted primitives
             bool first = true;
+#pragma unroll 1
             while (accepted) {
                 int i = __ffsll((long long)accepted) - 1;
                 accepted &= accepted - 1;
@@ -527,6 +542,7 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
     // Scene::sample_lights, scene.rs:36-86 — starts from the possibly stale state.hit_dist
     R ldist = h.hit_dist;
     int lbest = -1;
+#pragma unroll 1
     for (uint32_t i = 0; i < s.n_lights; ++i) {
         DLight<R> L = sv.lights[i];
         if (L.type != PTB_LIGHT_SPHERICAL) continue;
@@ -547,17 +563,19 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
 }
 
 // Scene::any_hit, analytical.rs:130-145 (+ max_dist unless the scene flag says the impl ignores it)
-template <class R> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
     const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
-    if (s.use_bvh) {
+    if (BVH) {
         if (bvh_any(s, o, d, max_dist, ignore)) return true;
     } else {
+#pragma unroll 1
         for (uint32_t i = 0; i < s.n_spheres; ++i) {
             DSphere<R> sp = sv.spheres[i];
             R t = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
             if (t >= R(0) && (ignore || t < max_dist)) return true;
         }
     }
+#pragma unroll 1
     for (uint32_t i = 0; i < s.n_planes; ++i) {
         DPlane<R> pl = sv.planes[i];
         R t = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
@@ -618,38 +636,30 @@ template <class R> PTB_DEV void onb(V3<R> n, V3<R>& t, V3<R>& b) {
     b = cross(n, t);
 }
 
-// samplers, tracer.rs:242-274, 324-333
-template <class R> PTB_DEV V3<R> cosine_sample_hemisphere(R r1, R r2) {
+// samplers, tracer.rs:242-274, 324-333.  Each takes (sin, cos) of its azimuth so that ONE sincos
+// serves whichever lobe was picked (code size: the fused kernel is instruction-cache bound).
+template <class R> PTB_DEV V3<R> cosine_sample_hemisphere(R r1, R sn, R cs) {
     R r = m_sqrt(r1);
-    R phi = Const<R>::TWO_PI * r2;
-    R s, c;
-    m_sincos(phi, &s, &c);
-    R x = r * c, y = r * s;
+    R x = r * cs, y = r * sn;
     return V3<R>(x, y, m_sqrt(m_max(R(0), R(1) - x * x - y * y)));
 }
-template <class R> PTB_DEV V3<R> sample_gtr1(R rgh, R r1) {                      // r2 unused: quirk A.4
+template <class R> PTB_DEV V3<R> sample_gtr1(R rgh, R r1, R sn, R cs) {          // r2 unused: quirk A.4 (phi = r1 * TWO_PI)
     R a = m_max(R(0.001), rgh);
     R a2 = a * a;
-    R phi = r1 * Const<R>::TWO_PI;
     R cos_theta = m_sqrt((R(1) - m_pow(a2, R(1) - r1)) / (R(1) - a2));
     R sin_theta = m_clamp(m_sqrt(R(1) - (cos_theta * cos_theta)), R(0), R(1));
-    R sp, cp;
-    m_sincos(phi, &sp, &cp);
-    return V3<R>(sin_theta * cp, sin_theta * sp, cos_theta);
+    return V3<R>(sin_theta * cs, sin_theta * sn, cos_theta);
 }
-template <class R> PTB_DEV V3<R> sample_ggxvndf(V3<R> v, R ax, R ay, R r1, R r2) {
+template <class R> PTB_DEV V3<R> sample_ggxvndf(V3<R> v, R ax, R ay, R r1, R sn, R cs) {
     V3<R> vh = normalize(V3<R>(ax * v.x, ay * v.y, v.z));
     R lensq = vh.x * vh.x + vh.y * vh.y;
     V3<R> t_1;
-    if (lensq > R(0)) { R il = R(1) / m_sqrt(lensq); t_1 = V3<R>(-vh.y * il, vh.x * il, R(0) * il); }
+    if (lensq > R(0)) { R il = R(1) / m_sqrt(lensq); t_1 = V3<R>(-vh.y * il, vh.x * il, R(0)); }
     else t_1 = V3<R>(1, 0, 0);
     V3<R> t_2 = cross(vh, t_1);
     R r = m_sqrt(r1);
-    R phi = R(2) * Const<R>::PI * r2;
-    R s_, c_;
-    m_sincos(phi, &s_, &c_);
-    R t1 = r * c_;
-    R t2 = r * s_;
+    R t1 = r * cs;
+    R t2 = r * sn;
     R s = R(0.5) * (R(1) + vh.z);
     t2 = (R(1) - s) * m_sqrt(R(1) - t1 * t1) + s * t2;
     V3<R> nh = t1 * t_1 + t2 * t_2 + m_sqrt(m_max(R(0), R(1) - t1 * t1 - t2 * t2)) * vh;
@@ -710,10 +720,9 @@ template <class R> PTB_DEV V3<R> eval_diffuse(const Mat<R>& m, V3<R> c_sheen, V3
     pdf = l.z * Const<R>::INV_PI;
     return ((R(1) - m.metallic) * (R(1) - m.spec_trans)) * ((Const<R>::INV_PI * mix1(fd, ss, m.subsurface)) * m.rgb + fsheen);
 }
-template <class R> PTB_DEV V3<R> eval_spec_reflection(const Mat<R>& m, R eta, V3<R> spec_col, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
+template <class R> PTB_DEV V3<R> eval_spec_reflection(const Mat<R>& m, R fm, V3<R> spec_col, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
     pdf = 0;
     if (l.z <= R(0)) return V3<R>(0, 0, 0);
-    R fm = disney_fresnel(m, eta, dot(l, h), dot(v, h));
     V3<R> f = mix3(spec_col, V3<R>(1, 1, 1), fm);
     R d = gtr2aniso(h.z, h.x, h.y, m.ax, m.ay);
     R g1 = smithganiso(m_abs(v.z), v.x, v.y, m.ax, m.ay);
@@ -721,11 +730,10 @@ template <class R> PTB_DEV V3<R> eval_spec_reflection(const Mat<R>& m, R eta, V3
     pdf = g1 * d / (R(4) * v.z);
     return div_s((d * g2) * f, R(4) * l.z * v.z);
 }
-template <class R> PTB_DEV V3<R> eval_spec_refraction(const Mat<R>& m, R eta, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
+template <class R> PTB_DEV V3<R> eval_spec_refraction(const Mat<R>& m, R eta, R f, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
     pdf = 0;
     if (l.z >= R(0)) return V3<R>(0, 0, 0);
     R vdh = dot(v, h), ldh = dot(l, h);
-    R f = dielectric_fresnel(m_abs(vdh), eta);
     R d = gtr2aniso(h.z, h.x, h.y, m.ax, m.ay);
     R g1 = smithganiso(m_abs(v.z), v.x, v.y, m.ax, m.ay);
     R g2 = g1 * smithganiso(m_abs(l.z), l.x, l.y, m.ax, m.ay);
@@ -754,39 +762,47 @@ template <class R> PTB_DEV V3<R> eval_clearcoat(const Mat<R>& m, V3<R> v, V3<R> 
 // lobe ids
 enum { LOBE_DIFFUSE = 0, LOBE_CLEARCOAT = 1, LOBE_REFLECT = 2, LOBE_REFRACT = 3 };
 
-// Tracer::disney_eval, tracer.rs:555-626 (returns |l.z| * f)
-template <class R> PTB_DEV V3<R> disney_eval(const Mat<R>& m, const ShadeCtx<R>& c, V3<R> l_world, R& bsdf_pdf, uint32_t* ev = nullptr) {
-    bsdf_pdf = 0;
-    V3<R> f(0, 0, 0);
+// What to evaluate at a local direction pair (l, h): which lobes, and the factor each lobe's pdf
+// is multiplied with.  disney_eval (NEE) and disney_sample (BSDF sampling) both reduce to this,
+// so the four eval_* bodies exist ONCE in the integrator.
+template <class R> struct LobeQuery {
+    V3<R> l, h;          // local frame
+    uint32_t mask;       // bit k: evaluate lobe k
+    R pw[4];             // pdf weight per lobe id
+    R diel;              // dielectric_fresnel(|v.h|, eta): tracer.rs:390 and the dielectric half of 374/437
+    R fm;                // disney_fresnel(l.h, v.h), tracer.rs:374 (same operands as 531/596 => same value)
+};
+
+// f = sum of the enabled lobes (reference order: diffuse, spec reflection, spec refraction,
+// clearcoat; tracer.rs:601-623), pdf = sum lobe_pdf * weight.
+template <class R>
+PTB_DEV void eval_lobes(const Mat<R>& m, const ShadeCtx<R>& c, const LobeQuery<R>& q, V3<R>& f, R& pdf_out, uint32_t* ev) {
+    f = V3<R>(0, 0, 0);
+    pdf_out = 0;
+    R pdf;
+    if (q.mask & (1u << LOBE_DIFFUSE)) { f = f + eval_diffuse(m, c.sheen_col, c.v, q.l, q.h, pdf); pdf_out += pdf * q.pw[LOBE_DIFFUSE]; if (ev) ev[LOBE_DIFFUSE]++; }
+    if (q.mask & (1u << LOBE_REFLECT)) { f = f + eval_spec_reflection(m, q.fm, c.spec_col, c.v, q.l, q.h, pdf); pdf_out += pdf * q.pw[LOBE_REFLECT]; if (ev) ev[LOBE_REFLECT]++; }
+    if (q.mask & (1u << LOBE_REFRACT)) { f = f + eval_spec_refraction(m, c.eta, q.diel, c.v, q.l, q.h, pdf); pdf_out += pdf * q.pw[LOBE_REFRACT]; if (ev) ev[LOBE_REFRACT]++; }
+    if (q.mask & (1u << LOBE_CLEARCOAT)) { f = f + eval_clearcoat(m, c.v, q.l, q.h, pdf); pdf_out += pdf * q.pw[LOBE_CLEARCOAT]; if (ev) ev[LOBE_CLEARCOAT]++; }
+}
+
+// Query of Tracer::disney_eval, tracer.rs:555-600, for the world-space light direction.
+template <class R> PTB_DEV void query_for_eval(const Mat<R>& m, const ShadeCtx<R>& c, V3<R> l_world, LobeQuery<R>& q) {
     const V3<R> v = c.v;
     const V3<R> l = to_local(c, l_world);
     V3<R> h = l.z > R(0) ? normalize(l + v) : normalize(l + c.eta * v);
     if (h.z < R(0)) h = -h;
     R wd, wr, wt, wc;
-    R fresnel = disney_fresnel(m, c.eta, dot(l, h), dot(v, h));
-    lobe_probabilities(m, c.spec_col, fresnel, wd, wr, wt, wc);
-    R pdf;
-    if (wd > R(0) && l.z > R(0)) { f = f + eval_diffuse(m, c.sheen_col, v, l, h, pdf); bsdf_pdf += pdf * wd; if (ev) ev[LOBE_DIFFUSE]++; }
-    if (wr > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_spec_reflection(m, c.eta, c.spec_col, v, l, h, pdf); bsdf_pdf += pdf * wr; if (ev) ev[LOBE_REFLECT]++; }
-    if (wt > R(0) && l.z < R(0)) { f = f + eval_spec_refraction(m, c.eta, v, l, h, pdf); bsdf_pdf += pdf * wt; if (ev) ev[LOBE_REFRACT]++; }
-    if (wc > R(0) && l.z > R(0) && v.z > R(0)) { f = f + eval_clearcoat(m, v, l, h, pdf); bsdf_pdf += pdf * wc; if (ev) ev[LOBE_CLEARCOAT]++; }
-    return m_abs(l.z) * f;
-}
-
-// Lobe selection of disney_sample, tracer.rs:488-523: CDF order diffuse, clearcoat, specular.
-// Returns the lobe class (DIFFUSE / CLEARCOAT / REFLECT meaning "specular, coin not yet tossed"),
-// rescales r1 as the reference does and returns the lobe weights.
-template <class R> struct LobePick { int lobe; R r1; R wd, wr, wt, wc; };
-template <class R> PTB_DEV LobePick<R> pick_lobe(const Mat<R>& m, const ShadeCtx<R>& c, R r1) {
-    LobePick<R> p;
-    R approx_fresnel = disney_fresnel(m, c.eta, c.v.z, c.v.z);
-    lobe_probabilities(m, c.spec_col, approx_fresnel, p.wd, p.wr, p.wt, p.wc);
-    R cdf0 = p.wd;
-    R cdf1 = cdf0 + p.wc;
-    if (r1 < cdf0) { p.lobe = LOBE_DIFFUSE; p.r1 = r1 / cdf0; }
-    else if (r1 < cdf1) { p.lobe = LOBE_CLEARCOAT; p.r1 = (r1 - cdf0) / (cdf1 - cdf0); }
-    else { p.lobe = LOBE_REFLECT; p.r1 = (r1 - cdf1) / (R(1) - cdf1); }
-    return p;
+    q.diel = dielectric_fresnel(m_abs(dot(v, h)), c.eta);
+    q.fm = mix1(q.diel, schlick_fresnel(dot(l, h)), m.metallic);                    // = disney_fresnel, tracer.rs:596
+    lobe_probabilities(m, c.spec_col, q.fm, wd, wr, wt, wc);
+    q.l = l; q.h = h;
+    q.pw[LOBE_DIFFUSE] = wd; q.pw[LOBE_CLEARCOAT] = wc; q.pw[LOBE_REFLECT] = wr; q.pw[LOBE_REFRACT] = wt;
+    q.mask = 0;
+    if (wd > R(0) && l.z > R(0)) q.mask |= 1u << LOBE_DIFFUSE;                       // tracer.rs:602
+    if (wr > R(0) && l.z > R(0) && v.z > R(0)) q.mask |= 1u << LOBE_REFLECT;        // tracer.rs:608
+    if (wt > R(0) && l.z < R(0)) q.mask |= 1u << LOBE_REFRACT;                      // tracer.rs:614
+    if (wc > R(0) && l.z > R(0) && v.z > R(0)) q.mask |= 1u << LOBE_CLEARCOAT;      // tracer.rs:620
 }
 
 template <class R> PTB_DEV V3<R> reflect(V3<R> i, V3<R> n) {                        // tracer.rs:464-466
@@ -800,58 +816,70 @@ template <class R> PTB_DEV V3<R> refract(V3<R> i, V3<R> n, R eta) {             
     return eta * i - (eta * ndi + m_sqrt(k)) * n;
 }
 
-// The three lobe samplers of disney_sample (tracer.rs:501-549).  Each returns f (local-frame lobe
-// value, NOT yet times |n.l|), writes l (local) and pdf (already times the lobe weight).
-template <class R> PTB_DEV V3<R> sample_lobe_diffuse(const Mat<R>& m, const ShadeCtx<R>& c, const LobePick<R>& p, R r2, V3<R>& l, R& pdf) {
-    l = cosine_sample_hemisphere(p.r1, r2);
-    V3<R> h = normalize(l + c.v);
-    V3<R> f = eval_diffuse(m, c.sheen_col, c.v, l, h, pdf);
-    pdf *= p.wd;
-    return f;
-}
-template <class R> PTB_DEV V3<R> sample_lobe_clearcoat(const Mat<R>& m, const ShadeCtx<R>& c, const LobePick<R>& p, V3<R>& l, R& pdf) {
-    V3<R> h = sample_gtr1(m.clearcoat_roughness, p.r1);
-    if (h.z < R(0)) h = -h;
-    l = normalize(reflect(-c.v, h));
-    V3<R> f = eval_clearcoat(m, c.v, l, h, pdf);
-    pdf *= p.wc;
-    return f;
-}
-// specular lobe: `l_prev_world` is the stale `l` the reference reads at tracer.rs:531 (quirk A.5)
+// Query of Tracer::disney_sample, tracer.rs:441-549: lobe pick by CDF order diffuse, clearcoat,
+// specular (495-523), direction sampling, and the factor the chosen lobe's pdf is scaled with
+// (507, 520, 540-548).  (r1, r2, coin) are the draws at 446, 447, 534; l_prev_world is the stale
+// `l` read at 531 (quirk A.5).  Returns the lobe id.
 template <class R>
-PTB_DEV V3<R> sample_lobe_specular(const Mat<R>& m, const ShadeCtx<R>& c, const LobePick<R>& p, R r2, R coin, V3<R> l_prev_world,
-                                   V3<R>& l, R& pdf, int& lobe) {
-    V3<R> h = sample_ggxvndf(c.v, m.ax, m.ay, p.r1, r2);
-    if (h.z < R(0)) h = -h;
-    R fresnel = disney_fresnel(m, c.eta, dot(l_prev_world, h), dot(c.v, h));
-    R ff = R(1) - ((R(1) - fresnel) * m.spec_trans * (R(1) - m.metallic));
-    V3<R> f;
-    if (coin < ff) {
-        l = normalize(reflect(-c.v, h));
-        f = eval_spec_reflection(m, c.eta, c.spec_col, c.v, l, h, pdf);
-        pdf *= ff;
-        lobe = LOBE_REFLECT;
+PTB_DEV int query_for_sample(const Mat<R>& m, const ShadeCtx<R>& c, R r1, R r2, R coin, V3<R> l_prev_world, LobeQuery<R>& q) {
+    R wd, wr, wt, wc;
+    R approx_fresnel = disney_fresnel(m, c.eta, c.v.z, c.v.z);
+    lobe_probabilities(m, c.spec_col, approx_fresnel, wd, wr, wt, wc);
+    const R cdf0 = wd;
+    const R cdf1 = cdf0 + wc;
+    int lobe;
+    if (r1 < cdf0) { lobe = LOBE_DIFFUSE; r1 = r1 / cdf0; }
+    else if (r1 < cdf1) { lobe = LOBE_CLEARCOAT; r1 = (r1 - cdf0) / (cdf1 - cdf0); }
+    else { lobe = LOBE_REFLECT; r1 = (r1 - cdf1) / (R(1) - cdf1); }
+    // azimuth: TWO_PI * r2 (diffuse 328, spec 265), r1 * TWO_PI for the clearcoat lobe (246, quirk A.4)
+    R sn, cs;
+    m_sincos(Const<R>::TWO_PI * (lobe == LOBE_CLEARCOAT ? r1 : r2), &sn, &cs);
+    V3<R> l, h;
+    R w;
+    q.diel = 0; q.fm = 0;
+    if (lobe == LOBE_DIFFUSE) {
+        l = cosine_sample_hemisphere(r1, sn, cs);
+        h = normalize(l + c.v);
+        w = wd;
     } else {
-        l = normalize(refract(-c.v, h, c.eta));
-        f = eval_spec_refraction(m, c.eta, c.v, l, h, pdf);
-        pdf *= R(1) - ff;
-        lobe = LOBE_REFRACT;
+        h = lobe == LOBE_CLEARCOAT ? sample_gtr1(m.clearcoat_roughness, r1, sn, cs) : sample_ggxvndf(c.v, m.ax, m.ay, r1, sn, cs);
+        if (h.z < R(0)) h = -h;
+        w = wc;
+        bool refr = false;
+        if (lobe != LOBE_CLEARCOAT) {
+            q.diel = dielectric_fresnel(m_abs(dot(c.v, h)), c.eta);
+            R fresnel = mix1(q.diel, schlick_fresnel(dot(l_prev_world, h)), m.metallic);   // tracer.rs:531, stale l
+            R ff = R(1) - ((R(1) - fresnel) * m.spec_trans * (R(1) - m.metallic));
+            refr = !(coin < ff);
+            w = (refr ? R(1) - ff : ff) * (wr + wt);
+            if (refr) lobe = LOBE_REFRACT;
+        }
+        l = normalize(refr ? refract(-c.v, h, c.eta) : reflect(-c.v, h));
+        q.fm = mix1(q.diel, schlick_fresnel(dot(l, h)), m.metallic);                       // tracer.rs:374 with the new l
     }
-    pdf *= p.wr + p.wt;
-    return f;
+    q.l = l; q.h = h;
+    q.mask = 1u << lobe;
+    q.pw[0] = q.pw[1] = q.pw[2] = q.pw[3] = w;
+    return lobe;
 }
 
-// Tracer::disney_sample, tracer.rs:441-553: returns |n.l| * f, writes l (world), pdf, lobe.
+// Tracer::disney_eval, tracer.rs:555-626 (returns |l.z| * f) — standalone form for the parity kernels
+template <class R> PTB_DEV V3<R> disney_eval(const Mat<R>& m, const ShadeCtx<R>& c, V3<R> l_world, R& bsdf_pdf, uint32_t* ev = nullptr) {
+    LobeQuery<R> q;
+    query_for_eval(m, c, l_world, q);
+    V3<R> f;
+    eval_lobes(m, c, q, f, bsdf_pdf, ev);
+    return m_abs(q.l.z) * f;
+}
+// Tracer::disney_sample, tracer.rs:441-553: returns |n.l| * f, writes l (world), pdf, lobe — standalone form
 template <class R>
 PTB_DEV V3<R> disney_sample(const Mat<R>& m, const ShadeCtx<R>& c, R r1, R r2, R coin, V3<R> l_prev_world, V3<R>& l_world, R& pdf,
                             int& lobe) {
-    LobePick<R> p = pick_lobe(m, c, r1);
-    V3<R> l, f;
-    lobe = p.lobe;
-    if (p.lobe == LOBE_DIFFUSE) f = sample_lobe_diffuse(m, c, p, r2, l, pdf);
-    else if (p.lobe == LOBE_CLEARCOAT) f = sample_lobe_clearcoat(m, c, p, l, pdf);
-    else f = sample_lobe_specular(m, c, p, r2, coin, l_prev_world, l, pdf, lobe);
-    l_world = to_world(c, l);
+    LobeQuery<R> q;
+    lobe = query_for_sample(m, c, r1, r2, coin, l_prev_world, q);
+    V3<R> f;
+    eval_lobes(m, c, q, f, pdf, (uint32_t*)nullptr);
+    l_world = to_world(c, q.l);
     return m_abs(dot(c.n, l_world)) * f;
 }
 
@@ -919,7 +947,7 @@ template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, 
 
 // Runs ONE bounce; returns true while the path continues.  `u` holds the 8 slot draws of this
 // bounce (slots 2..7 are used here).  COUNT enables event counters.
-template <class R, bool COUNT>
+template <class R, bool COUNT, bool BVH>
 PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, uint32_t rr_start, PathCounters* pc) {
     if (rr_start != 0 && p.bounce >= rr_start && p.bounce > 0) {
         // Russian roulette EXTENSION (the reference has none, quirk A.12); off in every parity run.
@@ -935,7 +963,7 @@ PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R
     }
     Mat<R> mat;
     if (COUNT) pc->closest_hit++;
-    HitRec<R> h = closest_hit(s, sv, p.o, p.d, p.hit_dist, mat);
+    HitRec<R> h = closest_hit<R, BVH>(s, sv, p.o, p.d, p.hit_dist, mat);
     p.hit_dist = h.hit_dist;
     if (!h.hit) {                                               // tracer.rs:66-69
         V3<R> bg = background(s, p.d);
@@ -962,36 +990,56 @@ PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R
     ShadeCtx<R> c;
     shade_ctx_init(c, mat, eta, ffn, -p.d);
 
-    // direct_light, tracer.rs:126-170
+    // direct_light, tracer.rs:126-170 — light sample, cull, shadow ray
+    bool nee = false;
+    LightSample<R> ls;
+    R light_area = 0;
     if (s.n_lights > 0) {
         uint32_t li = (uint32_t)(u[2] * s.n_lights_f);          // tracer.rs:137-139
         V3<R> scatter_pos = fhp + s.eps * ffn;
-        LightSample<R> ls = sample_light(sv.lights[li], s.n_lights_f, scatter_pos, u[3], u[4]);
-        if (sv.lights[li].type == PTB_LIGHT_SPHERICAL && dot(ls.direction, ls.normal) < R(0)) {
+        const DLight<R> L = sv.lights[li];
+        ls = sample_light(L, s.n_lights_f, scatter_pos, u[3], u[4]);
+        light_area = L.area;
+        if (L.type == PTB_LIGHT_SPHERICAL && dot(ls.direction, ls.normal) < R(0)) {
             if (COUNT) pc->any_hit++;
-            bool shadow = any_hit(s, sv, scatter_pos, ls.direction, ls.dist - s.eps);
-            if (!shadow) {
-                R bpdf;
-                if (COUNT) pc->eval_calls++;
-                V3<R> f = disney_eval(mat, c, ls.direction, bpdf, COUNT ? pc->ev : nullptr);
-                R w = R(1);
-                if (sv.lights[li].area > R(0)) w = power_heuristic(ls.pdf, bpdf);
-                if (bpdf > R(0)) {
-                    V3<R> ld = (w * ls.emission) * div_s(f, ls.pdf);
-                    p.rad = p.rad + ld * p.thr;
-                    if (COUNT) pc->nee_contrib++;
-                }
-            }
+            nee = !any_hit<R, BVH>(s, sv, scatter_pos, ls.direction, ls.dist - s.eps);
         }
     }
 
-    // disney_sample, tracer.rs:92-97; stale `l` = previous sampled direction = current ray dir (A.5)
-    V3<R> l_prev = p.bounce == 0 ? V3<R>(0, 0, 0) : p.d;
-    V3<R> l;
-    R pdf;
-    int lobe;
-    V3<R> f = disney_sample(mat, c, u[5], u[6], u[7], l_prev, l, pdf, lobe);
-    if (COUNT) { pc->lobe[lobe]++; pc->ev[lobe]++; }
+    // BSDF evaluation, ONE copy of the lobe code for both uses:
+    //   pass 0 = disney_eval towards the light sample (tracer.rs:155), only for un-shadowed lanes;
+    //   pass 1 = disney_sample (tracer.rs:92); stale `l` = previous sampled direction = ray dir (A.5)
+    V3<R> f, l_world;
+    R pdf = 0;
+    int lobe = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0 && !nee) continue;
+        LobeQuery<R> q;
+        if (pass == 0) {
+            if (COUNT) pc->eval_calls++;
+            query_for_eval(mat, c, ls.direction, q);
+        } else {
+            V3<R> l_prev = p.bounce == 0 ? V3<R>(0, 0, 0) : p.d;
+            lobe = query_for_sample(mat, c, u[5], u[6], u[7], l_prev, q);
+            if (COUNT) pc->lobe[lobe]++;
+        }
+        eval_lobes(mat, c, q, f, pdf, COUNT ? pc->ev : (uint32_t*)nullptr);
+        if (pass == 0) {
+            f = m_abs(q.l.z) * f;                                   // tracer.rs:625
+            R w = R(1);
+            if (light_area > R(0)) w = power_heuristic(ls.pdf, pdf); // tracer.rs:157-160
+            if (pdf > R(0)) {                                       // tracer.rs:162-164
+                V3<R> ld = (w * ls.emission) * div_s(f, ls.pdf);
+                p.rad = p.rad + ld * p.thr;
+                if (COUNT) pc->nee_contrib++;
+            }
+        } else {
+            l_world = to_world(c, q.l);                             // tracer.rs:551-552
+            f = m_abs(dot(c.n, l_world)) * f;
+        }
+    }
+    const V3<R> l = l_world;
     if (!(pdf > R(0))) {
         if (COUNT) pc->end_pdf++;
         return false;

@@ -43,7 +43,7 @@ constexpr uint32_t FUSED_CHUNK = 256;   // pixels reserved per atomic = one 16x1
 // HBM at all.  Pixels are handed out tile by tile (16x16) through one global atomic per tile;
 // within a warp they are distributed with ballot/popc prefix ranks.  Every pixel's samples are
 // summed in sample order by one lane, so the image is bit-reproducible run to run.
-template <class R, bool COUNT>
+template <class R, bool COUNT, bool BVH>
 __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_constant__ DScene<R> s, const RenderArgs a) {
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, &sm);
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_con
                 alive = true;
                 if (COUNT) n_samples++;
             }
-            alive = path_bounce<R, COUNT>(s, sv, p, u, a.rr_start, &pc);
+            alive = path_bounce<R, COUNT, BVH>(s, sv, p, u, a.rr_start, &pc);
             if (!alive) {
                 acc = acc + p.rad;
                 s_idx++;
@@ -162,7 +162,7 @@ template <class R> __global__ void k_resolve(const typename Vec4T<R>::type* accu
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     auto v = accum[i];
-    if (v.w > R(0)) out[i] = mk4(v.x / v.w, v.y / v.w, v.z / v.w, R(1));
+    if (v.w > R(0)) out[i] = mk4(div_rn(v.x, v.w), div_rn(v.y, v.w), div_rn(v.z, v.w), R(1));
     else out[i] = mk4(R(0), R(0), R(0), R(0));
 }
 // mean image + frame count -> accumulators
@@ -193,7 +193,7 @@ template <class R> __global__ void k_convert_u8(const typename Vec4T<R>::type* i
     if (i >= n) return;
     auto v = in[i];
     if (from_accum) {
-        if (v.w > R(0)) v = mk4(v.x / v.w, v.y / v.w, v.z / v.w, R(1));
+        if (v.w > R(0)) v = mk4(div_rn(v.x, v.w), div_rn(v.y, v.w), div_rn(v.z, v.w), R(1));
         else v = mk4(R(0), R(0), R(0), R(0));
     }
     out[i] = make_uchar4(encode_gamma(v.x), encode_gamma(v.y), encode_gamma(v.z), encode_linear(v.w));
@@ -202,7 +202,7 @@ template <class R> __global__ void k_convert_u8(const typename Vec4T<R>::type* i
 // one thread per FRAME pixel; j counts frame rows from the END; strict `>` bounds; no gamma.
 template <class R>
 __global__ void k_convert_u8_at(const typename Vec4T<R>::type* accum, uint32_t bw, uint32_t bh, uchar4* frame, uint32_t at0, uint32_t at1,
-                                uint32_t fw, uint32_t fh) {
+                                uint32_t fw, uint32_t fh, int from_accum) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= fw * fh) return;
     uint32_t frow = t / fw, ii = t % fw;
@@ -212,8 +212,10 @@ __global__ void k_convert_u8_at(const typename Vec4T<R>::type* accum, uint32_t b
     uint32_t y = fh - (i / fw);
     if (x > at0 && x < at0 + bw && y > at1 && y < at1 + bh) {
         auto v = accum[(x - at0) + (y - at1) * bw];
-        if (v.w > R(0)) v = mk4(v.x / v.w, v.y / v.w, v.z / v.w, R(1));
-        else v = mk4(R(0), R(0), R(0), R(0));
+        if (from_accum) {
+            if (v.w > R(0)) v = mk4(div_rn(v.x, v.w), div_rn(v.y, v.w), div_rn(v.z, v.w), R(1));
+            else v = mk4(R(0), R(0), R(0), R(0));
+        }
         frame[t] = make_uchar4(encode_linear(v.x), encode_linear(v.y), encode_linear(v.z), encode_linear(v.w));
     }
 }
@@ -253,7 +255,8 @@ __global__ void k_test_closest_hit(const __grid_constant__ DScene<R> s, size_t n
     PTB_TEST_PROLOGUE
     if (i >= n) return;
     Mat<R> m;
-    HitRec<R> h = closest_hit(s, sv, ld3(o, n, i), ld3(d, n, i), hd_in[i], m);
+    HitRec<R> h = s.use_bvh ? closest_hit<R, true>(s, sv, ld3(o, n, i), ld3(d, n, i), hd_in[i], m)
+                            : closest_hit<R, false>(s, sv, ld3(o, n, i), ld3(d, n, i), hd_in[i], m);
     hit[i] = h.hit; em[i] = h.is_emitter; hd_out[i] = h.hit_dist;
     st3(nrm, n, i, h.normal);
     mat_out[i] = h.material;
@@ -266,7 +269,7 @@ __global__ void k_test_any_hit(const __grid_constant__ DScene<R> s, size_t n, co
     const SceneView<R> sv = stage_scene(s, &sm);
     PTB_TEST_PROLOGUE
     if (i >= n) return;
-    hit[i] = any_hit(s, sv, ld3(o, n, i), ld3(d, n, i), md[i]);
+    hit[i] = s.use_bvh ? any_hit<R, true>(s, sv, ld3(o, n, i), ld3(d, n, i), md[i]) : any_hit<R, false>(s, sv, ld3(o, n, i), ld3(d, n, i), md[i]);
 }
 template <class R> __global__ void k_test_background(const __grid_constant__ DScene<R> s, size_t n, const R* d, R* rgb) {
     PTB_TEST_PROLOGUE

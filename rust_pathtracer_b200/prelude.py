@@ -292,20 +292,21 @@ class ColorBuffer:
         i = y * self.width * 4 + x * 4
         return [self.pixels[i], self.pixels[i + 1], self.pixels[i + 2], self.pixels[i + 3]]
 
-    def _device_current(self) -> bool:
-        t = self._tracer
-        return t is not None and t._alive() and t._device_frames() == self.frames and t._size == (self.width, self.height)
+    def _bound_tracer(self):
+        if self._tracer is None or not self._tracer._alive():
+            raise RuntimeError("ColorBuffer conversions run on the device: render into the buffer with a Tracer first "
+                               "(there is no CPU path)")
+        return self._tracer
 
     def convert_to_u8(self, frame) -> None:                         # buffer.rs:55-64
-        """Gamma-encode into `frame` (w*h*4 bytes).  Runs on the device: from the resident image
-        when this buffer was last written by a tracer, otherwise after uploading `pixels`."""
+        """Gamma-encode `self.pixels` into `frame` (w*h*4 bytes) on the device.  Like the reference
+        this converts the HOST pixels (a public field the app may have edited, any alpha): H2D, kernel,
+        D2H.  `Tracer.convert_to_u8` is the zero-upload variant for the device-resident image."""
         out = np.frombuffer(frame, dtype=np.uint8) if not isinstance(frame, np.ndarray) else frame
         assert out.size >= self.width * self.height * 4
-        if self._tracer is None or not self._tracer._alive():
-            raise RuntimeError("ColorBuffer.convert_to_u8 runs on the device: render into the buffer with a Tracer first")
-        if not self._device_current():
-            self._tracer._upload(self)
-        self._tracer._convert_to_u8(out)
+        t = self._bound_tracer()
+        fn = getattr(t._lib, f"ptb_convert_pixels_to_u8_{self.precision}")
+        _abi.check(fn(t._handle(), self.width * self.height, self.pixels.ctypes.data, out.ctypes.data))
 
     def to_u8_vec(self) -> np.ndarray:                              # buffer.rs:37-52
         out = np.zeros(self.width * self.height * 4, dtype=np.uint8)
@@ -314,11 +315,9 @@ class ColorBuffer:
 
     def convert_to_u8_at(self, frame, at: Sequence[int]) -> None:   # buffer.rs:67-102
         out = np.frombuffer(frame, dtype=np.uint8) if not isinstance(frame, np.ndarray) else frame
-        if self._tracer is None or not self._tracer._alive():
-            raise RuntimeError("ColorBuffer.convert_to_u8_at runs on the device: render into the buffer with a Tracer first")
-        if not self._device_current():
-            self._tracer._upload(self)
-        self._tracer._convert_to_u8_at(out, at)
+        t = self._bound_tracer()
+        fn = getattr(t._lib, f"ptb_convert_pixels_to_u8_at_{self.precision}")
+        _abi.check(fn(t._handle(), self.pixels.ctypes.data, self.width, self.height, out.ctypes.data, at[0], at[1], at[2], at[3]))
 
 
 class Tracer:
@@ -383,10 +382,12 @@ class Tracer:
         _abi.check(fn(self._handle(), buffer.pixels.ctypes.data, buffer.frames))
         buffer._tracer = self
 
-    def _convert_to_u8(self, out: np.ndarray):
+    def convert_to_u8(self, out: np.ndarray):
+        """buffer.rs:55-64 of the DEVICE-RESIDENT image (no upload): kernel + D2H of w*h*4 bytes."""
         _abi.check(self._lib.ptb_convert_to_u8(self._handle(), out.ctypes.data))
 
-    def _convert_to_u8_at(self, out: np.ndarray, at):
+    def convert_to_u8_at(self, out: np.ndarray, at):
+        """buffer.rs:67-102 of the device-resident image into the host frame `out` (at = x, y, frame_w, frame_h)."""
         _abi.check(self._lib.ptb_convert_to_u8_at(self._handle(), out.ctypes.data, at[0], at[1], at[2], at[3]))
 
     # -- the hot path ---------------------------------------------------------------------------

@@ -103,5 +103,5 @@ class DeviceFns:
 
     def convert_to_u8(self, rgba):
         rgba = _a(rgba).reshape(-1); n = rgba.size // 4; out = np.empty(n * 4, np.uint8)
-        self.chk(self.lib.ptb_test_convert_to_u8_f32(self.h, n, _p(rgba), _p(out)))
+        self.chk(self.lib.ptb_convert_pixels_to_u8_f32(self.h, n, _p(rgba), _p(out)))
         return out

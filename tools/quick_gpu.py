@@ -1,26 +1,25 @@
-"""Scratch GPU check: smoke + timing of the fused integrator (not a test, not the bench)."""
+"""Scratch GPU check: timing of the integrators (not a test, not the bench)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-import __graft_entry__ as g
 import rust_pathtracer_b200 as rp
 
-g.smoke()
 scene = rp.AnalyticalScene.new()
-for (W, H, spp) in [(1920, 1080, 64), (3840, 2160, 32), (3840, 2160, 128)]:
-    pt = rp.Tracer.new(scene)
-    buf = rp.ColorBuffer.new(W, H)
-    pt.render_spp(buf, 4, download=False)
-    pt.synchronize()
-    for rep in range(3):
-        pt.render_spp(buf, spp, download=False)
-        ms = pt.last_render_ms()
-        print(f"{W}x{H} spp={spp}: {ms:.2f} ms  -> {W*H*spp/ms/1e3:.1f} Msamples/s", flush=True)
-    pt.close()
-ptc = rp.Tracer.new(scene, collect_counters=True)
-buf = rp.ColorBuffer.new(800, 600)
-ptc.render_spp(buf, 16)
-c = ptc.counters(); s = c["samples"]
-print({k: round(v / s, 4) for k, v in c.items()})
-img = buf.pixels.reshape(600, 800, 4)
-print("mean rgb", img[..., :3].reshape(-1, 3).mean(0))
+cfgs = [(1920, 1080, 64), (3840, 2160, 64)]
+if len(sys.argv) > 1:
+    cfgs = [tuple(int(x) for x in sys.argv[1].split("x"))]
+for integ in (rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_WAVEFRONT):
+    for (W, H, spp) in cfgs:
+        try:
+            pt = rp.Tracer.new(scene, integrator=integ)
+            buf = rp.ColorBuffer.new(W, H)
+            pt.render_spp(buf, 4, download=False)
+            pt.synchronize()
+            best = 1e9
+            for rep in range(3):
+                pt.render_spp(buf, spp, download=False)
+                best = min(best, pt.last_render_ms())
+            print(f"integrator={integ} {W}x{H} spp={spp}: {best:.2f} ms  -> {W*H*spp/best/1e3:.1f} Msamples/s", flush=True)
+            pt.close()
+        except Exception as e:
+            print(f"integrator={integ}: {e}")
