@@ -94,9 +94,10 @@ enum {
 
 /* Integrator selection (ptb_config.integrator). */
 enum {
-    PTB_INTEGRATOR_AUTO      = 0,
+    PTB_INTEGRATOR_AUTO      = 0, /* wavefront for f32 scenes, fused for f64                        */
     PTB_INTEGRATOR_FUSED     = 1, /* persistent per-lane path loop with in-register regeneration   */
-    PTB_INTEGRATOR_WAVEFRONT = 2  /* SoA queues, one kernel per stage, ballot/popc compaction      */
+    PTB_INTEGRATOR_WAVEFRONT = 2  /* SoA path-state queues in shared memory, one stage per kind of
+                                     work, queue sorted by lobe class between stages (f32 only)     */
 };
 
 /* ---- POD scene description, declared once per precision ----------------------------------- */

@@ -302,6 +302,9 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     d.use_bvh = use_bvh; d.patch_materials = patch;
     d.depth = sc->depth; d.flags = sc->flags; d.eps = sc->eps;
     d.n_lights_f = (R)sc->n_lights;
+    d.has_emissive = 0;
+    for (const auto& m : mats)
+        if (m.emission[0] != R(0) || m.emission[1] != R(0) || m.emission[2] != R(0)) d.has_emissive = 1;
 
     // the camera basis is derived by derive_camera() once the frame size is known
     for (int k = 0; k < 3; ++k) d.cam_origin[k] = sc->camera.origin[k];
@@ -576,11 +579,13 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
     if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
     if (spp == 0) return PTB_OK;
     CU(cudaSetDevice(t->device));
-    uint32_t integ = t->cfg.integrator == PTB_INTEGRATOR_AUTO ? PTB_INTEGRATOR_FUSED : t->cfg.integrator;
+    // AUTO: the shared-memory wavefront integrator for f32 (measured faster, profiles/), the fused one for f64
+    uint32_t integ = t->cfg.integrator;
+    if (integ == PTB_INTEGRATOR_AUTO) integ = t->precision == 4 ? PTB_INTEGRATOR_WAVEFRONT : PTB_INTEGRATOR_FUSED;
     if (integ == PTB_INTEGRATOR_WAVEFRONT) {
         if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the wavefront integrator is built for f32 only");
-        r = wavefront_render(t->wf, t->s32.d, t->accum, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters, t->ev0, t->ev1,
-                             &t->launches, g_err);
+        r = wavefront_render(t->wf, t->s32.d, t->accum, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters,
+                             t->work_counter, t->ev0, t->ev1, &t->launches, g_err);
         if (r) return r;
         t->timed = true;
     } else {

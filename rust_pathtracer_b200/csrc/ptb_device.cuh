@@ -208,6 +208,7 @@ template <class R> struct DScene {
     const BvhNode* bvh;                 // NULL when the scene is small
     const uint32_t* bvh_prim;           // sphere indices in leaf order
     uint32_t use_bvh;
+    uint32_t has_emissive;              // 1 if any material has non-zero emission
     uint32_t patch_materials;           // 1 if any set_mask != PTB_MAT_ALL (order-dependent patching)
     uint32_t depth, flags;
     R eps;
@@ -399,17 +400,6 @@ template <class R> PTB_DEV V3<R> background(const DScene<R>& s, V3<R> d) {
     return a;
 }
 
-// Result of Scene::closest_hit (analytical.rs:36-127 + scene.rs:36-86)
-template <class R> struct HitRec {
-    bool hit, is_emitter;
-    R hit_dist;            // state.hit_dist after the call (stale value kept when nothing was hit, A.1)
-    V3<R> normal;          // geometry normal of the closest geometric hit (valid if geom)
-    bool geom;             // a sphere/plane was accepted this call
-    uint32_t material;     // material index of the final geometric hit, 0xffffffff if none
-    R light_pdf;           // light_sample.pdf   (valid if is_emitter)
-    V3<R> light_emission;  // light_sample.emission
-};
-
 // BVH traversal (closest): returns best sphere index or -1, updates best_t.
 template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
     int best = -1;
@@ -479,16 +469,27 @@ template <class R> PTB_DEV bool bvh_any(const DScene<R>& s, V3<R> o, V3<R> d, R 
     return false;
 }
 
-// Scene::closest_hit for the exported scene.  `hit_dist_in` is State::hit_dist carried across
-// bounces (A.1).  Fills `mat` (un-finalized) when geometry was accepted.
+// Scene::closest_hit for the exported scene, geometry part (analytical.rs:36-127 + scene.rs:36-86):
+// which primitive / light the ray hits.  `hit_dist_in` is State::hit_dist carried across bounces
+// (quirk A.1).  Material and normal are resolved separately (hit_material / hit_normal) so the
+// wavefront integrator can do that in its shading stage.
+template <class R> struct HitCore {
+    bool hit, is_emitter, geom;
+    R hit_dist;            // state.hit_dist after the call (stale value kept when nothing was hit)
+    int prim;              // closest geometric primitive: < n_spheres sphere, else plane; -1 none
+    uint64_t accepted;     // bit i: primitive i was "closest so far" when tested (patching scenes only)
+    R light_pdf;           // light_sample.pdf (valid if is_emitter)
+    V3<R> light_emission;  // light_sample.emission
+};
+
 template <class R, bool BVH>
-PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, Mat<R>& mat) {
-    HitRec<R> h;
-    h.hit = false; h.is_emitter = false; h.geom = false; h.hit_dist = hit_dist_in; h.material = 0xffffffffu;
-    h.light_pdf = 0; h.light_emission = V3<R>(0, 0, 0); h.normal = V3<R>(0, 0, 0);
+PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in) {
+    HitCore<R> h;
+    h.hit = false; h.is_emitter = false; h.geom = false; h.hit_dist = hit_dist_in;
+    h.light_pdf = 0; h.light_emission = V3<R>(0, 0, 0);
     R dist = Const<R>::MAXV;
-    int best = -1;                 // < n_spheres: sphere; else plane (best - n_spheres)
-    uint64_t accepted = 0;         // bit i set: primitive i was "closest so far" when tested (patching scenes only)
+    int best = -1;
+    uint64_t accepted = 0;
     if (BVH) {
         best = bvh_closest(s, o, d, dist);
     } else {
@@ -509,36 +510,8 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
             dist = t; best = (int)(s.n_spheres + i); accepted |= (1ull << ((s.n_spheres + i) & 63u));
         }
     }
-    if (best >= 0) {
-        h.hit = true; h.geom = true; h.hit_dist = dist;
-        uint32_t mi;
-        if ((uint32_t)best < s.n_spheres) {
-            DSphere<R> sp = BVH ? s.spheres[best] : sv.spheres[best];
-            V3<R> c(sp.cx, sp.cy, sp.cz);
-            V3<R> hp = o + dist * d;                   // analytical.rs:45-46
-            h.normal = normalize(hp - c);
-            mi = BVH ? s.sphere_material[best] : sv.sphere_material[best];
-        } else {
-            DPlane<R> pl = sv.planes[best - s.n_spheres];
-            h.normal = V3<R>(pl.nx, pl.ny, pl.nz);     // analytical.rs:105
-            mi = sv.plane_material[best - s.n_spheres];
-        }
-        h.material = mi;
-        if (BVH || !s.patch_materials) {
-            mat_load(mat, sv.materials[mi], d);
-        } else {
-            // replay the reference's assignment order over the accepted primitives
-            bool first = true;
-#pragma unroll 1
-            while (accepted) {
-                int i = __ffsll((long long)accepted) - 1;
-                accepted &= accepted - 1;
-                uint32_t m = (uint32_t)i < s.n_spheres ? sv.sphere_material[i] : sv.plane_material[i - s.n_spheres];
-                if (first) { mat_load(mat, sv.materials[m], d); first = false; }
-                else mat_patch(mat, sv.materials[m], d);
-            }
-        }
-    }
+    h.prim = best; h.accepted = accepted;
+    if (best >= 0) { h.hit = true; h.geom = true; h.hit_dist = dist; }
     // Scene::sample_lights, scene.rs:36-86 — starts from the possibly stale state.hit_dist
     R ldist = h.hit_dist;
     int lbest = -1;
@@ -558,6 +531,111 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
         h.is_emitter = true;
         h.hit_dist = ldist;
         h.hit = true;
+    }
+    return h;
+}
+
+// normal of primitive `prim` at distance t along (o, d): analytical.rs:45-46 (sphere), :105 (plane)
+template <class R, bool BVH>
+PTB_DEV V3<R> hit_normal(const DScene<R>& s, const SceneView<R>& sv, int prim, V3<R> o, V3<R> d, R t) {
+    if ((uint32_t)prim < s.n_spheres) {
+        DSphere<R> sp = BVH ? s.spheres[prim] : sv.spheres[prim];
+        V3<R> hp = o + t * d;
+        return normalize(hp - V3<R>(sp.cx, sp.cy, sp.cz));
+    }
+    DPlane<R> pl = sv.planes[prim - s.n_spheres];
+    return V3<R>(pl.nx, pl.ny, pl.nz);
+}
+
+template <class R, bool BVH> PTB_DEV uint32_t prim_material(const DScene<R>& s, const SceneView<R>& sv, int prim) {
+    if ((uint32_t)prim < s.n_spheres) return BVH ? s.sphere_material[prim] : sv.sphere_material[prim];
+    return sv.plane_material[prim - s.n_spheres];
+}
+
+// material at the hit (un-finalized): the closest primitive's, or — scenes with partial set_masks —
+// the reference's assignment order replayed over the accepted primitives (see PTB_MAT_* in ptb200.h)
+template <class R, bool BVH>
+PTB_DEV uint32_t hit_material(const DScene<R>& s, const SceneView<R>& sv, int prim, uint64_t accepted, V3<R> d, Mat<R>& mat) {
+    const uint32_t mi = prim_material<R, BVH>(s, sv, prim);
+    if (BVH || !s.patch_materials) {
+        mat_load(mat, BVH ? s.materials[mi] : sv.materials[mi], d);
+    } else {
+        bool first = true;
+#pragma unroll 1
+        while (accepted) {
+            int i = __ffsll((long long)accepted) - 1;
+            accepted &= accepted - 1;
+            uint32_t m = prim_material<R, BVH>(s, sv, i);
+            if (first) { mat_load(mat, sv.materials[m], d); first = false; }
+            else mat_patch(mat, sv.materials[m], d);
+        }
+    }
+    return mi;
+}
+
+// Lobe class of the material at the hit — which Disney lobes can carry weight (tracer.rs:423-426):
+// bit 0 diffuse ((1-metallic)(1-spec_trans) > 0), bit 1 clearcoat (clearcoat(1-metallic) > 0),
+// bit 2 transmission (spec_trans(1-metallic) > 0).  The wavefront integrator sorts its shading
+// queue by this key so that a warp evaluates the same lobes.
+template <class R> PTB_DEV uint32_t lobe_class_of(R metallic, R spec_trans, R clearcoat) {
+    const R nm = R(1) - metallic;
+    return (nm * (R(1) - spec_trans) > R(0) ? 1u : 0u) | (clearcoat * nm > R(0) ? 2u : 0u) | (spec_trans * nm > R(0) ? 4u : 0u);
+}
+template <class R, bool BVH>
+PTB_DEV uint32_t hit_lobe_class(const DScene<R>& s, const SceneView<R>& sv, int prim, uint64_t accepted) {
+    if (BVH || !s.patch_materials) {
+        const uint32_t mi = prim_material<R, BVH>(s, sv, prim);
+        const DMaterial<R>& dm = BVH ? s.materials[mi] : sv.materials[mi];
+        return lobe_class_of(dm.metallic, dm.spec_trans, dm.clearcoat);
+    }
+    R metallic = 0, spec_trans = 0, clearcoat = 0;
+    bool first = true;
+#pragma unroll 1
+    while (accepted) {
+        int i = __ffsll((long long)accepted) - 1;
+        accepted &= accepted - 1;
+        const DMaterial<R>& dm = sv.materials[prim_material<R, BVH>(s, sv, i)];
+        const uint32_t k = first ? (uint32_t)PTB_MAT_ALL : dm.set_mask;
+        first = false;
+        if (k & PTB_MAT_METALLIC) metallic = dm.metallic;
+        if (k & PTB_MAT_SPEC_TRANS) spec_trans = dm.spec_trans;
+        if (k & PTB_MAT_CLEARCOAT) clearcoat = dm.clearcoat;
+    }
+    return lobe_class_of(metallic, spec_trans, clearcoat);
+}
+
+// Result of the complete Scene::closest_hit (used by the parity kernels)
+template <class R> struct HitRec {
+    bool hit, is_emitter;
+    R hit_dist;
+    V3<R> normal;          // geometry normal of the closest geometric hit (valid if geom)
+    bool geom;
+    uint32_t material;     // material index of the final geometric hit, 0xffffffff if none
+    R light_pdf;
+    V3<R> light_emission;
+};
+template <class R, bool BVH>
+PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, Mat<R>& mat) {
+    HitCore<R> c = closest_hit_core<R, BVH>(s, sv, o, d, hit_dist_in);
+    HitRec<R> h;
+    h.hit = c.hit; h.is_emitter = c.is_emitter; h.hit_dist = c.hit_dist; h.geom = c.geom;
+    h.light_pdf = c.light_pdf; h.light_emission = c.light_emission;
+    h.normal = V3<R>(0, 0, 0); h.material = 0xffffffffu;
+    if (c.geom) {
+        // geometry distance: equals hit_dist unless a nearer light replaced it
+        R tg = c.hit_dist;
+        if (c.is_emitter) {
+            // recompute the primitive's own t (only the parity kernels get here)
+            if ((uint32_t)c.prim < s.n_spheres) {
+                DSphere<R> sp = BVH ? s.spheres[c.prim] : sv.spheres[c.prim];
+                tg = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
+            } else {
+                DPlane<R> pl = sv.planes[c.prim - s.n_spheres];
+                tg = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
+            }
+        }
+        h.normal = hit_normal<R, BVH>(s, sv, c.prim, o, d, tg);
+        h.material = hit_material<R, BVH>(s, sv, c.prim, c.accepted, d, mat);
     }
     return h;
 }
@@ -945,45 +1023,15 @@ template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, 
     p.bounce = 0;
 }
 
-// Runs ONE bounce; returns true while the path continues.  `u` holds the 8 slot draws of this
-// bounce (slots 2..7 are used here).  COUNT enables event counters.
+// Second half of a bounce, tracer.rs:72-101 for a path that hit geometry (not a light): finalize,
+// next-event estimation, BSDF sampling, throughput update, next ray.  `normal` is the geometric
+// normal, `mat` the un-finalized material at the hit.  `u` holds the 8 slot draws of this bounce.
+// Returns true while the path continues.
 template <class R, bool COUNT, bool BVH>
-PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, uint32_t rr_start, PathCounters* pc) {
-    if (rr_start != 0 && p.bounce >= rr_start && p.bounce > 0) {
-        // Russian roulette EXTENSION (the reference has none, quirk A.12); off in every parity run.
-        // Survival probability from the throughput (GLSL-PathTracer's rule), decided by slot 0 of
-        // this bounce, which is free after bounce 0 (slots 0,1 are the camera jitter).
-        R q = m_max(p.thr.x, m_max(p.thr.y, p.thr.z)) + R(0.001);
-        q = q > R(0.95) ? R(0.95) : q;
-        if (u[0] >= q) {
-            if (COUNT) pc->end_rr++;
-            return false;
-        }
-        p.thr = (R(1) / q) * p.thr;
-    }
-    Mat<R> mat;
-    if (COUNT) pc->closest_hit++;
-    HitRec<R> h = closest_hit<R, BVH>(s, sv, p.o, p.d, p.hit_dist, mat);
-    p.hit_dist = h.hit_dist;
-    if (!h.hit) {                                               // tracer.rs:66-69
-        V3<R> bg = background(s, p.d);
-        p.rad = p.rad + bg * p.thr;
-        if (COUNT) pc->end_sky++;
-        return false;
-    }
-    if (!h.geom) mat_defaults(mat);                             // tracer.rs:63: only a light was hit
-    if (h.is_emitter) {                                         // tracer.rs:72-87
-        // finalize() would run first but none of its outputs reach the radiance; emission of the
-        // geometry material (if any) is still added (tracer.rs:74)
-        p.rad = p.rad + mat.emission * p.thr;
-        R w = power_heuristic(p.prev_pdf, h.light_pdf);         // `state.depth > 0` is always true (A.2)
-        p.rad = p.rad + (w * h.light_emission) * p.thr;
-        if (COUNT) pc->end_emitter++;
-        return false;
-    }
+PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, Mat<R>& mat, const R* u, PathCounters* pc) {
     V3<R> fhp, ffn;
     R eta;
-    state_finalize(p.o, p.d, h.hit_dist, h.normal, mat, fhp, ffn, eta);
+    state_finalize(p.o, p.d, p.hit_dist, normal, mat, fhp, ffn, eta);
     p.rad = p.rad + mat.emission * p.thr;                       // tracer.rs:74
     if (COUNT) pc->shade++;
 
@@ -1054,6 +1102,64 @@ PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R
         return false;
     }
     return true;
+}
+
+
+// Russian roulette EXTENSION at the start of bounce > 0 (the reference has none, quirk A.12; off in
+// every parity run): survival probability from the throughput (GLSL-PathTracer's rule), decided by
+// slot 0 of this bounce, which is free after bounce 0 (slots 0,1 are the camera jitter).
+template <class R> PTB_DEV bool russian_roulette_survives(PathState<R>& p, R u0) {
+    R q = m_max(p.thr.x, m_max(p.thr.y, p.thr.z)) + R(0.001);
+    q = q > R(0.95) ? R(0.95) : q;
+    if (u0 >= q) return false;
+    p.thr = (R(1) / q) * p.thr;
+    return true;
+}
+
+// First half of a bounce, tracer.rs:63-87: closest_hit, background on a miss, MIS-weighted emission
+// on a light hit.  Returns 0 = path ended, 1 = geometry hit (continue with path_shade).
+template <class R, bool COUNT, bool BVH>
+PTB_DEV int path_intersect(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, HitCore<R>& h, PathCounters* pc) {
+    if (COUNT) pc->closest_hit++;
+    h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
+    p.hit_dist = h.hit_dist;
+    if (!h.hit) {                                               // tracer.rs:66-69
+        V3<R> bg = background(s, p.d);
+        p.rad = p.rad + bg * p.thr;
+        if (COUNT) pc->end_sky++;
+        return 0;
+    }
+    if (h.is_emitter) {                                         // tracer.rs:72-87
+        // finalize() would run first but none of its outputs reach the radiance; the emission of
+        // the geometry's material (if geometry was also hit) is still added (tracer.rs:74)
+        if (h.geom && s.has_emissive) {
+            Mat<R> mat;
+            hit_material<R, BVH>(s, sv, h.prim, h.accepted, p.d, mat);
+            p.rad = p.rad + mat.emission * p.thr;
+        }
+        R w = power_heuristic(p.prev_pdf, h.light_pdf);         // `state.depth > 0` is always true (A.2)
+        p.rad = p.rad + (w * h.light_emission) * p.thr;
+        if (COUNT) pc->end_emitter++;
+        return 0;
+    }
+    return 1;
+}
+
+// Runs ONE bounce (both halves); returns true while the path continues.  COUNT enables event counters.
+template <class R, bool COUNT, bool BVH>
+PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, uint32_t rr_start, PathCounters* pc) {
+    if (rr_start != 0 && p.bounce >= rr_start && p.bounce > 0) {
+        if (!russian_roulette_survives(p, u[0])) {
+            if (COUNT) pc->end_rr++;
+            return false;
+        }
+    }
+    HitCore<R> h;
+    if (!path_intersect<R, COUNT, BVH>(s, sv, p, h, pc)) return false;
+    Mat<R> mat;
+    hit_material<R, BVH>(s, sv, h.prim, h.accepted, p.d, mat);
+    V3<R> normal = hit_normal<R, BVH>(s, sv, h.prim, p.o, p.d, h.hit_dist);
+    return path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, pc);
 }
 
 }  // namespace ptb

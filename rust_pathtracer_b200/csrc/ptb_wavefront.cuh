@@ -1,16 +1,316 @@
-// ptb_wavefront.cuh — wavefront integrator (SoA queues, one kernel per stage).  Placeholder until
-// the stage kernels land; the fused integrator is the default.
+// ptb_wavefront.cuh — the wavefront integrator: SoA path-state queues, one stage per kind of work,
+// queues compacted / sorted between stages, persistent CTAs — with the queues held in the SM's
+// 227 KB of SHARED MEMORY instead of HBM.
+//
+// Why shared memory: the demo scene costs ~1.4 kFLOP and ~2 bounces per sample.
+// A classic HBM wavefront streams ~1 KB of ray / path state per sample through the queues, which
+// caps it at ~6 Gsamples/s on a 6.5 TB/s part before any arithmetic is done (SURVEY.md §7 "the
+// roofline that actually binds").  One SM can hold 2048 paths x 88 B = 176 KB of state, enough for
+// every stage to run with full warps, so the state never leaves the SM: HBM traffic stays at the
+// 32 B per pixel of the accumulator read-modify-write.
+//
+// One CTA (512 threads) per SM owns a pool of P = 2048 path slots.  Each iteration runs two stages
+// over the pool, separated by CTA barriers, so that ALL warps of the SM execute the same stage code
+// at the same time (small instruction-cache footprint, the fused kernel's main stall):
+//
+//   stage 1  "generate + intersect"  — every slot: a finished slot regenerates in place (next
+//            sample of its pixel, or a new pixel handed out per warp with ballot/popc from a global
+//            tile counter), then camera-ray generation / closest_hit (+ spherical lights with the
+//            stale hit_dist quirk), background lookup on a miss, MIS-weighted emission on a light
+//            hit.  Paths that hit geometry enter the shading queue: they take a ticket in the
+//            counter of their LOBE CLASS (which Disney lobes their material can express).
+//   sort     a counting sort by lobe class turns the tickets into a compacted, class-ordered index
+//            list (the queue proper).
+//   stage 2  "shade" — threads walk the queue in order, so a warp shades paths of one lobe class:
+//            finalize, light sampling + any_hit shadow ray, Disney eval with MIS, Disney sample,
+//            throughput update, next ray (or termination).
+//
+// A slot owns one pixel for `spp` consecutive samples and sums them in sample order, so the image is
+// bit-reproducible run to run, exactly like the fused integrator.
 #pragma once
 #include <string>
+
 #include "ptb_kernels.cuh"
 
 namespace ptb {
+
+constexpr int WF_THREADS = 512;
+constexpr int WF_WARPS = WF_THREADS / 32;
+constexpr uint32_t WF_POOL = 2048;          // path slots per CTA
+constexpr int WF_CLASSES = 8;               // lobe classes (3 bits, lobe_class_of)
+
+// per-slot float arrays (SoA: array k occupies words [k*P, (k+1)*P))
+enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TX, F_TY, F_TZ, F_RX, F_RY, F_RZ, F_HITDIST, F_PREVPDF, F_AX, F_AY, F_AZ, WF_NF };
+// per-slot u32 arrays
+enum { U_PIX, U_PXY, U_SIDX, U_FLAGS, U_PRIM, U_ACC_LO, U_ACC_HI, WF_NU };
+// flags word: bit0 alive, bit1 have_pixel, bit2 done, bits 8..23 bounce
+constexpr uint32_t FL_ALIVE = 1u, FL_PIXEL = 2u, FL_DONE = 4u;
+
+struct WfSmem {
+    uint32_t scene[PTB_SMEM_SCENE_BYTES / 4];
+    float f[WF_NF][WF_POOL];
+    uint32_t u[WF_NU][WF_POOL];
+    uint16_t key[WF_POOL];          // lobe class of a queued slot, 0xffff = not queued
+    uint16_t ticket[WF_POOL];       // position inside its class
+    uint16_t order[WF_POOL];        // the shading queue: slot indices, class-ordered
+    uint32_t cnt[WF_CLASSES];       // tickets handed out per class
+    uint32_t off[WF_CLASSES + 1];   // class start offsets; off[WF_CLASSES] = queue length
+    uint32_t n_done;                // slots that can never get work again
+};
+
+template <bool COUNT, bool BVH>
+__global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid_constant__ DScene<float> s, const RenderArgs a) {
+    using R = float;
+    extern __shared__ __align__(16) unsigned char wf_raw[];
+    WfSmem& sm = *reinterpret_cast<WfSmem*>(wf_raw);
+    const SceneView<R> sv = stage_scene(s, reinterpret_cast<SceneSmem<R>*>(sm.scene));
+    float4* accum = reinterpret_cast<float4*>(a.accum);
+
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const R inv_w = R(1) / (R)a.W, inv_h = R(1) / (R)a.H;
+
+    for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) { sm.u[U_FLAGS][i] = 0; sm.u[U_SIDX][i] = 0; sm.key[i] = 0xffffu; }
+    if (tid < WF_CLASSES) sm.cnt[tid] = 0;
+    if (tid == 0) sm.n_done = 0;
+    __syncthreads();
+
+    uint32_t w_next = 0, w_end = 0;          // warp-uniform cursor into the warp's current 16x16 pixel tile
+    PathCounters pc;
+    uint32_t n_samples = 0;
+    if (COUNT) {
+        pc.closest_hit = pc.any_hit = pc.shade = pc.nee_contrib = pc.eval_calls = 0;
+        pc.lobe[0] = pc.lobe[1] = pc.lobe[2] = pc.lobe[3] = 0;
+        pc.end_sky = pc.end_emitter = pc.end_pdf = pc.end_depth = pc.end_rr = 0;
+        pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
+    }
+
+    while (true) {
+        // ================================ stage 1: generate + intersect ================================
+#pragma unroll 1
+        for (uint32_t base = warp * 32u; base < WF_POOL; base += WF_WARPS * 32u) {
+            const uint32_t i = base + lane;
+            uint32_t fl = sm.u[U_FLAGS][i];
+            uint32_t sidx = sm.u[U_SIDX][i];
+            bool alive = fl & FL_ALIVE, have_pixel = fl & FL_PIXEL, done = fl & FL_DONE;
+            const bool was_done = done;
+            uint32_t pix = sm.u[U_PIX][i], pxy = sm.u[U_PXY][i];
+
+            // ---- pixel hand-out (same scheme as the fused integrator) ----
+            bool want = !alive && !done && (!have_pixel || sidx == a.spp);
+            if (want && have_pixel) {
+                float4 v = accum[pix];
+                v.x += sm.f[F_AX][i]; v.y += sm.f[F_AY][i]; v.z += sm.f[F_AZ][i]; v.w += (R)a.spp;
+                accum[pix] = v;
+                have_pixel = false;
+            }
+            unsigned need = __ballot_sync(FULL, want);
+            while (need) {
+                if (w_next == w_end) {
+                    uint32_t b = 0;
+                    if (lane == 0) b = atomicAdd(a.work_counter, FUSED_CHUNK);
+                    b = __shfl_sync(FULL, b, 0);
+                    if (b >= a.n_items) {
+                        if (want) { done = true; want = false; }
+                        break;
+                    }
+                    w_next = b; w_end = b + FUSED_CHUNK;
+                }
+                const uint32_t avail = w_end - w_next;
+                const uint32_t rank = __popc(need & lt_mask);
+                if (want && rank < avail) {
+                    const uint32_t idx = w_next + rank;
+                    const uint32_t tile = idx >> 8, within = idx & 255u;
+                    const uint32_t px = (tile % a.tiles_x) * 16u + (within & 15u);
+                    const uint32_t prow = (tile / a.tiles_x) * 16u + (within >> 4);
+                    if (px < a.W && prow < a.H) {
+                        pix = prow * a.W + px; pxy = px | (prow << 16);
+                        have_pixel = true; want = false; sidx = 0;
+                        sm.f[F_AX][i] = 0; sm.f[F_AY][i] = 0; sm.f[F_AZ][i] = 0;
+                    }
+                }
+                const uint32_t n_need = __popc(need);
+                w_next += n_need < avail ? n_need : avail;
+                need = __ballot_sync(FULL, want);
+            }
+            if (done && !was_done) atomicAdd(&sm.n_done, 1u);
+
+            // ---- one closest_hit for every live / starting path ----
+            const bool start = !alive && !done;
+            if (alive || start) {
+                PathState<R> p;
+                p.bounce = start ? 0u : (fl >> 8) & 0xffffu;
+                bool dead = false;
+                if (start) {
+                    Rng<R> rng(pix, a.sample_base + sidx, a.seed);
+                    R u4[4];
+                    rng.block(0, 0, u4);
+                    path_begin(s, p, pxy & 0xffffu, pxy >> 16, a.W, a.H, inv_w, inv_h, u4[0], u4[1]);
+                    alive = true;
+                    if (COUNT) n_samples++;
+                } else {
+                    p.o = V3<R>(sm.f[F_OX][i], sm.f[F_OY][i], sm.f[F_OZ][i]);
+                    p.d = V3<R>(sm.f[F_DX][i], sm.f[F_DY][i], sm.f[F_DZ][i]);
+                    p.thr = V3<R>(sm.f[F_TX][i], sm.f[F_TY][i], sm.f[F_TZ][i]);
+                    p.rad = V3<R>(sm.f[F_RX][i], sm.f[F_RY][i], sm.f[F_RZ][i]);
+                    p.hit_dist = sm.f[F_HITDIST][i];
+                    p.prev_pdf = sm.f[F_PREVPDF][i];
+                    if (a.rr_start != 0 && p.bounce >= a.rr_start) {
+                        Rng<R> rng(pix, a.sample_base + sidx, a.seed);
+                        R u4[4];
+                        rng.block(p.bounce, 0, u4);
+                        if (!russian_roulette_survives(p, u4[0])) { dead = true; if (COUNT) pc.end_rr++; }
+                    }
+                }
+                HitCore<R> h;
+                if (!dead && !path_intersect<R, COUNT, BVH>(s, sv, p, h, &pc)) dead = true;
+                if (dead) {
+                    sm.f[F_AX][i] += p.rad.x; sm.f[F_AY][i] += p.rad.y; sm.f[F_AZ][i] += p.rad.z;
+                    sidx++;
+                    alive = false;
+                } else {
+                    // queue for shading: ticket inside the path's lobe class
+                    const uint32_t cls = hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
+                    sm.key[i] = (uint16_t)cls;
+                    sm.ticket[i] = (uint16_t)atomicAdd(&sm.cnt[cls], 1u);
+                    sm.u[U_PRIM][i] = (uint32_t)h.prim;
+                    sm.u[U_ACC_LO][i] = (uint32_t)h.accepted;
+                    sm.u[U_ACC_HI][i] = (uint32_t)(h.accepted >> 32);
+                    sm.f[F_HITDIST][i] = p.hit_dist;
+                    if (start || a.rr_start != 0) {
+                        sm.f[F_TX][i] = p.thr.x; sm.f[F_TY][i] = p.thr.y; sm.f[F_TZ][i] = p.thr.z;
+                    }
+                    if (start) {
+                        sm.f[F_OX][i] = p.o.x; sm.f[F_OY][i] = p.o.y; sm.f[F_OZ][i] = p.o.z;
+                        sm.f[F_DX][i] = p.d.x; sm.f[F_DY][i] = p.d.y; sm.f[F_DZ][i] = p.d.z;
+                        sm.f[F_RX][i] = 0; sm.f[F_RY][i] = 0; sm.f[F_RZ][i] = 0;
+                        sm.f[F_PREVPDF][i] = 0;
+                    }
+                }
+                fl = (p.bounce << 8);
+            } else {
+                fl = 0;
+            }
+            sm.u[U_FLAGS][i] = (fl & 0xffff00u) | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u) | (done ? FL_DONE : 0u);
+            sm.u[U_SIDX][i] = sidx;
+            sm.u[U_PIX][i] = pix;
+            sm.u[U_PXY][i] = pxy;
+        }
+        __syncthreads();
+
+        // ================================ sort: tickets -> class-ordered queue ================================
+        if (tid == 0) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int c = 0; c < WF_CLASSES; ++c) { sm.off[c] = run; run += sm.cnt[c]; }
+            sm.off[WF_CLASSES] = run;
+        }
+        __syncthreads();
+        const uint32_t n_queue = sm.off[WF_CLASSES];
+        const bool all_done = sm.n_done == WF_POOL;
+#pragma unroll 1
+        for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) {
+            const uint32_t k = sm.key[i];
+            if (k != 0xffffu) {
+                sm.order[sm.off[k] + sm.ticket[i]] = (uint16_t)i;
+                sm.key[i] = 0xffffu;
+            }
+        }
+        __syncthreads();
+        if (tid < WF_CLASSES) sm.cnt[tid] = 0;
+        if (n_queue == 0 && all_done) break;
+
+        // ================================ stage 2: shade ================================
+#pragma unroll 1
+        for (uint32_t j = tid; j < n_queue; j += WF_THREADS) {
+            const uint32_t i = sm.order[j];
+            PathState<R> p;
+            p.o = V3<R>(sm.f[F_OX][i], sm.f[F_OY][i], sm.f[F_OZ][i]);
+            p.d = V3<R>(sm.f[F_DX][i], sm.f[F_DY][i], sm.f[F_DZ][i]);
+            p.thr = V3<R>(sm.f[F_TX][i], sm.f[F_TY][i], sm.f[F_TZ][i]);
+            p.rad = V3<R>(sm.f[F_RX][i], sm.f[F_RY][i], sm.f[F_RZ][i]);
+            p.hit_dist = sm.f[F_HITDIST][i];
+            p.prev_pdf = 0;
+            const uint32_t fl = sm.u[U_FLAGS][i];
+            p.bounce = (fl >> 8) & 0xffffu;
+            const int prim = (int)sm.u[U_PRIM][i];
+            const uint64_t accepted = (uint64_t)sm.u[U_ACC_LO][i] | ((uint64_t)sm.u[U_ACC_HI][i] << 32);
+            const uint32_t sidx = sm.u[U_SIDX][i];
+            Rng<R> rng(sm.u[U_PIX][i], a.sample_base + sidx, a.seed);
+            R u[8];
+            rng.draws(p.bounce, u);
+            Mat<R> mat;
+            hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+            const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+            const bool cont = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, &pc);
+            if (cont) {
+                sm.f[F_OX][i] = p.o.x; sm.f[F_OY][i] = p.o.y; sm.f[F_OZ][i] = p.o.z;
+                sm.f[F_DX][i] = p.d.x; sm.f[F_DY][i] = p.d.y; sm.f[F_DZ][i] = p.d.z;
+                sm.f[F_TX][i] = p.thr.x; sm.f[F_TY][i] = p.thr.y; sm.f[F_TZ][i] = p.thr.z;
+                sm.f[F_RX][i] = p.rad.x; sm.f[F_RY][i] = p.rad.y; sm.f[F_RZ][i] = p.rad.z;
+                sm.f[F_PREVPDF][i] = p.prev_pdf;
+                sm.u[U_FLAGS][i] = (fl & ~0xffff00u) | (p.bounce << 8);
+            } else {
+                sm.f[F_AX][i] += p.rad.x; sm.f[F_AY][i] += p.rad.y; sm.f[F_AZ][i] += p.rad.z;
+                sm.u[U_SIDX][i] = sidx + 1u;
+                sm.u[U_FLAGS][i] = fl & ~FL_ALIVE;
+            }
+        }
+        __syncthreads();
+    }
+
+    if (COUNT) {
+        DeviceCounters* c = a.counters;
+        atomicAdd(&c->samples, (unsigned long long)n_samples);
+        atomicAdd(&c->closest_hit, (unsigned long long)pc.closest_hit);
+        atomicAdd(&c->any_hit, (unsigned long long)pc.any_hit);
+        atomicAdd(&c->shade, (unsigned long long)pc.shade);
+        atomicAdd(&c->nee_contrib, (unsigned long long)pc.nee_contrib);
+        atomicAdd(&c->eval_calls, (unsigned long long)pc.eval_calls);
+        for (int i = 0; i < 4; ++i) atomicAdd(&c->lobe[i], (unsigned long long)pc.lobe[i]);
+        for (int i = 0; i < 4; ++i) atomicAdd(&c->ev[i], (unsigned long long)pc.ev[i]);
+        atomicAdd(&c->end_sky, (unsigned long long)pc.end_sky);
+        atomicAdd(&c->end_emitter, (unsigned long long)pc.end_emitter);
+        atomicAdd(&c->end_pdf, (unsigned long long)pc.end_pdf);
+        atomicAdd(&c->end_depth, (unsigned long long)pc.end_depth);
+        atomicAdd(&c->end_rr, (unsigned long long)pc.end_rr);
+    }
+}
+
 struct WavefrontState {
+    bool configured = false;
     void release() {}
 };
-inline int wavefront_render(WavefrontState&, const DScene<float>&, void*, uint32_t, uint32_t, uint32_t, uint64_t, const ptb_config&, cudaStream_t,
-                            int, DeviceCounters*, cudaEvent_t, cudaEvent_t, uint64_t*, std::string& err) {
-    err = "wavefront integrator not built yet";
-    return PTB_E_UNSUPPORTED;
+
+// host launcher: one persistent CTA per SM
+inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* accum, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
+                            const ptb_config& cfg, cudaStream_t stream, int sm_count, DeviceCounters* counters, unsigned int* work_counter,
+                            cudaEvent_t ev0, cudaEvent_t ev1, uint64_t* launches, std::string& err) {
+    RenderArgs a{};
+    a.accum = accum; a.W = W; a.H = H; a.spp = spp; a.sample_base = sample_base; a.seed = cfg.seed; a.rr_start = cfg.rr_start;
+    a.tiles_x = (W + 15u) / 16u;
+    a.n_items = a.tiles_x * ((H + 15u) / 16u) * 256u;
+    a.work_counter = work_counter;
+    a.counters = counters;
+    const bool count = cfg.collect_counters != 0;
+    void (*kern)(const DScene<float>, const RenderArgs) =
+        d.use_bvh ? (count ? k_render_wavefront<true, true> : k_render_wavefront<false, true>)
+                  : (count ? k_render_wavefront<true, false> : k_render_wavefront<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfSmem));
+    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(wavefront smem): ") + cudaGetErrorString(e); return PTB_E_CUDA; }
+    wf.configured = true;
+    uint32_t max_useful = (a.n_items + WF_POOL - 1) / WF_POOL;
+    int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, max_useful));
+    if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess ||
+        (e = cudaEventRecord(ev0, stream)) != cudaSuccess) { err = cudaGetErrorString(e); return PTB_E_CUDA; }
+    kern<<<grid, WF_THREADS, sizeof(WfSmem), stream>>>(d, a);
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaEventRecord(ev1, stream)) != cudaSuccess) {
+        err = std::string("k_render_wavefront launch: ") + cudaGetErrorString(e);
+        return PTB_E_CUDA;
+    }
+    (*launches)++;
+    return PTB_OK;
 }
+
 }  // namespace ptb

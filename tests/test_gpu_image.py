@@ -309,3 +309,51 @@ def test_degenerate_scenes(rp):
     pt.render_spp(buf, 1)
     assert pt.counters()["end_emitter"] == 0
     pt.close()
+
+
+@pytest.mark.parametrize("wh_spp", [(200, 150, 4), (97, 61, 3), (640, 360, 2)])
+def test_wavefront_integrator_parity(rp, scene, oracle_demo, wh_spp):
+    """the shared-memory wavefront integrator traces exactly the same paths as the fused one"""
+    W, H, S = wh_spp
+    img = {}
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("wave", rp._abi.PTB_INTEGRATOR_WAVEFRONT)):
+        pt = rp.Tracer.new(scene, integrator=integ, collect_counters=True)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        img[name] = (buf.pixels.copy(), pt.counters())
+        pt.close()
+    assert (pix_rel(img["wave"][0], img["fused"][0]) < 1e-5).mean() > 0.995
+    assert np.all(img["wave"][0].reshape(-1, 4)[:, 3] == 1.0)
+    cw, cf = img["wave"][1], img["fused"][1]
+    assert cw["samples"] == cf["samples"] == W * H * S
+    for k in cw:
+        assert abs(cw[k] - cf[k]) <= max(3, 2e-4 * W * H * S), (k, cw[k], cf[k])
+    ref, _, _, _ = oracle_demo.render(W, H, S)
+    assert (pix_rel(img["wave"][0], ref) < 1e-4).mean() >= 0.99
+    # bit-reproducible run to run
+    pt = rp.Tracer.new(scene, integrator=rp._abi.PTB_INTEGRATOR_WAVEFRONT)
+    b1 = rp.ColorBuffer.new(W, H); b2 = rp.ColorBuffer.new(W, H)
+    pt.render_spp(b1, S); pt.render_spp(b2, S)
+    assert np.array_equal(b1.pixels, b2.pixels)
+    pt.close()
+
+
+def test_wavefront_bvh_and_rr(rp):
+    sc = _small_field(rp, 800, 2)
+    W, H, S = 96, 54, 2
+    img = {}
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("wave", rp._abi.PTB_INTEGRATOR_WAVEFRONT)):
+        pt = rp.Tracer.new(sc, integrator=integ, bvh_threshold=1)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        img[name] = buf.pixels.copy()
+        pt.close()
+    assert (pix_rel(img["wave"], img["fused"]) < 1e-5).mean() > 0.99
+    sc = rp.divergence_stress_scene(side=6, depth=16)
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("wave", rp._abi.PTB_INTEGRATOR_WAVEFRONT)):
+        pt = rp.Tracer.new(sc, integrator=integ, rr_start=3)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, 8)
+        img[name] = buf.pixels.copy()
+        pt.close()
+    assert (pix_rel(img["wave"], img["fused"]) < 1e-5).mean() > 0.99
