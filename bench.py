@@ -183,7 +183,9 @@ def run_own(args):
         ct.close()
 
     # ---- device-resident arm: `value` ---------------------------------------------------------------------
-    dt = DistributedTracer(scene, W, H, device=dev)
+    integ = {"auto": rp._abi.PTB_INTEGRATOR_AUTO, "fused": rp._abi.PTB_INTEGRATOR_FUSED, "wavefront": rp._abi.PTB_INTEGRATOR_WAVEFRONT}[args.integrator]
+    kernel_name = "k_render_fused<float,false,false>" if args.integrator == "fused" else "k_render_wavefront<false,false>"
+    dt = DistributedTracer(scene, W, H, device=dev, integrator=integ)
     stream = torch.cuda.current_stream(dev)
     reduced = None
     for _ in range(args.warmup):
@@ -233,7 +235,7 @@ def run_own(args):
     # running-mean image into a page-locked ColorBuffer.
     pinned = torch.empty(W * H * 4, dtype=torch.float32).pin_memory()
     host_buf = rp.ColorBuffer.new(W, H, storage=pinned.numpy())
-    et = DistributedTracer(scene, W, H, device=dev)
+    et = DistributedTracer(scene, W, H, device=dev, integrator=integ)
     scene_bytes = et.tracer.scene_bytes
 
     def e2e_step():
@@ -269,7 +271,7 @@ def run_own(args):
             pk = peak[0] if peak else nominal
             roofline = {"bound": "fp32", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
                         "peak_source": "measured live: tools/fp32_peak.cu FMA saturation" if peak else "nominal SMs*128*2*f_max",
-                        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "k_render_fused<float,false>", "kernel_ms": kms,
+                        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": kernel_name, "kernel_ms": kms,
                         "flops_per_sample": fps, "samples_per_launch": W * H * cnt,
                         "hbm": {"algorithmic_bytes_per_launch": W * H * 32, "achieved_gbs": W * H * 32 / (kms * 1e-3) / 1e9,
                                 "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -279,7 +281,7 @@ def run_own(args):
                "data": "synthetic",
                "config": {"workload": f"AnalyticalScene {W}x{H} depth 4 f32, {S} spp per step sample-split over {world} GPU(s) + 1 NCCL reduce "
                                       f"(BASELINE.json configs[2]; {args.steps} steps = {S * args.steps} spp)",
-                          "integrator": "fused persistent (k_render_fused)", "l2": f"accumulators {W * H * 16 / 1e6:.1f} MB > 126 MB L2; "
+                          "integrator": kernel_name, "l2": f"accumulators {W * H * 16 / 1e6:.1f} MB > 126 MB L2; "
                           "no other input", "image_finite_alpha_one": image_ok},
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": W * H * 16},
@@ -301,6 +303,7 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
+    ap.add_argument("--integrator", default="auto", choices=["auto", "fused", "wavefront"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-kernel-timing", action="store_true", help="sync after every step to time each launch (perturbs `value`)")
     args = ap.parse_args()

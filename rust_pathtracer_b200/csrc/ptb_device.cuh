@@ -238,13 +238,14 @@ constexpr uint32_t PTB_SMEM_SCENE_BYTES = 12 * 1024;    // capacity of the share
 template <class R> struct alignas(16) SceneSmem { uint32_t words[PTB_SMEM_SCENE_BYTES / 4]; };
 
 // Cooperative copy of the (small) scene blob into shared memory; call from all threads of the CTA.
-template <class R> __device__ inline SceneView<R> stage_scene(const DScene<R>& s, SceneSmem<R>* sm) {
+template <class R> __device__ inline SceneView<R> stage_scene(const DScene<R>& s, void* smem_words, uint32_t capacity_bytes) {
     const char* base = (const char*)s.blob;
-    if (s.blob_bytes <= PTB_SMEM_SCENE_BYTES) {
+    if (s.blob_bytes <= capacity_bytes) {
         const uint32_t* src = (const uint32_t*)s.blob;
-        for (uint32_t i = threadIdx.x; i < s.blob_bytes / 4u; i += blockDim.x) sm->words[i] = src[i];
+        uint32_t* dst = (uint32_t*)smem_words;
+        for (uint32_t i = threadIdx.x; i < s.blob_bytes / 4u; i += blockDim.x) dst[i] = src[i];
         __syncthreads();
-        base = (const char*)sm->words;
+        base = (const char*)smem_words;
     }
     SceneView<R> v;
     v.spheres = (const DSphere<R>*)(base + s.off_spheres);

@@ -46,7 +46,7 @@ constexpr uint32_t FUSED_CHUNK = 256;   // pixels reserved per atomic = one 16x1
 template <class R, bool COUNT, bool BVH>
 __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_constant__ DScene<R> s, const RenderArgs a) {
     __shared__ SceneSmem<R> sm;
-    const SceneView<R> sv = stage_scene(s, &sm);
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
     using V4 = typename Vec4T<R>::type;
     V4* accum = reinterpret_cast<V4*>(a.accum);
 
@@ -251,7 +251,7 @@ template <class R>
 __global__ void k_test_closest_hit(const __grid_constant__ DScene<R> s, size_t n, const R* o, const R* d, const R* hd_in, uint32_t* hit,
                                    uint32_t* em, R* hd_out, R* nrm, uint32_t* mat_out, R* lpdf, R* lem) {
     __shared__ SceneSmem<R> sm;
-    const SceneView<R> sv = stage_scene(s, &sm);
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
     PTB_TEST_PROLOGUE
     if (i >= n) return;
     Mat<R> m;
@@ -266,7 +266,7 @@ __global__ void k_test_closest_hit(const __grid_constant__ DScene<R> s, size_t n
 template <class R>
 __global__ void k_test_any_hit(const __grid_constant__ DScene<R> s, size_t n, const R* o, const R* d, const R* md, uint32_t* hit) {
     __shared__ SceneSmem<R> sm;
-    const SceneView<R> sv = stage_scene(s, &sm);
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
     PTB_TEST_PROLOGUE
     if (i >= n) return;
     hit[i] = s.use_bvh ? any_hit<R, true>(s, sv, ld3(o, n, i), ld3(d, n, i), md[i]) : any_hit<R, false>(s, sv, ld3(o, n, i), ld3(d, n, i), md[i]);

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
     using R = float;
     extern __shared__ __align__(16) unsigned char wf_raw[];
     WfSmem& sm = *reinterpret_cast<WfSmem*>(wf_raw);
-    const SceneView<R> sv = stage_scene(s, reinterpret_cast<SceneSmem<R>*>(sm.scene));
+    const SceneView<R> sv = stage_scene(s, sm.scene, PTB_SMEM_SCENE_BYTES);
     float4* accum = reinterpret_cast<float4*>(a.accum);
 
     const unsigned FULL = 0xffffffffu;
