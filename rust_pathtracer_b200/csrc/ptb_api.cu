@@ -41,10 +41,10 @@ static int fail(int code, const char* fmt, ...) {
 // device buffers of one scene
 template <class R> struct SceneBuffers {
     DScene<R> d{};
-    void* blob = nullptr; void* bvh = nullptr; void* bvh_prim = nullptr;
+    void* blob = nullptr; void* bvh = nullptr; void* bvh_prim = nullptr; void* bvh_spheres = nullptr;
     size_t bytes = 0;
     void release() {
-        for (void** p : {&blob, &bvh, &bvh_prim}) {
+        for (void** p : {&blob, &bvh, &bvh_prim, &bvh_spheres}) {
             if (*p) cudaFree(*p);
             *p = nullptr;
         }
@@ -272,24 +272,29 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     // pack the arrays into one blob (16-byte aligned sections) so a CTA stages it with one loop
     std::vector<unsigned char> blob;
     auto append = [&](const void* src, size_t bytes) {
-        size_t off = (blob.size() + 15) & ~size_t(15);
+        size_t off = (blob.size() + 31) & ~size_t(31);
         blob.resize(off + bytes);
         if (bytes) memcpy(blob.data() + off, src, bytes);
         return (uint32_t)off;
     };
     DScene<R>& d = sb.d;
-    d.off_spheres = append(spheres.data(), spheres.size() * sizeof(DSphere<R>));
     d.off_planes = append(planes.data(), planes.size() * sizeof(DPlane<R>));
-    d.off_materials = append(mats.data(), mats.size() * sizeof(DMaterial<R>));
     d.off_lights = append(lights.data(), lights.size() * sizeof(DLight<R>));
-    d.off_sphere_material = append(smat.data(), smat.size() * sizeof(uint32_t));
     d.off_plane_material = append(pmat.data(), pmat.size() * sizeof(uint32_t));
-    blob.resize((blob.size() + 15) & ~size_t(15));
+    blob.resize((blob.size() + 31) & ~size_t(31));
+    d.small_bytes = (uint32_t)blob.size();          // head section: always worth staging in shared memory
+    d.off_spheres = append(spheres.data(), spheres.size() * sizeof(DSphere<R>));
+    d.off_sphere_material = append(smat.data(), smat.size() * sizeof(uint32_t));
+    d.off_materials = append(mats.data(), mats.size() * sizeof(DMaterial<R>));
+    blob.resize((blob.size() + 31) & ~size_t(31));
 
     sb.release();
     CU(upload_vec(&sb.blob, blob, t->stream, sb.bytes));
     CU(upload_vec(&sb.bvh, nodes, t->stream, sb.bytes));
     CU(upload_vec(&sb.bvh_prim, prim, t->stream, sb.bytes));
+    std::vector<DSphere<R>> leaf_spheres(prim.size());
+    for (size_t i = 0; i < prim.size(); ++i) leaf_spheres[i] = spheres[prim[i]];
+    CU(upload_vec(&sb.bvh_spheres, leaf_spheres, t->stream, sb.bytes));
     CU(cudaStreamSynchronize(t->stream));   // host vectors go out of scope
 
     const char* base = (const char*)sb.blob;
@@ -299,6 +304,16 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     d.planes = (const DPlane<R>*)(base + d.off_planes); d.plane_material = (const uint32_t*)(base + d.off_plane_material);
     d.materials = (const DMaterial<R>*)(base + d.off_materials); d.lights = (const DLight<R>*)(base + d.off_lights);
     d.bvh = use_bvh ? (const BvhNode*)sb.bvh : nullptr; d.bvh_prim = (const uint32_t*)sb.bvh_prim;
+    d.bvh_spheres = (const DSphere<R>*)sb.bvh_spheres;
+    for (int k = 0; k < 3; ++k) { d.light_lo[k] = 3e38f; d.light_hi[k] = -3e38f; }
+    for (const auto& l : lights) {
+        if (l.type != PTB_LIGHT_SPHERICAL) continue;
+        const double c[3] = {(double)l.px, (double)l.py, (double)l.pz}, r = std::fabs((double)l.radius) * 1.0001 + 1e-6;
+        for (int k = 0; k < 3; ++k) {
+            d.light_lo[k] = std::min(d.light_lo[k], std::nextafterf((float)(c[k] - r), -3e38f));
+            d.light_hi[k] = std::max(d.light_hi[k], std::nextafterf((float)(c[k] + r), 3e38f));
+        }
+    }
     d.use_bvh = use_bvh; d.patch_materials = patch;
     d.depth = sc->depth; d.flags = sc->flags; d.eps = sc->eps;
     d.n_lights_f = (R)sc->n_lights;
@@ -579,9 +594,12 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
     if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
     if (spp == 0) return PTB_OK;
     CU(cudaSetDevice(t->device));
-    // AUTO: the shared-memory wavefront integrator for f32 (measured faster, profiles/), the fused one for f64
+    // AUTO: the shared-memory wavefront integrator for small f32 scenes (measured faster, profiles/); the fused one for
+    // f64 and for large BVH scenes (measured: 100k spheres + 64 lights 479 vs 223 Msamples/s; 4096 spheres 1064 vs 1237),
+    // whose deep, divergent traversal wants more resident warps than one 512-thread CTA per SM
     uint32_t integ = t->cfg.integrator;
-    if (integ == PTB_INTEGRATOR_AUTO) integ = t->precision == 4 ? PTB_INTEGRATOR_WAVEFRONT : PTB_INTEGRATOR_FUSED;
+    if (integ == PTB_INTEGRATOR_AUTO)
+        integ = (t->precision == 4 && !(t->s32.d.use_bvh && t->s32.d.n_spheres > 16384u)) ? PTB_INTEGRATOR_WAVEFRONT : PTB_INTEGRATOR_FUSED;
     if (integ == PTB_INTEGRATOR_WAVEFRONT) {
         if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the wavefront integrator is built for f32 only");
         r = wavefront_render(t->wf, t->s32.d, t->accum, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters,

@@ -185,12 +185,12 @@ template <class R> struct DMaterial {
     uint32_t set_mask, albedo_kind;
     R checker_a, checker_b, checker_scale, checker_offset;
 };
-template <class R> struct DSphere { R cx, cy, cz, r; };                 // float4 for f32
+template <class R> struct alignas(4 * sizeof(R)) DSphere { R cx, cy, cz, r; };   // one 16-byte (f32) / 32-byte (f64) vector load
 template <class R> struct DPlane { R px, py, pz, nx, ny, nz; };
 template <class R> struct DLight { R px, py, pz, radius, ex, ey, ez, area; uint32_t type, pad[3]; };
 
 // 32-byte BVH node over spheres (f32 bounds even for the f64 build; bounds are conservative).
-struct BvhNode {
+struct alignas(32) BvhNode {
     float lo[3]; uint32_t left_or_first;   // inner: left child index (right = left + 1); leaf: first prim
     float hi[3]; uint32_t count;           // 0 = inner, >0 = leaf prim count
 };
@@ -198,7 +198,7 @@ struct BvhNode {
 template <class R> struct DScene {
     uint32_t n_spheres, n_planes, n_materials, n_lights;
     const void* blob;                   // packed scene arrays in HBM (see stage_scene)
-    uint32_t blob_bytes, off_spheres, off_planes, off_materials, off_lights, off_sphere_material, off_plane_material;
+    uint32_t blob_bytes, small_bytes, off_spheres, off_planes, off_materials, off_lights, off_sphere_material, off_plane_material;
     const DSphere<R>* spheres;          // the same arrays, addressed directly (BVH leaves, parity kernels)
     const uint32_t* sphere_material;
     const DPlane<R>* planes;
@@ -207,6 +207,8 @@ template <class R> struct DScene {
     const DLight<R>* lights;
     const BvhNode* bvh;                 // NULL when the scene is small
     const uint32_t* bvh_prim;           // sphere indices in leaf order
+    const DSphere<R>* bvh_spheres;      // the spheres themselves in leaf order (leaf = one contiguous read)
+    float light_lo[3], light_hi[3];     // bounding box of all spherical lights (cull for sample_lights)
     uint32_t use_bvh;
     uint32_t has_emissive;              // 1 if any material has non-zero emission
     uint32_t patch_materials;           // 1 if any set_mask != PTB_MAT_ALL (order-dependent patching)
@@ -220,10 +222,10 @@ template <class R> struct DScene {
     R n_lights_f;                       // number_of_lights() as F (tracer.rs:138,214)
 };
 
-// Scene arrays as the kernels read them.  Small scenes are staged in shared memory: the host packs
-// [spheres | planes | materials | lights | sphere_material | plane_material] into ONE blob
-// (DScene::blob, blob_bytes) and every CTA copies it with a single loop; larger scenes are read
-// from HBM through L1/L2.
+// Scene arrays as the kernels read them.  The host packs [planes | lights | plane_material | spheres |
+// sphere_material | materials] into ONE blob (DScene::blob); a CTA stages the whole blob in shared
+// memory with a single loop when it fits, otherwise just the small head section (planes, lights),
+// and reads the rest from HBM through L1/L2.
 template <class R> struct SceneView {
     const DSphere<R>* spheres;
     const uint32_t* sphere_material;
@@ -239,21 +241,22 @@ template <class R> struct alignas(16) SceneSmem { uint32_t words[PTB_SMEM_SCENE_
 
 // Cooperative copy of the (small) scene blob into shared memory; call from all threads of the CTA.
 template <class R> __device__ inline SceneView<R> stage_scene(const DScene<R>& s, void* smem_words, uint32_t capacity_bytes) {
-    const char* base = (const char*)s.blob;
-    if (s.blob_bytes <= capacity_bytes) {
-        const uint32_t* src = (const uint32_t*)s.blob;
-        uint32_t* dst = (uint32_t*)smem_words;
-        for (uint32_t i = threadIdx.x; i < s.blob_bytes / 4u; i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-        base = (const char*)smem_words;
-    }
+    // whole blob if it fits, else at least its small head section (planes, lights, plane materials)
+    const uint32_t n = s.blob_bytes <= capacity_bytes ? s.blob_bytes : (s.small_bytes <= capacity_bytes ? s.small_bytes : 0u);
+    const uint32_t* src = (const uint32_t*)s.blob;
+    uint32_t* dst = (uint32_t*)smem_words;
+    for (uint32_t i = threadIdx.x; i < n / 4u; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    const char* g = (const char*)s.blob;
+    const char* m = (const char*)smem_words;
+    auto at = [&](uint32_t off) { return off < n ? m + off : g + off; };
     SceneView<R> v;
-    v.spheres = (const DSphere<R>*)(base + s.off_spheres);
-    v.planes = (const DPlane<R>*)(base + s.off_planes);
-    v.materials = (const DMaterial<R>*)(base + s.off_materials);
-    v.lights = (const DLight<R>*)(base + s.off_lights);
-    v.sphere_material = (const uint32_t*)(base + s.off_sphere_material);
-    v.plane_material = (const uint32_t*)(base + s.off_plane_material);
+    v.planes = (const DPlane<R>*)at(s.off_planes);
+    v.lights = (const DLight<R>*)at(s.off_lights);
+    v.plane_material = (const uint32_t*)at(s.off_plane_material);
+    v.spheres = (const DSphere<R>*)at(s.off_spheres);
+    v.sphere_material = (const uint32_t*)at(s.off_sphere_material);
+    v.materials = (const DMaterial<R>*)at(s.off_materials);
     return v;
 }
 
@@ -401,73 +404,92 @@ template <class R> PTB_DEV V3<R> background(const DScene<R>& s, V3<R> d) {
     return a;
 }
 
-// BVH traversal (closest): returns best sphere index or -1, updates best_t.
-template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
+// Ray / box slab test in f32, inflated by a relative margin so that rounding can never cull a true
+// hit.  Returns the entry distance, or +inf when the box is missed or starts beyond `limit`.
+struct RayF { float ox, oy, oz, idx, idy, idz; };
+PTB_DEV float box_entry(const float* lo, const float* hi, const RayF& r, float limit) {
+    float tx0 = (lo[0] - r.ox) * r.idx, tx1 = (hi[0] - r.ox) * r.idx;
+    float ty0 = (lo[1] - r.oy) * r.idy, ty1 = (hi[1] - r.oy) * r.idy;
+    float tz0 = (lo[2] - r.oz) * r.idz, tz1 = (hi[2] - r.oz) * r.idz;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    tn *= 0.9999f;
+    return (tn <= tf * 1.0001f && tn <= limit) ? tn : 3.0e38f;
+}
+PTB_DEV BvhNode load_node(const BvhNode* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = __ldg(q), b = __ldg(q + 1);
+    BvhNode n;
+    n.lo[0] = a.x; n.lo[1] = a.y; n.lo[2] = a.z; n.left_or_first = __float_as_uint(a.w);
+    n.hi[0] = b.x; n.hi[1] = b.y; n.hi[2] = b.z; n.count = __float_as_uint(b.w);
+    return n;
+}
+
+// Sphere BVH traversal.  Children of an inner node are adjacent, so both boxes are fetched with one
+// 64-byte read and the nearer child is descended first (the farther one is stacked with its entry
+// distance and skipped on pop if the closest hit found meanwhile is nearer).  ANY = shadow-ray mode:
+// first hit within max_dist returns.  Closest mode keeps the reference's tie rule (ascending index,
+// strict `d < dist` => the lowest sphere index wins equal distances).  Returns the sphere index or -1.
+template <class R, bool ANY>
+PTB_DEV int bvh_traverse(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
     int best = -1;
-    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-    const float idx = 1.0f / (float)d.x, idy = 1.0f / (float)d.y, idz = 1.0f / (float)d.z;
-    uint32_t stack[48];
+    RayF r;
+    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+    r.idx = 1.0f / (float)d.x; r.idy = 1.0f / (float)d.y; r.idz = 1.0f / (float)d.z;
+    constexpr int STACK = 40;
+    uint32_t stack_n[STACK];
+    float stack_t[STACK];
     int sp = 0;
-    uint32_t node = 0;
+    BvhNode root = load_node(s.bvh);
+    if (box_entry(root.lo, root.hi, r, (float)best_t) >= 3.0e38f) return -1;
+    uint32_t cur_lf = root.left_or_first, cur_cnt = root.count;
     while (true) {
-        const BvhNode nd = s.bvh[node];
-        // slab test, inflated by a relative margin so that f32 rounding can never cull a true hit
-        float tx0 = (nd.lo[0] - ox) * idx, tx1 = (nd.hi[0] - ox) * idx;
-        float ty0 = (nd.lo[1] - oy) * idy, ty1 = (nd.hi[1] - oy) * idy;
-        float tz0 = (nd.lo[2] - oz) * idz, tz1 = (nd.hi[2] - oz) * idz;
-        float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-        float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
-        bool overlap = tn * 0.9999f <= tf * 1.0001f && (float)best_t >= tn * 0.9999f;
-        if (overlap) {
-            if (nd.count == 0) {
-                stack[sp++] = nd.left_or_first + 1;
-                node = nd.left_or_first;
+        if (cur_cnt) {
+            for (uint32_t i = 0; i < cur_cnt; ++i) {
+                const DSphere<R> sph = s.bvh_spheres[cur_lf + i];
+                R t = isect_sphere(o, d, V3<R>(sph.cx, sph.cy, sph.cz), sph.r);
+                if (t >= R(0)) {
+                    if (ANY) { if (t < best_t) return (int)s.bvh_prim[cur_lf + i]; }
+                    else {
+                        const int si = (int)s.bvh_prim[cur_lf + i];
+                        if (t < best_t || (t == best_t && si < best)) { best_t = t; best = si; }
+                    }
+                }
+            }
+        } else {
+            const BvhNode a = load_node(s.bvh + cur_lf), b = load_node(s.bvh + cur_lf + 1);
+            const float ta = box_entry(a.lo, a.hi, r, (float)best_t), tb = box_entry(b.lo, b.hi, r, (float)best_t);
+            const bool ha = ta < 3.0e38f, hb = tb < 3.0e38f;
+            if (ha || hb) {
+                const bool a_near = ha && (!hb || ta <= tb);
+                if (ha && hb && sp < STACK) {
+                    stack_n[sp] = a_near ? cur_lf + 1 : cur_lf;
+                    stack_t[sp] = a_near ? tb : ta;
+                    ++sp;
+                }
+                if (a_near) { cur_lf = a.left_or_first; cur_cnt = a.count; }
+                else { cur_lf = b.left_or_first; cur_cnt = b.count; }
                 continue;
             }
-            for (uint32_t i = 0; i < nd.count; ++i) {
-                uint32_t si = s.bvh_prim[nd.left_or_first + i];
-                DSphere<R> sp_ = s.spheres[si];
-                R t = isect_sphere(o, d, V3<R>(sp_.cx, sp_.cy, sp_.cz), sp_.r);
-                // reference order: ascending index, strict `d < dist` => lowest index wins ties
-                if (t >= R(0) && (t < best_t || (t == best_t && (int)si < best))) { best_t = t; best = (int)si; }
+        }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] <= (float)best_t) {
+                const BvhNode n = load_node(s.bvh + stack_n[sp]);
+                cur_lf = n.left_or_first; cur_cnt = n.count;
+                found = true;
+                break;
             }
         }
-        if (sp == 0) break;
-        node = stack[--sp];
+        if (!found) break;
     }
     return best;
 }
+template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) { return bvh_traverse<R, false>(s, o, d, best_t); }
 template <class R> PTB_DEV bool bvh_any(const DScene<R>& s, V3<R> o, V3<R> d, R max_dist, bool ignore_max) {
-    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-    const float idx = 1.0f / (float)d.x, idy = 1.0f / (float)d.y, idz = 1.0f / (float)d.z;
-    const float tmax = ignore_max ? 3.0e38f : (float)max_dist;
-    uint32_t stack[48];
-    int sp = 0;
-    uint32_t node = 0;
-    while (true) {
-        const BvhNode nd = s.bvh[node];
-        float tx0 = (nd.lo[0] - ox) * idx, tx1 = (nd.hi[0] - ox) * idx;
-        float ty0 = (nd.lo[1] - oy) * idy, ty1 = (nd.hi[1] - oy) * idy;
-        float tz0 = (nd.lo[2] - oz) * idz, tz1 = (nd.hi[2] - oz) * idz;
-        float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-        float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
-        bool overlap = tn * 0.9999f <= tf * 1.0001f && tmax >= tn * 0.9999f;
-        if (overlap) {
-            if (nd.count == 0) {
-                stack[sp++] = nd.left_or_first + 1;
-                node = nd.left_or_first;
-                continue;
-            }
-            for (uint32_t i = 0; i < nd.count; ++i) {
-                DSphere<R> sp_ = s.spheres[s.bvh_prim[nd.left_or_first + i]];
-                R t = isect_sphere(o, d, V3<R>(sp_.cx, sp_.cy, sp_.cz), sp_.r);
-                if (t >= R(0) && (ignore_max || t < max_dist)) return true;
-            }
-        }
-        if (sp == 0) break;
-        node = stack[--sp];
-    }
-    return false;
+    R limit = ignore_max ? Const<R>::MAXV : max_dist;
+    return bvh_traverse<R, true>(s, o, d, limit) >= 0;
 }
 
 // Scene::closest_hit for the exported scene, geometry part (analytical.rs:36-127 + scene.rs:36-86):
@@ -516,8 +538,17 @@ PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, 
     // Scene::sample_lights, scene.rs:36-86 — starts from the possibly stale state.hit_dist
     R ldist = h.hit_dist;
     int lbest = -1;
+    // A light can only win with 0 <= t < ldist: nothing to test when ldist <= 0 (a fresh path that missed all
+    // geometry: hit_dist is still -1) or — for scenes with many lights — when the ray misses the lights' bounding box.
+    uint32_t n_test = ldist > R(0) ? s.n_lights : 0u;
+    if (n_test >= 4u) {
+        RayF r;
+        r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+        r.idx = 1.0f / (float)d.x; r.idy = 1.0f / (float)d.y; r.idz = 1.0f / (float)d.z;
+        if (box_entry(s.light_lo, s.light_hi, r, (float)ldist) >= 3.0e38f) n_test = 0u;
+    }
 #pragma unroll 1
-    for (uint32_t i = 0; i < s.n_lights; ++i) {
+    for (uint32_t i = 0; i < n_test; ++i) {
         DLight<R> L = sv.lights[i];
         if (L.type != PTB_LIGHT_SPHERICAL) continue;
         R t = isect_sphere(o, d, V3<R>(L.px, L.py, L.pz), L.radius);
