@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, SPP_PER_STEP = 3840, 2160, 128
 METRIC, UNIT = "path_msamples_per_s_4k", "Msamples/s"
+WORKLOAD = "AnalyticalScene (renderer/src/analytical.rs) 3840x2160, depth 4, f32 — BASELINE.json configs[2]"
 
 # Algorithmic FLOP cost per call (1 FLOP = add/sub/mul/div/sqrt/min/max/abs/
 # compare-select or one libm call, FMA = 2) for the demo scene; DESIGN.md "Work model".
@@ -143,8 +144,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"AnalyticalScene {WIDTH}x{HEIGHT} depth 4 f32 (BASELINE.json configs[2])",
-                                        "step": sample},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "step": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
@@ -279,8 +279,9 @@ def run_own(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
-               "config": {"workload": f"AnalyticalScene {W}x{H} depth 4 f32, {S} spp per step sample-split over {world} GPU(s) + 1 NCCL reduce "
-                                      f"(BASELINE.json configs[2]; {args.steps} steps = {S * args.steps} spp)",
+               "config": {"workload": WORKLOAD if (W, H) == (WIDTH, HEIGHT) else f"AnalyticalScene {W}x{H}, depth 4, f32 (non-default size)",
+                          "step": f"{S} spp over the frame, sample-split over {world} GPU(s), then ONE NCCL sum-reduce of the float4 accumulators "
+                                  f"({args.steps} steps = {S * args.steps} spp)",
                           "integrator": kernel_name, "l2": f"accumulators {W * H * 16 / 1e6:.1f} MB > 126 MB L2; "
                           "no other input", "image_finite_alpha_one": image_ok},
                "clocks": clocks, "gpu_launches": int(launches),
