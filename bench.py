@@ -233,27 +233,44 @@ def run_own(args):
     # ---- e2e arm: through Tracer.render_spp with HOST buffers ----------------------------------------------
     # per step: scene export H2D, this rank's share of the samples, NCCL reduce, and on rank 0 the D2H of the
     # running-mean image into a page-locked ColorBuffer.
-    pinned = torch.empty(W * H * 4, dtype=torch.float32).pin_memory()
-    host_buf = rp.ColorBuffer.new(W, H, storage=pinned.numpy())
+    # The D2H of step k overlaps the tracing of step k+1: two page-locked host buffers alternate, the copy runs on a side
+    # stream behind an event, and the timed region ends only when the last copy has landed.
+    pinned = [torch.empty(W * H * 4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_bufs = [rp.ColorBuffer.new(W, H, storage=p_.numpy()) for p_ in pinned]
     et = DistributedTracer(scene, W, H, device=dev, integrator=integ)
     scene_bytes = et.tracer.scene_bytes
+    copy_stream = torch.cuda.Stream(device=dev)
+    step_no = [0]
 
     def e2e_step():
+        main = torch.cuda.current_stream(dev)
         et.tracer.sync_scene()                                  # H2D: the step's input (the scene description)
         et.render(S)
         out = et.reduce(0)
         if rank == 0:
             mean = resolve_mean(out)
-            pinned.copy_(mean, non_blocking=True)               # D2H: the step's result into ColorBuffer.pixels
-            host_buf.frames = et.samples_done
+            ready = torch.cuda.Event()
+            ready.record(main)
+            k = step_no[0] & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                pinned[k].copy_(mean, non_blocking=True)        # D2H: the step's result into ColorBuffer.pixels
+                mean.record_stream(copy_stream)
+            host_bufs[k].frames = et.samples_done
+        step_no[0] += 1
+
+    def e2e_drain():
+        copy_stream.synchronize()
         torch.cuda.current_stream(dev).synchronize()
 
     for _ in range(min(2, args.warmup)):
         e2e_step()
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
+    e2e_drain()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:

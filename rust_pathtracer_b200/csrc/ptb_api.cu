@@ -42,12 +42,14 @@ static int fail(int code, const char* fmt, ...) {
 template <class R> struct SceneBuffers {
     DScene<R> d{};
     void* blob = nullptr; void* bvh = nullptr; void* bvh_prim = nullptr; void* bvh_spheres = nullptr;
-    size_t bytes = 0;
+    size_t cap_blob = 0, cap_bvh = 0, cap_prim = 0, cap_spheres = 0;   // allocations are reused across set_scene calls:
+    size_t bytes = 0;                                                  // cudaFree would synchronise the whole device
     void release() {
         for (void** p : {&blob, &bvh, &bvh_prim, &bvh_spheres}) {
             if (*p) cudaFree(*p);
             *p = nullptr;
         }
+        cap_blob = cap_bvh = cap_prim = cap_spheres = 0;
         bytes = 0;
     }
 };
@@ -168,11 +170,16 @@ template <class R> struct PodTypes;
 template <> struct PodTypes<float> { using scene = ptb_scene_f32; using material = ptb_material_f32; };
 template <> struct PodTypes<double> { using scene = ptb_scene_f64; using material = ptb_material_f64; };
 
-template <class T> static cudaError_t upload_vec(void** dst, const std::vector<T>& v, cudaStream_t st, size_t& bytes) {
-    *dst = nullptr;
+template <class T> static cudaError_t upload_vec(void** dst, size_t& cap, const std::vector<T>& v, cudaStream_t st, size_t& bytes) {
     size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(dst, n);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    if (n > cap || !*dst) {
+        if (*dst) cudaFree(*dst);
+        *dst = nullptr; cap = 0;
+        e = cudaMalloc(dst, n);
+        if (e != cudaSuccess) return e;
+        cap = n;
+    }
     bytes += n;
     if (!v.empty()) e = cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
     return e;
@@ -288,13 +295,13 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     d.off_materials = append(mats.data(), mats.size() * sizeof(DMaterial<R>));
     blob.resize((blob.size() + 31) & ~size_t(31));
 
-    sb.release();
-    CU(upload_vec(&sb.blob, blob, t->stream, sb.bytes));
-    CU(upload_vec(&sb.bvh, nodes, t->stream, sb.bytes));
-    CU(upload_vec(&sb.bvh_prim, prim, t->stream, sb.bytes));
+    sb.bytes = 0;
+    CU(upload_vec(&sb.blob, sb.cap_blob, blob, t->stream, sb.bytes));
+    CU(upload_vec(&sb.bvh, sb.cap_bvh, nodes, t->stream, sb.bytes));
+    CU(upload_vec(&sb.bvh_prim, sb.cap_prim, prim, t->stream, sb.bytes));
     std::vector<DSphere<R>> leaf_spheres(prim.size());
     for (size_t i = 0; i < prim.size(); ++i) leaf_spheres[i] = spheres[prim[i]];
-    CU(upload_vec(&sb.bvh_spheres, leaf_spheres, t->stream, sb.bytes));
+    CU(upload_vec(&sb.bvh_spheres, sb.cap_spheres, leaf_spheres, t->stream, sb.bytes));
     CU(cudaStreamSynchronize(t->stream));   // host vectors go out of scope
 
     const char* base = (const char*)sb.blob;
