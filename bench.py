@@ -38,8 +38,10 @@ WORKLOAD = "AnalyticalScene (renderer/src/analytical.rs) 3840x2160, depth 4, f32
 F_K = dict(gen_ray=94, closest_hit=130, finalize=36, direct_light=127, nee_contrib=16, any_hit=45, eval_common=217,
            ev_diffuse=75, ev_reflect=103, ev_refract=100, ev_clearcoat=73, sample_common=200, lobe_diffuse=26,
            lobe_clearcoat=52, lobe_reflect=156, lobe_refract=169, background=18, glue_bounce=12, glue_sample=20)
-# DRAM bytes per launch of k_render_fused from the committed `ncu --set full` capture (profiles/); None until captured
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+# DRAM bytes per launch of the render kernel at 3840x2160 from the committed `ncu --set full` capture
+# (profiles/r01_ncu_wavefront.md, r01-d: dram__bytes_read.sum 135.8 MB + dram__bytes_write.sum 83.5 MB; the accumulator
+# read-modify-write is 265.4 MB algorithmic — part of the writes is still dirty in L2 when the kernel ends).  Independent of spp.
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 135820544 + 83538176
 
 
 def flops_per_sample(c: dict) -> float:
@@ -288,7 +290,7 @@ def run_own(args):
             pk = peak[0] if peak else nominal
             roofline = {"bound": "fp32", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
                         "peak_source": "measured live: tools/fp32_peak.cu FMA saturation" if peak else "nominal SMs*128*2*f_max",
-                        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": kernel_name, "kernel_ms": kms,
+                        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (W, H) == (WIDTH, HEIGHT) else None, "kernel": kernel_name, "kernel_ms": kms,
                         "flops_per_sample": fps, "samples_per_launch": W * H * cnt,
                         "hbm": {"algorithmic_bytes_per_launch": W * H * 32, "achieved_gbs": W * H * 32 / (kms * 1e-3) / 1e9,
                                 "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

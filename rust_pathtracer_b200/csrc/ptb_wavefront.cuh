@@ -56,6 +56,7 @@ struct WfSmem {
     uint32_t cnt[WF_CLASSES];       // tickets handed out per class
     uint32_t off[WF_CLASSES + 1];   // class start offsets; off[WF_CLASSES] = queue length
     uint32_t n_done;                // slots that can never get work again
+    uint32_t cursor2;               // next 32-entry chunk of the stage-2 queue
 };
 
 template <bool COUNT, bool BVH>
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
 
     for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) { sm.u[U_FLAGS][i] = 0; sm.u[U_SIDX][i] = 0; sm.key[i] = 0xffffu; }
     if (tid < WF_CLASSES) sm.cnt[tid] = 0;
-    if (tid == 0) sm.n_done = 0;
+    if (tid == 0) { sm.n_done = 0; sm.cursor2 = 0; }
     __syncthreads();
 
     uint32_t w_next = 0, w_end = 0;          // warp-uniform cursor into the warp's current 16x16 pixel tile
@@ -88,6 +89,8 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
 
     while (true) {
         // ================================ stage 1: generate + intersect ================================
+        // static slot ownership: each warp keeps its own 128 slots, because the pixel-tile cursor (w_next, w_end) lives
+        // in the warp's registers and the tile's remaining pixels must be consumed by the same warp
 #pragma unroll 1
         for (uint32_t base = warp * 32u; base < WF_POOL; base += WF_WARPS * 32u) {
             const uint32_t i = base + lane;
@@ -201,10 +204,14 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
 
         // ================================ sort: tickets -> class-ordered queue ================================
         if (tid == 0) {
+            // classes with more lobes cost more to shade: queue them first so the dynamic chunking of stage 2
+            // ends on cheap chunks (longest-processing-time-first)
+            const int order_by_cost[WF_CLASSES] = {7, 3, 5, 6, 1, 2, 4, 0};
             uint32_t run = 0;
 #pragma unroll
-            for (int c = 0; c < WF_CLASSES; ++c) { sm.off[c] = run; run += sm.cnt[c]; }
+            for (int k = 0; k < WF_CLASSES; ++k) { const int c = order_by_cost[k]; sm.off[c] = run; run += sm.cnt[c]; }
             sm.off[WF_CLASSES] = run;
+            sm.cursor2 = 0;
         }
         __syncthreads();
         const uint32_t n_queue = sm.off[WF_CLASSES];
@@ -223,7 +230,15 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
 
         // ================================ stage 2: shade ================================
 #pragma unroll 1
-        for (uint32_t j = tid; j < n_queue; j += WF_THREADS) {
+        // warps take 32-entry chunks of the queue dynamically (one shared-memory atomic per chunk); expensive lobe
+        // classes are queued first, so the stage ends on cheap chunks
+        while (true) {
+            uint32_t chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&sm.cursor2, 1u);
+            chunk = __shfl_sync(FULL, chunk, 0);
+            if (chunk * 32u >= n_queue) break;
+            const uint32_t j = chunk * 32u + lane;
+            if (j >= n_queue) continue;
             const uint32_t i = sm.order[j];
             PathState<R> p;
             p.o = V3<R>(sm.f[F_OX][i], sm.f[F_OY][i], sm.f[F_OZ][i]);
