@@ -1153,6 +1153,10 @@ template <class R> PTB_DEV bool russian_roulette_survives(PathState<R>& p, R u0)
 // on a light hit.  Returns 0 = path ended, 1 = geometry hit (continue with path_shade).
 template <class R, bool COUNT, bool BVH>
 PTB_DEV int path_intersect(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, HitCore<R>& h, PathCounters* pc) {
+    if (p.bounce >= s.depth) {                                  // recursion_depth() == 0: `for _ in 0..0` never runs (tracer.rs:61)
+        if (COUNT) pc->end_depth++;
+        return 0;
+    }
     if (COUNT) pc->closest_hit++;
     h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
     p.hit_dist = h.hit_dist;

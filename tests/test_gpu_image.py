@@ -303,6 +303,17 @@ def test_degenerate_scenes(rp):
     c = pt.counters()
     assert c["closest_hit"] == c["samples"]
     pt.close()
+    # depth 0: the bounce loop never runs (tracer.rs:61) -> black image with alpha 1, no closest_hit at all
+    e = rp.AnalyticalScene.new().device_export(); e.depth = 0
+    for integ in (rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_WAVEFRONT):
+        pt = rp.Tracer.new(rp.ExportedScene(e), collect_counters=True, integrator=integ)
+        b0 = rp.ColorBuffer.new(32, 16)
+        pt.render_spp(b0, 2)
+        c = pt.counters()
+        assert c["closest_hit"] == 0 and c["samples"] == 32 * 16 * 2
+        px = b0.pixels.reshape(-1, 4)
+        assert np.all(px[:, :3] == 0.0) and np.all(px[:, 3] == 1.0)
+        pt.close()
     # lights but no geometry, and a light in front of the camera: stale hit_dist = -1 hides it (A.1) -> pure sky
     e = rp.DeviceScene(lights=[rp.AnalyticalLight.spherical((0, 0, 0), 1.0, (5, 5, 5))])
     pt = rp.Tracer.new(rp.ExportedScene(e), collect_counters=True)
