@@ -1149,6 +1149,24 @@ template <class R> PTB_DEV bool russian_roulette_survives(PathState<R>& p, R u0)
     return true;
 }
 
+// tracer.rs:66-69: the path left the scene
+template <class R> PTB_DEV void path_add_sky(const DScene<R>& s, PathState<R>& p) {
+    V3<R> bg = background(s, p.d);
+    p.rad = p.rad + bg * p.thr;
+}
+// tracer.rs:72-87: the path hit a light.  finalize() would run first but none of its outputs reach the
+// radiance; the emission of the geometry's material (if geometry was also hit) is still added (tracer.rs:74)
+template <class R, bool BVH>
+PTB_DEV void path_add_emitter(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const HitCore<R>& h) {
+    if (h.geom && s.has_emissive) {
+        Mat<R> mat;
+        hit_material<R, BVH>(s, sv, h.prim, h.accepted, p.d, mat);
+        p.rad = p.rad + mat.emission * p.thr;
+    }
+    R w = power_heuristic(p.prev_pdf, h.light_pdf);             // `state.depth > 0` is always true (A.2)
+    p.rad = p.rad + (w * h.light_emission) * p.thr;
+}
+
 // First half of a bounce, tracer.rs:63-87: closest_hit, background on a miss, MIS-weighted emission
 // on a light hit.  Returns 0 = path ended, 1 = geometry hit (continue with path_shade).
 template <class R, bool COUNT, bool BVH>
@@ -1160,22 +1178,13 @@ PTB_DEV int path_intersect(const DScene<R>& s, const SceneView<R>& sv, PathState
     if (COUNT) pc->closest_hit++;
     h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
     p.hit_dist = h.hit_dist;
-    if (!h.hit) {                                               // tracer.rs:66-69
-        V3<R> bg = background(s, p.d);
-        p.rad = p.rad + bg * p.thr;
+    if (!h.hit) {
+        path_add_sky(s, p);
         if (COUNT) pc->end_sky++;
         return 0;
     }
-    if (h.is_emitter) {                                         // tracer.rs:72-87
-        // finalize() would run first but none of its outputs reach the radiance; the emission of
-        // the geometry's material (if geometry was also hit) is still added (tracer.rs:74)
-        if (h.geom && s.has_emissive) {
-            Mat<R> mat;
-            hit_material<R, BVH>(s, sv, h.prim, h.accepted, p.d, mat);
-            p.rad = p.rad + mat.emission * p.thr;
-        }
-        R w = power_heuristic(p.prev_pdf, h.light_pdf);         // `state.depth > 0` is always true (A.2)
-        p.rad = p.rad + (w * h.light_emission) * p.thr;
+    if (h.is_emitter) {
+        path_add_emitter<R, BVH>(s, sv, p, h);
         if (COUNT) pc->end_emitter++;
         return 0;
     }

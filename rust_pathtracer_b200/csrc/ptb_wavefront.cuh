@@ -37,7 +37,8 @@ namespace ptb {
 constexpr int WF_THREADS = 512;
 constexpr int WF_WARPS = WF_THREADS / 32;
 constexpr uint32_t WF_POOL = 2048;          // path slots per CTA
-constexpr int WF_CLASSES = 8;               // lobe classes (3 bits, lobe_class_of)
+constexpr int WF_CLASSES = 9;               // queue keys: 8 lobe classes (3 bits, lobe_class_of) + WF_MISS
+constexpr uint32_t WF_MISS = 8;             // the path left the scene: background lookup, done with full warps in stage 2
 
 // per-slot float arrays (SoA: array k occupies words [k*P, (k+1)*P))
 enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TX, F_TY, F_TZ, F_RX, F_RY, F_RZ, F_HITDIST, F_PREVPDF, F_AX, F_AY, F_AZ, WF_NF };
@@ -167,17 +168,34 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
                     }
                 }
                 HitCore<R> h;
-                if (!dead && !path_intersect<R, COUNT, BVH>(s, sv, p, h, &pc)) dead = true;
+                bool sky = false;
+                if (!dead) {
+                    if (p.bounce >= s.depth) {                         // recursion depth 0 (tracer.rs:61)
+                        dead = true;
+                        if (COUNT) pc.end_depth++;
+                    } else {
+                        if (COUNT) pc.closest_hit++;
+                        h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
+                        p.hit_dist = h.hit_dist;
+                        if (!h.hit) {
+                            sky = true;                                // background is evaluated in stage 2 (compacted)
+                        } else if (h.is_emitter) {
+                            path_add_emitter<R, BVH>(s, sv, p, h);
+                            dead = true;
+                            if (COUNT) pc.end_emitter++;
+                        }
+                    }
+                }
                 if (dead) {
                     sm.f[F_AX][i] += p.rad.x; sm.f[F_AY][i] += p.rad.y; sm.f[F_AZ][i] += p.rad.z;
                     sidx++;
                     alive = false;
                 } else {
-                    // queue for shading: ticket inside the path's lobe class
-                    const uint32_t cls = hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
+                    // queue for stage 2: ticket inside the path's key (lobe class of the hit material, or WF_MISS)
+                    const uint32_t cls = sky ? WF_MISS : hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
                     sm.key[i] = (uint16_t)cls;
                     sm.ticket[i] = (uint16_t)atomicAdd(&sm.cnt[cls], 1u);
-                    sm.u[U_PRIM][i] = (uint32_t)h.prim;
+                    sm.u[U_PRIM][i] = sky ? 0xffffffffu : (uint32_t)h.prim;
                     sm.u[U_ACC_LO][i] = (uint32_t)h.accepted;
                     sm.u[U_ACC_HI][i] = (uint32_t)(h.accepted >> 32);
                     sm.f[F_HITDIST][i] = p.hit_dist;
@@ -206,7 +224,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
         if (tid == 0) {
             // classes with more lobes cost more to shade: queue them first so the dynamic chunking of stage 2
             // ends on cheap chunks (longest-processing-time-first)
-            const int order_by_cost[WF_CLASSES] = {7, 3, 5, 6, 1, 2, 4, 0};
+            const int order_by_cost[WF_CLASSES] = {7, 3, 5, 6, 1, 2, 4, 0, (int)WF_MISS};
             uint32_t run = 0;
 #pragma unroll
             for (int k = 0; k < WF_CLASSES; ++k) { const int c = order_by_cost[k]; sm.off[c] = run; run += sm.cnt[c]; }
@@ -250,6 +268,14 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
             const uint32_t fl = sm.u[U_FLAGS][i];
             p.bounce = (fl >> 8) & 0xffffu;
             const int prim = (int)sm.u[U_PRIM][i];
+            if (prim < 0) {                                             // WF_MISS entry: background, path ends (tracer.rs:66-69)
+                path_add_sky(s, p);
+                if (COUNT) pc.end_sky++;
+                sm.f[F_AX][i] += p.rad.x; sm.f[F_AY][i] += p.rad.y; sm.f[F_AZ][i] += p.rad.z;
+                sm.u[U_SIDX][i] = sm.u[U_SIDX][i] + 1u;
+                sm.u[U_FLAGS][i] = fl & ~FL_ALIVE;
+                continue;
+            }
             const uint64_t accepted = (uint64_t)sm.u[U_ACC_LO][i] | ((uint64_t)sm.u[U_ACC_HI][i] << 32);
             const uint32_t sidx = sm.u[U_SIDX][i];
             Rng<R> rng(sm.u[U_PIX][i], a.sample_base + sidx, a.seed);
