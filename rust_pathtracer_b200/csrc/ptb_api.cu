@@ -42,14 +42,16 @@ static int fail(int code, const char* fmt, ...) {
 template <class R> struct SceneBuffers {
     DScene<R> d{};
     void* blob = nullptr; void* bvh = nullptr; void* bvh_prim = nullptr; void* bvh_spheres = nullptr;
+    void* lbvh = nullptr; void* lbvh_prim = nullptr; void* lbvh_spheres = nullptr;
+    size_t cap_lbvh = 0, cap_lprim = 0, cap_lspheres = 0;
     size_t cap_blob = 0, cap_bvh = 0, cap_prim = 0, cap_spheres = 0;   // allocations are reused across set_scene calls:
     size_t bytes = 0;                                                  // cudaFree would synchronise the whole device
     void release() {
-        for (void** p : {&blob, &bvh, &bvh_prim, &bvh_spheres}) {
+        for (void** p : {&blob, &bvh, &bvh_prim, &bvh_spheres, &lbvh, &lbvh_prim, &lbvh_spheres}) {
             if (*p) cudaFree(*p);
             *p = nullptr;
         }
-        cap_blob = cap_bvh = cap_prim = cap_spheres = 0;
+        cap_blob = cap_bvh = cap_prim = cap_spheres = cap_lbvh = cap_lprim = cap_lspheres = 0;
         bytes = 0;
     }
 };
@@ -252,28 +254,48 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         o.type = l.type; o.pad[0] = o.pad[1] = o.pad[2] = 0;
     }
 
-    // BVH
-    std::vector<BvhNode> nodes;
-    std::vector<uint32_t> prim;
-    if (use_bvh) {
+    // BVH over the spheres, and over the spherical lights when there are many (binned SAH, f32 bounds rounded outward)
+    auto build_bvh = [](size_t n, auto center_of, auto radius_of, std::vector<BvhNode>& nodes_out, std::vector<uint32_t>& prim_out) {
         BvhBuilder b;
-        b.pbox.resize(sc->n_spheres); b.pcen.resize(3 * (size_t)sc->n_spheres); b.prim.resize(sc->n_spheres);
-        for (uint32_t i = 0; i < sc->n_spheres; ++i) {
+        b.pbox.resize(n); b.pcen.resize(3 * n); b.prim.resize(n);
+        for (size_t i = 0; i < n; ++i) {
             for (int k = 0; k < 3; ++k) {
-                double c = (double)sc->spheres[i].center[k], r = std::fabs((double)sc->spheres[i].radius);
-                // outward-rounded f32 bounds with a small relative pad
+                double c = center_of(i, k), r = std::fabs(radius_of(i));
                 float lo = (float)(c - r), hi = (float)(c + r);
                 lo = std::nextafterf(lo - std::fabs(lo) * 1e-6f, -3e38f);
                 hi = std::nextafterf(hi + std::fabs(hi) * 1e-6f, 3e38f);
-                b.pbox[i].lo[k] = lo; b.pbox[i].hi[k] = hi; b.pcen[3 * (size_t)i + k] = (float)c;
+                b.pbox[i].lo[k] = lo; b.pbox[i].hi[k] = hi; b.pcen[3 * i + k] = (float)c;
             }
-            b.prim[i] = i;
+            b.prim[i] = (uint32_t)i;
         }
-        b.nodes.reserve(2 * (size_t)sc->n_spheres);
+        b.nodes.reserve(2 * n + 1);
         b.nodes.push_back(BvhNode{});
-        b.build_node(0, 0, sc->n_spheres);
-        nodes.swap(b.nodes);
-        prim.swap(b.prim);
+        b.build_node(0, 0, (uint32_t)n);
+        nodes_out.swap(b.nodes);
+        prim_out.swap(b.prim);
+    };
+    std::vector<BvhNode> nodes;
+    std::vector<uint32_t> prim;
+    if (use_bvh)
+        build_bvh(sc->n_spheres, [&](size_t i, int k) { return (double)sc->spheres[i].center[k]; },
+                  [&](size_t i) { return (double)sc->spheres[i].radius; }, nodes, prim);
+    std::vector<BvhNode> lnodes;
+    std::vector<uint32_t> lprim;
+    std::vector<DSphere<R>> lleaf;
+    {
+        std::vector<uint32_t> sph_lights;          // indices of the spherical lights (others are never hit, scene.rs:69)
+        for (uint32_t i = 0; i < sc->n_lights; ++i)
+            if (sc->lights[i].type == PTB_LIGHT_SPHERICAL) sph_lights.push_back(i);
+        if (sph_lights.size() >= 16) {
+            build_bvh(sph_lights.size(), [&](size_t i, int k) { return (double)sc->lights[sph_lights[i]].position[k]; },
+                      [&](size_t i) { return (double)sc->lights[sph_lights[i]].radius; }, lnodes, lprim);
+            lleaf.resize(lprim.size());
+            for (size_t i = 0; i < lprim.size(); ++i) {
+                const auto& l = sc->lights[sph_lights[lprim[i]]];
+                lleaf[i] = DSphere<R>{l.position[0], l.position[1], l.position[2], l.radius};
+                lprim[i] = sph_lights[lprim[i]];     // leaf order -> light index
+            }
+        }
     }
 
     // pack the arrays into one blob (16-byte aligned sections) so a CTA stages it with one loop
@@ -302,6 +324,9 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     std::vector<DSphere<R>> leaf_spheres(prim.size());
     for (size_t i = 0; i < prim.size(); ++i) leaf_spheres[i] = spheres[prim[i]];
     CU(upload_vec(&sb.bvh_spheres, sb.cap_spheres, leaf_spheres, t->stream, sb.bytes));
+    CU(upload_vec(&sb.lbvh, sb.cap_lbvh, lnodes, t->stream, sb.bytes));
+    CU(upload_vec(&sb.lbvh_prim, sb.cap_lprim, lprim, t->stream, sb.bytes));
+    CU(upload_vec(&sb.lbvh_spheres, sb.cap_lspheres, lleaf, t->stream, sb.bytes));
     CU(cudaStreamSynchronize(t->stream));   // host vectors go out of scope
 
     const char* base = (const char*)sb.blob;
@@ -312,6 +337,9 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     d.materials = (const DMaterial<R>*)(base + d.off_materials); d.lights = (const DLight<R>*)(base + d.off_lights);
     d.bvh = use_bvh ? (const BvhNode*)sb.bvh : nullptr; d.bvh_prim = (const uint32_t*)sb.bvh_prim;
     d.bvh_spheres = (const DSphere<R>*)sb.bvh_spheres;
+    d.light_bvh = lnodes.empty() ? nullptr : (const BvhNode*)sb.lbvh;
+    d.light_bvh_spheres = (const DSphere<R>*)sb.lbvh_spheres;
+    d.light_bvh_prim = (const uint32_t*)sb.lbvh_prim;
     for (int k = 0; k < 3; ++k) { d.light_lo[k] = 3e38f; d.light_hi[k] = -3e38f; }
     for (const auto& l : lights) {
         if (l.type != PTB_LIGHT_SPHERICAL) continue;

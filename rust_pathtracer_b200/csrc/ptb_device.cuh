@@ -209,6 +209,9 @@ template <class R> struct DScene {
     const uint32_t* bvh_prim;           // sphere indices in leaf order
     const DSphere<R>* bvh_spheres;      // the spheres themselves in leaf order (leaf = one contiguous read)
     float light_lo[3], light_hi[3];     // bounding box of all spherical lights (cull for sample_lights)
+    const BvhNode* light_bvh;           // BVH over the spherical lights (NULL below 16 lights: linear scan as in scene.rs:68)
+    const DSphere<R>* light_bvh_spheres;
+    const uint32_t* light_bvh_prim;
     uint32_t use_bvh;
     uint32_t has_emissive;              // 1 if any material has non-zero emission
     uint32_t patch_materials;           // 1 if any set_mask != PTB_MAT_ALL (order-dependent patching)
@@ -430,7 +433,8 @@ PTB_DEV BvhNode load_node(const BvhNode* p) {
 // first hit within max_dist returns.  Closest mode keeps the reference's tie rule (ascending index,
 // strict `d < dist` => the lowest sphere index wins equal distances).  Returns the sphere index or -1.
 template <class R, bool ANY>
-PTB_DEV int bvh_traverse(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
+PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __restrict__ leaf_spheres, const uint32_t* __restrict__ leaf_prim,
+                         V3<R> o, V3<R> d, R& best_t) {
     int best = -1;
     RayF r;
     r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
@@ -439,24 +443,24 @@ PTB_DEV int bvh_traverse(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
     uint32_t stack_n[STACK];
     float stack_t[STACK];
     int sp = 0;
-    BvhNode root = load_node(s.bvh);
+    BvhNode root = load_node(nodes);
     if (box_entry(root.lo, root.hi, r, (float)best_t) >= 3.0e38f) return -1;
     uint32_t cur_lf = root.left_or_first, cur_cnt = root.count;
     while (true) {
         if (cur_cnt) {
             for (uint32_t i = 0; i < cur_cnt; ++i) {
-                const DSphere<R> sph = s.bvh_spheres[cur_lf + i];
+                const DSphere<R> sph = leaf_spheres[cur_lf + i];
                 R t = isect_sphere(o, d, V3<R>(sph.cx, sph.cy, sph.cz), sph.r);
                 if (t >= R(0)) {
-                    if (ANY) { if (t < best_t) return (int)s.bvh_prim[cur_lf + i]; }
+                    if (ANY) { if (t < best_t) return (int)leaf_prim[cur_lf + i]; }
                     else {
-                        const int si = (int)s.bvh_prim[cur_lf + i];
+                        const int si = (int)leaf_prim[cur_lf + i];
                         if (t < best_t || (t == best_t && si < best)) { best_t = t; best = si; }
                     }
                 }
             }
         } else {
-            const BvhNode a = load_node(s.bvh + cur_lf), b = load_node(s.bvh + cur_lf + 1);
+            const BvhNode a = load_node(nodes + cur_lf), b = load_node(nodes + cur_lf + 1);
             const float ta = box_entry(a.lo, a.hi, r, (float)best_t), tb = box_entry(b.lo, b.hi, r, (float)best_t);
             const bool ha = ta < 3.0e38f, hb = tb < 3.0e38f;
             if (ha || hb) {
@@ -475,7 +479,7 @@ PTB_DEV int bvh_traverse(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
         while (sp > 0) {
             --sp;
             if (stack_t[sp] <= (float)best_t) {
-                const BvhNode n = load_node(s.bvh + stack_n[sp]);
+                const BvhNode n = load_node(nodes + stack_n[sp]);
                 cur_lf = n.left_or_first; cur_cnt = n.count;
                 found = true;
                 break;
@@ -485,10 +489,12 @@ PTB_DEV int bvh_traverse(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
     }
     return best;
 }
-template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) { return bvh_traverse<R, false>(s, o, d, best_t); }
+template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
+    return bvh_traverse<R, false>(s.bvh, s.bvh_spheres, s.bvh_prim, o, d, best_t);
+}
 template <class R> PTB_DEV bool bvh_any(const DScene<R>& s, V3<R> o, V3<R> d, R max_dist, bool ignore_max) {
     R limit = ignore_max ? Const<R>::MAXV : max_dist;
-    return bvh_traverse<R, true>(s, o, d, limit) >= 0;
+    return bvh_traverse<R, true>(s.bvh, s.bvh_spheres, s.bvh_prim, o, d, limit) >= 0;
 }
 
 // Scene::closest_hit for the exported scene, geometry part (analytical.rs:36-127 + scene.rs:36-86):
@@ -545,6 +551,11 @@ PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, 
         r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
         r.idx = 1.0f / (float)d.x; r.idy = 1.0f / (float)d.y; r.idz = 1.0f / (float)d.z;
         if (box_entry(s.light_lo, s.light_hi, r, (float)ldist) >= 3.0e38f) n_test = 0u;
+    }
+    if (n_test && s.light_bvh) {
+        // many lights: same traversal, same tie rule (ascending index, strict `d < dist`) as the sphere BVH
+        lbest = bvh_traverse<R, false>(s.light_bvh, s.light_bvh_spheres, s.light_bvh_prim, o, d, ldist);
+        n_test = 0u;
     }
 #pragma unroll 1
     for (uint32_t i = 0; i < n_test; ++i) {

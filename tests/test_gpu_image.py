@@ -368,3 +368,40 @@ def test_wavefront_bvh_and_rr(rp):
         img[name] = buf.pixels.copy()
         pt.close()
     assert (pix_rel(img["wave"], img["fused"]) < 1e-5).mean() > 0.99
+
+
+def test_light_bvh_matches_linear_scan(rp, po):
+    """>= 16 spherical lights switch Scene::sample_lights (scene.rs:36-86) from the linear scan to a light BVH"""
+    sc = rp.sphere_field_scene(n_spheres=200, n_lights_side=5)       # 25 lights
+    export = sc.device_export()
+    dev = DeviceFns(rp, export)
+    osc = po.OracleScene(export)                                       # linear scan over the lights
+    rng = np.random.default_rng(5)
+    n = 40000
+    o = np.stack([rng.uniform(-60, 60, n), rng.uniform(0, 8, n), rng.uniform(-120, 0, n)]).astype(np.float32)
+    # aim most rays at a random light so that plenty of them hit one
+    L = np.array([[*l.light.position] for l in export.lights], np.float64)
+    tgt = L[rng.integers(0, len(L), n)].T + rng.normal(scale=0.35, size=(3, n))
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=0)
+    d = d.astype(np.float32)
+    hd = rng.choice([-1.0, 5.0, 1e30], size=n, p=[0.1, 0.2, 0.7]).astype(np.float32)
+    ref, got = osc.closest_hit(o, d, hd), dev.closest_hit(o, d, hd)
+    same = (ref["hit"] == got["hit"]) & (ref["is_emitter"] == got["is_emitter"])
+    assert (~same).sum() <= 5
+    em = same & (ref["is_emitter"] == 1)
+    assert em.sum() > 5000
+    assert (np.abs(got["hit_dist"][em] - ref["hit_dist"][em]) / np.maximum(ref["hit_dist"][em], 1.0)).max() < 2e-5
+    assert np.array_equal(got["light_emission"][:, em], ref["light_emission"][:, em])
+    well = em & (ref["light_pdf"] < 1e6)
+    assert np.percentile(np.abs(got["light_pdf"][well] / ref["light_pdf"][well] - 1), 99) < 1e-4
+    assert np.array_equal(got["hit_dist"][same & (ref["hit"] == 0)], hd[same & (ref["hit"] == 0)])
+    dev.close()
+    # and at image level against the oracle
+    W, H, S = 80, 45, 2
+    pt = rp.Tracer.new(sc)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render_spp(buf, S)
+    ref_img, _, _, _ = osc.render(W, H, S)
+    assert (pix_rel(buf.pixels, ref_img) < 1e-4).mean() >= 0.95
+    pt.close()
