@@ -276,9 +276,10 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     };
     std::vector<BvhNode> nodes;
     std::vector<uint32_t> prim;
-    if (use_bvh)
+    auto build_sphere_bvh = [&]() {
         build_bvh(sc->n_spheres, [&](size_t i, int k) { return (double)sc->spheres[i].center[k]; },
                   [&](size_t i) { return (double)sc->spheres[i].radius; }, nodes, prim);
+    };
     std::vector<BvhNode> lnodes;
     std::vector<uint32_t> lprim;
     std::vector<DSphere<R>> lleaf;
@@ -286,7 +287,9 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         std::vector<uint32_t> sph_lights;          // indices of the spherical lights (others are never hit, scene.rs:69)
         for (uint32_t i = 0; i < sc->n_lights; ++i)
             if (sc->lights[i].type == PTB_LIGHT_SPHERICAL) sph_lights.push_back(i);
-        if (sph_lights.size() >= 16) {
+        // the light BVH lives in the BVH kernels only: scenes with partial material masks (no sphere BVH possible) keep the linear scan
+        if (sph_lights.size() >= 16 && !patch && sc->n_spheres > 0 && !(sc->flags & PTB_SCENE_NO_BVH)) {
+            use_bvh = true;
             build_bvh(sph_lights.size(), [&](size_t i, int k) { return (double)sc->lights[sph_lights[i]].position[k]; },
                       [&](size_t i) { return (double)sc->lights[sph_lights[i]].radius; }, lnodes, lprim);
             lleaf.resize(lprim.size());
@@ -297,6 +300,7 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
             }
         }
     }
+    if (use_bvh) build_sphere_bvh();
 
     // pack the arrays into one blob (16-byte aligned sections) so a CTA stages it with one loop
     std::vector<unsigned char> blob;

@@ -552,7 +552,7 @@ PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, 
         r.idx = 1.0f / (float)d.x; r.idy = 1.0f / (float)d.y; r.idz = 1.0f / (float)d.z;
         if (box_entry(s.light_lo, s.light_hi, r, (float)ldist) >= 3.0e38f) n_test = 0u;
     }
-    if (n_test && s.light_bvh) {
+    if (BVH && n_test && s.light_bvh) {      // (only the BVH kernels carry traversal code and its stack)
         // many lights: same traversal, same tie rule (ascending index, strict `d < dist`) as the sphere BVH
         lbest = bvh_traverse<R, false>(s.light_bvh, s.light_bvh_spheres, s.light_bvh_prim, o, d, ldist);
         n_test = 0u;
