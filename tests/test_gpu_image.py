@@ -121,6 +121,11 @@ def test_statistical_parity_4096spp(rp, scene, po, demo_export):
         ref, _, _, _ = osc.render(W, H, B, sample_base=k * B)
         ob.append(ref.reshape(-1, 4)[:, :3].astype(np.float64))
     gb, ob = np.stack(gb), np.stack(ob)
+    # the reference never filters NaN radiance: an exactly grazing clearcoat hit gives 0/0 (tracer.rs:414-418) about once
+    # per 6e8 samples and poisons the pixel; which sample does it hangs on the last bit, so compare the finite pixels
+    finite = np.isfinite(gb).all((0, 2)) & np.isfinite(ob).all((0, 2))
+    assert finite.mean() > 0.999
+    gb, ob = gb[:, finite], ob[:, finite]
     gm, om = gb.mean(0), ob.mean(0)
     w = np.array([0.212671, 0.715160, 0.072169])
     lg, lo = gm @ w, om @ w
