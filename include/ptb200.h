@@ -171,7 +171,7 @@ typedef struct ptb_config {
     uint32_t integrator;      /* PTB_INTEGRATOR_*                                                 */
     uint64_t seed;            /* base seed of the counter RNG (0 in all parity tests)             */
     uint32_t rr_start;        /* Russian-roulette start bounce; 0 = off (reference has none, A.12)*/
-    uint32_t wave_paths;      /* wavefront: paths per wave (0 = default 1<<20)                    */
+    uint32_t wave_paths;      /* reserved, must be 0 (the wavefront pool is fixed: 2048 path slots/SM)*/
     uint32_t bvh_threshold;   /* sphere count from which the BVH is used (0 = default 64)         */
     uint32_t collect_counters;/* 1 = count closest_hit/any_hit/lobe/ending events (slower)        */
 } ptb_config;

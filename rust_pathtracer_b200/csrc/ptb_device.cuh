@@ -40,8 +40,6 @@ PTB_DEV float m_log2(float a) { return log2f(a); }
 PTB_DEV double m_log2(double a) { return log2(a); }
 PTB_DEV float m_floor(float a) { return floorf(a); }
 PTB_DEV double m_floor(double a) { return floor(a); }
-PTB_DEV float m_fmod(float a, float b) { return fmodf(a, b); }
-PTB_DEV double m_fmod(double a, double b) { return fmod(a, b); }
 // IEEE division where a branch decision hangs on the last bit (checker cell, film coordinates)
 PTB_DEV float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 PTB_DEV double div_rn(double a, double b) { return a / b; }

@@ -5,9 +5,9 @@
 // Why shared memory: the demo scene costs ~1.4 kFLOP and ~2 bounces per sample.
 // A classic HBM wavefront streams ~1 KB of ray / path state per sample through the queues, which
 // caps it at ~6 Gsamples/s on a 6.5 TB/s part before any arithmetic is done (SURVEY.md §7 "the
-// roofline that actually binds").  One SM can hold 2048 paths x 88 B = 176 KB of state, enough for
-// every stage to run with full warps, so the state never leaves the SM: HBM traffic stays at the
-// 32 B per pixel of the accumulator read-modify-write.
+// roofline that actually binds").  One SM can hold 2048 paths x 96 B = 192 KB of state (221 KB with the
+// queue arrays and the scene copy), enough for every stage to run with full warps, so the state never
+// leaves the SM: HBM traffic stays at the 32 B per pixel of the accumulator read-modify-write.
 //
 // One CTA (512 threads) per SM owns a pool of P = 2048 path slots.  Each iteration runs two stages
 // over the pool, separated by CTA barriers, so that ALL warps of the SM execute the same stage code
@@ -16,14 +16,15 @@
 //   stage 1  "generate + intersect"  — every slot: a finished slot regenerates in place (next
 //            sample of its pixel, or a new pixel handed out per warp with ballot/popc from a global
 //            tile counter), then camera-ray generation / closest_hit (+ spherical lights with the
-//            stale hit_dist quirk), background lookup on a miss, MIS-weighted emission on a light
-//            hit.  Paths that hit geometry enter the shading queue: they take a ticket in the
-//            counter of their LOBE CLASS (which Disney lobes their material can express).
-//   sort     a counting sort by lobe class turns the tickets into a compacted, class-ordered index
-//            list (the queue proper).
-//   stage 2  "shade" — threads walk the queue in order, so a warp shades paths of one lobe class:
-//            finalize, light sampling + any_hit shadow ray, Disney eval with MIS, Disney sample,
-//            throughput update, next ray (or termination).
+//            stale hit_dist quirk), MIS-weighted emission on a light hit.  Surviving paths enter the
+//            stage-2 queue: they take a ticket in the counter of their key — the LOBE CLASS of the
+//            hit material (which Disney lobes it can express) or WF_MISS (the path left the scene).
+//   sort     a counting sort by key turns the tickets into a compacted, key-ordered index list
+//            (the queue proper), most expensive classes first.
+//   stage 2  "shade" — warps take 32-entry chunks of the queue, so a warp shades paths of one lobe
+//            class: finalize, light sampling + any_hit shadow ray, Disney eval with MIS, Disney
+//            sample, throughput update, next ray (or termination); WF_MISS chunks do the background
+//            lookup with full warps.
 //
 // A slot owns one pixel for `spp` consecutive samples and sums them in sample order, so the image is
 // bit-reproducible run to run, exactly like the fused integrator.
