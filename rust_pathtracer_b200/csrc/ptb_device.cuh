@@ -508,14 +508,12 @@ template <class R> struct HitCore {
     V3<R> light_emission;  // light_sample.emission
 };
 
+// sphere part of closest_hit: the closest sphere (index, distance) — the part a dedicated traversal kernel can run
 template <class R, bool BVH>
-PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in) {
-    HitCore<R> h;
-    h.hit = false; h.is_emitter = false; h.geom = false; h.hit_dist = hit_dist_in;
-    h.light_pdf = 0; h.light_emission = V3<R>(0, 0, 0);
-    R dist = Const<R>::MAXV;
-    int best = -1;
-    uint64_t accepted = 0;
+PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, int& best, R& dist, uint64_t& accepted) {
+    dist = Const<R>::MAXV;
+    best = -1;
+    accepted = 0;
     if (BVH) {
         best = bvh_closest(s, o, d, dist);
     } else {
@@ -528,6 +526,15 @@ PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, 
             }
         }
     }
+}
+
+// the rest of closest_hit given the sphere result: planes, then Scene::sample_lights
+template <class R, bool BVH>
+PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, int best, R dist,
+                                      uint64_t accepted) {
+    HitCore<R> h;
+    h.hit = false; h.is_emitter = false; h.geom = false; h.hit_dist = hit_dist_in;
+    h.light_pdf = 0; h.light_emission = V3<R>(0, 0, 0);
 #pragma unroll 1
     for (uint32_t i = 0; i < s.n_planes; ++i) {
         DPlane<R> pl = sv.planes[i];
@@ -576,6 +583,15 @@ PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, 
 }
 
 // normal of primitive `prim` at distance t along (o, d): analytical.rs:45-46 (sphere), :105 (plane)
+template <class R, bool BVH>
+PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in) {
+    int best;
+    R dist;
+    uint64_t accepted;
+    closest_spheres<R, BVH>(s, sv, o, d, best, dist, accepted);
+    return closest_hit_finish<R, BVH>(s, sv, o, d, hit_dist_in, best, dist, accepted);
+}
+
 template <class R, bool BVH>
 PTB_DEV V3<R> hit_normal(const DScene<R>& s, const SceneView<R>& sv, int prim, V3<R> o, V3<R> d, R t) {
     if ((uint32_t)prim < s.n_spheres) {
@@ -680,11 +696,12 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
     return h;
 }
 
-// Scene::any_hit, analytical.rs:130-145 (+ max_dist unless the scene flag says the impl ignores it)
-template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+// Scene::any_hit, analytical.rs:130-145 (+ max_dist unless the scene flag says the impl ignores it), in two parts
+// so that a dedicated traversal kernel can run the sphere part
+template <class R, bool BVH> PTB_DEV bool any_hit_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
     const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
-    if (BVH) {
-        if (bvh_any(s, o, d, max_dist, ignore)) return true;
+    if constexpr (BVH) {
+        return bvh_any(s, o, d, max_dist, ignore);
     } else {
 #pragma unroll 1
         for (uint32_t i = 0; i < s.n_spheres; ++i) {
@@ -692,7 +709,11 @@ template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const Scen
             R t = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
             if (t >= R(0) && (ignore || t < max_dist)) return true;
         }
+        return false;
     }
+}
+template <class R> PTB_DEV bool any_hit_planes(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+    const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
 #pragma unroll 1
     for (uint32_t i = 0; i < s.n_planes; ++i) {
         DPlane<R> pl = sv.planes[i];
@@ -700,6 +721,9 @@ template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const Scen
         if (t >= R(0) && (ignore || t < max_dist)) return true;
     }
     return false;
+}
+template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+    return any_hit_spheres<R, BVH>(s, sv, o, d, max_dist) || any_hit_planes(s, sv, o, d, max_dist);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1065,37 +1089,50 @@ template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, 
     p.bounce = 0;
 }
 
-// Second half of a bounce, tracer.rs:72-101 for a path that hit geometry (not a light): finalize,
-// next-event estimation, BSDF sampling, throughput update, next ray.  `normal` is the geometric
-// normal, `mat` the un-finalized material at the hit.  `u` holds the 8 slot draws of this bounce.
-// Returns true while the path continues.
-template <class R, bool COUNT, bool BVH>
-PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, Mat<R>& mat, const R* u, PathCounters* pc) {
+// Second half of a bounce, tracer.rs:72-101, for a path that hit geometry (not a light), in three pieces so that
+// the global-memory wavefront can run the shadow ray in its own kernel between them:
+//   shade_setup       finalize (globals.rs:50-62), emission (tracer.rs:74), shading frame / specular colours
+//   shade_nee_sample  direct_light up to the shadow ray (tracer.rs:131-150): light pick, light sample, cull
+//   shade_finish      disney_eval + MIS towards the light (tracer.rs:155-164), disney_sample (92-97), next ray (100-101)
+template <class R> struct ShadeSetup {
     V3<R> fhp, ffn;
     R eta;
-    state_finalize(p.o, p.d, p.hit_dist, normal, mat, fhp, ffn, eta);
+    ShadeCtx<R> c;
+};
+template <class R> struct NeeSample {
+    bool wants_shadow_ray;     // the sample passed the back-face cull: visibility decides whether it contributes
+    LightSample<R> ls;
+    R light_area;
+    V3<R> scatter_pos;
+};
+
+template <class R, bool COUNT>
+PTB_DEV void shade_setup(const DScene<R>& s, PathState<R>& p, V3<R> normal, Mat<R>& mat, ShadeSetup<R>& su, PathCounters* pc) {
+    state_finalize(p.o, p.d, p.hit_dist, normal, mat, su.fhp, su.ffn, su.eta);
     p.rad = p.rad + mat.emission * p.thr;                       // tracer.rs:74
     if (COUNT) pc->shade++;
+    shade_ctx_init(su.c, mat, su.eta, su.ffn, -p.d);
+}
 
-    ShadeCtx<R> c;
-    shade_ctx_init(c, mat, eta, ffn, -p.d);
-
-    // direct_light, tracer.rs:126-170 — light sample, cull, shadow ray
-    bool nee = false;
-    LightSample<R> ls;
-    R light_area = 0;
+template <class R>
+PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const ShadeSetup<R>& su, const R* u, NeeSample<R>& ns) {
+    ns.wants_shadow_ray = false;
+    ns.light_area = 0;
     if (s.n_lights > 0) {
         uint32_t li = (uint32_t)(u[2] * s.n_lights_f);          // tracer.rs:137-139
-        V3<R> scatter_pos = fhp + s.eps * ffn;
+        ns.scatter_pos = su.fhp + s.eps * su.ffn;
         const DLight<R> L = sv.lights[li];
-        ls = sample_light(L, s.n_lights_f, scatter_pos, u[3], u[4]);
-        light_area = L.area;
-        if (L.type == PTB_LIGHT_SPHERICAL && dot(ls.direction, ls.normal) < R(0)) {
-            if (COUNT) pc->any_hit++;
-            nee = !any_hit<R, BVH>(s, sv, scatter_pos, ls.direction, ls.dist - s.eps);
-        }
+        ns.ls = sample_light(L, s.n_lights_f, ns.scatter_pos, u[3], u[4]);
+        ns.light_area = L.area;
+        ns.wants_shadow_ray = L.type == PTB_LIGHT_SPHERICAL && dot(ns.ls.direction, ns.ls.normal) < R(0);   // tracer.rs:148
     }
+}
 
+// `nee`: the light sample is visible (passed the cull and the shadow ray).  Returns true while the path continues.
+template <class R, bool COUNT>
+PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat, const ShadeSetup<R>& su, bool nee, const LightSample<R>& ls,
+                          R light_area, const R* u, PathCounters* pc) {
+    const ShadeCtx<R>& c = su.c;
     // BSDF evaluation, ONE copy of the lobe code for both uses:
     //   pass 0 = disney_eval towards the light sample (tracer.rs:155), only for un-shadowed lanes;
     //   pass 1 = disney_sample (tracer.rs:92); stale `l` = previous sampled direction = ray dir (A.5)
@@ -1137,7 +1174,7 @@ PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>
     p.thr = p.thr * div_s(f, pdf);
     p.prev_pdf = pdf;
     p.d = l;                                                    // tracer.rs:100-101
-    p.o = fhp + s.eps * l;
+    p.o = su.fhp + s.eps * l;
     p.bounce++;
     if (p.bounce >= s.depth) {
         if (COUNT) pc->end_depth++;
@@ -1146,6 +1183,20 @@ PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>
     return true;
 }
 
+// the three pieces in one go (fused integrator, shared-memory wavefront)
+template <class R, bool COUNT, bool BVH>
+PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, Mat<R>& mat, const R* u, PathCounters* pc) {
+    ShadeSetup<R> su;
+    shade_setup<R, COUNT>(s, p, normal, mat, su, pc);
+    NeeSample<R> ns;
+    shade_nee_sample(s, sv, su, u, ns);
+    bool nee = false;
+    if (ns.wants_shadow_ray) {
+        if (COUNT) pc->any_hit++;
+        nee = !any_hit<R, BVH>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
+    }
+    return shade_finish<R, COUNT>(s, p, mat, su, nee, ns.ls, ns.light_area, u, pc);
+}
 
 // Russian roulette EXTENSION at the start of bounce > 0 (the reference has none, quirk A.12; off in
 // every parity run): survival probability from the throughput (GLSL-PathTracer's rule), decided by
