@@ -96,8 +96,11 @@ enum {
 enum {
     PTB_INTEGRATOR_AUTO      = 0, /* wavefront for f32 scenes, fused for f64                        */
     PTB_INTEGRATOR_FUSED     = 1, /* persistent per-lane path loop with in-register regeneration   */
-    PTB_INTEGRATOR_WAVEFRONT = 2  /* SoA path-state queues in shared memory, one stage per kind of
+    PTB_INTEGRATOR_WAVEFRONT = 2, /* SoA path-state queues in shared memory, one stage per kind of
                                      work, queue sorted by lobe class between stages (f32 only)     */
+    PTB_INTEGRATOR_STREAM    = 3  /* SoA ray / path-state queues in HBM, one KERNEL per kind of work
+                                     (generate, closest_hit, shade per lobe class, any_hit,
+                                     accumulate), ballot/popc compaction between them (f32 only)    */
 };
 
 /* ---- POD scene description, declared once per precision ----------------------------------- */
@@ -171,7 +174,7 @@ typedef struct ptb_config {
     uint32_t integrator;      /* PTB_INTEGRATOR_*                                                 */
     uint64_t seed;            /* base seed of the counter RNG (0 in all parity tests)             */
     uint32_t rr_start;        /* Russian-roulette start bounce; 0 = off (reference has none, A.12)*/
-    uint32_t wave_paths;      /* reserved, must be 0 (the wavefront pool is fixed: 2048 path slots/SM)*/
+    uint32_t wave_paths;      /* STREAM integrator: paths carried per wave (0 = default 8 Mi)      */
     uint32_t bvh_threshold;   /* sphere count from which the BVH is used (0 = default 64)         */
     uint32_t collect_counters;/* 1 = count closest_hit/any_hit/lobe/ending events (slower)        */
 } ptb_config;

@@ -17,7 +17,7 @@ PTB_ALBEDO_CONSTANT, PTB_ALBEDO_CHECKER_DIR_RATIO = 0, 1
 PTB_LIGHT_RECTANGULAR, PTB_LIGHT_SPHERICAL, PTB_LIGHT_DISTANT = 0, 1, 2
 PTB_BG_CONSTANT, PTB_BG_GRADIENT_Y = 0, 1
 PTB_SCENE_ANYHIT_IGNORES_MAX_DIST, PTB_SCENE_FORCE_BVH, PTB_SCENE_NO_BVH = 1, 2, 4
-PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT = 0, 1, 2
+PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT, PTB_INTEGRATOR_STREAM = 0, 1, 2, 3
 
 PTB_MAT_RGB, PTB_MAT_EMISSION, PTB_MAT_ANISOTROPIC, PTB_MAT_METALLIC = 1 << 0, 1 << 1, 1 << 2, 1 << 3
 PTB_MAT_ROUGHNESS, PTB_MAT_SUBSURFACE, PTB_MAT_SPECULAR_TINT, PTB_MAT_SHEEN = 1 << 4, 1 << 5, 1 << 6, 1 << 7

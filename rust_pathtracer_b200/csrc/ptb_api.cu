@@ -16,6 +16,7 @@
 #include "../../include/ptb200.h"
 #include "ptb_kernels.cuh"
 #include "ptb_wavefront.cuh"
+#include "ptb_stream.cuh"
 
 using namespace ptb;
 
@@ -84,6 +85,7 @@ struct ptb_tracer {
     int sm_count = 0;
     int fused_blocks_f32 = 0, fused_blocks_f64 = 0;
     WavefrontState wf;
+    StreamState st;
 };
 
 static size_t real_size(const ptb_tracer* t) { return (size_t)t->precision; }
@@ -416,7 +418,7 @@ int ptb_create(const ptb_config* cfg, ptb_tracer** out) {
     ptb_config c{};
     if (cfg) c = *cfg;
     if (c.device < 0 || c.device >= n) return fail(PTB_E_NO_DEVICE, "device %d out of range (have %d)", c.device, n);
-    if (c.integrator > PTB_INTEGRATOR_WAVEFRONT) return fail(PTB_E_INVALID, "unknown integrator %u", c.integrator);
+    if (c.integrator > PTB_INTEGRATOR_STREAM) return fail(PTB_E_INVALID, "unknown integrator %u", c.integrator);
     CU(cudaSetDevice(c.device));
     ptb_tracer* t = new ptb_tracer();
     t->cfg = c;
@@ -443,6 +445,7 @@ void ptb_destroy(ptb_tracer* t) {
     t->s32.release();
     t->s64.release();
     t->wf.release();
+    t->st.release();
     if (t->own_accum && t->accum) cudaFree(t->accum);
     if (t->staging) cudaFree(t->staging);
     if (t->work_counter) cudaFree(t->work_counter);
@@ -643,6 +646,12 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
         if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the wavefront integrator is built for f32 only");
         r = wavefront_render(t->wf, t->s32.d, t->accum, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters,
                              t->work_counter, t->ev0, t->ev1, &t->launches, g_err);
+        if (r) return r;
+        t->timed = true;
+    } else if (integ == PTB_INTEGRATOR_STREAM) {
+        if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the streaming wavefront integrator is built for f32 only");
+        r = stream_render(t->st, t->s32.d, t->accum, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters, t->ev0, t->ev1,
+                          &t->launches, g_err);
         if (r) return r;
         t->timed = true;
     } else {

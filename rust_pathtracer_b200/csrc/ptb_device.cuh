@@ -1129,9 +1129,14 @@ PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const 
 }
 
 // `nee`: the light sample is visible (passed the cull and the shadow ray).  Returns true while the path continues.
-template <class R, bool COUNT>
+// DEFER (global-memory wavefront): `nee` only says that the sample passed the cull; the contribution `ld * throughput`
+// (tracer.rs:164 and :89) is handed to `sink(contribution, flags)` instead of being added, and the shadow-ray kernel adds
+// it if the ray turns out unoccluded — the same additions in the same order, without keeping the shading context alive
+// across kernels.  flags: bits 0..3 = lobes evaluated towards the light, bit 4 = pdf > 0 (the sample can contribute).
+struct NoSink { template <class V> PTB_DEV void operator()(V, uint32_t) const {} };
+template <class R, bool COUNT, bool DEFER = false, class Sink = NoSink>
 PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat, const ShadeSetup<R>& su, bool nee, const LightSample<R>& ls,
-                          R light_area, const R* u, PathCounters* pc) {
+                          R light_area, const R* u, PathCounters* pc, const Sink& sink = Sink()) {
     const ShadeCtx<R>& c = su.c;
     // BSDF evaluation, ONE copy of the lobe code for both uses:
     //   pass 0 = disney_eval towards the light sample (tracer.rs:155), only for un-shadowed lanes;
@@ -1144,22 +1149,27 @@ PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat
         if (pass == 0 && !nee) continue;
         LobeQuery<R> q;
         if (pass == 0) {
-            if (COUNT) pc->eval_calls++;
+            if (COUNT && !DEFER) pc->eval_calls++;
             query_for_eval(mat, c, ls.direction, q);
         } else {
             V3<R> l_prev = p.bounce == 0 ? V3<R>(0, 0, 0) : p.d;
             lobe = query_for_sample(mat, c, u[5], u[6], u[7], l_prev, q);
             if (COUNT) pc->lobe[lobe]++;
         }
-        eval_lobes(mat, c, q, f, pdf, COUNT ? pc->ev : (uint32_t*)nullptr);
+        eval_lobes(mat, c, q, f, pdf, COUNT && !(DEFER && pass == 0) ? pc->ev : (uint32_t*)nullptr);
         if (pass == 0) {
             f = m_abs(q.l.z) * f;                                   // tracer.rs:625
             R w = R(1);
             if (light_area > R(0)) w = power_heuristic(ls.pdf, pdf); // tracer.rs:157-160
             if (pdf > R(0)) {                                       // tracer.rs:162-164
                 V3<R> ld = (w * ls.emission) * div_s(f, ls.pdf);
-                p.rad = p.rad + ld * p.thr;
-                if (COUNT) pc->nee_contrib++;
+                if (DEFER) sink(ld * p.thr, q.mask | 16u);
+                else {
+                    p.rad = p.rad + ld * p.thr;
+                    if (COUNT) pc->nee_contrib++;
+                }
+            } else if (DEFER) {
+                sink(V3<R>(0, 0, 0), q.mask);
             }
         } else {
             l_world = to_world(c, q.l);                             // tracer.rs:551-552

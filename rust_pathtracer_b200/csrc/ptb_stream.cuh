@@ -1,0 +1,490 @@
+// ptb_stream.cuh — the global-memory ("streaming") wavefront integrator: one kernel per kind of work
+// over SoA ray / path-state queues in HBM, compacted with warp ballot/popc, persistent warps that pull
+// 32-entry chunks from the queues.
+//
+// The shared-memory wavefront (ptb_wavefront.cuh) keeps a pool of 2048 paths per SM; that is the right
+// shape while the scene fits next to the pool and a bounce costs ~1 kFLOP.  Large BVH scenes (BASELINE
+// configs 4 and 5) are bound by the latency of dependent node fetches instead, and want (a) far more
+// resident warps on the traversal than a 126-register shading kernel allows and (b) shading warps that
+// are full and lobe-coherent although neighbouring rays hit unrelated materials.  Separate kernels give
+// both: the traversal kernels carry only a ray and a stack, the shade kernel runs at its own register
+// budget over per-lobe-class queues.
+//
+// A WAVE is a set of P paths (a range of pixels x S consecutive samples each, at most `wave_paths`),
+// carried through the bounces together; every path owns one slot of the SoA state for the whole wave:
+//
+//   k_stream_generate   camera rays (tracer.rs:34-59)                                      -> ray queue 0
+//   per bounce b:
+//     k_stream_closest  Scene::closest_hit (+ sample_lights) per queued ray; emitter hits are finished
+//                       here; everything else is queued by key = lobe class of the hit material, or
+//                       ST_MISS                                                            -> shade queues
+//     k_stream_shade    per key, full warps: background for ST_MISS; else finalize, light sample,
+//                       Disney eval towards the light (contribution DEFERRED), Disney sample,
+//                       throughput, next ray                                  -> ray queue b+1, shadow queue
+//     k_stream_shadow   Scene::any_hit per queued shadow ray; an unoccluded ray adds its deferred
+//                       contribution to the path's radiance (tracer.rs:150-164)
+//   k_stream_accumulate one thread per pixel sums its S radiances in sample order into the accumulator
+//
+// Queue lengths live in device memory (one BounceCtr per bounce), the host never reads them: every stage
+// is launched with a persistent grid whose warps pull chunks until the queue is drained.  Path results do
+// not depend on queue order and every path / pixel is summed by exactly one thread, so the image is
+// bit-reproducible run to run like the other two integrators'.
+//
+// HBM traffic per path-bounce: closest reads 32 B of ray and writes a 16 B hit record and a 4 B queue
+// entry; shade reads 80 B and writes 48 B of state, 4 B of queue and a 48 B shadow entry; shadow reads
+// 48 B and read-modify-writes 32 B — about 310 B, against the 32 B per PIXEL of the on-chip integrators.
+// That is what caps this design near 6 Gsamples/s on the demo scene and why AUTO uses it
+// only where traversal latency, not arithmetic, is the bound.
+#pragma once
+#include <string>
+
+#include "ptb_kernels.cuh"
+
+namespace ptb {
+
+constexpr int ST_THREADS = 256;
+constexpr uint32_t ST_KEYS = 9;          // 8 lobe classes (lobe_class_of) + ST_MISS
+constexpr uint32_t ST_MISS = 8;          // the path left the scene: background lookup (tracer.rs:66-69)
+constexpr uint32_t ST_DEFAULT_WAVE = 1u << 23;
+
+struct BounceCtr {                       // 128 bytes per bounce, zeroed at the start of a wave
+    uint32_t n_ray;                      // rays entering this bounce
+    uint32_t cur_ray;                    // chunk cursor of k_stream_closest
+    uint32_t n_shade[ST_KEYS];           // shade-queue length per key
+    uint32_t cur_shade;                  // chunk cursor of k_stream_shade
+    uint32_t n_shadow;                   // shadow rays of this bounce
+    uint32_t cur_shadow;                 // chunk cursor of k_stream_shadow
+    uint32_t pad[32 - 14];
+};
+static_assert(sizeof(BounceCtr) == 128, "BounceCtr layout");
+
+struct StreamArgs {
+    // path state, one slot per path of the wave (SoA of float4)
+    float4* a0;          // o.x o.y o.z d.x
+    float4* a1;          // d.y d.z hit_dist prev_pdf
+    float4* a2;          // throughput.xyz, sample index within the wave (bits)
+    float4* a3;          // radiance.xyz, pixel index (bits; 0xffffffff = outside the frame)
+    uint4* hit;          // prim, accepted lo, accepted hi, hit_dist (bits)
+    uint32_t* rayq[2];   // ray queues (slot indices), ping-pong by bounce parity
+    uint32_t* shadeq;    // ST_KEYS queues of `cap` slot indices
+    float4* s0;          // shadow queue: scatter_pos.xyz, max_dist
+    float4* s1;          //               direction.xyz, slot (bits)
+    float4* s2;          //               deferred contribution.xyz, flags (bits 0..3 lobes evaluated, bit 4 pdf > 0)
+    BounceCtr* ctr;
+    float4* accum;
+    uint32_t W, H, tiles_x, n_items;
+    uint32_t pix0, npix; // this wave's range of tiled pixel indices
+    uint32_t S;          // samples per pixel in this wave
+    uint32_t P;          // paths in this wave = npix * S
+    uint32_t cap;        // stride of the shade queues
+    uint64_t sample0;    // global index of the wave's first sample
+    uint64_t seed;
+    uint32_t rr_start;
+    DeviceCounters* counters;
+};
+
+PTB_DEV void pc_clear(PathCounters& pc) {
+    pc.closest_hit = pc.any_hit = pc.shade = pc.nee_contrib = pc.eval_calls = 0;
+    pc.lobe[0] = pc.lobe[1] = pc.lobe[2] = pc.lobe[3] = 0;
+    pc.end_sky = pc.end_emitter = pc.end_pdf = pc.end_depth = pc.end_rr = 0;
+    pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
+}
+PTB_DEV void pc_flush(const PathCounters& pc, uint32_t n_samples, DeviceCounters* c) {
+    auto add = [](unsigned long long* p, uint32_t v) { if (v) atomicAdd(p, (unsigned long long)v); };
+    add(&c->samples, n_samples);
+    add(&c->closest_hit, pc.closest_hit); add(&c->any_hit, pc.any_hit); add(&c->shade, pc.shade);
+    add(&c->nee_contrib, pc.nee_contrib); add(&c->eval_calls, pc.eval_calls);
+    for (int i = 0; i < 4; ++i) { add(&c->lobe[i], pc.lobe[i]); add(&c->ev[i], pc.ev[i]); }
+    add(&c->end_sky, pc.end_sky); add(&c->end_emitter, pc.end_emitter); add(&c->end_pdf, pc.end_pdf);
+    add(&c->end_depth, pc.end_depth); add(&c->end_rr, pc.end_rr);
+}
+
+// warp-aggregated queue push for the lanes that are converged here (any subset of the warp): one atomic per group
+PTB_DEV uint32_t queue_reserve(uint32_t* counter) {
+    const unsigned m = __activemask();
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+// tiled pixel index -> pixel coordinates (16x16 tiles, as the other integrators hand pixels out)
+PTB_DEV bool tiled_pixel(const StreamArgs& a, uint32_t ip, uint32_t& px, uint32_t& prow) {
+    const uint32_t tile = ip >> 8, within = ip & 255u;
+    px = (tile % a.tiles_x) * 16u + (within & 15u);
+    prow = (tile / a.tiles_x) * 16u + (within >> 4);
+    return px < a.W && prow < a.H;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(ST_THREADS) k_stream_generate(const __grid_constant__ DScene<float> s, const StreamArgs a) {
+    using R = float;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const R inv_w = R(1) / (R)a.W, inv_h = R(1) / (R)a.H;
+    bool live = false;
+    if (i < a.P) {
+        const uint32_t il = a.S == 1u ? i : i / a.S;
+        const uint32_t sl = a.S == 1u ? 0u : i - il * a.S;
+        uint32_t px, prow;
+        live = tiled_pixel(a, a.pix0 + il, px, prow);
+        if (live) {
+            const uint32_t pix = prow * a.W + px;
+            Rng<R> rng(pix, a.sample0 + sl, a.seed);
+            R u4[4];
+            rng.block(0, 0, u4);
+            PathState<R> p;
+            path_begin(s, p, px, prow, a.W, a.H, inv_w, inv_h, u4[0], u4[1]);
+            a.a0[i] = make_float4(p.o.x, p.o.y, p.o.z, p.d.x);
+            a.a1[i] = make_float4(p.d.y, p.d.z, p.hit_dist, 0.0f);
+            a.a2[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sl));
+            a.a3[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(pix));
+        } else {
+            a.a3[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xffffffffu));
+        }
+    }
+    if (COUNT) {
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if ((threadIdx.x & 31u) == 0 && m) {
+            atomicAdd(&a.counters->samples, (unsigned long long)__popc(m));
+            if (s.depth == 0) atomicAdd(&a.counters->end_depth, (unsigned long long)__popc(m));
+        }
+    }
+    if (live && s.depth > 0) a.rayq[0][queue_reserve(&a.ctr[0].n_ray)] = i;      // recursion_depth() == 0: no bounce runs (tracer.rs:61)
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT, bool BVH>
+__global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+    using R = float;
+    __shared__ SceneSmem<R> sm;
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
+    BounceCtr& ctr = a.ctr[bounce];
+    const uint32_t n = ctr.n_ray;
+    const uint32_t* __restrict__ q = a.rayq[bounce & 1u];
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    PathCounters pc;
+    if (COUNT) pc_clear(pc);
+
+    while (true) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&ctr.cur_ray, 32u);
+        chunk = __shfl_sync(FULL, chunk, 0);
+        if (chunk >= n) break;
+        const uint32_t j = chunk + lane;
+        uint32_t key = 0xffu, slot = 0;
+        if (j < n) {
+            slot = q[j];
+            const float4 A0 = a.a0[slot], A1 = a.a1[slot];
+            PathState<R> p;
+            p.o = V3<R>(A0.x, A0.y, A0.z);
+            p.d = V3<R>(A0.w, A1.x, A1.y);
+            p.hit_dist = A1.z;
+            p.prev_pdf = A1.w;
+            p.bounce = bounce;
+            bool dead = false;
+            if (a.rr_start != 0 && bounce >= a.rr_start && bounce > 0) {
+                float4 A2 = a.a2[slot];
+                const float4 A3 = a.a3[slot];
+                p.thr = V3<R>(A2.x, A2.y, A2.z);
+                Rng<R> rng(__float_as_uint(A3.w), a.sample0 + __float_as_uint(A2.w), a.seed);
+                R u4[4];
+                rng.block(bounce, 0, u4);
+                if (!russian_roulette_survives(p, u4[0])) { dead = true; if (COUNT) pc.end_rr++; }
+                else { A2.x = p.thr.x; A2.y = p.thr.y; A2.z = p.thr.z; a.a2[slot] = A2; }
+            }
+            if (!dead) {
+                if (COUNT) pc.closest_hit++;
+                const HitCore<R> h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
+                if (!h.hit) {
+                    key = ST_MISS;
+                } else if (h.is_emitter) {
+                    const float4 A2 = a.a2[slot];
+                    float4 A3 = a.a3[slot];
+                    p.thr = V3<R>(A2.x, A2.y, A2.z);
+                    p.rad = V3<R>(A3.x, A3.y, A3.z);
+                    path_add_emitter<R, BVH>(s, sv, p, h);
+                    A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z;
+                    a.a3[slot] = A3;
+                    if (COUNT) pc.end_emitter++;
+                } else {
+                    key = hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
+                    a.hit[slot] = make_uint4((uint32_t)h.prim, (uint32_t)h.accepted, (uint32_t)(h.accepted >> 32), __float_as_uint(h.hit_dist));
+                }
+            }
+        }
+        // queue by key: one atomic per (warp, key)
+        const unsigned peers = __match_any_sync(FULL, key);
+        if (key != 0xffu) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&ctr.n_shade[key], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            a.shadeq[(size_t)key * a.cap + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = slot;
+        }
+    }
+    if (COUNT) pc_flush(pc, 0, a.counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sink of the deferred next-event contribution: writes the shadow-queue entry
+struct ShadowSink {
+    const StreamArgs* a;
+    BounceCtr* ctr;
+    uint32_t slot;
+    V3<float> pos, dir;
+    float max_dist;
+    bool keep_all;      // counting builds queue every culled-in sample so that the event counters match the reference's calls
+    PTB_DEV void operator()(V3<float> contrib, uint32_t flags) const {
+        if (!keep_all && !(flags & 16u)) return;                 // pdf <= 0: the ray could not contribute (tracer.rs:162)
+        const uint32_t k = queue_reserve(&ctr->n_shadow);
+        a->s0[k] = make_float4(pos.x, pos.y, pos.z, max_dist);
+        a->s1[k] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(slot));
+        a->s2[k] = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(flags));
+    }
+};
+
+template <bool COUNT, bool BVH>
+__global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+    using R = float;
+    __shared__ SceneSmem<R> sm;
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
+    BounceCtr& ctr = a.ctr[bounce];
+    BounceCtr& next = a.ctr[bounce + 1];
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    // chunk table: keys in descending shading cost (more lobes first), so the stage ends on cheap chunks
+    const int order_by_cost[ST_KEYS] = {7, 3, 5, 6, 1, 2, 4, 0, (int)ST_MISS};
+    uint32_t first_chunk[ST_KEYS + 1];
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < (int)ST_KEYS; ++k) { first_chunk[k] = run; run += (ctr.n_shade[order_by_cost[k]] + 31u) >> 5; }
+        first_chunk[ST_KEYS] = run;
+    }
+    PathCounters pc;
+    if (COUNT) pc_clear(pc);
+
+    while (true) {
+        uint32_t ch = 0;
+        if (lane == 0) ch = atomicAdd(&ctr.cur_shade, 1u);
+        ch = __shfl_sync(FULL, ch, 0);
+        if (ch >= first_chunk[ST_KEYS]) break;
+        int k = 0;
+#pragma unroll
+        for (int t = 1; t < (int)ST_KEYS; ++t) k += ch >= first_chunk[t] ? 1 : 0;
+        uint32_t key = 0, base_chunk = 0;
+#pragma unroll
+        for (int t = 0; t < (int)ST_KEYS; ++t) if (t == k) { key = (uint32_t)order_by_cost[t]; base_chunk = first_chunk[t]; }
+        const uint32_t idx = (ch - base_chunk) * 32u + lane;
+        if (idx >= ctr.n_shade[key]) continue;
+        const uint32_t slot = a.shadeq[(size_t)key * a.cap + idx];
+        const float4 A0 = a.a0[slot], A1 = a.a1[slot], A2 = a.a2[slot];
+        float4 A3 = a.a3[slot];
+        PathState<R> p;
+        p.o = V3<R>(A0.x, A0.y, A0.z);
+        p.d = V3<R>(A0.w, A1.x, A1.y);
+        p.thr = V3<R>(A2.x, A2.y, A2.z);
+        p.rad = V3<R>(A3.x, A3.y, A3.z);
+        p.prev_pdf = 0;
+        p.bounce = bounce;
+        if (key == ST_MISS) {                                    // tracer.rs:66-69
+            path_add_sky(s, p);
+            if (COUNT) pc.end_sky++;
+            A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z;
+            a.a3[slot] = A3;
+            continue;
+        }
+        const uint4 H = a.hit[slot];
+        const int prim = (int)H.x;
+        const uint64_t accepted = (uint64_t)H.y | ((uint64_t)H.z << 32);
+        p.hit_dist = __uint_as_float(H.w);
+        Rng<R> rng(__float_as_uint(A3.w), a.sample0 + __float_as_uint(A2.w), a.seed);
+        R u[8];
+        rng.draws(bounce, u);
+        Mat<R> mat;
+        hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+        const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+        ShadeSetup<R> su;
+        shade_setup<R, COUNT>(s, p, normal, mat, su, &pc);
+        if (s.has_emissive) { A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z; a.a3[slot] = A3; }     // tracer.rs:74
+        NeeSample<R> ns;
+        shade_nee_sample(s, sv, su, u, ns);
+        if (COUNT && ns.wants_shadow_ray) pc.any_hit++;
+        ShadowSink sink{&a, &ctr, slot, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT};
+        const bool cont = shade_finish<R, COUNT, true, ShadowSink>(s, p, mat, su, ns.wants_shadow_ray, ns.ls, ns.light_area, u, &pc, sink);
+        if (cont) {
+            a.a0[slot] = make_float4(p.o.x, p.o.y, p.o.z, p.d.x);
+            a.a1[slot] = make_float4(p.d.y, p.d.z, p.hit_dist, p.prev_pdf);
+            a.a2[slot] = make_float4(p.thr.x, p.thr.y, p.thr.z, A2.w);
+            a.rayq[(bounce + 1u) & 1u][queue_reserve(&next.n_ray)] = slot;
+        }
+    }
+    if (COUNT) pc_flush(pc, 0, a.counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT, bool BVH>
+__global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+    using R = float;
+    __shared__ SceneSmem<R> sm;
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
+    BounceCtr& ctr = a.ctr[bounce];
+    const uint32_t n = ctr.n_shadow;
+    const uint32_t lane = threadIdx.x & 31u;
+    PathCounters pc;
+    if (COUNT) pc_clear(pc);
+    while (true) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&ctr.cur_shadow, 32u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n) break;
+        const uint32_t j = chunk + lane;
+        if (j >= n) continue;
+        const float4 S0 = a.s0[j], S1 = a.s1[j];
+        const bool occluded = any_hit<R, BVH>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
+        if (!occluded) {
+            const float4 S2 = a.s2[j];
+            const uint32_t flags = __float_as_uint(S2.w);
+            if (flags & 16u) {                                   // tracer.rs:162-164
+                const uint32_t slot = __float_as_uint(S1.w);
+                float4 A3 = a.a3[slot];
+                A3.x += S2.x; A3.y += S2.y; A3.z += S2.z;
+                a.a3[slot] = A3;
+                if (COUNT) pc.nee_contrib++;
+            }
+            if (COUNT) {
+                pc.eval_calls++;
+                for (int k = 0; k < 4; ++k) pc.ev[k] += (flags >> k) & 1u;
+            }
+        }
+    }
+    if (COUNT) pc_flush(pc, 0, a.counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_THREADS) k_stream_accumulate(const StreamArgs a) {
+    const uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= a.npix) return;
+    uint32_t px, prow;
+    if (!tiled_pixel(a, a.pix0 + il, px, prow)) return;
+    float sx = 0, sy = 0, sz = 0;
+    const float4* r = a.a3 + (size_t)il * a.S;
+    for (uint32_t k = 0; k < a.S; ++k) { const float4 v = r[k]; sx += v.x; sy += v.y; sz += v.z; }
+    const uint32_t pix = prow * a.W + px;
+    float4 v = a.accum[pix];
+    v.x += sx; v.y += sy; v.z += sz; v.w += (float)a.S;
+    a.accum[pix] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct StreamState {
+    void* mem = nullptr;         // one allocation holding every queue
+    size_t mem_bytes = 0;
+    uint32_t cap = 0;            // paths per wave the allocation was sized for
+    BounceCtr* ctr = nullptr;
+    uint32_t ctr_bounces = 0;
+    int grid_closest[4] = {0, 0, 0, 0}, grid_shade[4] = {0, 0, 0, 0}, grid_shadow[4] = {0, 0, 0, 0};   // index = COUNT*2 + BVH
+    void release() {
+        if (mem) cudaFree(mem);
+        if (ctr) cudaFree(ctr);
+        mem = nullptr; ctr = nullptr; mem_bytes = 0; cap = 0; ctr_bounces = 0;
+    }
+};
+
+inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
+                         const ptb_config& cfg, cudaStream_t stream, int sm_count, DeviceCounters* counters, cudaEvent_t ev0, cudaEvent_t ev1,
+                         uint64_t* launches, std::string& err) {
+    cudaError_t e;
+    auto cuda_fail = [&](const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return PTB_E_CUDA; };
+    StreamArgs a{};
+    a.W = W; a.H = H;
+    a.tiles_x = (W + 15u) / 16u;
+    a.n_items = a.tiles_x * ((H + 15u) / 16u) * 256u;
+    a.seed = cfg.seed; a.rr_start = cfg.rr_start; a.counters = counters; a.accum = (float4*)accum;
+
+    // wave shape: all pixels x S samples when the frame is small, else pixel ranges x 1 sample
+    uint32_t want = cfg.wave_paths ? cfg.wave_paths : ST_DEFAULT_WAVE;
+    want = std::max<uint32_t>(256u, want & ~255u);
+    uint32_t pix_per_wave, S;
+    if (a.n_items >= want) { pix_per_wave = want; S = 1; }
+    else { pix_per_wave = a.n_items; S = std::max<uint32_t>(1u, std::min<uint32_t>(std::min<uint32_t>(spp, want / a.n_items), 4096u)); }
+    const uint32_t cap = pix_per_wave * S;
+
+    if (st.cap < cap) {
+        if (st.mem) { cudaStreamSynchronize(stream); cudaFree(st.mem); st.mem = nullptr; st.cap = 0; }
+        const size_t per_path = 4 * 16 + 16 + 2 * 4 + ST_KEYS * 4 + 3 * 16;
+        st.mem_bytes = (size_t)cap * per_path;
+        if ((e = cudaMalloc(&st.mem, st.mem_bytes)) != cudaSuccess) return cuda_fail("cudaMalloc(stream queues)");
+        st.cap = cap;
+    }
+    const uint32_t n_ctr = d.depth + 2u;
+    if (st.ctr_bounces < n_ctr) {
+        if (st.ctr) { cudaStreamSynchronize(stream); cudaFree(st.ctr); st.ctr = nullptr; }
+        if ((e = cudaMalloc((void**)&st.ctr, (size_t)n_ctr * sizeof(BounceCtr))) != cudaSuccess) return cuda_fail("cudaMalloc(stream counters)");
+        st.ctr_bounces = n_ctr;
+    }
+    {
+        char* p = (char*)st.mem;
+        const size_t c = st.cap;
+        a.a0 = (float4*)p; p += c * 16; a.a1 = (float4*)p; p += c * 16; a.a2 = (float4*)p; p += c * 16; a.a3 = (float4*)p; p += c * 16;
+        a.hit = (uint4*)p; p += c * 16;
+        a.s0 = (float4*)p; p += c * 16; a.s1 = (float4*)p; p += c * 16; a.s2 = (float4*)p; p += c * 16;
+        a.rayq[0] = (uint32_t*)p; p += c * 4; a.rayq[1] = (uint32_t*)p; p += c * 4;
+        a.shadeq = (uint32_t*)p;
+        a.cap = st.cap;
+        a.ctr = st.ctr;
+    }
+
+    const bool count = cfg.collect_counters != 0;
+    const bool bvh = d.use_bvh != 0;
+    const int vi = (count ? 2 : 0) + (bvh ? 1 : 0);
+    using StageKernel = void (*)(const DScene<float>, const StreamArgs, const uint32_t);
+    const StageKernel k_closest = bvh ? (count ? k_stream_closest<true, true> : k_stream_closest<false, true>)
+                                      : (count ? k_stream_closest<true, false> : k_stream_closest<false, false>);
+    const StageKernel k_shade = bvh ? (count ? k_stream_shade<true, true> : k_stream_shade<false, true>)
+                                    : (count ? k_stream_shade<true, false> : k_stream_shade<false, false>);
+    const StageKernel k_shadow = bvh ? (count ? k_stream_shadow<true, true> : k_stream_shadow<false, true>)
+                                     : (count ? k_stream_shadow<true, false> : k_stream_shadow<false, false>);
+    auto grid_of = [&](int& slot, StageKernel k) {
+        if (slot == 0) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, ST_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            slot = per_sm * sm_count;
+        }
+        return slot;
+    };
+    const int g_closest = grid_of(st.grid_closest[vi], k_closest), g_shade = grid_of(st.grid_shade[vi], k_shade),
+              g_shadow = grid_of(st.grid_shadow[vi], k_shadow);
+
+    if ((e = cudaEventRecord(ev0, stream)) != cudaSuccess) return cuda_fail("cudaEventRecord");
+    for (uint32_t s0 = 0; s0 < spp; s0 += S) {
+        const uint32_t Sw = std::min(S, spp - s0);
+        for (uint32_t pix0 = 0; pix0 < a.n_items; pix0 += pix_per_wave) {
+            a.pix0 = pix0; a.npix = std::min(pix_per_wave, a.n_items - pix0); a.S = Sw; a.P = a.npix * Sw;
+            a.sample0 = sample_base + s0;
+            if ((e = cudaMemsetAsync(st.ctr, 0, (size_t)n_ctr * sizeof(BounceCtr), stream)) != cudaSuccess) return cuda_fail("cudaMemsetAsync");
+            const unsigned g_gen = (a.P + ST_THREADS - 1) / ST_THREADS;
+            if (count) k_stream_generate<true><<<g_gen, ST_THREADS, 0, stream>>>(d, a);
+            else k_stream_generate<false><<<g_gen, ST_THREADS, 0, stream>>>(d, a);
+            (*launches)++;
+            const int cap_grid = (int)std::max<uint32_t>(1u, (a.P + ST_THREADS - 1) / ST_THREADS);
+            for (uint32_t b = 0; b < d.depth; ++b) {
+                k_closest<<<std::min(g_closest, cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
+                k_shade<<<std::min(g_shade, cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
+                k_shadow<<<std::min(g_shadow, cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
+                (*launches) += 3;
+            }
+            k_stream_accumulate<<<(a.npix + ST_THREADS - 1) / ST_THREADS, ST_THREADS, 0, stream>>>(a);
+            (*launches)++;
+            if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail("stream wavefront launch");
+        }
+    }
+    if ((e = cudaEventRecord(ev1, stream)) != cudaSuccess) return cuda_fail("cudaEventRecord");
+    return PTB_OK;
+}
+
+}  // namespace ptb

@@ -310,7 +310,7 @@ def test_degenerate_scenes(rp):
     pt.close()
     # depth 0: the bounce loop never runs (tracer.rs:61) -> black image with alpha 1, no closest_hit at all
     e = rp.AnalyticalScene.new().device_export(); e.depth = 0
-    for integ in (rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_WAVEFRONT):
+    for integ in (rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_STREAM):
         pt = rp.Tracer.new(rp.ExportedScene(e), collect_counters=True, integrator=integ)
         b0 = rp.ColorBuffer.new(32, 16)
         pt.render_spp(b0, 2)
@@ -373,6 +373,67 @@ def test_wavefront_bvh_and_rr(rp):
         img[name] = buf.pixels.copy()
         pt.close()
     assert (pix_rel(img["wave"], img["fused"]) < 1e-5).mean() > 0.99
+
+
+@pytest.mark.parametrize("wh_spp_wave", [(200, 150, 4, 0), (97, 61, 3, 4096), (640, 360, 2, 100000), (64, 48, 5, 256)])
+def test_stream_integrator_parity(rp, scene, oracle_demo, wh_spp_wave):
+    """the global-memory wavefront (one kernel per stage over HBM queues) traces exactly the same paths as the fused
+    integrator, whatever the wave shape: whole frame x several samples, pixel ranges x one sample, partial last waves"""
+    W, H, S, wave = wh_spp_wave
+    img = {}
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
+        pt = rp.Tracer.new(scene, integrator=integ, collect_counters=True, wave_paths=wave)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        img[name] = (buf.pixels.copy(), pt.counters())
+        pt.close()
+    assert (pix_rel(img["stream"][0], img["fused"][0]) < 1e-5).mean() > 0.995
+    assert np.all(img["stream"][0].reshape(-1, 4)[:, 3] == 1.0)
+    cs, cf = img["stream"][1], img["fused"][1]
+    assert cs["samples"] == cf["samples"] == W * H * S
+    for k in cs:
+        assert abs(cs[k] - cf[k]) <= max(3, 2e-4 * W * H * S), (k, cs[k], cf[k])
+    ref, _, _, _ = oracle_demo.render(W, H, S)
+    assert (pix_rel(img["stream"][0], ref) < 1e-4).mean() >= 0.99
+    # bit-reproducible run to run although the queue order is not; the non-counting build prunes zero-pdf shadow rays
+    pt = rp.Tracer.new(scene, integrator=rp._abi.PTB_INTEGRATOR_STREAM, wave_paths=wave)
+    b1 = rp.ColorBuffer.new(W, H); b2 = rp.ColorBuffer.new(W, H)
+    pt.render_spp(b1, S); pt.render_spp(b2, S)
+    assert np.array_equal(b1.pixels, b2.pixels)
+    assert (pix_rel(b1.pixels, img["stream"][0]) < 1e-5).mean() > 0.995
+    pt.close()
+
+
+def test_stream_bvh_and_rr(rp):
+    sc = _small_field(rp, 800, 2)
+    W, H, S = 96, 54, 2
+    img = {}
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
+        pt = rp.Tracer.new(sc, integrator=integ, bvh_threshold=1, collect_counters=True)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        img[name] = (buf.pixels.copy(), pt.counters())
+        pt.close()
+    assert (pix_rel(img["stream"][0], img["fused"][0]) < 1e-5).mean() > 0.99
+    for k in img["fused"][1]:
+        assert abs(img["stream"][1][k] - img["fused"][1][k]) <= max(3, 1e-3 * W * H * S), k
+    sc = rp.divergence_stress_scene(side=6, depth=16)
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
+        pt = rp.Tracer.new(sc, integrator=integ, rr_start=3)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, 8)
+        img[name] = buf.pixels.copy()
+        pt.close()
+    assert (pix_rel(img["stream"], img["fused"]) < 1e-5).mean() > 0.99
+    # 25 lights: light BVH inside k_stream_closest
+    sc = rp.sphere_field_scene(n_spheres=300, n_lights_side=5)
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
+        pt = rp.Tracer.new(sc, integrator=integ)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, 3)
+        img[name] = buf.pixels.copy()
+        pt.close()
+    assert (pix_rel(img["stream"], img["fused"]) < 1e-5).mean() > 0.99
 
 
 def test_light_bvh_matches_linear_scan(rp, po):
@@ -451,7 +512,7 @@ def test_random_scenes_parity(rp, po, seed):
     e = _random_scene(rp, seed)
     W, H, S = 120, 80, 3
     ref, _, _, oc = po.OracleScene(e).render(W, H, S, counters=True)
-    for integ in (rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_WAVEFRONT):
+    for integ in (rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_STREAM):
         pt = rp.Tracer.new(rp.ExportedScene(e), integrator=integ, collect_counters=True)
         buf = rp.ColorBuffer.new(W, H)
         pt.render_spp(buf, S)

@@ -30,7 +30,7 @@ def run(name, scene, W, H, spp, integ, reps=3, **kw):
     pc.close()
     rays = (c["closest_hit"] + c["any_hit"]) / max(1, c["samples"])
     ms = W * H * spp / best / 1e3
-    return {"config": name, "integrator": {A.PTB_INTEGRATOR_FUSED: "fused", A.PTB_INTEGRATOR_WAVEFRONT: "wavefront"}[integ], "width": W, "height": H,
+    return {"config": name, "integrator": {A.PTB_INTEGRATOR_FUSED: "fused", A.PTB_INTEGRATOR_WAVEFRONT: "wavefront", A.PTB_INTEGRATOR_STREAM: "stream"}[integ], "width": W, "height": H,
             "spp": spp, "kernel_ms": round(best, 3), "msamples_per_s": round(ms, 1), "rays_per_sample": round(rays, 3),
             "grays_per_s": round(ms * rays / 1e3, 3), "bounces_per_sample": round(c["closest_hit"] / max(1, c["samples"]), 3)}
 
@@ -63,7 +63,10 @@ def main():
         out.append({"config": "cfg1 AnalyticalScene 800x600 f64 (F switch), 16 spp", "integrator": "fused", "kernel_ms": round(ms, 3),
                     "msamples_per_s": round(800 * 600 * 16 / ms / 1e3, 1)})
         pt.close()
-    for integ in (A.PTB_INTEGRATOR_FUSED, A.PTB_INTEGRATOR_WAVEFRONT):
+    integs = (A.PTB_INTEGRATOR_FUSED, A.PTB_INTEGRATOR_WAVEFRONT, A.PTB_INTEGRATOR_STREAM)
+    if os.environ.get("PTB_INTEGRATORS"):
+        integs = tuple(int(x) for x in os.environ["PTB_INTEGRATORS"].split(","))
+    for integ in integs:
         if "2" in which:
             out.append(run("cfg2 AnalyticalScene 1920x1080, 256 spp", demo, 1920, 1080, 256, integ))
         if "3" in which:
