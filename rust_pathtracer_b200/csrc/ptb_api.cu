@@ -303,6 +303,9 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         }
     }
     if (use_bvh) build_sphere_bvh();
+    for (const auto* nv : {&nodes, &lnodes})
+        for (const BvhNode& nd : *nv)
+            if (nd.count > 7u) return fail(PTB_E_INVALID, "internal: BVH leaf with %u primitives (node references carry 3 count bits)", nd.count);
 
     // pack the arrays into one blob (16-byte aligned sections) so a CTA stages it with one loop
     std::vector<unsigned char> blob;

@@ -54,7 +54,8 @@ struct BounceCtr {                       // 128 bytes per bounce, zeroed at the 
     uint32_t cur_shade;                  // chunk cursor of k_stream_shade
     uint32_t n_shadow;                   // shadow rays of this bounce
     uint32_t cur_shadow;                 // chunk cursor of k_stream_shadow
-    uint32_t pad[32 - 14];
+    uint32_t cur_finish;                 // chunk cursor of k_stream_finish (BVH scenes)
+    uint32_t pad[32 - 15];
 };
 static_assert(sizeof(BounceCtr) == 128, "BounceCtr layout");
 
@@ -156,7 +157,44 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_generate(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// What follows Scene::closest_hit for one ray (tracer.rs:66-87): a path that hit a light is finished here, everything
+// else gets its queue key — the lobe class of the hit material, or ST_MISS.  Returns the key, 0xff for "no shading".
 template <bool COUNT, bool BVH>
+PTB_DEV uint32_t stream_after_hit(const DScene<float>& s, const SceneView<float>& sv, const StreamArgs& a, uint32_t slot, V3<float> d, float prev_pdf,
+                                  const HitCore<float>& h, PathCounters& pc) {
+    using R = float;
+    if (!h.hit) return ST_MISS;
+    if (h.is_emitter) {
+        const float4 A2 = a.a2[slot];
+        float4 A3 = a.a3[slot];
+        PathState<R> p;
+        p.d = d; p.prev_pdf = prev_pdf;
+        p.thr = V3<R>(A2.x, A2.y, A2.z);
+        p.rad = V3<R>(A3.x, A3.y, A3.z);
+        path_add_emitter<R, BVH>(s, sv, p, h);
+        A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z;
+        a.a3[slot] = A3;
+        if (COUNT) pc.end_emitter++;
+        return 0xffu;
+    }
+    a.hit[slot] = make_uint4((uint32_t)h.prim, (uint32_t)h.accepted, (uint32_t)(h.accepted >> 32), __float_as_uint(h.hit_dist));
+    return hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
+}
+// queue `slot` by key, one atomic per (warp, key); every lane of the warp calls this (key 0xff = nothing to queue)
+PTB_DEV void push_by_key(const StreamArgs& a, BounceCtr& ctr, uint32_t key, uint32_t slot) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key != 0xffu) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&ctr.n_shade[key], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        a.shadeq[(size_t)key * a.cap + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = slot;
+    }
+}
+
+// Small scenes (no BVH): the whole of Scene::closest_hit in one kernel.
+template <bool COUNT>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     __shared__ SceneSmem<R> sm;
@@ -165,66 +203,243 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_cons
     const uint32_t n = ctr.n_ray;
     const uint32_t* __restrict__ q = a.rayq[bounce & 1u];
     const uint32_t lane = threadIdx.x & 31u;
-    const unsigned FULL = 0xffffffffu;
     PathCounters pc;
     if (COUNT) pc_clear(pc);
-
     while (true) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(&ctr.cur_ray, 32u);
-        chunk = __shfl_sync(FULL, chunk, 0);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= n) break;
         const uint32_t j = chunk + lane;
         uint32_t key = 0xffu, slot = 0;
         if (j < n) {
             slot = q[j];
             const float4 A0 = a.a0[slot], A1 = a.a1[slot];
-            PathState<R> p;
-            p.o = V3<R>(A0.x, A0.y, A0.z);
-            p.d = V3<R>(A0.w, A1.x, A1.y);
-            p.hit_dist = A1.z;
-            p.prev_pdf = A1.w;
-            p.bounce = bounce;
-            bool dead = false;
-            if (a.rr_start != 0 && bounce >= a.rr_start && bounce > 0) {
-                float4 A2 = a.a2[slot];
-                const float4 A3 = a.a3[slot];
-                p.thr = V3<R>(A2.x, A2.y, A2.z);
-                Rng<R> rng(__float_as_uint(A3.w), a.sample0 + __float_as_uint(A2.w), a.seed);
-                R u4[4];
-                rng.block(bounce, 0, u4);
-                if (!russian_roulette_survives(p, u4[0])) { dead = true; if (COUNT) pc.end_rr++; }
-                else { A2.x = p.thr.x; A2.y = p.thr.y; A2.z = p.thr.z; a.a2[slot] = A2; }
+            const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
+            if (COUNT) pc.closest_hit++;
+            const HitCore<R> h = closest_hit_core<R, false>(s, sv, o, d, A1.z);
+            key = stream_after_hit<COUNT, false>(s, sv, a, slot, d, A1.w, h, pc);
+        }
+        push_by_key(a, ctr, key, slot);
+    }
+    if (COUNT) pc_flush(pc, 0, a.counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BVH scenes: sphere-BVH traversal in a kernel of its own, for closest-hit rays (ANY = false: reads the ray queue, writes
+// (sphere index, distance) into the hit records) and for shadow rays (ANY = true: reads the shadow queue and adds the
+// deferred next-event contribution of every unoccluded ray).
+//
+// ncu on the first version (one ray per lane per 32-ray chunk, profiles/r01_ncu_stream.md): 77 % of the issue slots busy
+// at 9.5 of 32 lanes — the traversal is bound by SIMT divergence, not by memory latency: the rays of a warp need very
+// different numbers of steps and the warp runs for the longest.  So lanes are PERSISTENT here: a lane whose ray is done
+// writes its result and, as soon as ST_REFILL lanes of the warp are idle, the idle lanes pull new rays from the queue
+// (one warp-aggregated atomic) while the others keep their traversal state.
+//
+// Second finding (same file): with refill the box tests run at 26 lanes, but the leaf sphere tests and the stack pops that
+// follow them ran at 3-4 lanes and made up a third of the issue slots.  So a leaf is POSTPONED (Aila & Laine's speculative
+// while-while): the lane parks the leaf reference, pops the next node and keeps traversing; parked leaves are intersected
+// together once ST_LEAF_MIN lanes hold one, or no lane can advance otherwise.  Node references carry the leaf count in
+// their low 3 bits, so neither the stack pop nor the parked leaf needs to touch the node array again.
+constexpr int ST_REFILL = 8;
+constexpr int ST_LEAF_MIN = 12;
+constexpr int ST_STACK = 40;
+constexpr uint32_t ST_NONE = 0xffffffffu;
+
+PTB_DEV uint32_t node_ref(uint32_t left_or_first, uint32_t count) { return (left_or_first << 3) | count; }   // count <= 7 (builder: <= 4)
+
+// slab test with the origin folded in: t = b * (1/d) - o * (1/d), one FMA per plane.  Conservative like box_entry: entry and
+// exit are widened by 1e-4 relative; a NaN slab (d == 0 on that axis: inf - inf) is ignored by min/max, i.e. treated as hit.
+struct RayS { float idx, idy, idz, nox, noy, noz; };
+PTB_DEV float box_entry_s(float4 lo, float4 hi, const RayS& r, float limit) {
+    const float tx0 = fmaf(lo.x, r.idx, r.nox), tx1 = fmaf(hi.x, r.idx, r.nox);
+    const float ty0 = fmaf(lo.y, r.idy, r.noy), ty1 = fmaf(hi.y, r.idy, r.noy);
+    const float tz0 = fmaf(lo.z, r.idz, r.noz), tz1 = fmaf(hi.z, r.idz, r.noz);
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    tn *= 0.9999f;
+    return (tn <= tf * 1.0001f && tn <= limit) ? tn : 3.0e38f;
+}
+
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(ST_THREADS) k_stream_trace(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+    using R = float;
+    __shared__ SceneSmem<R> sm;
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);       // planes (shadow rays test them first)
+    BounceCtr& ctr = a.ctr[bounce];
+    const uint32_t n = ANY ? ctr.n_shadow : ctr.n_ray;
+    uint32_t* const cursor = ANY ? &ctr.cur_shadow : &ctr.cur_ray;
+    const uint32_t* __restrict__ q = a.rayq[bounce & 1u];
+    const float4* __restrict__ nodes = reinterpret_cast<const float4*>(s.bvh);    // node i = nodes[2i] (lo, link), nodes[2i+1] (hi, count)
+    const DSphere<R>* __restrict__ leaf_spheres = s.bvh_spheres;
+    const uint32_t* __restrict__ leaf_prim = s.bvh_prim;
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool ignore_max = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
+    const uint32_t root_ref = node_ref(__float_as_uint(__ldg(nodes).w), __float_as_uint(__ldg(nodes + 1).w));
+    PathCounters pc;
+    if (COUNT) pc_clear(pc);
+
+    bool active = false, exhausted = false;
+    uint32_t slot = 0;                       // closest: path slot; any: shadow-queue index
+    V3<R> o(0, 0, 0), d(0, 0, 1);
+    RayS r{};
+    R best_t = 0;
+    int best = -1;
+    uint32_t cur = ST_NONE;                  // node to visit next (inner or leaf reference)
+    uint32_t pend = 0;                       // parked leaf reference (0 = none)
+    int sp = 0;
+    uint32_t stack_n[ST_STACK];
+    float stack_t[ST_STACK];
+
+    while (true) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle) {
+            if (!exhausted && (__popc(idle) >= ST_REFILL || idle == FULL)) {
+                const uint32_t cnt = (uint32_t)__popc(idle);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, cnt);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + cnt >= n) exhausted = true;
+                const uint32_t my = base + (uint32_t)__popc(idle & lt_mask);
+                if (!active && my < n) {
+                    bool go = true;
+                    if (ANY) {
+                        slot = my;
+                        const float4 S0 = a.s0[my], S1 = a.s1[my];
+                        o = V3<R>(S0.x, S0.y, S0.z); d = V3<R>(S1.x, S1.y, S1.z);
+                        best_t = ignore_max ? Const<R>::MAXV : S0.w;
+                        if (any_hit_planes(s, sv, o, d, S0.w)) go = false;            // occluded by a plane: nothing to add
+                    } else {
+                        slot = q[my];
+                        const float4 A0 = a.a0[slot], A1 = a.a1[slot];
+                        o = V3<R>(A0.x, A0.y, A0.z); d = V3<R>(A0.w, A1.x, A1.y);
+                        best_t = Const<R>::MAXV;
+                        if (COUNT) pc.closest_hit++;
+                    }
+                    if (go) {
+                        best = -1;
+                        // (a direction component of exactly 0 would make o * inf - b * inf a NaN or a wrongly signed infinity)
+                        r.idx = 1.0f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
+                        r.idy = 1.0f / (fabsf(d.y) > 1e-30f ? d.y : copysignf(1e-30f, d.y));
+                        r.idz = 1.0f / (fabsf(d.z) > 1e-30f ? d.z : copysignf(1e-30f, d.z));
+                        r.nox = -o.x * r.idx; r.noy = -o.y * r.idy; r.noz = -o.z * r.idz;
+                        cur = root_ref; pend = 0; sp = 0;
+                        active = true;
+                    }
+                }
+            } else if (idle == FULL) {
+                break;
             }
-            if (!dead) {
-                if (COUNT) pc.closest_hit++;
-                const HitCore<R> h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
-                if (!h.hit) {
-                    key = ST_MISS;
-                } else if (h.is_emitter) {
-                    const float4 A2 = a.a2[slot];
-                    float4 A3 = a.a3[slot];
-                    p.thr = V3<R>(A2.x, A2.y, A2.z);
-                    p.rad = V3<R>(A3.x, A3.y, A3.z);
-                    path_add_emitter<R, BVH>(s, sv, p, h);
-                    A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z;
-                    a.a3[slot] = A3;
-                    if (COUNT) pc.end_emitter++;
-                } else {
-                    key = hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
-                    a.hit[slot] = make_uint4((uint32_t)h.prim, (uint32_t)h.accepted, (uint32_t)(h.accepted >> 32), __float_as_uint(h.hit_dist));
+        }
+        // ---- one inner node: both children with one 64-byte read, nearer first
+        if (active && cur != ST_NONE && (cur & 7u) == 0u) {
+            const float4* c = nodes + (size_t)(cur >> 3) * 2u;
+            const float4 alo = __ldg(c), ahi = __ldg(c + 1), blo = __ldg(c + 2), bhi = __ldg(c + 3);
+            const float ta = box_entry_s(alo, ahi, r, best_t), tb = box_entry_s(blo, bhi, r, best_t);
+            const bool ha = ta < 3.0e38f, hb = tb < 3.0e38f;
+            const uint32_t ra = node_ref(__float_as_uint(alo.w), __float_as_uint(ahi.w)), rb = node_ref(__float_as_uint(blo.w), __float_as_uint(bhi.w));
+            const bool a_near = ha && (!hb || ta <= tb);
+            const uint32_t near_ref = a_near ? ra : rb;
+            if (ha && hb && sp < ST_STACK) {
+                // (far child written as ra ^ rb ^ near and max(ta, tb): nvcc 12.9 compiled the mirrored select
+                //  `a_near ? rb : ra` next to `a_near ? ra : rb` into an unconditional store of rb — found with a per-ray
+                //  differential check against bvh_traverse)
+                stack_n[sp] = ra ^ rb ^ near_ref;
+                stack_t[sp] = fmaxf(ta, tb);
+                ++sp;
+            }
+            cur = (ha || hb) ? near_ref : ST_NONE;
+        }
+        // ---- park a leaf, pop the next node
+        if (active) {
+            if (cur != ST_NONE && (cur & 7u) != 0u && pend == 0u) { pend = cur; cur = ST_NONE; }
+            if (cur == ST_NONE) {
+                while (sp > 0) {
+                    --sp;
+                    if (stack_t[sp] <= best_t) { cur = stack_n[sp]; break; }
                 }
             }
         }
-        // queue by key: one atomic per (warp, key)
-        const unsigned peers = __match_any_sync(FULL, key);
-        if (key != 0xffu) {
-            const int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(&ctr.n_shade[key], (uint32_t)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            a.shadeq[(size_t)key * a.cap + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = slot;
+        // ---- parked leaves, together
+        const unsigned m_pend = __ballot_sync(FULL, active && pend != 0u);
+        const unsigned m_inner = __ballot_sync(FULL, active && cur != ST_NONE && (cur & 7u) == 0u);
+        bool finished = false;
+        if (m_pend && (__popc(m_pend) >= ST_LEAF_MIN || m_inner == 0u)) {
+            if (active && pend != 0u) {
+                const uint32_t first = pend >> 3, cnt = pend & 7u;
+                pend = 0u;
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    const DSphere<R> sph = leaf_spheres[first + i];
+                    const R t = isect_sphere(o, d, V3<R>(sph.cx, sph.cy, sph.cz), sph.r);
+                    if (t >= R(0)) {
+                        if (ANY) { if (t < best_t) { best = 0; finished = true; } }
+                        else {
+                            const int si = (int)leaf_prim[first + i];
+                            if (t < best_t || (t == best_t && si < best)) { best_t = t; best = si; }
+                        }
+                    }
+                }
+            }
         }
+        if (active && cur == ST_NONE && pend == 0u && sp == 0) finished = true;
+        if (active && finished) {
+            active = false;
+            if (ANY) {
+                if (best < 0) {                                       // unoccluded: tracer.rs:162-164
+                    const float4 S1 = a.s1[slot], S2 = a.s2[slot];
+                    const uint32_t flags = __float_as_uint(S2.w);
+                    if (flags & 16u) {
+                        const uint32_t ps = __float_as_uint(S1.w);
+                        float4 A3 = a.a3[ps];
+                        A3.x += S2.x; A3.y += S2.y; A3.z += S2.z;
+                        a.a3[ps] = A3;
+                        if (COUNT) pc.nee_contrib++;
+                    }
+                    if (COUNT) {
+                        pc.eval_calls++;
+                        for (int k = 0; k < 4; ++k) pc.ev[k] += (flags >> k) & 1u;
+                    }
+                }
+            } else {
+                a.hit[slot] = make_uint4((uint32_t)best, 0u, 0u, __float_as_uint(best_t));
+            }
+        }
+    }
+    if (COUNT) pc_flush(pc, 0, a.counters);
+}
+
+// BVH scenes: the rest of Scene::closest_hit after the sphere traversal — planes, Scene::sample_lights (light BVH when
+// there are many lights), emitter hits, queue keys.  Full, coherent warps.
+template <bool COUNT>
+__global__ void __launch_bounds__(ST_THREADS) k_stream_finish(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+    using R = float;
+    __shared__ SceneSmem<R> sm;
+    const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
+    BounceCtr& ctr = a.ctr[bounce];
+    const uint32_t n = ctr.n_ray;
+    const uint32_t* __restrict__ q = a.rayq[bounce & 1u];
+    const uint32_t lane = threadIdx.x & 31u;
+    PathCounters pc;
+    if (COUNT) pc_clear(pc);
+    while (true) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&ctr.cur_finish, 32u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n) break;
+        const uint32_t j = chunk + lane;
+        uint32_t key = 0xffu, slot = 0;
+        if (j < n) {
+            slot = q[j];
+            const float4 A0 = a.a0[slot], A1 = a.a1[slot];
+            const uint4 H = a.hit[slot];
+            const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
+            const HitCore<R> h = closest_hit_finish<R, true>(s, sv, o, d, A1.z, (int)H.x, __uint_as_float(H.w), 0ull);
+            key = stream_after_hit<COUNT, true>(s, sv, a, slot, d, A1.w, h, pc);
+        }
+        push_by_key(a, ctr, key, slot);
     }
     if (COUNT) pc_flush(pc, 0, a.counters);
 }
@@ -315,7 +530,13 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
         shade_nee_sample(s, sv, su, u, ns);
         if (COUNT && ns.wants_shadow_ray) pc.any_hit++;
         ShadowSink sink{&a, &ctr, slot, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT};
-        const bool cont = shade_finish<R, COUNT, true, ShadowSink>(s, p, mat, su, ns.wants_shadow_ray, ns.ls, ns.light_area, u, &pc, sink);
+        const bool cont0 = shade_finish<R, COUNT, true, ShadowSink>(s, p, mat, su, ns.wants_shadow_ray, ns.ls, ns.light_area, u, &pc, sink);
+        bool cont = cont0;
+        if (cont && a.rr_start != 0 && p.bounce >= a.rr_start) {     // RR extension at the start of bounce p.bounce (slot 0 of that bounce)
+            R u4[4];
+            rng.block(p.bounce, 0, u4);
+            if (!russian_roulette_survives(p, u4[0])) { cont = false; if (COUNT) pc.end_rr++; }
+        }
         if (cont) {
             a.a0[slot] = make_float4(p.o.x, p.o.y, p.o.z, p.d.x);
             a.a1[slot] = make_float4(p.d.y, p.d.z, p.hit_dist, p.prev_pdf);
@@ -327,7 +548,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool COUNT, bool BVH>
+// Small scenes (no BVH): Scene::any_hit over the shadow queue.
+template <bool COUNT>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     __shared__ SceneSmem<R> sm;
@@ -345,7 +567,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_const
         const uint32_t j = chunk + lane;
         if (j >= n) continue;
         const float4 S0 = a.s0[j], S1 = a.s1[j];
-        const bool occluded = any_hit<R, BVH>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
+        const bool occluded = any_hit<R, false>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
         if (!occluded) {
             const float4 S2 = a.s2[j];
             const uint32_t flags = __float_as_uint(S2.w);
@@ -387,7 +609,7 @@ struct StreamState {
     uint32_t cap = 0;            // paths per wave the allocation was sized for
     BounceCtr* ctr = nullptr;
     uint32_t ctr_bounces = 0;
-    int grid_closest[4] = {0, 0, 0, 0}, grid_shade[4] = {0, 0, 0, 0}, grid_shadow[4] = {0, 0, 0, 0};   // index = COUNT*2 + BVH
+    int grid[4][4] = {};         // persistent grid per [COUNT*2 + BVH][stage]
     void release() {
         if (mem) cudaFree(mem);
         if (ctr) cudaFree(ctr);
@@ -443,22 +665,31 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, u
     const bool bvh = d.use_bvh != 0;
     const int vi = (count ? 2 : 0) + (bvh ? 1 : 0);
     using StageKernel = void (*)(const DScene<float>, const StreamArgs, const uint32_t);
-    const StageKernel k_closest = bvh ? (count ? k_stream_closest<true, true> : k_stream_closest<false, true>)
-                                      : (count ? k_stream_closest<true, false> : k_stream_closest<false, false>);
-    const StageKernel k_shade = bvh ? (count ? k_stream_shade<true, true> : k_stream_shade<false, true>)
-                                    : (count ? k_stream_shade<true, false> : k_stream_shade<false, false>);
-    const StageKernel k_shadow = bvh ? (count ? k_stream_shadow<true, true> : k_stream_shadow<false, true>)
-                                     : (count ? k_stream_shadow<true, false> : k_stream_shadow<false, false>);
-    auto grid_of = [&](int& slot, StageKernel k) {
-        if (slot == 0) {
+    // stage kernels of a bounce, in launch order; small scenes: closest, shade, shadow; BVH scenes: trace, finish, shade, trace<ANY>
+    StageKernel stages[4];
+    int n_stages;
+    if (bvh) {
+        stages[0] = count ? k_stream_trace<false, true> : k_stream_trace<false, false>;
+        stages[1] = count ? k_stream_finish<true> : k_stream_finish<false>;
+        stages[2] = count ? k_stream_shade<true, true> : k_stream_shade<false, true>;
+        stages[3] = count ? k_stream_trace<true, true> : k_stream_trace<true, false>;
+        n_stages = 4;
+    } else {
+        stages[0] = count ? k_stream_closest<true> : k_stream_closest<false>;
+        stages[1] = count ? k_stream_shade<true, false> : k_stream_shade<false, false>;
+        stages[2] = count ? k_stream_shadow<true> : k_stream_shadow<false>;
+        n_stages = 3;
+    }
+    int grids[4];
+    for (int k = 0; k < n_stages; ++k) {
+        int& g = st.grid[vi][k];
+        if (g == 0) {
             int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, ST_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-            slot = per_sm * sm_count;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stages[k], ST_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            g = per_sm * sm_count;
         }
-        return slot;
-    };
-    const int g_closest = grid_of(st.grid_closest[vi], k_closest), g_shade = grid_of(st.grid_shade[vi], k_shade),
-              g_shadow = grid_of(st.grid_shadow[vi], k_shadow);
+        grids[k] = g;
+    }
 
     if ((e = cudaEventRecord(ev0, stream)) != cudaSuccess) return cuda_fail("cudaEventRecord");
     for (uint32_t s0 = 0; s0 < spp; s0 += S) {
@@ -473,10 +704,8 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, u
             (*launches)++;
             const int cap_grid = (int)std::max<uint32_t>(1u, (a.P + ST_THREADS - 1) / ST_THREADS);
             for (uint32_t b = 0; b < d.depth; ++b) {
-                k_closest<<<std::min(g_closest, cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
-                k_shade<<<std::min(g_shade, cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
-                k_shadow<<<std::min(g_shadow, cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
-                (*launches) += 3;
+                for (int k = 0; k < n_stages; ++k) stages[k]<<<std::min(grids[k], cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
+                (*launches) += (uint64_t)n_stages;
             }
             k_stream_accumulate<<<(a.npix + ST_THREADS - 1) / ST_THREADS, ST_THREADS, 0, stream>>>(a);
             (*launches)++;
