@@ -639,12 +639,15 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
     if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
     if (spp == 0) return PTB_OK;
     CU(cudaSetDevice(t->device));
-    // AUTO: the shared-memory wavefront integrator for small f32 scenes (measured faster, profiles/); the fused one for
-    // f64 and for large BVH scenes (measured: 100k spheres + 64 lights 479 vs 223 Msamples/s; 4096 spheres 1064 vs 1237),
-    // whose deep, divergent traversal wants more resident warps than one 512-thread CTA per SM
+    // AUTO (measured, profiles/): f64 -> fused; f32 small scenes -> the shared-memory wavefront (queues on the SM, no HBM
+    // traffic); f32 BVH scenes from 4096 spheres -> the global-memory wavefront, whose dedicated traversal kernels keep three
+    // times as many warps resident on the dependent node fetches (100k spheres + 64 lights: 482 fused / 265 shared-memory
+    // wavefront / 690 streaming Msamples/s)
     uint32_t integ = t->cfg.integrator;
-    if (integ == PTB_INTEGRATOR_AUTO)
-        integ = (t->precision == 4 && !(t->s32.d.use_bvh && t->s32.d.n_spheres > 16384u)) ? PTB_INTEGRATOR_WAVEFRONT : PTB_INTEGRATOR_FUSED;
+    if (integ == PTB_INTEGRATOR_AUTO) {
+        if (t->precision != 4) integ = PTB_INTEGRATOR_FUSED;
+        else integ = (t->s32.d.use_bvh && t->s32.d.n_spheres >= 4096u) ? PTB_INTEGRATOR_STREAM : PTB_INTEGRATOR_WAVEFRONT;
+    }
     if (integ == PTB_INTEGRATOR_WAVEFRONT) {
         if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the wavefront integrator is built for f32 only");
         r = wavefront_render(t->wf, t->s32.d, t->accum, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters,

@@ -46,6 +46,7 @@ constexpr int ST_THREADS = 256;
 constexpr uint32_t ST_KEYS = 9;          // 8 lobe classes (lobe_class_of) + ST_MISS
 constexpr uint32_t ST_MISS = 8;          // the path left the scene: background lookup (tracer.rs:66-69)
 constexpr uint32_t ST_DEFAULT_WAVE = 1u << 23;
+constexpr uint32_t ST_SPLIT_MIN_SPHERES = 16384u;   // BVH scenes above this use the persistent-lane traversal kernels from bounce 1 on
 
 struct BounceCtr {                       // 128 bytes per bounce, zeroed at the start of a wave
     uint32_t n_ray;                      // rays entering this bounce
@@ -193,8 +194,9 @@ PTB_DEV void push_by_key(const StreamArgs& a, BounceCtr& ctr, uint32_t key, uint
     }
 }
 
-// Small scenes (no BVH): the whole of Scene::closest_hit in one kernel.
-template <bool COUNT>
+// The whole of Scene::closest_hit in one kernel, one ray per lane per 32-ray chunk: small scenes (no BVH), and BVH scenes
+// while the rays of a chunk are coherent (camera rays) or the tree is shallow.
+template <bool COUNT, bool BVH>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     __shared__ SceneSmem<R> sm;
@@ -217,8 +219,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_cons
             const float4 A0 = a.a0[slot], A1 = a.a1[slot];
             const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
             if (COUNT) pc.closest_hit++;
-            const HitCore<R> h = closest_hit_core<R, false>(s, sv, o, d, A1.z);
-            key = stream_after_hit<COUNT, false>(s, sv, a, slot, d, A1.w, h, pc);
+            const HitCore<R> h = closest_hit_core<R, BVH>(s, sv, o, d, A1.z);
+            key = stream_after_hit<COUNT, BVH>(s, sv, a, slot, d, A1.w, h, pc);
         }
         push_by_key(a, ctr, key, slot);
     }
@@ -548,8 +550,8 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
-// Small scenes (no BVH): Scene::any_hit over the shadow queue.
-template <bool COUNT>
+// Scene::any_hit over the shadow queue, one ray per lane per 32-ray chunk (see k_stream_closest).
+template <bool COUNT, bool BVH>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     __shared__ SceneSmem<R> sm;
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_const
         const uint32_t j = chunk + lane;
         if (j >= n) continue;
         const float4 S0 = a.s0[j], S1 = a.s1[j];
-        const bool occluded = any_hit<R, false>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
+        const bool occluded = any_hit<R, BVH>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
         if (!occluded) {
             const float4 S2 = a.s2[j];
             const uint32_t flags = __float_as_uint(S2.w);
@@ -609,7 +611,7 @@ struct StreamState {
     uint32_t cap = 0;            // paths per wave the allocation was sized for
     BounceCtr* ctr = nullptr;
     uint32_t ctr_bounces = 0;
-    int grid[4][4] = {};         // persistent grid per [COUNT*2 + BVH][stage]
+    int grid[4][7] = {};         // persistent grid per [COUNT*2 + BVH][plain stage 0..2, split stage 0..3]
     void release() {
         if (mem) cudaFree(mem);
         if (ctr) cudaFree(ctr);
@@ -665,31 +667,36 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, u
     const bool bvh = d.use_bvh != 0;
     const int vi = (count ? 2 : 0) + (bvh ? 1 : 0);
     using StageKernel = void (*)(const DScene<float>, const StreamArgs, const uint32_t);
-    // stage kernels of a bounce, in launch order; small scenes: closest, shade, shadow; BVH scenes: trace, finish, shade, trace<ANY>
-    StageKernel stages[4];
-    int n_stages;
+    // Stage kernels of a bounce, in launch order.  Plain form: closest, shade, shadow (one ray per lane per chunk).
+    // Large BVH scenes from bounce 1 on (incoherent rays, deep tree): trace, finish, shade, trace<ANY> with persistent lanes —
+    // measured on 100k spheres: bounce 0 0.83 ms plain vs 1.85 ms split, bounce 1 1.72 ms plain vs 1.33 + 0.44 ms split
+    // (wash) ... while 4096 spheres run 1.3x faster in the plain form on every bounce (profiles/r01_ncu_stream.md).
+    StageKernel plain[3], split[4];
     if (bvh) {
-        stages[0] = count ? k_stream_trace<false, true> : k_stream_trace<false, false>;
-        stages[1] = count ? k_stream_finish<true> : k_stream_finish<false>;
-        stages[2] = count ? k_stream_shade<true, true> : k_stream_shade<false, true>;
-        stages[3] = count ? k_stream_trace<true, true> : k_stream_trace<true, false>;
-        n_stages = 4;
+        plain[0] = count ? k_stream_closest<true, true> : k_stream_closest<false, true>;
+        plain[1] = count ? k_stream_shade<true, true> : k_stream_shade<false, true>;
+        plain[2] = count ? k_stream_shadow<true, true> : k_stream_shadow<false, true>;
     } else {
-        stages[0] = count ? k_stream_closest<true> : k_stream_closest<false>;
-        stages[1] = count ? k_stream_shade<true, false> : k_stream_shade<false, false>;
-        stages[2] = count ? k_stream_shadow<true> : k_stream_shadow<false>;
-        n_stages = 3;
+        plain[0] = count ? k_stream_closest<true, false> : k_stream_closest<false, false>;
+        plain[1] = count ? k_stream_shade<true, false> : k_stream_shade<false, false>;
+        plain[2] = count ? k_stream_shadow<true, false> : k_stream_shadow<false, false>;
     }
-    int grids[4];
-    for (int k = 0; k < n_stages; ++k) {
-        int& g = st.grid[vi][k];
-        if (g == 0) {
+    split[0] = count ? k_stream_trace<false, true> : k_stream_trace<false, false>;
+    split[1] = count ? k_stream_finish<true> : k_stream_finish<false>;
+    split[2] = plain[1];
+    split[3] = count ? k_stream_trace<true, true> : k_stream_trace<true, false>;
+    const bool use_split = bvh && d.n_spheres > ST_SPLIT_MIN_SPHERES;
+    int g_plain[3], g_split[4];
+    auto grid_of = [&](int& slot, StageKernel k) {
+        if (slot == 0) {
             int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stages[k], ST_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-            g = per_sm * sm_count;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, ST_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+            slot = per_sm * sm_count;
         }
-        grids[k] = g;
-    }
+        return slot;
+    };
+    for (int k = 0; k < 3; ++k) g_plain[k] = grid_of(st.grid[vi][k], plain[k]);
+    for (int k = 0; k < 4; ++k) g_split[k] = use_split ? grid_of(st.grid[vi][3 + k], split[k]) : 0;
 
     if ((e = cudaEventRecord(ev0, stream)) != cudaSuccess) return cuda_fail("cudaEventRecord");
     for (uint32_t s0 = 0; s0 < spp; s0 += S) {
@@ -704,8 +711,13 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, u
             (*launches)++;
             const int cap_grid = (int)std::max<uint32_t>(1u, (a.P + ST_THREADS - 1) / ST_THREADS);
             for (uint32_t b = 0; b < d.depth; ++b) {
-                for (int k = 0; k < n_stages; ++k) stages[k]<<<std::min(grids[k], cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
-                (*launches) += (uint64_t)n_stages;
+                if (use_split && b >= 1u) {
+                    for (int k = 0; k < 4; ++k) split[k]<<<std::min(g_split[k], cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
+                    (*launches) += 4;
+                } else {
+                    for (int k = 0; k < 3; ++k) plain[k]<<<std::min(g_plain[k], cap_grid), ST_THREADS, 0, stream>>>(d, a, b);
+                    (*launches) += 3;
+                }
             }
             k_stream_accumulate<<<(a.npix + ST_THREADS - 1) / ST_THREADS, ST_THREADS, 0, stream>>>(a);
             (*launches)++;
