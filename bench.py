@@ -177,16 +177,20 @@ def run_own(args):
 
     # ---- FLOP model from device counters (small counted render of the same scene) -------------------
     fps = None
+    rays_per_sample = None
     if rank == 0:
         ct = rp.Tracer.new(scene, device=local, collect_counters=True)
         cb = rp.ColorBuffer.new(960, 540)
         ct.render_spp(cb, 4, download=False)
-        fps = flops_per_sample(ct.counters())
+        cts = ct.counters()
+        fps = flops_per_sample(cts)
+        rays_per_sample = (cts["closest_hit"] + cts["any_hit"]) / max(1, cts["samples"])
         ct.close()
 
     # ---- device-resident arm: `value` ---------------------------------------------------------------------
-    integ = {"auto": rp._abi.PTB_INTEGRATOR_AUTO, "fused": rp._abi.PTB_INTEGRATOR_FUSED, "wavefront": rp._abi.PTB_INTEGRATOR_WAVEFRONT}[args.integrator]
-    kernel_name = "k_render_fused<float,false,false>" if args.integrator == "fused" else "k_render_wavefront<false,false>"
+    integ = {"auto": rp._abi.PTB_INTEGRATOR_AUTO, "fused": rp._abi.PTB_INTEGRATOR_FUSED, "wavefront": rp._abi.PTB_INTEGRATOR_WAVEFRONT,
+             "stream": rp._abi.PTB_INTEGRATOR_STREAM}[args.integrator]
+    kernel_name = {"fused": "k_render_fused<float,false,false>", "stream": "k_stream_* (one kernel per stage)"}.get(args.integrator, "k_render_wavefront<false,false>")
     dt = DistributedTracer(scene, W, H, device=dev, integrator=integ)
     stream = torch.cuda.current_stream(dev)
     reduced = None
@@ -303,6 +307,7 @@ def run_own(args):
                                   f"({args.steps} steps = {S * args.steps} spp)",
                           "integrator": kernel_name, "l2": f"accumulators {W * H * 16 / 1e6:.1f} MB > 126 MB L2; "
                           "no other input", "image_finite_alpha_one": image_ok},
+               "rays_per_s": value * 1e6 * rays_per_sample if rays_per_sample else None,   # closest_hit + any_hit calls per second, whole job
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": W * H * 16},
                "roofline": roofline}
@@ -323,7 +328,7 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
-    ap.add_argument("--integrator", default="auto", choices=["auto", "fused", "wavefront"])
+    ap.add_argument("--integrator", default="auto", choices=["auto", "fused", "wavefront", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-kernel-timing", action="store_true", help="sync after every step to time each launch (perturbs `value`)")
     args = ap.parse_args()
