@@ -191,7 +191,8 @@ def run_own(args):
     integ = {"auto": rp._abi.PTB_INTEGRATOR_AUTO, "fused": rp._abi.PTB_INTEGRATOR_FUSED, "wavefront": rp._abi.PTB_INTEGRATOR_WAVEFRONT,
              "stream": rp._abi.PTB_INTEGRATOR_STREAM}[args.integrator]
     kernel_name = {"fused": "k_render_fused<float,false,false>", "stream": "k_stream_* (one kernel per stage)"}.get(args.integrator, "k_render_wavefront<false,false>")
-    dt = DistributedTracer(scene, W, H, device=dev, integrator=integ)
+    dt = DistributedTracer(scene, W, H, device=dev, integrator=integ, gather=args.gather)
+    gather_used = dt.gather if world > 1 else "none (single GPU)"
     stream = torch.cuda.current_stream(dev)
     reduced = None
     for _ in range(args.warmup):
@@ -243,7 +244,7 @@ def run_own(args):
     # stream behind an event, and the timed region ends only when the last copy has landed.
     pinned = [torch.empty(W * H * 4, dtype=torch.float32).pin_memory() for _ in range(2)]
     host_bufs = [rp.ColorBuffer.new(W, H, storage=p_.numpy()) for p_ in pinned]
-    et = DistributedTracer(scene, W, H, device=dev, integrator=integ)
+    et = DistributedTracer(scene, W, H, device=dev, integrator=integ, gather=args.gather)
     scene_bytes = et.tracer.scene_bytes
     copy_stream = torch.cuda.Stream(device=dev)
     step_no = [0]
@@ -303,9 +304,10 @@ def run_own(args):
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": WORKLOAD if (W, H) == (WIDTH, HEIGHT) else f"AnalyticalScene {W}x{H}, depth 4, f32 (non-default size)",
-                          "step": f"{S} spp over the frame, sample-split over {world} GPU(s), then ONE NCCL sum-reduce of the float4 accumulators "
+                          "step": f"{S} spp over the frame, sample-split over {world} GPU(s), partial sums gathered on rank 0 (config.gather: peer = stored "
+                                  f"over NVLink by the render kernel + one summing kernel; nccl = ONE NCCL sum-reduce of the float4 accumulators) "
                                   f"({args.steps} steps = {S * args.steps} spp)",
-                          "integrator": kernel_name, "l2": f"accumulators {W * H * 16 / 1e6:.1f} MB > 126 MB L2; "
+                          "integrator": kernel_name, "gather": gather_used, "l2": f"accumulators {W * H * 16 / 1e6:.1f} MB > 126 MB L2; "
                           "no other input", "image_finite_alpha_one": image_ok},
                "rays_per_s": value * 1e6 * rays_per_sample if rays_per_sample else None,   # closest_hit + any_hit calls per second, whole job
                "clocks": clocks, "gpu_launches": int(launches),
@@ -329,6 +331,8 @@ def main():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
     ap.add_argument("--integrator", default="auto", choices=["auto", "fused", "wavefront", "stream"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU: partial sums stored into rank 0's memory by the render kernel (peer) or one NCCL reduce per step (nccl)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-kernel-timing", action="store_true", help="sync after every step to time each launch (perturbs `value`)")
     args = ap.parse_args()

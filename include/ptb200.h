@@ -262,6 +262,25 @@ int  ptb_convert_pixels_to_u8_at_f32(ptb_tracer* t, const float* rgba, uint32_t 
 int  ptb_convert_pixels_to_u8_at_f64(ptb_tracer* t, const double* rgba, uint32_t width, uint32_t height,
                                      uint8_t* frame_rgba8, uint32_t x, uint32_t y, uint32_t frame_w, uint32_t frame_h);
 
+/* ---- multi-GPU: sample-split partial sums gathered over peer memory ------------ */
+/* The reference is single-process (rayon); the new build shards a progressive render by SAMPLE across the GPUs of one
+ * box.  The baseline is one NCCL sum-reduce of the float4 accumulators per step (rust_pathtracer_b200/distributed.py).
+ * These entry points fuse the transfer into the render kernel instead: a rank's kernel stores every pixel's partial sum
+ * of a ptb_render call directly into a slot buffer in the ROOT GPU's memory (NVLink peer stores), and the root adds the
+ * slots up in fixed order.  f32 scenes only; needs CUDA IPC + peer access between the GPUs (PTB_E_UNSUPPORTED otherwise —
+ * callers then fall back to the NCCL reduce). */
+#define PTB_PEER_HANDLE_BYTES 64
+/* root: allocate 2 x n_slots frame-sized slot buffers (double-buffered by step parity) and export them (cudaIpcMemHandle_t) */
+int  ptb_peer_slots_create(ptb_tracer* t, uint32_t n_slots, uint8_t* handle_out /* [PTB_PEER_HANDLE_BYTES] */);
+/* every other rank: map the root's slots */
+int  ptb_peer_slots_open(ptb_tracer* t, const uint8_t* handle /* [PTB_PEER_HANDLE_BYTES] */, uint32_t n_slots);
+/* ptb_render now STORES its per-pixel partial sums into slot `slot` of buffer `parity` (0/1) instead of adding them to
+ * the local accumulators; slot 0xffffffff restores local accumulation */
+int  ptb_peer_set_target(ptb_tracer* t, uint32_t slot, uint32_t parity);
+/* root, after all ranks' renders of the step have completed: accumulators += slot 0 + slot 1 + ... of buffer `parity` */
+int  ptb_peer_sum(ptb_tracer* t, uint32_t parity);
+int  ptb_peer_slots_close(ptb_tracer* t);
+
 int  ptb_get_counters(ptb_tracer* t, ptb_counters* out);
 int  ptb_reset_counters(ptb_tracer* t);
 /* kernels launched by this tracer since creation (for bench.py's gpu_launches) */

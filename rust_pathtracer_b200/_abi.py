@@ -18,6 +18,7 @@ PTB_LIGHT_RECTANGULAR, PTB_LIGHT_SPHERICAL, PTB_LIGHT_DISTANT = 0, 1, 2
 PTB_BG_CONSTANT, PTB_BG_GRADIENT_Y = 0, 1
 PTB_SCENE_ANYHIT_IGNORES_MAX_DIST, PTB_SCENE_FORCE_BVH, PTB_SCENE_NO_BVH = 1, 2, 4
 PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT, PTB_INTEGRATOR_STREAM = 0, 1, 2, 3
+PTB_PEER_HANDLE_BYTES = 64
 
 PTB_MAT_RGB, PTB_MAT_EMISSION, PTB_MAT_ANISOTROPIC, PTB_MAT_METALLIC = 1 << 0, 1 << 1, 1 << 2, 1 << 3
 PTB_MAT_ROUGHNESS, PTB_MAT_SUBSURFACE, PTB_MAT_SPECULAR_TINT, PTB_MAT_SHEEN = 1 << 4, 1 << 5, 1 << 6, 1 << 7
@@ -85,6 +86,7 @@ SYMBOLS = [
     "ptb_set_scene_f32", "ptb_set_scene_f64", "ptb_resize", "ptb_bind_accumulator", "ptb_clear",
     "ptb_upload_f32", "ptb_upload_f64", "ptb_download_f32", "ptb_download_f64", "ptb_frames",
     "ptb_render", "ptb_render_frame_f32", "ptb_render_frame_f64", "ptb_synchronize",
+    "ptb_peer_slots_create", "ptb_peer_slots_open", "ptb_peer_set_target", "ptb_peer_sum", "ptb_peer_slots_close",
     "ptb_convert_to_u8", "ptb_convert_to_u8_at", "ptb_convert_pixels_to_u8_f32", "ptb_convert_pixels_to_u8_f64",
     "ptb_convert_pixels_to_u8_at_f32", "ptb_convert_pixels_to_u8_at_f64", "ptb_get_counters", "ptb_reset_counters", "ptb_launch_count",
     "ptb_last_render_ms",
@@ -136,6 +138,11 @@ def load():
     lib.ptb_download_f64.argtypes = [C.c_void_p, C.c_void_p]
     lib.ptb_frames.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.ptb_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+    lib.ptb_peer_slots_create.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p]
+    lib.ptb_peer_slots_open.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+    lib.ptb_peer_set_target.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.ptb_peer_sum.argtypes = [C.c_void_p, C.c_uint32]
+    lib.ptb_peer_slots_close.argtypes = [C.c_void_p]
     lib.ptb_render_frame_f32.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     lib.ptb_render_frame_f64.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     lib.ptb_synchronize.argtypes = [C.c_void_p]

@@ -18,6 +18,8 @@ struct DeviceCounters {   // mirrors ptb_counters
 
 struct RenderArgs {
     void* accum;                 // W*H x (sum r, sum g, sum b, sample count) in R
+    void* flush_dst;             // non-NULL: a pixel's partial sum (sum r, g, b, spp) of this launch is STORED here instead of
+                                 // being added to `accum` — the root GPU's slot buffer, written over NVLink (ptb_peer_*)
     uint32_t W, H;
     uint32_t spp;
     uint64_t sample_base;
@@ -75,9 +77,13 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_con
         // ---- pixel hand-out -------------------------------------------------------------------
         bool want = !alive && !done && (!have_pixel || s_idx == a.spp);
         if (want && have_pixel) {
-            V4 v = accum[pix];
-            v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += (R)a.spp;
-            accum[pix] = v;
+            if (a.flush_dst) {
+                reinterpret_cast<V4*>(a.flush_dst)[pix] = mk4(acc.x, acc.y, acc.z, (R)a.spp);
+            } else {
+                V4 v = accum[pix];
+                v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += (R)a.spp;
+                accum[pix] = v;
+            }
             have_pixel = false;
         }
         unsigned need = __ballot_sync(FULL, want);
@@ -171,6 +177,18 @@ template <class R> __global__ void k_unresolve(const typename Vec4T<R>::type* me
     if (i >= n) return;
     auto v = mean[i];
     accum[i] = mk4(v.x * frames, v.y * frames, v.z * frames, frames);
+}
+
+// multi-GPU gather: accumulators += sum over the n_slots partial-sum buffers of one step, in slot order (deterministic)
+__global__ void k_peer_sum(float4* accum, const float4* slots, uint32_t n_slots, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = accum[i];
+    for (uint32_t r = 0; r < n_slots; ++r) {
+        const float4 p = slots[(size_t)r * n + i];
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    accum[i] = v;
 }
 
 // Rust `as u8` (saturating, NaN -> 0, truncating)

@@ -74,6 +74,8 @@ struct StreamArgs {
     float4* s2;          //               deferred contribution.xyz, flags (bits 0..3 lobes evaluated, bit 4 pdf > 0)
     BounceCtr* ctr;
     float4* accum;
+    float4* flush_dst;   // multi-GPU: partial sums of this call go here (the root GPU's slot) instead of into accum
+    uint32_t flush_store;// 1: the first wave that touches a pixel in this call stores, later waves add
     uint32_t W, H, tiles_x, n_items;
     uint32_t pix0, npix; // this wave's range of tiled pixel indices
     uint32_t S;          // samples per pixel in this wave
@@ -599,9 +601,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_accumulate(const StreamAr
     const float4* r = a.a3 + (size_t)il * a.S;
     for (uint32_t k = 0; k < a.S; ++k) { const float4 v = r[k]; sx += v.x; sy += v.y; sz += v.z; }
     const uint32_t pix = prow * a.W + px;
-    float4 v = a.accum[pix];
+    float4* dst = a.flush_dst ? a.flush_dst : a.accum;
+    float4 v = (a.flush_dst && a.flush_store) ? make_float4(0.f, 0.f, 0.f, 0.f) : dst[pix];
     v.x += sx; v.y += sy; v.z += sz; v.w += (float)a.S;
-    a.accum[pix] = v;
+    dst[pix] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -619,7 +622,7 @@ struct StreamState {
     }
 };
 
-inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
+inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, void* flush_dst, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
                          const ptb_config& cfg, cudaStream_t stream, int sm_count, DeviceCounters* counters, cudaEvent_t ev0, cudaEvent_t ev1,
                          uint64_t* launches, std::string& err) {
     cudaError_t e;
@@ -628,7 +631,7 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, u
     a.W = W; a.H = H;
     a.tiles_x = (W + 15u) / 16u;
     a.n_items = a.tiles_x * ((H + 15u) / 16u) * 256u;
-    a.seed = cfg.seed; a.rr_start = cfg.rr_start; a.counters = counters; a.accum = (float4*)accum;
+    a.seed = cfg.seed; a.rr_start = cfg.rr_start; a.counters = counters; a.accum = (float4*)accum; a.flush_dst = (float4*)flush_dst;
 
     // wave shape: all pixels x S samples when the frame is small, else pixel ranges x 1 sample
     uint32_t want = cfg.wave_paths ? cfg.wave_paths : ST_DEFAULT_WAVE;
@@ -704,6 +707,7 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, u
         for (uint32_t pix0 = 0; pix0 < a.n_items; pix0 += pix_per_wave) {
             a.pix0 = pix0; a.npix = std::min(pix_per_wave, a.n_items - pix0); a.S = Sw; a.P = a.npix * Sw;
             a.sample0 = sample_base + s0;
+            a.flush_store = s0 == 0 ? 1u : 0u;
             if ((e = cudaMemsetAsync(st.ctr, 0, (size_t)n_ctr * sizeof(BounceCtr), stream)) != cudaSuccess) return cuda_fail("cudaMemsetAsync");
             const unsigned g_gen = (a.P + ST_THREADS - 1) / ST_THREADS;
             if (count) k_stream_generate<true><<<g_gen, ST_THREADS, 0, stream>>>(d, a);

@@ -105,9 +105,13 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
             // ---- pixel hand-out (same scheme as the fused integrator) ----
             bool want = !alive && !done && (!have_pixel || sidx == a.spp);
             if (want && have_pixel) {
-                float4 v = accum[pix];
-                v.x += sm.f[F_AX][i]; v.y += sm.f[F_AY][i]; v.z += sm.f[F_AZ][i]; v.w += (R)a.spp;
-                accum[pix] = v;
+                if (a.flush_dst) {       // multi-GPU: this launch's partial sum goes straight into the root GPU's slot (peer store)
+                    reinterpret_cast<float4*>(a.flush_dst)[pix] = make_float4(sm.f[F_AX][i], sm.f[F_AY][i], sm.f[F_AZ][i], (R)a.spp);
+                } else {
+                    float4 v = accum[pix];
+                    v.x += sm.f[F_AX][i]; v.y += sm.f[F_AY][i]; v.z += sm.f[F_AZ][i]; v.w += (R)a.spp;
+                    accum[pix] = v;
+                }
                 have_pixel = false;
             }
             unsigned need = __ballot_sync(FULL, want);
@@ -326,11 +330,11 @@ struct WavefrontState {
 };
 
 // host launcher: one persistent CTA per SM
-inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* accum, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
+inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* accum, void* flush_dst, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
                             const ptb_config& cfg, cudaStream_t stream, int sm_count, DeviceCounters* counters, unsigned int* work_counter,
                             cudaEvent_t ev0, cudaEvent_t ev1, uint64_t* launches, std::string& err) {
     RenderArgs a{};
-    a.accum = accum; a.W = W; a.H = H; a.spp = spp; a.sample_base = sample_base; a.seed = cfg.seed; a.rr_start = cfg.rr_start;
+    a.accum = accum; a.flush_dst = flush_dst; a.W = W; a.H = H; a.spp = spp; a.sample_base = sample_base; a.seed = cfg.seed; a.rr_start = cfg.rr_start;
     a.tiles_x = (W + 15u) / 16u;
     a.n_items = a.tiles_x * ((H + 15u) / 16u) * 256u;
     a.work_counter = work_counter;

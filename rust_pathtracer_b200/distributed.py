@@ -43,9 +43,16 @@ def resolve_mean(accum):
 
 
 class DistributedTracer:
-    """A Tracer per rank whose accumulators live in a torch CUDA tensor so that NCCL can reduce them."""
+    """A Tracer per rank.  Two ways to bring the per-rank partial sums together on rank 0:
 
-    def __init__(self, scene, width: int, height: int, device=None, **tracer_kw):
+    * gather="peer" (default when it can be set up): every rank's render kernel stores each pixel's partial sum of the step
+      straight into a slot buffer in rank 0's GPU memory over NVLink (CUDA IPC + peer stores, `ptb_peer_*`); per step only
+      a stream-ordered barrier and one summing kernel on rank 0 remain.  The slots are summed in rank order: deterministic.
+    * gather="nccl": the baseline — accumulators live in a torch CUDA tensor per rank and ONE NCCL sum-reduce per step
+      combines them on rank 0 (also the fallback when IPC / peer access is unavailable).
+    """
+
+    def __init__(self, scene, width: int, height: int, device=None, gather: str = "auto", **tracer_kw):
         import torch
         import torch.distributed as dist
         from .prelude import Tracer
@@ -58,19 +65,78 @@ class DistributedTracer:
         self.tracer.bind_accumulator(self.accum.data_ptr(), width, height)
         self.tracer.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.samples_done = 0
+        self.gather = "nccl"
+        self.parity = 0
+        if gather not in ("auto", "peer", "nccl"):
+            raise ValueError("gather must be auto, peer or nccl")
+        if self.world > 1 and gather in ("auto", "peer") and self.tracer.precision == "f32":
+            ok = self._setup_peer()
+            if not ok and gather == "peer":
+                raise RuntimeError("peer gather unavailable (CUDA IPC / peer access)")
+            self.gather = "peer" if ok else "nccl"
+
+    def _setup_peer(self) -> bool:
+        """Root creates the slot buffers and broadcasts the IPC handle; everybody maps them; all ranks must succeed."""
+        import torch
+        import torch.distributed as dist
+        handle = [None]
+        ok = 1
+        if self.rank == 0:
+            try:
+                handle[0] = self.tracer.peer_slots_create(self.world)
+            except Exception:
+                ok = 0
+        dist.broadcast_object_list(handle, src=0, device=self.device)
+        if self.rank != 0:
+            try:
+                if handle[0] is None:
+                    raise RuntimeError("root could not create the slots")
+                self.tracer.peer_slots_open(handle[0], self.world)
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            try:
+                self.tracer.peer_slots_close()
+            except Exception:
+                pass
+            return False
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        return True
 
     def render(self, total_spp: int) -> None:
         """Trace this rank's share of the next `total_spp` global samples (asynchronous)."""
         base, count = split_samples(total_spp, self.world, self.rank)
-        if count:
+        if self.gather == "peer":
+            self.tracer.peer_set_target(self.rank, self.parity)
+            self.tracer.render_samples(count, self.samples_done + base)     # count == 0 clears the slot
+        elif count:
             self.tracer.render_samples(count, self.samples_done + base)
         self.samples_done += total_spp
 
     def reduce(self, dst: int = 0):
-        """One NCCL sum-reduce of the accumulators; returns the reduced copy on `dst` (None elsewhere)."""
+        """Bring the step's partial sums together on `dst`; returns the cumulative (sum r, g, b, count) there, None elsewhere."""
+        import torch.distributed as dist
+        if self.gather == "peer":
+            if dst != 0:
+                raise ValueError("the peer gather lands on rank 0")
+            # stream-ordered barrier: completes on a rank's stream only after every rank's render kernel — and with it its
+            # stores into rank 0's slots — has completed
+            dist.all_reduce(self._token)
+            if self.rank == 0:
+                self.tracer.peer_sum(self.parity)
+            self.parity ^= 1
+            return self.accum if self.rank == 0 else None
         out = self.accum.clone()
         reduce_accumulators(out, dst)
         return out if self.rank == dst else None
 
     def close(self):
+        if self.gather == "peer":
+            import torch.distributed as dist
+            dist.barrier()          # nobody unmaps / frees while a peer may still write
+            if self.rank != 0:
+                self.tracer.peer_slots_close()
+            dist.barrier()
         self.tracer.close()

@@ -454,6 +454,24 @@ class Tracer:
         """Raw ptb_render: add samples [sample_base, sample_base+spp) to the device accumulators."""
         _abi.check(self._lib.ptb_render(self._handle(), spp, sample_base))
 
+    # -- multi-GPU gather over peer memory (ptb_peer_*, include/ptb200.h) --
+    def peer_slots_create(self, n_slots: int) -> bytes:
+        buf = C.create_string_buffer(_abi.PTB_PEER_HANDLE_BYTES)
+        _abi.check(self._lib.ptb_peer_slots_create(self._handle(), n_slots, buf))
+        return buf.raw
+
+    def peer_slots_open(self, handle: bytes, n_slots: int) -> None:
+        _abi.check(self._lib.ptb_peer_slots_open(self._handle(), C.create_string_buffer(handle, _abi.PTB_PEER_HANDLE_BYTES), n_slots))
+
+    def peer_set_target(self, slot: int, parity: int = 0) -> None:
+        _abi.check(self._lib.ptb_peer_set_target(self._handle(), slot & 0xffffffff, parity))
+
+    def peer_sum(self, parity: int = 0) -> None:
+        _abi.check(self._lib.ptb_peer_sum(self._handle(), parity))
+
+    def peer_slots_close(self) -> None:
+        _abi.check(self._lib.ptb_peer_slots_close(self._handle()))
+
     def clear(self) -> None:
         _abi.check(self._lib.ptb_clear(self._handle()))
 

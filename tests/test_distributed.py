@@ -74,3 +74,50 @@ def test_resolve_mean_handles_empty_pixels():
     from rust_pathtracer_b200.distributed import resolve_mean
     a = torch.tensor([2.0, 4.0, 6.0, 2.0, 0.0, 0.0, 0.0, 0.0])
     assert resolve_mean(a).tolist() == [1.0, 2.0, 3.0, 1.0, 0.0, 0.0, 0.0, 0.0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("integ_name", ["FUSED", "WAVEFRONT", "STREAM"])
+def test_peer_slot_path_equals_local_accumulation(rp, integ_name):
+    """one GPU: partial sums stored into slot buffers (ptb_peer_*) and summed by k_peer_sum == the same samples accumulated
+    locally, bit for bit (the additions happen in the same order)"""
+    integ = getattr(rp._abi, "PTB_INTEGRATOR_" + integ_name)
+    scene = rp.AnalyticalScene.new()
+    W, H = 200, 120
+    plain = rp.Tracer.new(scene, integrator=integ)
+    b0 = rp.ColorBuffer.new(W, H)
+    plain._ensure_size(b0); plain.clear()
+    plain.render_samples(3, 0); plain.render_samples(2, 3)
+    plain.download(b0); plain.close()
+    pt = rp.Tracer.new(scene, integrator=integ)
+    b1 = rp.ColorBuffer.new(W, H)
+    pt._ensure_size(b1); pt.clear()
+    handle = pt.peer_slots_create(3)
+    assert len(handle) == rp._abi.PTB_PEER_HANDLE_BYTES
+    for parity in (0, 1):
+        pt.peer_set_target(0, parity); pt.render_samples(3, 0)
+        pt.peer_set_target(1, parity); pt.render_samples(2, 3)
+        pt.peer_set_target(2, parity); pt.render_samples(0, 5)          # a rank without samples: its slot must read as empty
+    pt.peer_set_target(0xffffffff)
+    pt.peer_sum(1)
+    pt.download(b1)
+    assert np.array_equal(b0.pixels, b1.pixels)
+    with pytest.raises(Exception):
+        pt.peer_set_target(3, 0)
+    pt.peer_slots_close(); pt.close()
+
+
+@pytest.mark.gpu
+def test_peer_gather_matches_nccl_reduce(rp):
+    """>= 2 GPUs: torchrun, one rank per GPU; the peer-memory gather, the NCCL reduce and a single-GPU render agree"""
+    import subprocess
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 2 if n < 8 else 8
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "peer_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and f"PEER_OK {world}" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
