@@ -210,8 +210,12 @@ struct Counters {
 // ctr = (block, high 32 bits of the sample index, seed lo, seed hi)
 // f32: block = bounce*2 + slot/4, word = slot%4, u = (word >> 8) * 2^-24
 // f64: block = bounce*4 + slot/2, words (2*(slot%2), 2*(slot%2)+1), u = ((w0<<32|w1) >> 11) * 2^-53
-// slots: 0,1 jitter (tracer.rs:45) | 2 light pick (137) | 3,4 light r1,r2 (191-192)
-//        | 5,6 bsdf r1,r2 (446-447) | 7 reflect/refract coin (534)
+// slots: 0,1 jitter (tracer.rs:45) | 2 light pick (137) | 3 reflect/refract coin (534)
+//        | 4,5 light r1,r2 (191-192) | 6,7 bsdf r1,r2 (446-447)
+// (the four draws every shaded bounce needs share the second block; the first block is only needed by bounce 0's jitter,
+//  by scenes with several lights and by materials that can refract)
+enum : uint32_t { SLOT_JITTER_X = 0, SLOT_JITTER_Y = 1, SLOT_LIGHT_PICK = 2, SLOT_COIN = 3, SLOT_LIGHT_R1 = 4, SLOT_LIGHT_R2 = 5,
+                  SLOT_BSDF_R1 = 6, SLOT_BSDF_R2 = 7 };
 inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
     for (int r = 0; r < 10; ++r) {
@@ -930,12 +934,12 @@ template <class R> struct Tracer {
         ScatterSampleRec<R> scatter_sample;
         size_t number_lights = scene->number_of_lights();
         if (number_lights > 0) {
-            R random = rng.draw(bounce, 2);
+            R random = rng.draw(bounce, SLOT_LIGHT_PICK);
             random *= (R)scene->number_of_lights();
             size_t index = (size_t)random;
             const Light<R>& light = scene->light_at(index);
             LightSampleRec<R> light_sample;
-            R r1 = rng.draw(bounce, 3), r2 = rng.draw(bounce, 4);
+            R r1 = rng.draw(bounce, SLOT_LIGHT_R1), r2 = rng.draw(bounce, SLOT_LIGHT_R2);
             sample_light(light, scatter_pos, light_sample, r1, r2);
             V3<R> li = light_sample.emission;
             if (dot(light_sample.direction, light_sample.normal) < R(0)) {
@@ -969,7 +973,7 @@ template <class R> struct Tracer {
         R xx = xf / (R)width;
         R yy = yf / height;
         CounterRng<R> rng(pixel_id, sample, seed);
-        R offx = rng.draw(0, 0), offy = rng.draw(0, 1);
+        R offx = rng.draw(0, SLOT_JITTER_X), offy = rng.draw(0, SLOT_JITTER_Y);
         Ray<R> ray = scene->camera().gen_ray(xx, R(1) - yy, offx, offy, (R)width, height);
 
         V3<R> radiance(0, 0, 0), throughput(1, 1, 1);
@@ -1002,7 +1006,7 @@ template <class R> struct Tracer {
             }
             if (ctr) ctr->shade++;
             radiance += direct_light(ray, state, rng, bounce, ctr) * throughput;
-            R r1 = rng.draw(bounce, 5), r2 = rng.draw(bounce, 6), coin = rng.draw(bounce, 7);
+            R r1 = rng.draw(bounce, SLOT_BSDF_R1), r2 = rng.draw(bounce, SLOT_BSDF_R2), coin = rng.draw(bounce, SLOT_COIN);
             scatter_sample.f = disney_sample(state, -ray.direction, state.ffnormal, scatter_sample.l, scatter_sample.pdf,
                                              r1, r2, coin, nullptr, ctr);
             if (scatter_sample.pdf > R(0)) {

@@ -111,8 +111,14 @@ template <class R> PTB_DEV R mix1(R a, R b, R v) { return (R(1) - v) * a + b * v
 
 // ------------------------------------------------------------------------------------------------
 // Counter RNG: Philox4x32-10, key = (pixel, sample lo), ctr = (block, sample hi, seed lo, seed hi).
-// Slot layout in SURVEY.md §8d.  Bit-exact with the CPU checker by construction
-// (integer arithmetic only; the uint->float conversions are exact).
+// Eight draw slots per bounce (f32: two blocks of four):
+//   0,1 jitter (tracer.rs:45; slot 0 of later bounces: Russian-roulette extension) | 2 light pick (137) | 3 reflect/refract coin (534)
+//   4,5 light r1,r2 (191-192) | 6,7 bsdf r1,r2 (446-447)
+// The four draws EVERY shaded bounce needs share the second block, so a shading stage computes one Philox block unless the
+// scene has several lights or the material can refract (SURVEY.md §8d lists the slots in call order; same draws, regrouped).
+// Bit-exact with the CPU checker by construction (integer arithmetic only; the uint->float conversions are exact).
+enum : uint32_t { SLOT_JITTER_X = 0, SLOT_JITTER_Y = 1, SLOT_LIGHT_PICK = 2, SLOT_COIN = 3, SLOT_LIGHT_R1 = 4, SLOT_LIGHT_R2 = 5,
+                  SLOT_BSDF_R1 = 6, SLOT_BSDF_R2 = 7 };
 struct Philox4 { uint32_t v[4]; };
 PTB_DEV Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -173,6 +179,15 @@ template <> struct Rng<double> {
         block(bounce, 1, out + 4);
     }
 };
+
+// The draws of a shaded bounce for the f32 staged integrators: slots 4..7 always; slots 2,3 (light pick, coin) only when
+// they can matter — with one light the pick is index 0 whatever the draw ((u * 1) as usize, u < 1), and without a
+// transmission lobe the coin decides nothing (ff = 1 - (1-F) * spec_trans * (1-metallic) = 1 > coin, tracer.rs:532-534).
+PTB_DEV void shade_draws(const Rng<float>& rng, uint32_t bounce, bool need_first_block, float u[8]) {
+    u[0] = u[1] = u[2] = u[3] = 0.0f;
+    if (need_first_block) rng.block(bounce, 0, u);
+    rng.block(bounce, 1, u + 4);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Device scene (what ptb_set_scene_* builds from the POD export)
@@ -1119,10 +1134,10 @@ PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const 
     ns.wants_shadow_ray = false;
     ns.light_area = 0;
     if (s.n_lights > 0) {
-        uint32_t li = (uint32_t)(u[2] * s.n_lights_f);          // tracer.rs:137-139
+        uint32_t li = (uint32_t)(u[SLOT_LIGHT_PICK] * s.n_lights_f);          // tracer.rs:137-139
         ns.scatter_pos = su.fhp + s.eps * su.ffn;
         const DLight<R> L = sv.lights[li];
-        ns.ls = sample_light(L, s.n_lights_f, ns.scatter_pos, u[3], u[4]);
+        ns.ls = sample_light(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
         ns.light_area = L.area;
         ns.wants_shadow_ray = L.type == PTB_LIGHT_SPHERICAL && dot(ns.ls.direction, ns.ls.normal) < R(0);   // tracer.rs:148
     }
@@ -1153,7 +1168,7 @@ PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat
             query_for_eval(mat, c, ls.direction, q);
         } else {
             V3<R> l_prev = p.bounce == 0 ? V3<R>(0, 0, 0) : p.d;
-            lobe = query_for_sample(mat, c, u[5], u[6], u[7], l_prev, q);
+            lobe = query_for_sample(mat, c, u[SLOT_BSDF_R1], u[SLOT_BSDF_R2], u[SLOT_COIN], l_prev, q);
             if (COUNT) pc->lobe[lobe]++;
         }
         eval_lobes(mat, c, q, f, pdf, COUNT && !(DEFER && pass == 0) ? pc->ev : (uint32_t*)nullptr);

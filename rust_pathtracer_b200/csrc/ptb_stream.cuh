@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
         p.hit_dist = __uint_as_float(H.w);
         Rng<R> rng(__float_as_uint(A3.w), a.sample0 + __float_as_uint(A2.w), a.seed);
         R u[8];
-        rng.draws(bounce, u);
+        shade_draws(rng, bounce, s.n_lights > 1u || (key & 4u) != 0u, u);      // the queue key is the lobe class: warp-uniform
         Mat<R> mat;
         hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
         const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);

@@ -284,10 +284,10 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
             const uint64_t accepted = (uint64_t)sm.u[U_ACC_LO][i] | ((uint64_t)sm.u[U_ACC_HI][i] << 32);
             const uint32_t sidx = sm.u[U_SIDX][i];
             Rng<R> rng(sm.u[U_PIX][i], a.sample_base + sidx, a.seed);
-            R u[8];
-            rng.draws(p.bounce, u);
             Mat<R> mat;
             hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+            R u[8];
+            shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
             const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
             const bool cont = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, &pc);
             if (cont) {
