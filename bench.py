@@ -114,7 +114,7 @@ def cpu_baseline(seconds_budget: float = 12.0, threads: int = 0) -> dict:
     sc = po.OracleScene(rp.AnalyticalScene.new().device_export())
     cores = threads or po.max_threads()
     px, frames, secs, ctr = sc.render(WIDTH, HEIGHT, 1, threads=cores, counters=True)      # also warms the thread pool
-    n_frames = max(1, min(16, int(seconds_budget / max(secs, 1e-3))))
+    n_frames = max(1, min(64, int(seconds_budget / max(secs, 1e-3))))
     px, frames, secs, _ = sc.render(WIDTH, HEIGHT, n_frames, threads=cores)
     samples = WIDTH * HEIGHT * n_frames
     return {"value": samples / secs / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
