@@ -236,8 +236,10 @@ int  ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base);
  * is 0 the accumulators are cleared, otherwise the host pixels are uploaded first (they are the
  * source of truth: `pixels` and `frames` are public fields the app may edit between calls);
  * then ONE sample per pixel is traced with sample index frames_before and the running mean is
- * written back to `pixels_rgba_inout`.  Synchronous.  Throughput-minded callers keep the image
- * device-resident instead: ptb_render + ptb_download. */
+ * written back to `pixels_rgba_inout`.  Synchronous.  The buffer is page-locked (cudaHostRegister)
+ * the first time it is seen and stays so until another buffer is passed or the tracer is destroyed
+ * — destroy the tracer (or pass a different buffer) before freeing it.  Throughput-minded callers
+ * keep the image device-resident instead: ptb_render + ptb_download. */
 int  ptb_render_frame_f32(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,
                           float* pixels_rgba_inout);
 int  ptb_render_frame_f64(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,

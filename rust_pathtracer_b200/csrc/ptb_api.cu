@@ -92,7 +92,19 @@ struct ptb_tracer {
     uint32_t peer_slots = 0;
     size_t peer_frame_bytes = 0;
     void* flush_dst = nullptr;      // current target of ptb_render's per-pixel partial sums (NULL: add to the accumulators)
+    // drop-in path: the caller's ColorBuffer.pixels, page-locked on first use so that the per-call H2D + D2H run as DMA
+    void* pinned_host = nullptr;
+    size_t pinned_bytes = 0;
 };
+
+// Page-lock the host buffer `render_frame` is called with (the same `ColorBuffer.pixels` every frame in the reference's
+// loop, renderer/src/main.rs:113-122).  Failure is not an error: the copies then go through the driver's staging path.
+static void pin_host_buffer(ptb_tracer* t, void* p, size_t bytes) {
+    if (t->pinned_host == p && t->pinned_bytes == bytes) return;
+    if (t->pinned_host) { cudaHostUnregister(t->pinned_host); t->pinned_host = nullptr; t->pinned_bytes = 0; }
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) { t->pinned_host = p; t->pinned_bytes = bytes; }
+    else cudaGetLastError();
+}
 
 static size_t real_size(const ptb_tracer* t) { return (size_t)t->precision; }
 
@@ -456,6 +468,7 @@ void ptb_destroy(ptb_tracer* t) {
     t->wf.release();
     t->st.release();
     if (t->peer_base) { if (t->peer_ipc) cudaIpcCloseMemHandle(t->peer_base); else if (t->peer_owner) cudaFree(t->peer_base); }
+    if (t->pinned_host) { cudaHostUnregister(t->pinned_host); cudaGetLastError(); }
     if (t->own_accum && t->accum) cudaFree(t->accum);
     if (t->staging) cudaFree(t->staging);
     if (t->work_counter) cudaFree(t->work_counter);
@@ -691,6 +704,7 @@ template <class R> static int render_frame_impl(ptb_tracer* t, uint32_t w, uint3
     if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
     int r;
     if (w != t->W || h != t->H || !t->accum) { if ((r = ptb_resize(t, w, h))) return r; }
+    pin_host_buffer(t, pixels, (size_t)w * h * 4 * sizeof(R));
     // the host buffer is the source of truth, exactly as in the reference where `pixels` and `frames`
     // are public fields the app may edit between calls
     if (frames_before == 0) { if ((r = ptb_clear(t))) return r; }
