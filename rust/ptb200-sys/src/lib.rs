@@ -11,6 +11,11 @@ pub const PTB_LIGHT_SPHERICAL: u32 = 1;
 pub const PTB_BG_CONSTANT: u32 = 0;
 pub const PTB_BG_GRADIENT_Y: u32 = 1;
 pub const PTB_SCENE_ANYHIT_IGNORES_MAX_DIST: u32 = 1;
+pub const PTB_INTEGRATOR_AUTO: u32 = 0;
+pub const PTB_INTEGRATOR_FUSED: u32 = 1;
+pub const PTB_INTEGRATOR_WAVEFRONT: u32 = 2;
+pub const PTB_INTEGRATOR_STREAM: u32 = 3;
+pub const PTB_PEER_HANDLE_BYTES: usize = 64;
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct ptb_material_f32 {
@@ -59,4 +64,11 @@ extern "C" {
     pub fn ptb_convert_pixels_to_u8_f32(t: *mut ptb_tracer, n_pixels: usize, rgba: *const f32, rgba8: *mut u8) -> c_int;
     pub fn ptb_convert_pixels_to_u8_at_f32(t: *mut ptb_tracer, rgba: *const f32, width: u32, height: u32, frame_rgba8: *mut u8,
                                            x: u32, y: u32, frame_w: u32, frame_h: u32) -> c_int;
+    // multi-GPU gather over peer memory (include/ptb200.h "ptb_peer_*"); handles are PTB_PEER_HANDLE_BYTES = 64 bytes
+    pub fn ptb_bind_accumulator(t: *mut ptb_tracer, device_ptr: *mut c_void, width: u32, height: u32) -> c_int;
+    pub fn ptb_peer_slots_create(t: *mut ptb_tracer, n_slots: u32, handle_out: *mut u8) -> c_int;
+    pub fn ptb_peer_slots_open(t: *mut ptb_tracer, handle: *const u8, n_slots: u32) -> c_int;
+    pub fn ptb_peer_set_target(t: *mut ptb_tracer, slot: u32, parity: u32) -> c_int;
+    pub fn ptb_peer_sum(t: *mut ptb_tracer, parity: u32) -> c_int;
+    pub fn ptb_peer_slots_close(t: *mut ptb_tracer) -> c_int;
 }
