@@ -425,6 +425,22 @@ def test_stream_bvh_and_rr(rp):
         img[name] = buf.pixels.copy()
         pt.close()
     assert (pix_rel(img["stream"], img["fused"]) < 1e-5).mean() > 0.99
+    # > 16384 spheres: from bounce 1 on the persistent-lane traversal kernels (k_stream_trace / k_stream_finish) take over
+    sc = rp.sphere_field_scene(n_spheres=20000, n_lights_side=5)
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
+        pt = rp.Tracer.new(sc, integrator=integ, collect_counters=True)
+        buf = rp.ColorBuffer.new(160, 90)
+        pt.render_spp(buf, 3)
+        img[name] = (buf.pixels.copy(), pt.counters())
+        pt.close()
+    assert (pix_rel(img["stream"][0], img["fused"][0]) < 1e-5).mean() > 0.99
+    for k in img["fused"][1]:
+        assert abs(img["stream"][1][k] - img["fused"][1][k]) <= max(3, 1e-3 * 160 * 90 * 3), k
+    pt = rp.Tracer.new(sc, integrator=rp._abi.PTB_INTEGRATOR_STREAM)      # non-counting build: zero-pdf shadow rays pruned
+    buf = rp.ColorBuffer.new(160, 90)
+    pt.render_spp(buf, 3)
+    pt.close()
+    assert (pix_rel(buf.pixels, img["fused"][0]) < 1e-5).mean() > 0.99
     # 25 lights: light BVH inside k_stream_closest
     sc = rp.sphere_field_scene(n_spheres=300, n_lights_side=5)
     for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
