@@ -100,7 +100,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    # PTB200_LIB: developer knob for A/B-ing two builds of the CUDA library (tools/ab_variants.py); it must exist
+    return os.environ.get("PTB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 class PtbError(RuntimeError):

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <type_traits>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -187,6 +189,86 @@ struct BvhBuilder {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+// Resolved-material table (RMat, ptb_device.cuh): host-side evaluation, in f32 with the reference's operation order
+// (x86-64 host code, no contraction).  `chain` = the materials of the accepted primitives in test order (one entry for
+// scenes whose materials assign every field); `odd` = the checker cell of the material that supplies the albedo.
+namespace {
+inline float h_mix(float a, float b, float v) { return (1.0f - v) * a + b * v; }                  // math.rs:33-39 / tracer.rs:228-231
+inline void h_rgb(const DMaterial<float>& dm, bool odd, float out[3]) {
+    if (dm.albedo_kind == PTB_ALBEDO_CHECKER_DIR_RATIO) { float c = odd ? dm.checker_b : dm.checker_a; out[0] = out[1] = out[2] = c; }
+    else { out[0] = dm.rgb[0]; out[1] = dm.rgb[1]; out[2] = dm.rgb[2]; }
+}
+// index (into chain) of the material whose albedo ends up in state.material.rgb; -1 if it is a constant colour
+inline int rm_checker_source(const std::vector<const DMaterial<float>*>& chain) {
+    int src = 0;
+    bool src_is_rgb_assign = (chain[0]->set_mask & PTB_MAT_RGB) != 0;
+    for (size_t i = 1; i < chain.size(); ++i)
+        if (chain[i]->set_mask & PTB_MAT_RGB) { src = (int)i; src_is_rgb_assign = true; }
+    return (src_is_rgb_assign && chain[src]->albedo_kind == PTB_ALBEDO_CHECKER_DIR_RATIO) ? src : -1;
+}
+inline RMat rm_resolve(const std::vector<const DMaterial<float>*>& chain, bool odd) {
+    RMat r;
+    memset(&r, 0, sizeof(r));
+    Mat<float>& m = r.m;
+    float rgb[3];
+    {   // first accepted primitive: Material::new() patched by it == its resolved values (mat_load)
+        const DMaterial<float>& dm = *chain[0];
+        if (dm.set_mask & PTB_MAT_RGB) h_rgb(dm, odd, rgb); else { rgb[0] = dm.rgb[0]; rgb[1] = dm.rgb[1]; rgb[2] = dm.rgb[2]; }
+        m.emission = V3<float>(dm.emission[0], dm.emission[1], dm.emission[2]);
+        m.anisotropic = dm.anisotropic; m.metallic = dm.metallic; m.roughness = dm.roughness; m.subsurface = dm.subsurface;
+        m.specular_tint = dm.specular_tint; m.sheen = dm.sheen; m.sheen_tint = dm.sheen_tint; m.clearcoat = dm.clearcoat;
+        m.clearcoat_gloss = dm.clearcoat_gloss; m.spec_trans = dm.spec_trans; m.ior = dm.ior;
+    }
+    for (size_t i = 1; i < chain.size(); ++i) {     // later accepted primitives assign their masked fields (mat_patch)
+        const DMaterial<float>& dm = *chain[i];
+        const uint32_t k = dm.set_mask;
+        if (k & PTB_MAT_RGB) h_rgb(dm, odd, rgb);
+        if (k & PTB_MAT_EMISSION) m.emission = V3<float>(dm.emission[0], dm.emission[1], dm.emission[2]);
+        if (k & PTB_MAT_ANISOTROPIC) m.anisotropic = dm.anisotropic;
+        if (k & PTB_MAT_METALLIC) m.metallic = dm.metallic;
+        if (k & PTB_MAT_ROUGHNESS) m.roughness = dm.roughness;
+        if (k & PTB_MAT_SUBSURFACE) m.subsurface = dm.subsurface;
+        if (k & PTB_MAT_SPECULAR_TINT) m.specular_tint = dm.specular_tint;
+        if (k & PTB_MAT_SHEEN) m.sheen = dm.sheen;
+        if (k & PTB_MAT_SHEEN_TINT) m.sheen_tint = dm.sheen_tint;
+        if (k & PTB_MAT_CLEARCOAT) m.clearcoat = dm.clearcoat;
+        if (k & PTB_MAT_CLEARCOAT_GLOSS) m.clearcoat_gloss = dm.clearcoat_gloss;
+        if (k & PTB_MAT_SPEC_TRANS) m.spec_trans = dm.spec_trans;
+        if (k & PTB_MAT_IOR) m.ior = dm.ior;
+    }
+    m.rgb = V3<float>(rgb[0], rgb[1], rgb[2]);
+    // lobe class from the un-finalized values (lobe_class_of)
+    {
+        const float nm = 1.0f - m.metallic;
+        r.lobe_class = (nm * (1.0f - m.spec_trans) > 0.0f ? 1u : 0u) | (m.clearcoat * nm > 0.0f ? 2u : 0u) | (m.spec_trans * nm > 0.0f ? 4u : 0u);
+    }
+    // Material::finalize, material.rs:117-131
+    m.roughness = std::fmax(m.roughness, 0.01f);
+    m.clearcoat_roughness = h_mix(0.1f, 0.001f, m.clearcoat_gloss);
+    const float aspect = std::sqrt(1.0f - m.anisotropic * 0.9f);
+    m.ax = std::fmax(m.roughness / aspect, 0.001f);
+    m.ay = std::fmax(m.roughness * aspect, 0.001f);
+    // get_spec_color, tracer.rs:335-341, for both values State::finalize can give eta (globals.rs:58-61)
+    const float lum = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
+    float ctint[3];
+    for (int k = 0; k < 3; ++k) ctint[k] = lum > 0.0f ? rgb[k] / lum : 1.0f;
+    r.eta[0] = 1.0f / m.ior;
+    r.eta[1] = m.ior;
+    for (int side = 0; side < 2; ++side) {
+        const float eta = r.eta[side];
+        const float f0 = (1.0f - eta) / (1.0f + eta);
+        for (int k = 0; k < 3; ++k) r.spec_col[side][k] = h_mix((f0 * f0) * h_mix(1.0f, ctint[k], m.specular_tint), rgb[k], m.metallic);
+    }
+    for (int k = 0; k < 3; ++k) r.sheen_col[k] = h_mix(1.0f, ctint[k], m.sheen_tint);
+    r.lum = lum;
+    r.wd0 = lum * (1.0f - m.metallic) * (1.0f - m.spec_trans);       // tracer.rs:423
+    r.wc0 = 0.25f * m.clearcoat * (1.0f - m.metallic);               // tracer.rs:426
+    return r;
+}
+constexpr uint32_t RM_MAX_PATCH_PRIMS = 6;      // partial-mask scenes: one key per subset of the primitives
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
 // scene upload
 template <class R> struct PodTypes;
 template <> struct PodTypes<float> { using scene = ptb_scene_f32; using material = ptb_material_f32; };
@@ -343,6 +425,41 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     d.off_sphere_material = append(smat.data(), smat.size() * sizeof(uint32_t));
     d.off_materials = append(mats.data(), mats.size() * sizeof(DMaterial<R>));
     blob.resize((blob.size() + 31) & ~size_t(31));
+    // resolved-material table: small f32 scenes whose whole blob (table included) fits the shared-memory scene copy
+    d.off_rm_keys = d.off_rm_table = d.rm_entries = 0;
+    if constexpr (std::is_same<R, float>::value) {
+        const uint32_t n_prims = sc->n_spheres + sc->n_planes;
+        const char* off_env = getenv("PTB200_NO_RESOLVED_MATERIALS");     // A/B switch for profiling the generic shade path
+        if (!use_bvh && sc->n_materials > 0 && n_prims > 0 && (!patch || n_prims <= RM_MAX_PATCH_PRIMS) && !(off_env && off_env[0] == '1')) {
+            std::vector<uint32_t> keys;
+            std::vector<RMat> table;
+            auto add_key = [&](const std::vector<const DMaterial<float>*>& chain, const std::vector<uint32_t>& chain_index) {
+                const int src = rm_checker_source(chain);
+                keys.push_back((uint32_t)table.size() | (src >= 0 ? (chain_index[src] + 1u) << 16 : 0u));
+                table.push_back(rm_resolve(chain, false));
+                if (src >= 0) table.push_back(rm_resolve(chain, true));
+            };
+            if (patch) {
+                keys.push_back(0u);                                           // the empty set is never looked up
+                for (uint32_t mask = 1; mask < (1u << n_prims); ++mask) {
+                    std::vector<const DMaterial<float>*> chain;
+                    std::vector<uint32_t> idx;
+                    for (uint32_t i = 0; i < n_prims; ++i)
+                        if (mask & (1u << i)) { idx.push_back(i < sc->n_spheres ? smat[i] : pmat[i - sc->n_spheres]); chain.push_back(&mats[idx.back()]); }
+                    add_key(chain, idx);
+                }
+            } else {
+                for (uint32_t i = 0; i < sc->n_materials; ++i) add_key({&mats[i]}, {i});
+            }
+            const size_t total = ((blob.size() + 31) & ~size_t(31)) + ((keys.size() * 4 + 31) & ~size_t(31)) + table.size() * sizeof(RMat) + 32;
+            if (table.size() < 0xffffu && total <= PTB_SMEM_SCENE_BYTES) {
+                d.off_rm_keys = append(keys.data(), keys.size() * sizeof(uint32_t));
+                d.off_rm_table = append(table.data(), table.size() * sizeof(RMat));
+                d.rm_entries = (uint32_t)table.size();
+                blob.resize((blob.size() + 31) & ~size_t(31));
+            }
+        }
+    }
 
     sb.bytes = 0;
     CU(upload_vec(&sb.blob, sb.cap_blob, blob, t->stream, sb.bytes));

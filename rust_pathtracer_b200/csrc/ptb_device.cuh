@@ -212,6 +212,7 @@ template <class R> struct DScene {
     uint32_t n_spheres, n_planes, n_materials, n_lights;
     const void* blob;                   // packed scene arrays in HBM (see stage_scene)
     uint32_t blob_bytes, small_bytes, off_spheres, off_planes, off_materials, off_lights, off_sphere_material, off_plane_material;
+    uint32_t off_rm_keys, off_rm_table, rm_entries;   // resolved-material table (RMat below); rm_entries == 0: not built
     const DSphere<R>* spheres;          // the same arrays, addressed directly (BVH leaves, parity kernels)
     const uint32_t* sphere_material;
     const DPlane<R>* planes;
@@ -833,6 +834,7 @@ template <class R> struct ShadeCtx {
     V3<R> v;             // to_local(v_world)
     V3<R> spec_col, sheen_col;
     R eta;
+    R lum, wd0, wc0;     // luminance(rgb), diffuse and clearcoat weights before normalisation (tracer.rs:423, 426)
 };
 template <class R> PTB_DEV V3<R> to_local(const ShadeCtx<R>& c, V3<R> w) { return V3<R>(dot(w, c.t), dot(w, c.b), dot(w, c.n)); }
 template <class R> PTB_DEV V3<R> to_world(const ShadeCtx<R>& c, V3<R> l) { return l.x * c.t + l.y * c.b + l.z * c.n; }
@@ -848,16 +850,18 @@ template <class R> PTB_DEV void shade_ctx_init(ShadeCtx<R>& c, const Mat<R>& m, 
     R f0 = (R(1) - eta) / (R(1) + eta);
     c.spec_col = mix3((f0 * f0) * mix3(V3<R>(1, 1, 1), ctint, m.specular_tint), m.rgb, m.metallic);
     c.sheen_col = mix3(V3<R>(1, 1, 1), ctint, m.sheen_tint);
+    c.lum = lum;
+    c.wd0 = lum * (R(1) - m.metallic) * (R(1) - m.spec_trans);
+    c.wc0 = R(0.25) * m.clearcoat * (R(1) - m.metallic);
 }
 
 // tracer.rs:421-433
 template <class R>
-PTB_DEV void lobe_probabilities(const Mat<R>& m, V3<R> spec_col, R approx_fresnel, R& wd, R& wr, R& wt, R& wc) {
-    R lum = luminance(m.rgb);
-    wd = lum * (R(1) - m.metallic) * (R(1) - m.spec_trans);
-    wr = luminance(mix3(spec_col, V3<R>(1, 1, 1), approx_fresnel));
-    wt = (R(1) - approx_fresnel) * (R(1) - m.metallic) * m.spec_trans * lum;
-    wc = R(0.25) * m.clearcoat * (R(1) - m.metallic);
+PTB_DEV void lobe_probabilities(const Mat<R>& m, const ShadeCtx<R>& c, R approx_fresnel, R& wd, R& wr, R& wt, R& wc) {
+    wd = c.wd0;
+    wr = luminance(mix3(c.spec_col, V3<R>(1, 1, 1), approx_fresnel));
+    wt = (R(1) - approx_fresnel) * (R(1) - m.metallic) * m.spec_trans * c.lum;
+    wc = c.wc0;
     R total = wd + wr + wt + wc;
     wd /= total; wr /= total; wt /= total; wc /= total;
 }
@@ -954,7 +958,7 @@ template <class R> PTB_DEV void query_for_eval(const Mat<R>& m, const ShadeCtx<R
     R wd, wr, wt, wc;
     q.diel = dielectric_fresnel(m_abs(dot(v, h)), c.eta);
     q.fm = mix1(q.diel, schlick_fresnel(dot(l, h)), m.metallic);                    // = disney_fresnel, tracer.rs:596
-    lobe_probabilities(m, c.spec_col, q.fm, wd, wr, wt, wc);
+    lobe_probabilities(m, c, q.fm, wd, wr, wt, wc);
     q.l = l; q.h = h;
     q.pw[LOBE_DIFFUSE] = wd; q.pw[LOBE_CLEARCOAT] = wc; q.pw[LOBE_REFLECT] = wr; q.pw[LOBE_REFRACT] = wt;
     q.mask = 0;
@@ -983,7 +987,7 @@ template <class R>
 PTB_DEV int query_for_sample(const Mat<R>& m, const ShadeCtx<R>& c, R r1, R r2, R coin, V3<R> l_prev_world, LobeQuery<R>& q) {
     R wd, wr, wt, wc;
     R approx_fresnel = disney_fresnel(m, c.eta, c.v.z, c.v.z);
-    lobe_probabilities(m, c.spec_col, approx_fresnel, wd, wr, wt, wc);
+    lobe_probabilities(m, c, approx_fresnel, wd, wr, wt, wc);
     const R cdf0 = wd;
     const R cdf1 = cdf0 + wc;
     int lobe;
@@ -1221,6 +1225,76 @@ PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>
         nee = !any_hit<R, BVH>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
     }
     return shade_finish<R, COUNT>(s, p, mat, su, nee, ns.ls, ns.light_area, u, pc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resolved-material table (f32 staged integrators, small scenes).  Everything a shaded bounce derives from the hit
+// material ALONE is a function of (which primitives were accepted, checker cell parity, entering / exiting): the
+// assignment replay of hit_material, Material::finalize (material.rs:117-131), get_spec_color (tracer.rs:335-341), the
+// eta pick of State::finalize (globals.rs:58-61) and the material-only lobe weights (tracer.rs:423, 426).  The host
+// evaluates these once per scene in plain f32 (x86-64, no contraction: the reference's own arithmetic) and the shade stage
+// reads the entry from shared memory instead of recomputing it per bounce; fields are fetched where they are used, so the
+// material does not occupy registers across the whole stage.
+struct alignas(16) RMat {
+    Mat<float> m;               // patched + finalized
+    float eta[2];               // [0] entering (1 / ior), [1] exiting (ior)
+    float spec_col[2][3];       // get_spec_color per side
+    float sheen_col[3];
+    float lum, wd0, wc0;
+    uint32_t lobe_class;
+};
+// key word of the table: bits 0..15 first entry, bits 16..31 = 1 + index of the material whose checker decides between
+// entry and entry + 1 (0: the albedo is constant)
+PTB_DEV bool checker_odd(float x, float y) {              // analytical.rs:107-111: the cell that takes checker_b
+    float x1 = fmod2_int(m_floor(x));
+    float y1 = fmod2_int(m_floor(y));
+    return !(fmod2_int(x1 + y1) < 1.0f);
+}
+PTB_DEV uint32_t rm_key_of(const DScene<float>& s, const SceneView<float>& sv, int prim, uint32_t accepted_lo) {
+    return s.patch_materials ? accepted_lo : prim_material<float, false>(s, sv, prim);
+}
+PTB_DEV const RMat& rm_lookup(const DScene<float>& s, const SceneView<float>& sv, const uint32_t* rm_keys, const RMat* rm_table, uint32_t key, V3<float> rd) {
+    const uint32_t k = rm_keys[key];
+    uint32_t e = k & 0xffffu;
+    const uint32_t cm = k >> 16;
+    if (cm) {
+        const DMaterial<float>& dm = sv.materials[cm - 1u];
+        if (checker_odd(div_rn(rd.x, rd.y) * dm.checker_scale + dm.checker_offset, div_rn(rd.z, rd.y) * dm.checker_scale + dm.checker_offset)) e += 1u;
+    }
+    return rm_table[e];
+}
+// shade_setup for a table entry
+template <bool COUNT>
+PTB_DEV void shade_setup_rm(PathState<float>& p, V3<float> normal, const RMat& rm, ShadeSetup<float>& su, PathCounters* pc) {
+    su.fhp = p.o + p.hit_dist * p.d;
+    const float nd = dot(normal, p.d);
+    su.ffn = nd <= 0.0f ? normal : -normal;
+    const int side = nd < 0.0f ? 0 : 1;
+    su.eta = rm.eta[side];
+    p.rad = p.rad + rm.m.emission * p.thr;                      // tracer.rs:74
+    if (COUNT) pc->shade++;
+    ShadeCtx<float>& c = su.c;
+    c.n = su.ffn;
+    onb(c.n, c.t, c.b);
+    c.v = to_local(c, -p.d);
+    c.eta = su.eta;
+    c.spec_col = V3<float>(rm.spec_col[side][0], rm.spec_col[side][1], rm.spec_col[side][2]);
+    c.sheen_col = V3<float>(rm.sheen_col[0], rm.sheen_col[1], rm.sheen_col[2]);
+    c.lum = rm.lum; c.wd0 = rm.wd0; c.wc0 = rm.wc0;
+}
+template <bool COUNT>
+PTB_DEV bool path_shade_rm(const DScene<float>& s, const SceneView<float>& sv, PathState<float>& p, V3<float> normal, const RMat& rm, const float* u,
+                           PathCounters* pc) {
+    ShadeSetup<float> su;
+    shade_setup_rm<COUNT>(p, normal, rm, su, pc);
+    NeeSample<float> ns;
+    shade_nee_sample(s, sv, su, u, ns);
+    bool nee = false;
+    if (ns.wants_shadow_ray) {
+        if (COUNT) pc->any_hit++;
+        nee = !any_hit<float, false>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
+    }
+    return shade_finish<float, COUNT>(s, p, rm.m, su, nee, ns.ls, ns.light_area, u, pc);
 }
 
 // Russian roulette EXTENSION at the start of bounce > 0 (the reference has none, quirk A.12; off in

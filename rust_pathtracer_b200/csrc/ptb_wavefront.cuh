@@ -35,9 +35,15 @@
 
 namespace ptb {
 
-constexpr int WF_THREADS = 512;
+#ifndef PTB_WF_THREADS
+#define PTB_WF_THREADS 512
+#endif
+constexpr int WF_THREADS = PTB_WF_THREADS;
 constexpr int WF_WARPS = WF_THREADS / 32;
-constexpr uint32_t WF_POOL = 2048;          // path slots per CTA
+#ifndef PTB_WF_POOL
+#define PTB_WF_POOL 2048
+#endif
+constexpr uint32_t WF_POOL = PTB_WF_POOL;       // path slots per CTA
 constexpr int WF_CLASSES = 9;               // queue keys: 8 lobe classes (3 bits, lobe_class_of) + WF_MISS
 constexpr uint32_t WF_MISS = 8;             // the path left the scene: background lookup, done with full warps in stage 2
 
@@ -61,12 +67,33 @@ struct WfSmem {
     uint32_t cursor2;               // next 32-entry chunk of the stage-2 queue
 };
 
-template <bool COUNT, bool BVH>
+// RM: the scene has a resolved-material table (RMat, ptb_device.cuh) and the host guarantees that the WHOLE blob sits in the
+// shared-memory copy, so every scene read of this instantiation is a shared-memory load (LDS, not a generic LD).
+template <bool COUNT, bool BVH, bool RM>
 __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid_constant__ DScene<float> s, const RenderArgs a) {
     using R = float;
+    static_assert(!(RM && BVH), "the resolved-material table is for scenes that live in shared memory");
     extern __shared__ __align__(16) unsigned char wf_raw[];
     WfSmem& sm = *reinterpret_cast<WfSmem*>(wf_raw);
-    const SceneView<R> sv = stage_scene(s, sm.scene, PTB_SMEM_SCENE_BYTES);
+    SceneView<R> sv;
+    const uint32_t* rm_keys = nullptr;
+    const RMat* rm_table = nullptr;
+    if constexpr (RM) {
+        const uint32_t* src = (const uint32_t*)s.blob;
+        for (uint32_t i = threadIdx.x; i < s.blob_bytes / 4u; i += WF_THREADS) sm.scene[i] = src[i];
+        __syncthreads();
+        const unsigned char* m = reinterpret_cast<const unsigned char*>(sm.scene);
+        sv.planes = (const DPlane<R>*)(m + s.off_planes);
+        sv.lights = (const DLight<R>*)(m + s.off_lights);
+        sv.plane_material = (const uint32_t*)(m + s.off_plane_material);
+        sv.spheres = (const DSphere<R>*)(m + s.off_spheres);
+        sv.sphere_material = (const uint32_t*)(m + s.off_sphere_material);
+        sv.materials = (const DMaterial<R>*)(m + s.off_materials);
+        rm_keys = (const uint32_t*)(m + s.off_rm_keys);
+        rm_table = (const RMat*)(m + s.off_rm_table);
+    } else {
+        sv = stage_scene(s, sm.scene, PTB_SMEM_SCENE_BYTES);
+    }
     float4* accum = reinterpret_cast<float4*>(a.accum);
 
     const unsigned FULL = 0xffffffffu;
@@ -197,7 +224,9 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
                     alive = false;
                 } else {
                     // queue for stage 2: ticket inside the path's key (lobe class of the hit material, or WF_MISS)
-                    const uint32_t cls = sky ? WF_MISS : hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
+                    uint32_t cls;
+                    if constexpr (RM) cls = sky ? WF_MISS : rm_table[rm_keys[rm_key_of(s, sv, h.prim, (uint32_t)h.accepted)] & 0xffffu].lobe_class;
+                    else cls = sky ? WF_MISS : hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
                     sm.key[i] = (uint16_t)cls;
                     sm.ticket[i] = (uint16_t)atomicAdd(&sm.cnt[cls], 1u);
                     sm.u[U_PRIM][i] = sky ? 0xffffffffu : (uint32_t)h.prim;
@@ -284,12 +313,20 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid
             const uint64_t accepted = (uint64_t)sm.u[U_ACC_LO][i] | ((uint64_t)sm.u[U_ACC_HI][i] << 32);
             const uint32_t sidx = sm.u[U_SIDX][i];
             Rng<R> rng(sm.u[U_PIX][i], a.sample_base + sidx, a.seed);
-            Mat<R> mat;
-            hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
             R u[8];
-            shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
-            const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-            const bool cont = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, &pc);
+            bool cont;
+            if constexpr (RM) {
+                const RMat& rm = rm_lookup(s, sv, rm_keys, rm_table, rm_key_of(s, sv, prim, (uint32_t)accepted), p.d);
+                shade_draws(rng, p.bounce, s.n_lights > 1u || (rm.lobe_class & 4u) != 0u, u);
+                const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+                cont = path_shade_rm<COUNT>(s, sv, p, normal, rm, u, &pc);
+            } else {
+                Mat<R> mat;
+                hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+                shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
+                const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+                cont = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, &pc);
+            }
             if (cont) {
                 sm.f[F_OX][i] = p.o.x; sm.f[F_OY][i] = p.o.y; sm.f[F_OZ][i] = p.o.z;
                 sm.f[F_DX][i] = p.d.x; sm.f[F_DY][i] = p.d.y; sm.f[F_DZ][i] = p.d.z;
@@ -340,9 +377,11 @@ inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* ac
     a.work_counter = work_counter;
     a.counters = counters;
     const bool count = cfg.collect_counters != 0;
+    const bool rm = d.rm_entries != 0 && !d.use_bvh;
     void (*kern)(const DScene<float>, const RenderArgs) =
-        d.use_bvh ? (count ? k_render_wavefront<true, true> : k_render_wavefront<false, true>)
-                  : (count ? k_render_wavefront<true, false> : k_render_wavefront<false, false>);
+        d.use_bvh ? (count ? k_render_wavefront<true, true, false> : k_render_wavefront<false, true, false>)
+        : rm      ? (count ? k_render_wavefront<true, false, true> : k_render_wavefront<false, false, true>)
+                  : (count ? k_render_wavefront<true, false, false> : k_render_wavefront<false, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfSmem));
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(wavefront smem): ") + cudaGetErrorString(e); return PTB_E_CUDA; }
     wf.configured = true;
