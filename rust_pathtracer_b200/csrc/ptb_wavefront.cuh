@@ -35,11 +35,18 @@
 
 namespace ptb {
 
+// threads per CTA (one CTA per SM).  The generic and BVH instantiations need ~125 registers in the shade stage: 512 threads.
+// With the resolved-material table the material is read from shared memory where it is used and the kernel fits 80
+// registers (8 bytes of spill), so 768 threads = 24 warps hide the stage's dependent-issue and barrier stalls better
+// (measured, 4K demo scene: 512 / 640 / 768 threads = 6067 / 6151 / 6451 Msamples/s; profiles/r01_ab_variants.txt).
 #ifndef PTB_WF_THREADS
 #define PTB_WF_THREADS 512
 #endif
-constexpr int WF_THREADS = PTB_WF_THREADS;
-constexpr int WF_WARPS = WF_THREADS / 32;
+#ifndef PTB_WF_THREADS_RM
+#define PTB_WF_THREADS_RM 768
+#endif
+constexpr int WF_THREADS_GENERIC = PTB_WF_THREADS;
+constexpr int WF_THREADS_RM = PTB_WF_THREADS_RM;
 #ifndef PTB_WF_POOL
 #define PTB_WF_POOL 2048
 #endif
@@ -70,8 +77,10 @@ struct WfSmem {
 // RM: the scene has a resolved-material table (RMat, ptb_device.cuh) and the host guarantees that the WHOLE blob sits in the
 // shared-memory copy, so every scene read of this instantiation is a shared-memory load (LDS, not a generic LD).
 template <bool COUNT, bool BVH, bool RM>
-__global__ void __launch_bounds__(WF_THREADS, 1) k_render_wavefront(const __grid_constant__ DScene<float> s, const RenderArgs a) {
+__global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_render_wavefront(const __grid_constant__ DScene<float> s, const RenderArgs a) {
     using R = float;
+    constexpr int WF_THREADS = RM ? WF_THREADS_RM : WF_THREADS_GENERIC;
+    constexpr int WF_WARPS = WF_THREADS / 32;
     static_assert(!(RM && BVH), "the resolved-material table is for scenes that live in shared memory");
     extern __shared__ __align__(16) unsigned char wf_raw[];
     WfSmem& sm = *reinterpret_cast<WfSmem*>(wf_raw);
@@ -389,7 +398,7 @@ inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* ac
     int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, max_useful));
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess ||
         (e = cudaEventRecord(ev0, stream)) != cudaSuccess) { err = cudaGetErrorString(e); return PTB_E_CUDA; }
-    kern<<<grid, WF_THREADS, sizeof(WfSmem), stream>>>(d, a);
+    kern<<<grid, rm ? WF_THREADS_RM : WF_THREADS_GENERIC, sizeof(WfSmem), stream>>>(d, a);
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaEventRecord(ev1, stream)) != cudaSuccess) {
         err = std::string("k_render_wavefront launch: ") + cudaGetErrorString(e);
         return PTB_E_CUDA;

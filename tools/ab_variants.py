@@ -18,13 +18,12 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     # name, -D flags, env
     ("generic_512_2048", [], {"PTB200_NO_RESOLVED_MATERIALS": "1"}),
-    ("rm_512_2048", [], {}),
-    ("rm_576_1728", ["-DPTB_WF_THREADS=576", "-DPTB_WF_POOL=1728"], {}),
-    ("rm_640_1920", ["-DPTB_WF_THREADS=640", "-DPTB_WF_POOL=1920"], {}),
-    ("rm_640_2048", ["-DPTB_WF_THREADS=640", "-DPTB_WF_POOL=2048"], {}),
-    ("rm_704_2112", ["-DPTB_WF_THREADS=704", "-DPTB_WF_POOL=2112"], {}),
-    ("rm_768_1536", ["-DPTB_WF_THREADS=768", "-DPTB_WF_POOL=1536"], {}),
-    ("rm_768_2048", ["-DPTB_WF_THREADS=768", "-DPTB_WF_POOL=2048"], {}),
+    ("rm_768_2048", [], {}),
+    ("rm_512_2048", ["-DPTB_WF_THREADS_RM=512", "-DPTB_WF_POOL=2048"], {}),
+    ("rm_640_1920", ["-DPTB_WF_THREADS_RM=640", "-DPTB_WF_POOL=1920"], {}),
+    ("rm_896_1792", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL=1792"], {}),
+    ("rm_896_2048", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL=2048"], {}),
+    ("rm_1024_2048", ["-DPTB_WF_THREADS_RM=1024", "-DPTB_WF_POOL=2048"], {}),
 ]
 
 
