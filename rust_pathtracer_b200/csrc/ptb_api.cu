@@ -452,7 +452,7 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
                 for (uint32_t i = 0; i < sc->n_materials; ++i) add_key({&mats[i]}, {i});
             }
             const size_t total = ((blob.size() + 31) & ~size_t(31)) + ((keys.size() * 4 + 31) & ~size_t(31)) + table.size() * sizeof(RMat) + 32;
-            if (table.size() < 0xffffu && total <= PTB_SMEM_SCENE_BYTES) {
+            if (table.size() < 0xffffu && total <= PTB_SMEM_SCENE_BYTES && total <= WF_SCENE_BYTES_RM) {
                 d.off_rm_keys = append(keys.data(), keys.size() * sizeof(uint32_t));
                 d.off_rm_table = append(table.data(), table.size() * sizeof(RMat));
                 d.rm_entries = (uint32_t)table.size();

@@ -408,6 +408,18 @@ template <class R> PTB_DEV void film_coords(uint32_t x, uint32_t row, uint32_t W
     py = R(1) - yy;
 }
 
+// the same quotients from a precomputed reciprocal and one FMA correction step (q = a*y; r = a - q*b exactly; q + r*y):
+// correctly rounded for the operands the host checked (RenderArgs::film_fast), three FMA-pipe instructions per quotient
+PTB_HD float div_by_fma(float a, float b, float rcp_b) {
+    float q = a * rcp_b;
+    float r = fmaf(-q, b, a);
+    return fmaf(r, rcp_b, q);
+}
+PTB_DEV void film_coords_fma(uint32_t x, uint32_t row, uint32_t W, uint32_t H, float rcp_w, float rcp_h, float& px, float& py) {
+    px = div_by_fma((float)x, (float)W, rcp_w);
+    py = 1.0f - div_by_fma((float)(row + 1u), (float)H, rcp_h);      // y = H - (H - 1 - row) = row + 1 exactly (H < 2^24)
+}
+
 // Scene::background, analytical.rs:28-32
 template <class R> PTB_DEV V3<R> background(const DScene<R>& s, V3<R> d) {
     V3<R> a(s.bg_a[0], s.bg_a[1], s.bg_a[2]);
@@ -1097,9 +1109,14 @@ struct PathCounters {   // per-thread event counts (only when collect_counters)
 };
 
 template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, uint32_t x, uint32_t row, uint32_t W, uint32_t H,
-                                           R inv_w, R inv_h, R j0, R j1) {
+                                           R inv_w, R inv_h, R j0, R j1, bool film_fast = false, float rcp_w = 0.0f, float rcp_h = 0.0f) {
     R px, py;
-    film_coords<R>(x, row, W, H, px, py);
+    if constexpr (sizeof(R) == 4) {
+        if (film_fast) film_coords_fma(x, row, W, H, rcp_w, rcp_h, px, py);
+        else film_coords<R>(x, row, W, H, px, py);
+    } else {
+        film_coords<R>(x, row, W, H, px, py);
+    }
     gen_ray(s, px, py, j0, j1, inv_w, inv_h, p.o, p.d);
     p.thr = V3<R>(1, 1, 1);
     p.rad = V3<R>(0, 0, 0);

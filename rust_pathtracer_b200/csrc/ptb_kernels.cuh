@@ -28,6 +28,11 @@ struct RenderArgs {
     uint32_t tiles_x, n_items;   // 16x16 pixel tiles; n_items = tiles * 256
     unsigned int* work_counter;  // global pixel-chunk dispenser
     DeviceCounters* counters;
+    // film coordinates without a division (wavefront integrator): rcp_w / rcp_h are the correctly rounded 1/W, 1/H and
+    // film_fast says that the host verified, for EVERY column and row of this frame size, that the FMA-corrected quotient
+    // (film_coords_fma) equals the IEEE x / W and y / H of tracer.rs:34-46 bit for bit
+    float rcp_w, rcp_h;
+    uint32_t film_fast;
 };
 
 constexpr int FUSED_THREADS = 256;

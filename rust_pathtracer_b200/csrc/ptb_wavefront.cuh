@@ -47,24 +47,37 @@ namespace ptb {
 #endif
 constexpr int WF_THREADS_GENERIC = PTB_WF_THREADS;
 constexpr int WF_THREADS_RM = PTB_WF_THREADS_RM;
+// shared-memory scene copy of the resolved-material instantiation (the host builds the table only if the blob fits)
+#ifndef PTB_WF_SCENE_BYTES_RM
+#define PTB_WF_SCENE_BYTES_RM 8192
+#endif
+constexpr uint32_t WF_SCENE_BYTES_RM = PTB_WF_SCENE_BYTES_RM;
 #ifndef PTB_WF_POOL
 #define PTB_WF_POOL 2048
 #endif
-constexpr uint32_t WF_POOL = PTB_WF_POOL;       // path slots per CTA
+constexpr uint32_t WF_POOL_GENERIC = PTB_WF_POOL;       // path slots per CTA
+// resolved-material instantiation: 2304 slots = 3 x 768, every warp owns exactly three 32-slot groups in stage 1 (2048 slots
+// left a third of the warps idle for one group in three); the slot state is two words smaller there (see U_* below)
+#ifndef PTB_WF_POOL_RM
+#define PTB_WF_POOL_RM 2304
+#endif
+constexpr uint32_t WF_POOL_RM = PTB_WF_POOL_RM;
 constexpr int WF_CLASSES = 9;               // queue keys: 8 lobe classes (3 bits, lobe_class_of) + WF_MISS
 constexpr uint32_t WF_MISS = 8;             // the path left the scene: background lookup, done with full warps in stage 2
 
 // per-slot float arrays (SoA: array k occupies words [k*P, (k+1)*P))
 enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TX, F_TY, F_TZ, F_RX, F_RY, F_RZ, F_HITDIST, F_PREVPDF, F_AX, F_AY, F_AZ, WF_NF };
-// per-slot u32 arrays
-enum { U_PIX, U_PXY, U_SIDX, U_FLAGS, U_PRIM, U_ACC_LO, U_ACC_HI, WF_NU };
+// per-slot u32 arrays.  The last two exist only in the generic instantiation: with a resolved-material table a scene has at
+// most 6 primitives whenever the accepted set matters (U_ACC_LO is enough), and the pixel index is derived from U_PXY.
+enum { U_PXY, U_SIDX, U_FLAGS, U_PRIM, U_ACC_LO, U_ACC_HI, U_PIX, WF_NU };
+constexpr int WF_NU_RM = 5;
 // flags word: bit0 alive, bit1 have_pixel, bit2 done, bits 8..23 bounce
 constexpr uint32_t FL_ALIVE = 1u, FL_PIXEL = 2u, FL_DONE = 4u;
 
-struct WfSmem {
-    uint32_t scene[PTB_SMEM_SCENE_BYTES / 4];
+template <uint32_t WF_POOL, uint32_t SCENE_BYTES, int NU> struct WfSmemT {
+    uint32_t scene[SCENE_BYTES / 4];
     float f[WF_NF][WF_POOL];
-    uint32_t u[WF_NU][WF_POOL];
+    uint32_t u[NU][WF_POOL];
     uint16_t key[WF_POOL];          // lobe class of a queued slot, 0xffff = not queued
     uint16_t ticket[WF_POOL];       // position inside its class
     uint16_t order[WF_POOL];        // the shading queue: slot indices, class-ordered
@@ -82,6 +95,8 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
     constexpr int WF_THREADS = RM ? WF_THREADS_RM : WF_THREADS_GENERIC;
     constexpr int WF_WARPS = WF_THREADS / 32;
     static_assert(!(RM && BVH), "the resolved-material table is for scenes that live in shared memory");
+    constexpr uint32_t WF_POOL = RM ? WF_POOL_RM : WF_POOL_GENERIC;
+    using WfSmem = WfSmemT<WF_POOL, RM ? WF_SCENE_BYTES_RM : PTB_SMEM_SCENE_BYTES, RM ? WF_NU_RM : (int)WF_NU>;
     extern __shared__ __align__(16) unsigned char wf_raw[];
     WfSmem& sm = *reinterpret_cast<WfSmem*>(wf_raw);
     SceneView<R> sv;
@@ -136,7 +151,9 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             uint32_t sidx = sm.u[U_SIDX][i];
             bool alive = fl & FL_ALIVE, have_pixel = fl & FL_PIXEL, done = fl & FL_DONE;
             const bool was_done = done;
-            uint32_t pix = sm.u[U_PIX][i], pxy = sm.u[U_PXY][i];
+            uint32_t pxy = sm.u[U_PXY][i];
+            uint32_t pix;
+            if constexpr (RM) pix = (pxy >> 16) * a.W + (pxy & 0xffffu); else pix = sm.u[U_PIX][i];
 
             // ---- pixel hand-out (same scheme as the fused integrator) ----
             bool want = !alive && !done && (!have_pixel || sidx == a.spp);
@@ -191,7 +208,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                     Rng<R> rng(pix, a.sample_base + sidx, a.seed);
                     R u4[4];
                     rng.block(0, 0, u4);
-                    path_begin(s, p, pxy & 0xffffu, pxy >> 16, a.W, a.H, inv_w, inv_h, u4[0], u4[1]);
+                    path_begin(s, p, pxy & 0xffffu, pxy >> 16, a.W, a.H, inv_w, inv_h, u4[0], u4[1], a.film_fast != 0u, a.rcp_w, a.rcp_h);
                     alive = true;
                     if (COUNT) n_samples++;
                 } else {
@@ -240,7 +257,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                     sm.ticket[i] = (uint16_t)atomicAdd(&sm.cnt[cls], 1u);
                     sm.u[U_PRIM][i] = sky ? 0xffffffffu : (uint32_t)h.prim;
                     sm.u[U_ACC_LO][i] = (uint32_t)h.accepted;
-                    sm.u[U_ACC_HI][i] = (uint32_t)(h.accepted >> 32);
+                    if constexpr (!RM) sm.u[U_ACC_HI][i] = (uint32_t)(h.accepted >> 32);
                     sm.f[F_HITDIST][i] = p.hit_dist;
                     if (start || a.rr_start != 0) {
                         sm.f[F_TX][i] = p.thr.x; sm.f[F_TY][i] = p.thr.y; sm.f[F_TZ][i] = p.thr.z;
@@ -258,7 +275,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             }
             sm.u[U_FLAGS][i] = (fl & 0xffff00u) | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u) | (done ? FL_DONE : 0u);
             sm.u[U_SIDX][i] = sidx;
-            sm.u[U_PIX][i] = pix;
+            if constexpr (!RM) sm.u[U_PIX][i] = pix;
             sm.u[U_PXY][i] = pxy;
         }
         __syncthreads();
@@ -319,9 +336,12 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                 sm.u[U_FLAGS][i] = fl & ~FL_ALIVE;
                 continue;
             }
-            const uint64_t accepted = (uint64_t)sm.u[U_ACC_LO][i] | ((uint64_t)sm.u[U_ACC_HI][i] << 32);
+            uint64_t accepted = (uint64_t)sm.u[U_ACC_LO][i];
+            uint32_t pix2;
+            if constexpr (RM) { const uint32_t pxy2 = sm.u[U_PXY][i]; pix2 = (pxy2 >> 16) * a.W + (pxy2 & 0xffffu); }
+            else { accepted |= (uint64_t)sm.u[U_ACC_HI][i] << 32; pix2 = sm.u[U_PIX][i]; }
             const uint32_t sidx = sm.u[U_SIDX][i];
-            Rng<R> rng(sm.u[U_PIX][i], a.sample_base + sidx, a.seed);
+            Rng<R> rng(pix2, a.sample_base + sidx, a.seed);
             R u[8];
             bool cont;
             if constexpr (RM) {
@@ -372,8 +392,21 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
 
 struct WavefrontState {
     bool configured = false;
+    uint32_t film_w = 0, film_h = 0;     // frame size the film_fast verdict below was established for
+    bool film_fast = false;
     void release() {}
 };
+
+// RenderArgs::film_fast: every column / row quotient of this frame size, FMA-corrected vs IEEE (W + H checks per frame size)
+inline bool film_coords_fma_exact(uint32_t W, uint32_t H) {
+    if (W == 0 || H == 0 || W >= (1u << 24) || H >= (1u << 24)) return false;
+    const float wf = (float)W, hf = (float)H, rw = 1.0f / wf, rh = 1.0f / hf;
+    for (uint32_t x = 0; x < W; ++x)
+        if (div_by_fma((float)x, wf, rw) != (float)x / wf) return false;
+    for (uint32_t y = 1; y <= H; ++y)
+        if (div_by_fma((float)y, hf, rh) != (float)y / hf) return false;
+    return true;
+}
 
 // host launcher: one persistent CTA per SM
 inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* accum, void* flush_dst, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
@@ -385,20 +418,28 @@ inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* ac
     a.n_items = a.tiles_x * ((H + 15u) / 16u) * 256u;
     a.work_counter = work_counter;
     a.counters = counters;
+    if (wf.film_w != W || wf.film_h != H) { wf.film_fast = film_coords_fma_exact(W, H); wf.film_w = W; wf.film_h = H; }
+    a.film_fast = wf.film_fast ? 1u : 0u;
+#ifdef PTB_NO_FILM_FMA
+    a.film_fast = 0u;
+#endif
+    a.rcp_w = 1.0f / (float)W; a.rcp_h = 1.0f / (float)H;
     const bool count = cfg.collect_counters != 0;
     const bool rm = d.rm_entries != 0 && !d.use_bvh;
     void (*kern)(const DScene<float>, const RenderArgs) =
         d.use_bvh ? (count ? k_render_wavefront<true, true, false> : k_render_wavefront<false, true, false>)
         : rm      ? (count ? k_render_wavefront<true, false, true> : k_render_wavefront<false, false, true>)
                   : (count ? k_render_wavefront<true, false, false> : k_render_wavefront<false, false, false>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WfSmem));
+    const size_t smem_bytes = rm ? sizeof(WfSmemT<WF_POOL_RM, WF_SCENE_BYTES_RM, WF_NU_RM>) : sizeof(WfSmemT<WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, (int)WF_NU>);
+    const uint32_t WF_POOL = rm ? WF_POOL_RM : WF_POOL_GENERIC;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(wavefront smem): ") + cudaGetErrorString(e); return PTB_E_CUDA; }
     wf.configured = true;
     uint32_t max_useful = (a.n_items + WF_POOL - 1) / WF_POOL;
     int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, max_useful));
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess ||
         (e = cudaEventRecord(ev0, stream)) != cudaSuccess) { err = cudaGetErrorString(e); return PTB_E_CUDA; }
-    kern<<<grid, rm ? WF_THREADS_RM : WF_THREADS_GENERIC, sizeof(WfSmem), stream>>>(d, a);
+    kern<<<grid, rm ? WF_THREADS_RM : WF_THREADS_GENERIC, smem_bytes, stream>>>(d, a);
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaEventRecord(ev1, stream)) != cudaSuccess) {
         err = std::string("k_render_wavefront launch: ") + cudaGetErrorString(e);
         return PTB_E_CUDA;

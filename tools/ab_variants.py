@@ -17,13 +17,11 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     # name, -D flags, env
-    ("generic_512_2048", [], {"PTB200_NO_RESOLVED_MATERIALS": "1"}),
-    ("rm_768_2048", [], {}),
-    ("rm_512_2048", ["-DPTB_WF_THREADS_RM=512", "-DPTB_WF_POOL=2048"], {}),
-    ("rm_640_1920", ["-DPTB_WF_THREADS_RM=640", "-DPTB_WF_POOL=1920"], {}),
-    ("rm_896_1792", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL=1792"], {}),
-    ("rm_896_2048", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL=2048"], {}),
-    ("rm_1024_2048", ["-DPTB_WF_THREADS_RM=1024", "-DPTB_WF_POOL=2048"], {}),
+    ("rm_768_2304_fma", [], {}),
+    ("rm_768_2304_nofma", ["-DPTB_NO_FILM_FMA"], {}),
+    ("rm_768_2048_fma", ["-DPTB_WF_POOL_RM=2048"], {}),
+    ("rm_768_2048_nofma", ["-DPTB_WF_POOL_RM=2048", "-DPTB_NO_FILM_FMA"], {}),
+    ("rm_768_2400_fma", ["-DPTB_WF_POOL_RM=2400"], {}),
 ]
 
 
@@ -77,7 +75,18 @@ def one(W, H, spp, ref_path):
         pt.render_spp(buf, spp, download=False)
         times.append(pt.last_render_ms())
     best = min(times)
-    print(json.dumps({"ms": best, "msamples_s": W * H * spp / best / 1e3, "times": times, "mean": float(img[:, :3].mean()), "diff_vs_first": diff}), flush=True)
+    extra = None
+    if os.environ.get("PTB_TIMING_REPORT"):
+        nw = int(os.environ["PTB_TIMING_REPORT"])
+        pt.reset_counters()
+        pt.render_spp(buf, spp, download=False)
+        pt.synchronize()
+        c = pt.counters()
+        s1, srt, s2, b1, b2 = c["lobe_diffuse"], c["lobe_clearcoat"], c["lobe_reflect"], c["ev_diffuse"], c["ev_clearcoat"]
+        tot = s1 + srt + s2
+        extra = {"s1_share": s1 / tot, "sort_share": srt / tot, "s2_share": s2 / tot, "s1_warp_busy": b1 / (nw * s1), "s2_warp_busy": b2 / (nw * s2),
+                 "cta_cycles_avg": tot / 148}
+    print(json.dumps({"ms": best, "msamples_s": W * H * spp / best / 1e3, "times": times, "mean": float(img[:, :3].mean()), "diff_vs_first": diff, "timing": extra}), flush=True)
     pt.close()
 
 
