@@ -31,10 +31,10 @@ PTB_DEV float m_abs(float x) { return fabsf(x); }
 PTB_DEV double m_abs(double x) { return fabs(x); }
 PTB_DEV float m_max(float a, float b) { return fmaxf(a, b); }   // f32::max: NaN-ignoring
 PTB_DEV double m_max(double a, double b) { return fmax(a, b); }
-// powf as exp2(b*log2(a)): ~3 ulp for the |b*log2(a)| <= 20 this path produces, a fraction of the
-// size of powf's full special-case tree (the fused kernel is instruction-cache bound).
-// a == 0 -> 0, a < 0 -> NaN, a == 1 -> 1, as powf.
-PTB_DEV float m_pow(float a, float b) { return exp2f(b * log2f(a)); }
+// powf as exp2(b*log2(a)) on the two MUFU instructions directly (lg2.approx / ex2.approx.ftz, no denormal pre-scaling:
+// every base on this path is a colour or a squared roughness >= 1e-6): ~3 ulp for the |b*log2(a)| <= 20 this path produces,
+// a fraction of the size of powf's special-case tree.  a == 0 -> 0, a < 0 -> NaN, a == 1 -> 1, as powf.
+PTB_DEV float m_pow(float a, float b) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b * __log2f(a))); return r; }
 PTB_DEV double m_pow(double a, double b) { return pow(a, b); }
 PTB_DEV float m_log2(float a) { return log2f(a); }
 PTB_DEV double m_log2(double a) { return log2(a); }
@@ -1170,7 +1170,9 @@ PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const 
 // it if the ray turns out unoccluded — the same additions in the same order, without keeping the shading context alive
 // across kernels.  flags: bits 0..3 = lobes evaluated towards the light, bit 4 = pdf > 0 (the sample can contribute).
 struct NoSink { template <class V> PTB_DEV void operator()(V, uint32_t) const {} };
-template <class R, bool COUNT, bool DEFER = false, class Sink = NoSink>
+// UNROLL: two copies of the lobe code, one per pass (the staged kernel that can afford the code size: +5 % there — the
+// compiler overlaps the independent passes; the fused kernel is instruction-cache bound and keeps the single copy).
+template <class R, bool COUNT, bool DEFER = false, class Sink = NoSink, bool UNROLL = false>
 PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat, const ShadeSetup<R>& su, bool nee, const LightSample<R>& ls,
                           R light_area, const R* u, PathCounters* pc, const Sink& sink = Sink()) {
     const ShadeCtx<R>& c = su.c;
@@ -1180,7 +1182,7 @@ PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat
     V3<R> f, l_world;
     R pdf = 0;
     int lobe = 0;
-#pragma unroll 1
+#pragma unroll (UNROLL ? 2 : 1)
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 0 && !nee) continue;
         LobeQuery<R> q;
@@ -1311,7 +1313,7 @@ PTB_DEV bool path_shade_rm(const DScene<float>& s, const SceneView<float>& sv, P
         if (COUNT) pc->any_hit++;
         nee = !any_hit<float, false>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
     }
-    return shade_finish<float, COUNT>(s, p, rm.m, su, nee, ns.ls, ns.light_area, u, pc);
+    return shade_finish<float, COUNT, false, NoSink, true>(s, p, rm.m, su, nee, ns.ls, ns.light_area, u, pc);
 }
 
 // Russian roulette EXTENSION at the start of bounce > 0 (the reference has none, quirk A.12; off in

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
     const unsigned FULL = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const R inv_w = R(1) / (R)a.W, inv_h = R(1) / (R)a.H;
+    const R inv_w = a.rcp_w, inv_h = a.rcp_h;     // pixel_size (pinhole.rs:41), correctly rounded on the host
 
     for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) { sm.u[U_FLAGS][i] = 0; sm.u[U_SIDX][i] = 0; sm.key[i] = 0xffffu; }
     if (tid < WF_CLASSES) sm.cnt[tid] = 0;

@@ -17,11 +17,10 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     # name, -D flags, env
-    ("rm_768_2304_fma", [], {}),
-    ("rm_768_2304_nofma", ["-DPTB_NO_FILM_FMA"], {}),
-    ("rm_768_2048_fma", ["-DPTB_WF_POOL_RM=2048"], {}),
-    ("rm_768_2048_nofma", ["-DPTB_WF_POOL_RM=2048", "-DPTB_NO_FILM_FMA"], {}),
-    ("rm_768_2400_fma", ["-DPTB_WF_POOL_RM=2400"], {}),
+    ("base", [], {}),
+    ("sph_unroll2", ["-DPTB_SPHERE_UNROLL=2"], {}),
+    ("t640_1920", ["-DPTB_WF_THREADS_RM=640", "-DPTB_WF_POOL_RM=1920"], {}),
+    ("t896_2240", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL_RM=2240"], {}),
 ]
 
 
