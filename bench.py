@@ -39,9 +39,9 @@ F_K = dict(gen_ray=94, closest_hit=130, finalize=36, direct_light=127, nee_contr
            ev_diffuse=75, ev_reflect=103, ev_refract=100, ev_clearcoat=73, sample_common=200, lobe_diffuse=26,
            lobe_clearcoat=52, lobe_reflect=156, lobe_refract=169, background=18, glue_bounce=12, glue_sample=20)
 # DRAM bytes per launch of the render kernel at 3840x2160 from the committed `ncu --set full` capture
-# (profiles/r01_ncu_wavefront.md, r01-h: dram__bytes_read.sum 135.5 MB + dram__bytes_write.sum 82.9 MB; the accumulator
+# (profiles/r01_ncu_wavefront.md, r01-i: dram__bytes_read.sum 134.6 MB + dram__bytes_write.sum 82.8 MB; the accumulator
 # read-modify-write is 265.4 MB algorithmic — part of the writes is still dirty in L2 when the kernel ends).  Independent of spp.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 135527424 + 82906624
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 134553088 + 82791936
 
 
 def flops_per_sample(c: dict) -> float:
@@ -190,7 +190,7 @@ def run_own(args):
     # ---- device-resident arm: `value` ---------------------------------------------------------------------
     integ = {"auto": rp._abi.PTB_INTEGRATOR_AUTO, "fused": rp._abi.PTB_INTEGRATOR_FUSED, "wavefront": rp._abi.PTB_INTEGRATOR_WAVEFRONT,
              "stream": rp._abi.PTB_INTEGRATOR_STREAM}[args.integrator]
-    kernel_name = {"fused": "k_render_fused<float,false,false>", "stream": "k_stream_* (one kernel per stage)"}.get(args.integrator, "k_render_wavefront<false,false>")
+    kernel_name = {"fused": "k_render_fused<float,false,false>", "stream": "k_stream_* (one kernel per stage)"}.get(args.integrator, "k_render_wavefront<COUNT=false,BVH=false,RM=true>")
     dt = DistributedTracer(scene, W, H, device=dev, integrator=integ, gather=args.gather)
     gather_used = dt.gather if world > 1 else "none (single GPU)"
     stream = torch.cuda.current_stream(dev)

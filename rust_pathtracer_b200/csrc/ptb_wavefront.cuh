@@ -49,7 +49,7 @@ constexpr int WF_THREADS_GENERIC = PTB_WF_THREADS;
 constexpr int WF_THREADS_RM = PTB_WF_THREADS_RM;
 // shared-memory scene copy of the resolved-material instantiation (the host builds the table only if the blob fits)
 #ifndef PTB_WF_SCENE_BYTES_RM
-#define PTB_WF_SCENE_BYTES_RM 8192
+#define PTB_WF_SCENE_BYTES_RM PTB_SMEM_SCENE_BYTES
 #endif
 constexpr uint32_t WF_SCENE_BYTES_RM = PTB_WF_SCENE_BYTES_RM;
 #ifndef PTB_WF_POOL

@@ -544,3 +544,61 @@ def test_random_scenes_parity(rp, po, seed):
         n = W * H * S
         for k in ("closest_hit", "any_hit", "shade", "end_sky", "end_emitter", "end_depth", "lobe_refract", "lobe_clearcoat"):
             assert abs(c[k] - oc[k]) <= max(5, 1e-3 * n), (seed, integ, k, c[k], oc[k])
+
+
+def _partial_mask_scene(rp, seed):
+    """a small scene whose materials assign only SOME fields (the reference's cumulative assignment): overlapping
+    spheres in front of each other + checker floor, so that many accepted-primitive sets occur; <= 6 primitives, which is what
+    the resolved-material table enumerates"""
+    r = np.random.default_rng(seed)
+    M = rp.Material
+    mats = [
+        M.assigning(rgb=rp.F3(*r.uniform(0.2, 1.0, 3)), roughness=float(r.uniform(0.05, 0.5)), metallic=1.0),
+        M.assigning(rgb=rp.F3(*r.uniform(0.2, 1.0, 3)), clearcoat=1.0, clearcoat_gloss=float(r.uniform(0.2, 1.0)), roughness=float(r.uniform(0.1, 0.6))),
+        M.assigning(roughness=float(r.uniform(0.2, 0.9)), sheen=float(r.uniform(0, 1)), specular_tint=float(r.uniform(0, 1))),
+        M.assigning(rgb=rp.F3(*r.uniform(0.2, 1.0, 3)), anisotropic=float(r.uniform(0, 0.8)), ior=float(r.uniform(1.2, 1.7))),
+        M.assigning(roughness=1.0, albedo_kind=rp._abi.PTB_ALBEDO_CHECKER_DIR_RATIO),
+    ]
+    n_sph = int(r.integers(3, 5))          # + the floor = 4..5 primitives: 15..31 accepted sets, the table fits its 12 KB
+    spheres = [rp.Sphere(rp.F3(float(r.uniform(-1.5, 1.5)), float(r.uniform(-0.3, 0.8)), float(-1.2 * k + r.uniform(-0.3, 0.3))), float(r.uniform(0.6, 1.1)),
+                         int(r.integers(0, 4))) for k in range(n_sph)]
+    planes = [rp.Plane(rp.F3(0, -1, 0), rp.F3(0, 1, 0), 4)]
+    lights = [rp.AnalyticalLight.spherical(rp.F3(3, 2.5, 2), 1.0, rp.F3(3, 3, 3))]
+    cam = rp.Pinhole.new()
+    cam.set(rp.F3(0.0, 0.3, 3.5), rp.F3(0, 0, -1))
+    cam.set_fov(75.0)
+    return rp.DeviceScene(spheres=spheres, planes=planes, materials=mats, lights=lights, camera=cam, background=rp.Background(),
+                          depth=4, flags=rp._abi.PTB_SCENE_ANYHIT_IGNORES_MAX_DIST, eps=0.005)
+
+
+@pytest.mark.parametrize("seed", [7, 8, 9])
+def test_resolved_material_table_equals_generic_path_and_oracle(rp, po, seed, monkeypatch):
+    """The wavefront integrator shades small scenes from a host-evaluated table (RMat, ptb_device.cuh) keyed by the accepted
+    primitive set / material, checker parity and side.  It must agree with the generic shade path (same kernel without the
+    table: PTB200_NO_RESOLVED_MATERIALS=1, read by ptb_set_scene_*) and with the oracle."""
+    e = _partial_mask_scene(rp, seed)
+    W, H, S = 160, 100, 4
+    ref, _, _, oc = po.OracleScene(e).render(W, H, S, counters=True)
+    imgs = {}
+    for name, env in (("table", None), ("generic", "1")):
+        if env is None:
+            monkeypatch.delenv("PTB200_NO_RESOLVED_MATERIALS", raising=False)
+        else:
+            monkeypatch.setenv("PTB200_NO_RESOLVED_MATERIALS", env)
+        pt = rp.Tracer.new(rp.ExportedScene(e), integrator=rp._abi.PTB_INTEGRATOR_WAVEFRONT, collect_counters=True)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        c = pt.counters()
+        pt.close()
+        imgs[name] = buf.pixels.copy()
+        rel = pix_rel(buf.pixels, ref)
+        assert (rel < 1e-4).mean() >= 0.99, (name, seed, (rel < 1e-4).mean())
+        assert np.median(rel) < 2e-6
+        for k in ("closest_hit", "any_hit", "shade", "end_sky", "end_emitter", "end_depth", "lobe_clearcoat", "lobe_diffuse"):
+            assert abs(c[k] - oc[k]) <= max(5, 1e-3 * W * H * S), (name, seed, k, c[k], oc[k])
+    monkeypatch.delenv("PTB200_NO_RESOLVED_MATERIALS", raising=False)
+    rel = pix_rel(imgs["table"], imgs["generic"])
+    assert (rel < 1e-4).mean() >= 0.995
+    # the two paths round differently (host-evaluated f32 without contraction vs device FMA): bit-identical images would mean
+    # that the table was silently not built for this scene
+    assert (rel > 0).any()

@@ -18,9 +18,6 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     # name, -D flags, env
     ("base", [], {}),
-    ("sph_unroll2", ["-DPTB_SPHERE_UNROLL=2"], {}),
-    ("t640_1920", ["-DPTB_WF_THREADS_RM=640", "-DPTB_WF_POOL_RM=1920"], {}),
-    ("t896_2240", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL_RM=2240"], {}),
 ]
 
 
