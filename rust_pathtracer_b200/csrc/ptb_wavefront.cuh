@@ -9,7 +9,7 @@
 // queue arrays and the scene copy), enough for every stage to run with full warps, so the state never
 // leaves the SM: HBM traffic stays at the 32 B per pixel of the accumulator read-modify-write.
 //
-// One CTA (512 threads) per SM owns a pool of P = 2048 path slots.  Each iteration runs two stages
+// One CTA per SM (512 threads, or 768 with the resolved-material table) owns a pool of P = 2048 / 2304 path slots.  Each iteration runs two stages
 // over the pool, separated by CTA barriers, so that ALL warps of the SM execute the same stage code
 // at the same time (small instruction-cache footprint, the fused kernel's main stall):
 //
