@@ -33,6 +33,10 @@ struct RenderArgs {
     // (film_coords_fma) equals the IEEE x / W and y / H of tracer.rs:34-46 bit for bit
     float rcp_w, rcp_h;
     uint32_t film_fast;
+    // tail items (wavefront integrator): work items [n_whole, n_items) are the frame's last tail_zt pixels (in tile order) cut
+    // into 2^tail_log2b sample blocks; item n_whole + b * tail_zt + z is block b of tail pixel z and its sum goes to tail_side
+    uint32_t n_whole, tail_zt, tail_log2b;
+    void* tail_side;
 };
 
 constexpr int FUSED_THREADS = 256;

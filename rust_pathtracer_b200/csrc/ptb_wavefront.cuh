@@ -71,8 +71,12 @@ enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TX, F_TY, F_TZ, F_RX, F_RY, F_RZ, F
 // most 6 primitives whenever the accepted set matters (U_ACC_LO is enough), and the pixel index is derived from U_PXY.
 enum { U_PXY, U_SIDX, U_FLAGS, U_PRIM, U_ACC_LO, U_ACC_HI, U_PIX, WF_NU };
 constexpr int WF_NU_RM = 5;
-// flags word: bit0 alive, bit1 have_pixel, bit2 done, bits 8..23 bounce
-constexpr uint32_t FL_ALIVE = 1u, FL_PIXEL = 2u, FL_DONE = 4u;
+// flags word: bit0 alive, bit1 have_pixel, bit2 done, bits 3..7 sample block (tail items), bits 8..23 bounce, bit 24 tail item
+constexpr uint32_t FL_ALIVE = 1u, FL_PIXEL = 2u, FL_DONE = 4u, FL_BLOCK = 1u << 24, FL_BLOCK_BITS = FL_BLOCK | (31u << 3);
+#ifndef PTB_WF_TAIL_LOG2
+#define PTB_WF_TAIL_LOG2 3
+#endif
+constexpr uint32_t WF_TAIL_LOG2_BLOCKS = PTB_WF_TAIL_LOG2;  // the last pixels of a frame are traced as up to 2^this sample blocks each (see wavefront_render)
 
 template <uint32_t WF_POOL, uint32_t SCENE_BYTES, int NU> struct WfSmemT {
     uint32_t scene[SCENE_BYTES / 4];
@@ -156,9 +160,22 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             if constexpr (RM) pix = (pxy >> 16) * a.W + (pxy & 0xffffu); else pix = sm.u[U_PIX][i];
 
             // ---- pixel hand-out (same scheme as the fused integrator) ----
-            bool want = !alive && !done && (!have_pixel || sidx == a.spp);
+            // Work items below a.n_whole are whole pixels (all spp samples); the items above are the frame's last a.tail_zt
+            // pixels cut into sample blocks, so that the ramp-down at the end of the launch lasts one block, not one pixel.
+            // A block's sum goes to a side buffer and k_tail_combine adds the blocks of a pixel in block order: the image
+            // stays independent of which slot traced what.
+            uint32_t blkbits = fl & FL_BLOCK_BITS;
+            const uint32_t blk = (fl >> 3) & 31u;
+            const uint32_t s_end = (fl & FL_BLOCK) ? ((blk + 1u) * a.spp) >> a.tail_log2b : a.spp;
+            bool want = !alive && !done && (!have_pixel || sidx == s_end);
             if (want && have_pixel) {
-                if (a.flush_dst) {       // multi-GPU: this launch's partial sum goes straight into the root GPU's slot (peer store)
+                if (fl & FL_BLOCK) {
+                    const uint32_t px0 = pxy & 0xffffu, pr0 = pxy >> 16;
+                    const uint32_t pidx = (((pr0 >> 4) * a.tiles_x + (px0 >> 4)) << 8) | ((pr0 & 15u) << 4) | (px0 & 15u);
+                    const uint32_t s_begin = (blk * a.spp) >> a.tail_log2b;
+                    reinterpret_cast<float4*>(a.tail_side)[(pidx - a.n_whole) + blk * a.tail_zt] =
+                        make_float4(sm.f[F_AX][i], sm.f[F_AY][i], sm.f[F_AZ][i], (R)(s_end - s_begin));
+                } else if (a.flush_dst) {       // multi-GPU: this launch's partial sum goes straight into the root GPU's slot (peer store)
                     reinterpret_cast<float4*>(a.flush_dst)[pix] = make_float4(sm.f[F_AX][i], sm.f[F_AY][i], sm.f[F_AZ][i], (R)a.spp);
                 } else {
                     float4 v = accum[pix];
@@ -182,13 +199,19 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                 const uint32_t avail = w_end - w_next;
                 const uint32_t rank = __popc(need & lt_mask);
                 if (want && rank < avail) {
-                    const uint32_t idx = w_next + rank;
+                    uint32_t idx = w_next + rank, nb = 0, s0 = 0;
+                    if (idx >= a.n_whole) {                                  // tail item: (pixel, sample block)
+                        const uint32_t k = idx - a.n_whole, b2 = k / a.tail_zt;
+                        idx = a.n_whole + (k - b2 * a.tail_zt);
+                        nb = FL_BLOCK | (b2 << 3);
+                        s0 = (b2 * a.spp) >> a.tail_log2b;
+                    }
                     const uint32_t tile = idx >> 8, within = idx & 255u;
                     const uint32_t px = (tile % a.tiles_x) * 16u + (within & 15u);
                     const uint32_t prow = (tile / a.tiles_x) * 16u + (within >> 4);
                     if (px < a.W && prow < a.H) {
                         pix = prow * a.W + px; pxy = px | (prow << 16);
-                        have_pixel = true; want = false; sidx = 0;
+                        have_pixel = true; want = false; sidx = s0; blkbits = nb;
                         sm.f[F_AX][i] = 0; sm.f[F_AY][i] = 0; sm.f[F_AZ][i] = 0;
                     }
                 }
@@ -273,7 +296,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             } else {
                 fl = 0;
             }
-            sm.u[U_FLAGS][i] = (fl & 0xffff00u) | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u) | (done ? FL_DONE : 0u);
+            sm.u[U_FLAGS][i] = (fl & 0xffff00u) | blkbits | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u) | (done ? FL_DONE : 0u);
             sm.u[U_SIDX][i] = sidx;
             if constexpr (!RM) sm.u[U_PIX][i] = pix;
             sm.u[U_PXY][i] = pxy;
@@ -394,8 +417,35 @@ struct WavefrontState {
     bool configured = false;
     uint32_t film_w = 0, film_h = 0;     // frame size the film_fast verdict below was established for
     bool film_fast = false;
-    void release() {}
+    void* tail_side = nullptr;           // float4[tail_zt << WF_TAIL_LOG2_BLOCKS]: block sums of the tail pixels
+    size_t tail_side_bytes = 0;
+    void release() { if (tail_side) cudaFree(tail_side); tail_side = nullptr; tail_side_bytes = 0; }
 };
+
+// Adds the sample blocks of every tail pixel in block order (fixed association: the result does not depend on which slot traced
+// which block) to the accumulator, or stores the sum into the peer slot like the render kernel does for whole pixels.
+__global__ void k_tail_combine(const RenderArgs a) {
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= a.tail_zt) return;
+    const uint32_t idx = a.n_whole + z, tile = idx >> 8, within = idx & 255u;
+    const uint32_t px = (tile % a.tiles_x) * 16u + (within & 15u), prow = (tile / a.tiles_x) * 16u + (within >> 4);
+    if (px >= a.W || prow >= a.H) return;
+    const float4* side = reinterpret_cast<const float4*>(a.tail_side);
+    float4 sum = side[z];
+    for (uint32_t b = 1; b < (1u << a.tail_log2b); ++b) {
+        const float4 v = side[z + b * a.tail_zt];
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    }
+    const uint32_t pix = prow * a.W + px;
+    if (a.flush_dst) {
+        reinterpret_cast<float4*>(a.flush_dst)[pix] = sum;
+    } else {
+        float4* accum = reinterpret_cast<float4*>(a.accum);
+        float4 v = accum[pix];
+        v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
+        accum[pix] = v;
+    }
+}
 
 // RenderArgs::film_fast: every column / row quotient of this frame size, FMA-corrected vs IEEE (W + H checks per frame size)
 inline bool film_coords_fma_exact(uint32_t W, uint32_t H) {
@@ -437,10 +487,35 @@ inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* ac
     wf.configured = true;
     uint32_t max_useful = (a.n_items + WF_POOL - 1) / WF_POOL;
     int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)sm_count, max_useful));
+    // Tail items: when the work counter runs dry every slot is somewhere inside its last pixel, and the launch ramps down
+    // over one pixel's worth of iterations (measured: -15 % at 1920x1080, -4 % at 3840x2160).  The last `grid * WF_POOL`
+    // pixels (one per slot) are therefore handed out as 8 sample blocks each, which shortens the ramp eightfold.
+    a.n_whole = a.n_items; a.tail_zt = 0; a.tail_log2b = 0; a.tail_side = nullptr;
+#ifndef PTB_WF_NO_TAIL
+    if (spp >= 2u && spp <= (1u << 24)) {
+        uint32_t log2b = 1;
+        while (log2b < WF_TAIL_LOG2_BLOCKS && (2u << log2b) <= spp) ++log2b;      // at least one sample per block
+        const uint32_t zt = std::min<uint32_t>(a.n_items, (((uint32_t)grid * WF_POOL + 255u) / 256u) * 256u);
+        const size_t need = ((size_t)zt << log2b) * sizeof(float4);
+        if (need > wf.tail_side_bytes) {
+            if (wf.tail_side) cudaFree(wf.tail_side);
+            wf.tail_side = nullptr; wf.tail_side_bytes = 0;
+            if ((e = cudaMalloc(&wf.tail_side, need)) != cudaSuccess) { err = std::string("cudaMalloc(tail blocks): ") + cudaGetErrorString(e); return PTB_E_CUDA; }
+            wf.tail_side_bytes = need;
+        }
+        a.n_whole = a.n_items - zt; a.tail_zt = zt; a.tail_log2b = log2b; a.tail_side = wf.tail_side;
+        a.n_items = a.n_whole + (zt << log2b);
+    }
+#endif
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess ||
         (e = cudaEventRecord(ev0, stream)) != cudaSuccess) { err = cudaGetErrorString(e); return PTB_E_CUDA; }
     kern<<<grid, rm ? WF_THREADS_RM : WF_THREADS_GENERIC, smem_bytes, stream>>>(d, a);
-    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaEventRecord(ev1, stream)) != cudaSuccess) {
+    if ((e = cudaGetLastError()) == cudaSuccess && a.tail_zt) {
+        k_tail_combine<<<(a.tail_zt + 255u) / 256u, 256, 0, stream>>>(a);
+        e = cudaGetLastError();
+        (*launches)++;
+    }
+    if (e != cudaSuccess || (e = cudaEventRecord(ev1, stream)) != cudaSuccess) {
         err = std::string("k_render_wavefront launch: ") + cudaGetErrorString(e);
         return PTB_E_CUDA;
     }

@@ -17,7 +17,9 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     # name, -D flags, env
-    ("base", [], {}),
+    ("tail8", [], {}),
+    ("tail16", ["-DPTB_WF_TAIL_LOG2=4"], {}),
+    ("tail32", ["-DPTB_WF_TAIL_LOG2=5"], {}),
 ]
 
 
