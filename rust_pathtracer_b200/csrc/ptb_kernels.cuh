@@ -40,7 +40,12 @@ struct RenderArgs {
 };
 
 constexpr int FUSED_THREADS = 256;
-constexpr uint32_t FUSED_CHUNK = 256;   // pixels reserved per atomic = one 16x16 tile
+// pixels a warp reserves per global atomic: two rows of a 16x16 tile (512 B of accumulator, flushed as two 256 B segments).
+// A whole tile per atomic starved warps on small frames: 960x540 is 2040 tiles for 3552 (wavefront) / 2368 (fused) warps.
+#ifndef PTB_CHUNK
+#define PTB_CHUNK 32
+#endif
+constexpr uint32_t FUSED_CHUNK = PTB_CHUNK;
 
 // ------------------------------------------------------------------------------------------------
 // Fused persistent integrator.

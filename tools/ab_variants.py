@@ -17,9 +17,9 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     # name, -D flags, env
-    ("tail8", [], {}),
-    ("tail16", ["-DPTB_WF_TAIL_LOG2=4"], {}),
-    ("tail32", ["-DPTB_WF_TAIL_LOG2=5"], {}),
+    ("chunk32", [], {}),
+    ("chunk64", ["-DPTB_CHUNK=64"], {}),
+    ("chunk256", ["-DPTB_CHUNK=256"], {}),
 ]
 
 
