@@ -602,3 +602,30 @@ def test_resolved_material_table_equals_generic_path_and_oracle(rp, po, seed, mo
     # the two paths round differently (host-evaluated f32 without contraction vs device FMA): bit-identical images would mean
     # that the table was silently not built for this scene
     assert (rel > 0).any()
+
+
+@pytest.mark.parametrize("wh_spp", [(97, 61, 11), (320, 200, 16), (64, 48, 37), (1280, 720, 9)])
+def test_wavefront_tail_blocks_match_whole_pixels(rp, scene, oracle_demo, wh_spp):
+    """The wavefront integrator hands the frame's last pixels (one per path slot) out as up to 8 sample blocks each and
+    k_tail_combine adds the blocks in block order (ptb_wavefront.cuh).  The samples are the same as without the split, so
+    the image must equal the fused integrator's (whole pixels only) up to f32 summation order — also when spp is not a
+    multiple of the block count, when every pixel of a small frame is a tail pixel, and when only part of a large one is."""
+    W, H, S = wh_spp
+    imgs = []
+    for integ in (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED):
+        pt = rp.Tracer.new(scene, integrator=integ)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        assert buf.frames == S
+        assert np.all(buf.pixels.reshape(-1, 4)[:, 3] == 1.0)          # every pixel received exactly S samples
+        imgs.append(buf.pixels.copy())
+        # a second batch continues the sample sequence: 2 S samples in two launches == the running mean of both
+        pt.render_spp(buf, S)
+        assert buf.frames == 2 * S and np.all(buf.pixels.reshape(-1, 4)[:, 3] == 1.0)
+        pt.close()
+    rel = pix_rel(imgs[0], imgs[1])
+    assert (rel < 1e-4).mean() >= 0.999, (rel < 1e-4).mean()          # fused and wavefront round a few branch decisions differently
+    assert np.median(rel) < 1e-6
+    if W * H * S <= 200 * 150 * 16:
+        ref, _, _, _ = oracle_demo.render(W, H, S)
+        assert (pix_rel(imgs[0], ref) < 1e-4).mean() >= 0.99
