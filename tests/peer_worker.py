@@ -31,10 +31,14 @@ for integ in (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED, rp
             out[(integ, gather)] = resolve_mean(res).cpu().numpy().copy()
         dt.close()
 if rank == 0:
-    single = rp.Tracer.new(scene, device=local)
-    buf = rp.ColorBuffer.new(W, H)
-    single.render_spp(buf, STEPS * SPP)
     for integ in (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_STREAM):
+        # the single-GPU image of the SAME integrator: the same samples through the same code, so only the f32 summation
+        # order differs (the wavefront integrator shades this scene from the host-evaluated material table, the other two
+        # from device arithmetic; a few pixels per 100 000 take a different branch between those two)
+        single = rp.Tracer.new(scene, device=local, integrator=integ)
+        buf = rp.ColorBuffer.new(W, H)
+        single.render_spp(buf, STEPS * SPP)
+        single.close()
         a, b = out[(integ, "nccl")], out[(integ, "peer")]
         assert np.all(b.reshape(-1, 4)[:, 3] == 1.0)
         # (not bit-equal: NCCL reduces the ranks' CUMULATIVE sums, the peer gather adds each step's partial sums in rank order)
