@@ -17,9 +17,10 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     # name, -D flags, env
-    ("chunk32", [], {}),
-    ("chunk64", ["-DPTB_CHUNK=64"], {}),
-    ("chunk256", ["-DPTB_CHUNK=256"], {}),
+    ("t768_2304", [], {}),
+    ("t736_2208", ["-DPTB_WF_THREADS_RM=736", "-DPTB_WF_POOL_RM=2208"], {}),
+    ("t704_2112", ["-DPTB_WF_THREADS_RM=704", "-DPTB_WF_POOL_RM=2112"], {}),
+    ("t800_2400", ["-DPTB_WF_THREADS_RM=800", "-DPTB_WF_POOL_RM=2400", "-DPTB_WF_SCENE_BYTES_RM=4096"], {}),
 ]
 
 
