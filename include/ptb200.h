@@ -330,6 +330,18 @@ int  ptb_test_finalize_f32(ptb_tracer* t, size_t n, uint32_t material_index, con
                            const float* dir3, const float* hit_dist, const float* normal3,
                            float* rough_out, float* ccrough_out, float* ax_out, float* ay_out,
                            float* eta_out, float* ffnormal3_out, float* fhp3_out);
+/* HOST-ONLY (no device, no tracer): the entry of the resolved-material table that ptb_set_scene_f32 builds for small scenes
+ *  for one accepted-primitive chain.  `chain` = material indices of the accepted primitives in test order
+ * (one index for scenes whose materials assign every field); `checker_odd` = which checker cell supplies the albedo.
+ * Replaces, per shaded bounce: the cumulative material assignment of closest_hit (analytical.rs:56-58, 82-85, 115-116),
+ * Material::finalize (material.rs:117-131), the eta pick of State::finalize (globals.rs:58-61), get_spec_color
+ * (tracer.rs:335-341) and the material-only lobe weights (tracer.rs:423, 426).
+ * out[PTB_RMAT_FLOATS]: rgb3, emission3, anisotropic, metallic, roughness, subsurface, specular_tint, sheen, sheen_tint,
+ * clearcoat, clearcoat_gloss, spec_trans, ior, clearcoat_roughness, ax, ay, eta_enter, eta_exit, spec_col_enter3,
+ * spec_col_exit3, sheen_col3, luminance, diffuse_weight, clearcoat_weight, lobe_class (as float). */
+#define PTB_RMAT_FLOATS 35
+int  ptb_test_resolved_material_f32(const ptb_scene_f32* scene, const uint32_t* chain, uint32_t chain_len,
+                                    uint32_t checker_odd, float* out);
 /* Tracer::disney_eval, tracer.rs:555-626.  n3 = shading normal (ffnormal), v3 = -ray.direction,
  * l3 = light direction (world), eta per element.  Outputs f3 (already times |l.z|) and pdf. */
 int  ptb_test_disney_eval_f32(ptb_tracer* t, size_t n, uint32_t material_index, const float* eta,

@@ -117,6 +117,24 @@ void t_finalize(const SceneBox<R>* sb, size_t n, uint32_t mi, const R* o, const 
         st3(fhp_out, n, i, st.fhp);
     }
 }
+// get_spec_color (tracer.rs:335-341) + the material-only lobe weights (tracer.rs:423, 426) of material `mi` after
+// Material::finalize, for a given eta: spec_col3, sheen_col3, luminance(rgb), diffuse weight, clearcoat weight
+template <class R>
+void t_spec_color(const SceneBox<R>* sb, uint32_t mi, R eta, const R* dir3, R* out9) {
+    State<R> st;
+    st.material = resolve_material(sb, mi, Ray<R>(V3<R>(), V3<R>(dir3[0], dir3[1], dir3[2])));
+    st.material.finalize();
+    V3<R> spec, sheen;
+    Tracer<R>::get_spec_color(st.material, eta, spec, sheen);
+    out9[0] = spec.x; out9[1] = spec.y; out9[2] = spec.z;
+    out9[3] = sheen.x; out9[4] = sheen.y; out9[5] = sheen.z;
+    R wd = 0, wr = 0, wt = 0, wc = 0;
+    const R lum = Tracer<R>::luminance(st.material.rgb);
+    out9[6] = lum;
+    out9[7] = lum * (R(1) - st.material.metallic) * (R(1) - st.material.spec_trans);        // tracer.rs:423 before normalisation
+    out9[8] = R(0.25) * st.material.clearcoat * (R(1) - st.material.metallic);              // tracer.rs:426
+    (void)wd; (void)wr; (void)wt; (void)wc;
+}
 template <class R>
 void t_disney_eval(const SceneBox<R>* sb, size_t n, uint32_t mi, const R* eta, const R* v, const R* nrm, const R* l, R* f_out,
                    R* pdf_out) {
@@ -269,6 +287,9 @@ size_t pto_counters_size(void) { return sizeof(Counters); }
     void pto_finalize_##SFX(void* sb, size_t n, uint32_t mi, const R* o, const R* d, const R* hd, const R* nrm, R* rough, \
                             R* ccr, R* ax, R* ay, R* eta, R* ffn, R* fhp) {                                             \
         t_finalize<R>(static_cast<SceneBox<R>*>(sb), n, mi, o, d, hd, nrm, rough, ccr, ax, ay, eta, ffn, fhp);          \
+    }                                                                                                                   \
+    void pto_spec_color_##SFX(void* sb, uint32_t mi, R eta, const R* dir3, R* out9) {                                    \
+        t_spec_color<R>(static_cast<SceneBox<R>*>(sb), mi, eta, dir3, out9);                                            \
     }                                                                                                                   \
     void pto_disney_eval_##SFX(void* sb, size_t n, uint32_t mi, const R* eta, const R* v, const R* nrm, const R* l, R* f, \
                                R* pdf) {                                                                                \

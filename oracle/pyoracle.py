@@ -151,6 +151,15 @@ class OracleScene:
         self._fn("finalize")(self.h, C.c_size_t(n), C.c_uint32(mi), _p(o), _p(d), _p(hd), _p(nr), *[_p(x) for x in s], _p(ffn), _p(fhp))
         return dict(roughness=s[0], clearcoat_roughness=s[1], ax=s[2], ay=s[3], eta=s[4], ffnormal=ffn, fhp=fhp)
 
+    def spec_color(self, mi, eta, direction=(0.0, -1.0, 0.0)):
+        """get_spec_color + material-only lobe weights of material `mi` (finalized) for `eta`; `direction` = ray direction
+        (decides the checker cell of a direction-ratio checker albedo)"""
+        d, out = self._a(direction), np.empty(9, self.np)
+        fn = self._fn("spec_color")
+        fn.restype = None
+        fn(self.h, C.c_uint32(mi), (C.c_float if self.p == "f32" else C.c_double)(eta), _p(d), _p(out))
+        return dict(spec_col=out[0:3].copy(), sheen_col=out[3:6].copy(), lum=out[6], wd0=out[7], wc0=out[8])
+
     def disney_eval(self, mi, eta, v, n_, l):
         eta, v, n_, l = self._a(eta), self._a(v), self._a(n_), self._a(l)
         n = v.shape[1]

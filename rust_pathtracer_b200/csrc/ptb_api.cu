@@ -289,6 +289,28 @@ template <class T> static cudaError_t upload_vec(void** dst, size_t& cap, const 
     return e;
 }
 
+// Material::new() defaults (material.rs:82-114) for everything a POD material does not assign
+template <class R, class PodMaterial> static DMaterial<R> resolve_pod_material(const PodMaterial& m) {
+    DMaterial<R> o;
+    const uint32_t k = m.set_mask;
+    for (int c = 0; c < 3; ++c) { o.rgb[c] = (k & PTB_MAT_RGB) ? m.rgb[c] : R(1.5); o.emission[c] = (k & PTB_MAT_EMISSION) ? m.emission[c] : R(0); }
+    o.anisotropic = (k & PTB_MAT_ANISOTROPIC) ? m.anisotropic : R(0);
+    o.metallic = (k & PTB_MAT_METALLIC) ? m.metallic : R(0);
+    o.roughness = (k & PTB_MAT_ROUGHNESS) ? m.roughness : R(0.5);
+    o.subsurface = (k & PTB_MAT_SUBSURFACE) ? m.subsurface : R(0);
+    o.specular_tint = (k & PTB_MAT_SPECULAR_TINT) ? m.specular_tint : R(0);
+    o.sheen = (k & PTB_MAT_SHEEN) ? m.sheen : R(0);
+    o.sheen_tint = (k & PTB_MAT_SHEEN_TINT) ? m.sheen_tint : R(0);
+    o.clearcoat = (k & PTB_MAT_CLEARCOAT) ? m.clearcoat : R(0);
+    o.clearcoat_gloss = (k & PTB_MAT_CLEARCOAT_GLOSS) ? m.clearcoat_gloss : R(0);
+    o.spec_trans = (k & PTB_MAT_SPEC_TRANS) ? m.spec_trans : R(0);
+    o.ior = (k & PTB_MAT_IOR) ? m.ior : R(1.45);
+    o.set_mask = k & PTB_MAT_ALL;
+    o.albedo_kind = m.albedo_kind;
+    o.checker_a = m.checker_a; o.checker_b = m.checker_b; o.checker_scale = m.checker_scale; o.checker_offset = m.checker_offset;
+    return o;
+}
+
 template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb, const typename PodTypes<R>::scene* sc) {
     if (!t || !sc) return fail(PTB_E_INVALID, "null tracer or scene");
     if ((sc->n_spheres && !sc->spheres) || (sc->n_planes && !sc->planes) || (sc->n_materials && !sc->materials) ||
@@ -324,27 +346,7 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         pmat[i] = p.material;
     }
     std::vector<DMaterial<R>> mats(sc->n_materials);
-    for (uint32_t i = 0; i < sc->n_materials; ++i) {
-        const auto& m = sc->materials[i];
-        DMaterial<R>& o = mats[i];
-        const uint32_t k = m.set_mask;
-        // Material::new() defaults (material.rs:82-114) for everything this material does not assign
-        for (int c = 0; c < 3; ++c) { o.rgb[c] = (k & PTB_MAT_RGB) ? m.rgb[c] : R(1.5); o.emission[c] = (k & PTB_MAT_EMISSION) ? m.emission[c] : R(0); }
-        o.anisotropic = (k & PTB_MAT_ANISOTROPIC) ? m.anisotropic : R(0);
-        o.metallic = (k & PTB_MAT_METALLIC) ? m.metallic : R(0);
-        o.roughness = (k & PTB_MAT_ROUGHNESS) ? m.roughness : R(0.5);
-        o.subsurface = (k & PTB_MAT_SUBSURFACE) ? m.subsurface : R(0);
-        o.specular_tint = (k & PTB_MAT_SPECULAR_TINT) ? m.specular_tint : R(0);
-        o.sheen = (k & PTB_MAT_SHEEN) ? m.sheen : R(0);
-        o.sheen_tint = (k & PTB_MAT_SHEEN_TINT) ? m.sheen_tint : R(0);
-        o.clearcoat = (k & PTB_MAT_CLEARCOAT) ? m.clearcoat : R(0);
-        o.clearcoat_gloss = (k & PTB_MAT_CLEARCOAT_GLOSS) ? m.clearcoat_gloss : R(0);
-        o.spec_trans = (k & PTB_MAT_SPEC_TRANS) ? m.spec_trans : R(0);
-        o.ior = (k & PTB_MAT_IOR) ? m.ior : R(1.45);
-        o.set_mask = k & PTB_MAT_ALL;
-        o.albedo_kind = m.albedo_kind;
-        o.checker_a = m.checker_a; o.checker_b = m.checker_b; o.checker_scale = m.checker_scale; o.checker_offset = m.checker_offset;
-    }
+    for (uint32_t i = 0; i < sc->n_materials; ++i) mats[i] = resolve_pod_material<R>(sc->materials[i]);
     std::vector<DLight<R>> lights(sc->n_lights);
     const R PI_R = Const<R>::PI;
     for (uint32_t i = 0; i < sc->n_lights; ++i) {
@@ -920,6 +922,25 @@ int ptb_convert_pixels_to_u8_at_f32(ptb_tracer* t, const float* rgba, uint32_t w
 int ptb_convert_pixels_to_u8_at_f64(ptb_tracer* t, const double* rgba, uint32_t w, uint32_t h, uint8_t* frame, uint32_t x, uint32_t y, uint32_t fw,
                                     uint32_t fh) { return convert_pixels_at_impl<double>(t, rgba, w, h, frame, x, y, fw, fh); }
 
+int ptb_test_resolved_material_f32(const ptb_scene_f32* sc, const uint32_t* chain, uint32_t chain_len, uint32_t checker_odd, float* out) {
+    if (!sc || !chain || !out || chain_len == 0) return fail(PTB_E_INVALID, "null argument or empty chain");
+    std::vector<DMaterial<float>> mats(chain_len);
+    std::vector<const DMaterial<float>*> ptrs(chain_len);
+    for (uint32_t i = 0; i < chain_len; ++i) {
+        if (chain[i] >= sc->n_materials) return fail(PTB_E_INVALID, "chain[%u]: material index out of range", i);
+        mats[i] = resolve_pod_material<float>(sc->materials[chain[i]]);
+        ptrs[i] = &mats[i];
+    }
+    const RMat r = rm_resolve(ptrs, checker_odd != 0);
+    const Mat<float>& m = r.m;
+    const float v[PTB_RMAT_FLOATS] = {m.rgb.x, m.rgb.y, m.rgb.z, m.emission.x, m.emission.y, m.emission.z, m.anisotropic, m.metallic, m.roughness,
+                                      m.subsurface, m.specular_tint, m.sheen, m.sheen_tint, m.clearcoat, m.clearcoat_gloss, m.spec_trans, m.ior,
+                                      m.clearcoat_roughness, m.ax, m.ay, r.eta[0], r.eta[1], r.spec_col[0][0], r.spec_col[0][1], r.spec_col[0][2],
+                                      r.spec_col[1][0], r.spec_col[1][1], r.spec_col[1][2], r.sheen_col[0], r.sheen_col[1], r.sheen_col[2],
+                                      r.lum, r.wd0, r.wc0, (float)r.lobe_class};
+    memcpy(out, v, sizeof(v));
+    return PTB_OK;
+}
 int ptb_get_counters(ptb_tracer* t, ptb_counters* out) {
     if (!t || !out) return fail(PTB_E_INVALID, "null argument");
     CU(cudaSetDevice(t->device));

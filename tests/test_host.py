@@ -70,3 +70,87 @@ def test_synthetic_scenes(rp):
     assert [tuple(a.center) for a in s.spheres] == [tuple(a.center) for a in s2.spheres]     # seeded
     d = rp.divergence_stress_scene(side=8, depth=16).device_export()
     assert len(d.spheres) == 64 and d.depth == 16
+
+
+def _resolved(rp, export, chain, odd=0):
+    lib = rp._abi.load()
+    sc, keep = export.to_c("f32")
+    out = (C.c_float * rp._abi.PTB_RMAT_FLOATS)()
+    ch = (C.c_uint32 * len(chain))(*chain)
+    rp._abi.check(lib.ptb_test_resolved_material_f32(C.byref(sc), ch, len(chain), odd, out))
+    v = np.array(out[:], np.float32)
+    names = ["anisotropic", "metallic", "roughness", "subsurface", "specular_tint", "sheen", "sheen_tint", "clearcoat", "clearcoat_gloss",
+             "spec_trans", "ior", "clearcoat_roughness", "ax", "ay", "eta_enter", "eta_exit"]
+    d = dict(rgb=v[0:3], emission=v[3:6], spec_enter=v[22:25], spec_exit=v[25:28], sheen_col=v[28:31], lum=v[31], wd0=v[32], wc0=v[33],
+             lobe_class=int(v[34]))
+    d.update({n: v[6 + i] for i, n in enumerate(names)})
+    return d
+
+
+def test_resolved_material_table_is_bit_exact_with_the_oracle(rp, po):
+    """The wavefront integrator shades small scenes from a table the HOST evaluates in ptb_set_scene_f32 (RMat).
+    Its entries must be the oracle's own values bit for bit: Material::finalize (material.rs:117-131), eta (globals.rs:58-61),
+    get_spec_color (tracer.rs:335-341) and the material-only lobe weights (tracer.rs:423, 426) — plain f32, same operation order.
+    No device involved: this is the host half of the shade path."""
+    r = np.random.default_rng(5)
+    M = rp.Material
+    mats = []
+    for k in range(24):
+        m = M(rgb=rp.F3(*r.uniform(0.0, 1.0, 3)), roughness=float(r.uniform(0.0, 1.0)), ior=float(r.uniform(1.05, 2.0)),
+              metallic=float(r.choice([0.0, 1.0, r.uniform(0, 1)])), anisotropic=float(r.uniform(0, 1)), subsurface=float(r.uniform(0, 1)),
+              specular_tint=float(r.uniform(0, 1)), sheen=float(r.uniform(0, 1)), sheen_tint=float(r.uniform(0, 1)),
+              clearcoat=float(r.choice([0.0, r.uniform(0, 1)])), clearcoat_gloss=float(r.uniform(0, 1)),
+              spec_trans=float(r.choice([0.0, r.uniform(0, 1)])), emission=rp.F3(*r.uniform(0, 2, 3)))
+        mats.append(m)
+    mats.append(M(rgb=rp.F3(0, 0, 0)))                                                      # zero luminance: ctint = 1 (tracer.rs:337)
+    mats.append(M(roughness=1.0, albedo_kind=rp._abi.PTB_ALBEDO_CHECKER_DIR_RATIO))          # the demo floor
+    e = rp.DeviceScene(spheres=[rp.Sphere(rp.F3(0, 0, 0), 1.0, i) for i in range(len(mats))], planes=[], materials=mats, lights=[],
+                       camera=rp.Pinhole.new(), background=rp.Background(), depth=4, flags=rp._abi.PTB_SCENE_NO_BVH, eps=0.005)
+    orc = po.OracleScene(e)
+    o = np.zeros((3, 2), np.float32); o[2] = 3.0
+    # two rays towards the sphere at the origin: from outside (entering) and from its centre (exiting)
+    origins = np.array([[0, 0], [0, 0], [3, 0]], np.float32)
+    d = np.array([[0, 0], [0, 0], [-1, -1]], np.float32)
+    nrm = np.array([[0, 0], [0, 0], [1, 1]], np.float32)        # n.d < 0: entering; second ray: normal (0,0,-1)·d > 0 below
+    nrm[2, 1] = -1.0
+    for mi in range(len(mats)):
+        for odd in ((0, 1) if mats[mi].albedo_kind else (0,)):
+            got = _resolved(rp, e, [mi], odd)
+            # a ray direction whose checker cell is even / odd for the direction-ratio checker (analytical.rs:107-113)
+            direction = (0.2, -1.0, 0.3) if odd == 0 else (2.2, -1.0, 0.3)
+            fin = orc.finalize(mi, origins, d, np.array([2.0, 1.0], np.float32), nrm)
+            for k_o, k_g in (("roughness", "roughness"), ("clearcoat_roughness", "clearcoat_roughness"), ("ax", "ax"), ("ay", "ay")):
+                assert fin[k_o][0] == got[k_g], (mi, k_o, fin[k_o][0], got[k_g])
+            assert fin["eta"][0] == got["eta_enter"] and fin["eta"][1] == got["eta_exit"], (mi, fin["eta"], got["eta_enter"], got["eta_exit"])
+            for side, eta in (("spec_enter", got["eta_enter"]), ("spec_exit", got["eta_exit"])):
+                sc = orc.spec_color(mi, float(eta), direction)
+                assert np.array_equal(sc["spec_col"], got[side]), (mi, side, sc["spec_col"], got[side])
+                assert np.array_equal(sc["sheen_col"], got["sheen_col"])
+                assert sc["lum"] == got["lum"] and sc["wd0"] == got["wd0"] and sc["wc0"] == got["wc0"], (mi, sc, got)
+            m = mats[mi]
+            want_class = (1 if (1 - m.metallic) * (1 - m.spec_trans) > 0 else 0) | (2 if m.clearcoat * (1 - m.metallic) > 0 else 0) | \
+                         (4 if m.spec_trans * (1 - m.metallic) > 0 else 0)
+            assert got["lobe_class"] == want_class
+    # checker cells: even -> checker_a, odd -> checker_b
+    fl = len(mats) - 1
+    assert np.all(_resolved(rp, e, [fl], 0)["rgb"] == np.float32(0.25)) and np.all(_resolved(rp, e, [fl], 1)["rgb"] == np.float32(0.1))
+
+
+def test_resolved_material_chain_replays_the_cumulative_assignment(rp, demo_export):
+    """Partial-mask materials (the reference's closest_hit assigns a few fields per primitive that is closest SO FAR,
+    analytical.rs:56-58, 82-85, 115-116): the table entry of an accepted chain is the first material's resolved values
+    patched by the later ones' masked fields — e.g. the orange sphere seen in front of the metal one keeps metallic = 1."""
+    e = demo_export
+    metal, orange, floor = e.spheres[0].material, e.spheres[1].material, e.planes[0].material
+    alone = _resolved(rp, e, [orange])
+    assert alone["metallic"] == 0.0 and alone["clearcoat"] == 1.0 and alone["lobe_class"] == 3
+    both = _resolved(rp, e, [metal, orange])
+    assert both["metallic"] == 1.0 and both["clearcoat"] == 1.0 and both["lobe_class"] == 0        # (1 - metallic) kills diffuse and clearcoat
+    assert np.allclose(both["rgb"], [1.0, 0.186, 0.0]) and both["roughness"] == np.float32(0.1)
+    assert both["clearcoat_roughness"] == np.float32(np.float32(1 - 1.0) * np.float32(0.1) + np.float32(0.001) * np.float32(1.0))
+    # the floor behind both spheres: checker albedo from the LAST accepted primitive, roughness 1, metallic / clearcoat left over
+    chain = _resolved(rp, e, [metal, orange, floor], 1)
+    assert np.all(chain["rgb"] == np.float32(0.1)) and chain["roughness"] == 1.0 and chain["metallic"] == 1.0 and chain["clearcoat"] == 1.0
+    only_floor = _resolved(rp, e, [floor], 0)
+    assert np.all(only_floor["rgb"] == np.float32(0.25)) and only_floor["metallic"] == 0.0 and only_floor["lobe_class"] == 1
+    assert only_floor["eta_enter"] == np.float32(1.0) / np.float32(1.45) and only_floor["eta_exit"] == np.float32(1.45)
