@@ -5,13 +5,14 @@
 // Why shared memory: the demo scene costs ~1.4 kFLOP and ~2 bounces per sample.
 // A classic HBM wavefront streams ~1 KB of ray / path state per sample through the queues, which
 // caps it at ~6 Gsamples/s on a 6.5 TB/s part before any arithmetic is done (SURVEY.md §7 "the
-// roofline that actually binds").  One SM can hold 2048 paths x 96 B = 192 KB of state (221 KB with the
-// queue arrays and the scene copy), enough for every stage to run with full warps, so the state never
-// leaves the SM: HBM traffic stays at the 32 B per pixel of the accumulator read-modify-write.
+// roofline that actually binds").  One SM can hold 2048 paths x 96 B (or 2304 x 88 B) of state — 221 / 229 KB
+// with the queue arrays and the scene copy —, enough for every stage to run with full warps, so the state
+// never leaves the SM: HBM traffic stays at the 32 B per pixel of the accumulator read-modify-write.
 //
-// One CTA per SM (512 threads, or 768 with the resolved-material table) owns a pool of P = 2048 / 2304 path slots.  Each iteration runs two stages
-// over the pool, separated by CTA barriers, so that ALL warps of the SM execute the same stage code
-// at the same time (small instruction-cache footprint, the fused kernel's main stall):
+// One CTA per SM (512 threads and 2048 slots; 768 threads and 2304 slots in the instantiation that shades from
+// the resolved-material table, RMat in ptb_device.cuh) owns the pool.  Each iteration runs two stages over it,
+// separated by CTA barriers, so that ALL warps of the SM execute the same stage code at the same time (small
+// instruction-cache footprint, the fused kernel's main stall):
 //
 //   stage 1  "generate + intersect"  — every slot: a finished slot regenerates in place (next
 //            sample of its pixel, or a new pixel handed out per warp with ballot/popc from a global
@@ -26,8 +27,9 @@
 //            sample, throughput update, next ray (or termination); WF_MISS chunks do the background
 //            lookup with full warps.
 //
-// A slot owns one pixel for `spp` consecutive samples and sums them in sample order, so the image is
-// bit-reproducible run to run, exactly like the fused integrator.
+// A slot owns one pixel for `spp` consecutive samples and sums them in sample order; the frame's last pixels (one
+// per slot) are cut into sample blocks that k_tail_combine adds in block order (see wavefront_render).  Either way
+// the image does not depend on scheduling: it is bit-reproducible run to run, like the fused integrator's.
 #pragma once
 #include <string>
 

@@ -16,11 +16,16 @@ VDIR = os.path.join(ROOT, "rust_pathtracer_b200", "variants")
 sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    # name, -D flags, env
-    ("t768_2304", [], {}),
-    ("t736_2208", ["-DPTB_WF_THREADS_RM=736", "-DPTB_WF_POOL_RM=2208"], {}),
-    ("t704_2112", ["-DPTB_WF_THREADS_RM=704", "-DPTB_WF_POOL_RM=2112"], {}),
-    ("t800_2400", ["-DPTB_WF_THREADS_RM=800", "-DPTB_WF_POOL_RM=2400", "-DPTB_WF_SCENE_BYTES_RM=4096"], {}),
+    # name, -D flags, env.  The experiments of round 1 (results: profiles/r01_ab_variants.txt) used, among others:
+    #   PTB_WF_THREADS_RM / PTB_WF_POOL_RM / PTB_WF_SCENE_BYTES_RM   launch shape of the resolved-material instantiation
+    #   PTB_WF_THREADS / PTB_WF_POOL                                 ... of the generic / BVH instantiations
+    #   PTB_CHUNK                                                    pixels reserved per hand-out atomic
+    #   PTB_WF_NO_TAIL, PTB_WF_TAIL_LOG2, PTB_NO_FILM_FMA            tail items off / block count, IEEE film quotients
+    #   env PTB200_NO_RESOLVED_MATERIALS=1                           generic shade path (no material table)
+    ("default", [], {}),
+    ("generic_shade", [], {"PTB200_NO_RESOLVED_MATERIALS": "1"}),
+    ("no_tail", ["-DPTB_WF_NO_TAIL"], {}),
+    ("chunk256", ["-DPTB_CHUNK=256"], {}),
 ]
 
 
