@@ -99,6 +99,17 @@ template <class R> PTB_DEV R length(V3<R> a) { return m_sqrt(dot(a, a)); }
 // sequences; f64 keeps IEEE division.
 PTB_DEV float m_rcp(float x) { return __fdividef(1.0f, x); }
 PTB_DEV double m_rcp(double x) { return 1.0 / x; }
+// f32 quotient as MUFU.RCP + FMUL (div.approx: <= 2 ulp for 2^-126 <= |b| <= 2^126, the same error class as the
+// div.full.f32 that `a / b` compiles to under -prec-div=false).  div.full spends two range compares and a predicated
+// rescaling multiply per operand on denominators outside that range — 8 issue slots per quotient, a quarter of the shading
+// stage's instructions — and no denominator of this path gets there without the reference's own result being inf / NaN
+// already (lobe weight sums, roughness products, cosines, squared distances, pdfs).  f64 keeps IEEE division.
+#ifdef PTB_FULL_DIV
+PTB_DEV float m_div(float a, float b) { return a / b; }
+#else
+PTB_DEV float m_div(float a, float b) { return __fdividef(a, b); }
+#endif
+PTB_DEV double m_div(double a, double b) { return a / b; }
 PTB_DEV V3<float> div_s(V3<float> a, float s) { float r = m_rcp(s); return V3<float>(a.x * r, a.y * r, a.z * r); }
 PTB_DEV V3<double> div_s(V3<double> a, double s) { return V3<double>(a.x / s, a.y / s, a.z / s); }
 PTB_DEV V3<float> normalize(V3<float> a) { float r = rsqrtf(dot(a, a)); return V3<float>(a.x * r, a.y * r, a.z * r); }
@@ -343,7 +354,7 @@ template <class R> PTB_DEV void mat_finalize(Mat<R>& m) {
     m.roughness = m_max(m.roughness, R(0.01));
     m.clearcoat_roughness = mix1(R(0.1), R(0.001), m.clearcoat_gloss);
     R aspect = m_sqrt(R(1) - m.anisotropic * R(0.9));
-    m.ax = m_max(m.roughness / aspect, R(0.001));
+    m.ax = m_max(m_div(m.roughness, aspect), R(0.001));
     m.ay = m_max(m.roughness * aspect, R(0.001));
 }
 
@@ -380,7 +391,7 @@ template <class R> PTB_DEV R isect_sphere(V3<R> o, V3<R> d, V3<R> c, R radius) {
 template <class R> PTB_DEV R isect_plane(V3<R> o, V3<R> d, V3<R> p, V3<R> n) {
     R denom = dot_rn(n, d);
     if (m_abs(denom) > R(0.0001)) {
-        R t = dot_rn(p - o, n) / denom;
+        R t = m_div(dot_rn(p - o, n), denom);
         if (t >= R(0)) return t;
     }
     return R(-1);
@@ -464,7 +475,7 @@ PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __
     int best = -1;
     RayF r;
     r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
-    r.idx = 1.0f / (float)d.x; r.idy = 1.0f / (float)d.y; r.idz = 1.0f / (float)d.z;
+    r.idx = m_rcp((float)d.x); r.idy = m_rcp((float)d.y); r.idz = m_rcp((float)d.z);
     constexpr int STACK = 40;
     uint32_t stack_n[STACK];
     float stack_t[STACK];
@@ -582,7 +593,7 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
     if (n_test >= 4u) {
         RayF r;
         r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
-        r.idx = 1.0f / (float)d.x; r.idy = 1.0f / (float)d.y; r.idz = 1.0f / (float)d.z;
+        r.idx = m_rcp((float)d.x); r.idy = m_rcp((float)d.y); r.idz = m_rcp((float)d.z);
         if (box_entry(s.light_lo, s.light_hi, r, (float)ldist) >= 3.0e38f) n_test = 0u;
     }
     if (BVH && n_test && s.light_bvh) {      // (only the BVH kernels carry traversal code and its stack)
@@ -601,7 +612,7 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
         DLight<R> L = sv.lights[lbest];
         V3<R> hp = o + ldist * d;
         R cos_theta = dot(-d, normalize(hp - V3<R>(L.px, L.py, L.pz)));
-        h.light_pdf = (ldist * ldist) / (L.area * cos_theta * R(0.5));       // scene.rs:75
+        h.light_pdf = m_div(ldist * ldist, L.area * cos_theta * R(0.5));       // scene.rs:75
         h.light_emission = V3<R>(L.ex, L.ey, L.ez);
         h.is_emitter = true;
         h.hit_dist = ldist;
@@ -756,7 +767,7 @@ template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const Scen
 
 // ------------------------------------------------------------------------------------------------
 // Disney BSDF terms (tracer.rs:222-439)
-template <class R> PTB_DEV R power_heuristic(R a, R b) { R t = a * a; return t / (b * b + t); }   // tracer.rs:223-226
+template <class R> PTB_DEV R power_heuristic(R a, R b) { R t = a * a; return m_div(t, b * b + t); }   // tracer.rs:223-226
 template <class R> PTB_DEV R luminance(V3<R> c) { return R(0.212671) * c.x + R(0.715160) * c.y + R(0.072169) * c.z; }
 PTB_DEV float sat01(float x) { return __saturatef(x); }          // one instruction; differs from f32::clamp only for NaN input
 PTB_DEV double sat01(double x) { return m_clamp(x, 0.0, 1.0); }
@@ -769,32 +780,32 @@ template <class R> PTB_DEV R dielectric_fresnel(R cos_theta_i, R eta) {         
     R sin_theta_tsq = eta * eta * (R(1) - cos_theta_i * cos_theta_i);
     if (sin_theta_tsq > R(1)) return R(1);
     R cos_theta_t = m_sqrt(m_max(R(1) - sin_theta_tsq, R(0)));
-    R rs = (eta * cos_theta_t - cos_theta_i) / (eta * cos_theta_t + cos_theta_i);
-    R rp = (eta * cos_theta_i - cos_theta_t) / (eta * cos_theta_i + cos_theta_t);
+    R rs = m_div(eta * cos_theta_t - cos_theta_i, eta * cos_theta_t + cos_theta_i);
+    R rp = m_div(eta * cos_theta_i - cos_theta_t, eta * cos_theta_i + cos_theta_t);
     return R(0.5) * (rs * rs + rp * rp);
 }
 template <class R> PTB_DEV R gtr1(R ndoth, R a) {                                                  // tracer.rs:233-240 (log2: A.3)
     if (a >= R(1)) return Const<R>::INV_PI;
     R a2 = a * a;
     R t = R(1) + (a2 - R(1)) * ndoth * ndoth;
-    return (a2 - R(1)) / (Const<R>::PI * m_log2(a2) * t);
+    return m_div(a2 - R(1), Const<R>::PI * m_log2(a2) * t);
 }
 template <class R> PTB_DEV R smithg(R ndotv, R alphag) {                                           // tracer.rs:276-280
     R a = alphag * alphag;
     R b = ndotv * ndotv;
-    return (R(2) * ndotv) / (ndotv + m_sqrt(a + b - a * b));
+    return m_div(R(2) * ndotv, ndotv + m_sqrt(a + b - a * b));
 }
 template <class R> PTB_DEV R gtr2aniso(R ndoth, R hdotx, R hdoty, R ax, R ay) {                    // tracer.rs:294-299
-    R a = hdotx / ax;
-    R b = hdoty / ay;
+    R a = m_div(hdotx, ax);
+    R b = m_div(hdoty, ay);
     R c = a * a + b * b + ndoth * ndoth;
-    return R(1) / (Const<R>::PI * ax * ay * c * c);
+    return m_rcp(Const<R>::PI * ax * ay * c * c);
 }
 template <class R> PTB_DEV R smithganiso(R ndotv, R vdotx, R vdoty, R ax, R ay) {                  // tracer.rs:301-306
     R a = vdotx * ax;
     R b = vdoty * ay;
     R c = ndotv;
-    return (R(2) * ndotv) / (ndotv + m_sqrt(a * a + b * b + c * c));
+    return m_div(R(2) * ndotv, ndotv + m_sqrt(a * a + b * b + c * c));
 }
 template <class R> PTB_DEV R disney_fresnel(const Mat<R>& m, R eta, R ldoth, R vdoth) {            // tracer.rs:435-439
     R metallic_fresnel = schlick_fresnel(ldoth);
@@ -818,7 +829,7 @@ template <class R> PTB_DEV V3<R> cosine_sample_hemisphere(R r1, R sn, R cs) {
 template <class R> PTB_DEV V3<R> sample_gtr1(R rgh, R r1, R sn, R cs) {          // r2 unused: quirk A.4 (phi = r1 * TWO_PI)
     R a = m_max(R(0.001), rgh);
     R a2 = a * a;
-    R cos_theta = m_sqrt((R(1) - m_pow(a2, R(1) - r1)) / (R(1) - a2));
+    R cos_theta = m_sqrt(m_div(R(1) - m_pow(a2, R(1) - r1), R(1) - a2));
     R sin_theta = m_clamp(m_sqrt(R(1) - (cos_theta * cos_theta)), R(0), R(1));
     return V3<R>(sin_theta * cs, sin_theta * sn, cos_theta);
 }
@@ -826,7 +837,7 @@ template <class R> PTB_DEV V3<R> sample_ggxvndf(V3<R> v, R ax, R ay, R r1, R sn,
     V3<R> vh = normalize(V3<R>(ax * v.x, ay * v.y, v.z));
     R lensq = vh.x * vh.x + vh.y * vh.y;
     V3<R> t_1;
-    if (lensq > R(0)) { R il = R(1) / m_sqrt(lensq); t_1 = V3<R>(-vh.y * il, vh.x * il, R(0)); }
+    if (lensq > R(0)) { R il = m_rcp(m_sqrt(lensq)); t_1 = V3<R>(-vh.y * il, vh.x * il, R(0)); }
     else t_1 = V3<R>(1, 0, 0);
     V3<R> t_2 = cross(vh, t_1);
     R r = m_sqrt(r1);
@@ -859,7 +870,7 @@ template <class R> PTB_DEV void shade_ctx_init(ShadeCtx<R>& c, const Mat<R>& m, 
     // get_spec_color, tracer.rs:335-341
     R lum = luminance(m.rgb);
     V3<R> ctint = lum > R(0) ? div_s(m.rgb, lum) : V3<R>(1, 1, 1);
-    R f0 = (R(1) - eta) / (R(1) + eta);
+    R f0 = m_div(R(1) - eta, R(1) + eta);
     c.spec_col = mix3((f0 * f0) * mix3(V3<R>(1, 1, 1), ctint, m.specular_tint), m.rgb, m.metallic);
     c.sheen_col = mix3(V3<R>(1, 1, 1), ctint, m.sheen_tint);
     c.lum = lum;
@@ -875,7 +886,7 @@ PTB_DEV void lobe_probabilities(const Mat<R>& m, const ShadeCtx<R>& c, R approx_
     wt = (R(1) - approx_fresnel) * (R(1) - m.metallic) * m.spec_trans * c.lum;
     wc = c.wc0;
     R total = wd + wr + wt + wc;
-    wd /= total; wr /= total; wt /= total; wc /= total;
+    wd = m_div(wd, total); wr = m_div(wr, total); wt = m_div(wt, total); wc = m_div(wc, total);
 }
 
 // lobe evaluations in the local frame, tracer.rs:343-419
@@ -890,7 +901,7 @@ template <class R> PTB_DEV V3<R> eval_diffuse(const Mat<R>& m, V3<R> c_sheen, V3
     R fd = mix1(R(1), fd90, fl) * mix1(R(1), fd90, fv);
     R fss90 = ldh * ldh * m.roughness;
     R fss = mix1(R(1), fss90, fl) * mix1(R(1), fss90, fv);
-    R ss = R(1.25) * (fss * (R(1) / (l.z + v.z) - R(0.5)) + R(0.5));
+    R ss = R(1.25) * (fss * (m_rcp(l.z + v.z) - R(0.5)) + R(0.5));
     V3<R> fsheen = (fh * m.sheen) * c_sheen;
     pdf = l.z * Const<R>::INV_PI;
     return ((R(1) - m.metallic) * (R(1) - m.spec_trans)) * ((Const<R>::INV_PI * mix1(fd, ss, m.subsurface)) * m.rgb + fsheen);
@@ -902,7 +913,7 @@ template <class R> PTB_DEV V3<R> eval_spec_reflection(const Mat<R>& m, R fm, V3<
     R d = gtr2aniso(h.z, h.x, h.y, m.ax, m.ay);
     R g1 = smithganiso(m_abs(v.z), v.x, v.y, m.ax, m.ay);
     R g2 = g1 * smithganiso(m_abs(l.z), l.x, l.y, m.ax, m.ay);
-    pdf = g1 * d / (R(4) * v.z);
+    pdf = m_div(g1 * d, R(4) * v.z);
     return div_s((d * g2) * f, R(4) * l.z * v.z);
 }
 template <class R> PTB_DEV V3<R> eval_spec_refraction(const Mat<R>& m, R eta, R f, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
@@ -915,9 +926,9 @@ template <class R> PTB_DEV V3<R> eval_spec_refraction(const Mat<R>& m, R eta, R 
     R denom = ldh + vdh * eta;
     denom *= denom;
     R eta2 = eta * eta;
-    R jacobian = m_abs(ldh) / denom;
-    pdf = g1 * m_max(R(0), vdh) * d * jacobian / v.z;
-    R s = (R(1) - m.metallic) * m.spec_trans * (R(1) - f) * d * g2 * m_abs(vdh) * jacobian * eta2 / m_abs(l.z * v.z);
+    R jacobian = m_div(m_abs(ldh), denom);
+    pdf = m_div(g1 * m_max(R(0), vdh) * d * jacobian, v.z);
+    R s = m_div((R(1) - m.metallic) * m.spec_trans * (R(1) - f) * d * g2 * m_abs(vdh) * jacobian * eta2, m_abs(l.z * v.z));
     return s * V3<R>(m_pow(m.rgb.x, R(0.5)), m_pow(m.rgb.y, R(0.5)), m_pow(m.rgb.z, R(0.5)));
 }
 template <class R> PTB_DEV V3<R> eval_clearcoat(const Mat<R>& m, V3<R> v, V3<R> l, V3<R> h, R& pdf) {
@@ -928,9 +939,9 @@ template <class R> PTB_DEV V3<R> eval_clearcoat(const Mat<R>& m, V3<R> v, V3<R> 
     R f = mix1(R(0.04), R(1), fh);
     R d = gtr1(h.z, m.clearcoat_roughness);
     R g = smithg(l.z, R(0.25)) * smithg(v.z, R(0.25));
-    R jacobian = R(1) / (R(4) * vdh);
+    R jacobian = m_rcp(R(4) * vdh);
     pdf = d * h.z * jacobian;
-    R s = m.clearcoat * f * d * g / (R(4) * l.z * v.z);
+    R s = m_div(m.clearcoat * f * d * g, R(4) * l.z * v.z);
     return s * V3<R>(R(0.25), R(0.25), R(0.25));
 }
 
@@ -1003,9 +1014,9 @@ PTB_DEV int query_for_sample(const Mat<R>& m, const ShadeCtx<R>& c, R r1, R r2, 
     const R cdf0 = wd;
     const R cdf1 = cdf0 + wc;
     int lobe;
-    if (r1 < cdf0) { lobe = LOBE_DIFFUSE; r1 = r1 / cdf0; }
-    else if (r1 < cdf1) { lobe = LOBE_CLEARCOAT; r1 = (r1 - cdf0) / (cdf1 - cdf0); }
-    else { lobe = LOBE_REFLECT; r1 = (r1 - cdf1) / (R(1) - cdf1); }
+    if (r1 < cdf0) { lobe = LOBE_DIFFUSE; r1 = m_div(r1, cdf0); }
+    else if (r1 < cdf1) { lobe = LOBE_CLEARCOAT; r1 = m_div(r1 - cdf0, cdf1 - cdf0); }
+    else { lobe = LOBE_REFLECT; r1 = m_div(r1 - cdf1, R(1) - cdf1); }
     // azimuth: TWO_PI * r2 (diffuse 328, spec 265), r1 * TWO_PI for the clearcoat lobe (246, quirk A.4)
     R sn, cs;
     m_sincos(Const<R>::TWO_PI * (lobe == LOBE_CLEARCOAT ? r1 : r2), &sn, &cs);
@@ -1081,7 +1092,7 @@ template <class R> PTB_DEV LightSample<R> sample_light(const DLight<R>& L, R n_l
     ls.direction = div_s(ls.direction, ls.dist);
     ls.normal = normalize(surf - lp);
     ls.emission = n_lights_f * V3<R>(L.ex, L.ey, L.ez);
-    ls.pdf = dist_sq / (L.area * R(0.5) * m_abs(dot(ls.normal, ls.direction)));
+    ls.pdf = m_div(dist_sq, L.area * R(0.5) * m_abs(dot(ls.normal, ls.direction)));
     return ls;
 }
 
@@ -1091,7 +1102,7 @@ template <class R> PTB_DEV void state_finalize(V3<R> o, V3<R> d, R hit_dist, V3<
     R nd = dot(normal, d);
     ffn = nd <= R(0) ? normal : -normal;
     mat_finalize(m);
-    eta = nd < R(0) ? R(1) / m.ior : m.ior;
+    eta = nd < R(0) ? m_rcp(m.ior) : m.ior;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1323,7 +1334,7 @@ template <class R> PTB_DEV bool russian_roulette_survives(PathState<R>& p, R u0)
     R q = m_max(p.thr.x, m_max(p.thr.y, p.thr.z)) + R(0.001);
     q = q > R(0.95) ? R(0.95) : q;
     if (u0 >= q) return false;
-    p.thr = (R(1) / q) * p.thr;
+    p.thr = m_rcp(q) * p.thr;
     return true;
 }
 

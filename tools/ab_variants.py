@@ -22,10 +22,9 @@ VARIANTS = [
     #   PTB_CHUNK                                                    pixels reserved per hand-out atomic
     #   PTB_WF_NO_TAIL, PTB_WF_TAIL_LOG2, PTB_NO_FILM_FMA            tail items off / block count, IEEE film quotients
     #   env PTB200_NO_RESOLVED_MATERIALS=1                           generic shade path (no material table)
+    #   PTB_FULL_DIV                                                 f32 quotients as div.full (`a / b`) instead of rcp + mul
     ("default", [], {}),
-    ("generic_shade", [], {"PTB200_NO_RESOLVED_MATERIALS": "1"}),
-    ("no_tail", ["-DPTB_WF_NO_TAIL"], {}),
-    ("chunk256", ["-DPTB_CHUNK=256"], {}),
+    ("full_div", ["-DPTB_FULL_DIV"], {}),
 ]
 
 
