@@ -24,7 +24,9 @@ VARIANTS = [
     #   env PTB200_NO_RESOLVED_MATERIALS=1                           generic shade path (no material table)
     #   PTB_FULL_DIV                                                 f32 quotients as div.full (`a / b`) instead of rcp + mul
     ("default", [], {}),
-    ("full_div", ["-DPTB_FULL_DIV"], {}),
+    ("t896_1792", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL_RM=1792"], {}),
+    ("t1024_2048", ["-DPTB_WF_THREADS_RM=1024", "-DPTB_WF_POOL_RM=2048"], {}),
+    ("t640_2560", ["-DPTB_WF_THREADS_RM=640", "-DPTB_WF_POOL_RM=2560", "-DPTB_WF_SCENE_BYTES_RM=4096"], {}),
 ]
 
 
