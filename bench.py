@@ -39,10 +39,10 @@ F_K = dict(gen_ray=94, closest_hit=130, finalize=36, direct_light=127, nee_contr
            ev_diffuse=75, ev_reflect=103, ev_refract=100, ev_clearcoat=73, sample_common=200, lobe_diffuse=26,
            lobe_clearcoat=52, lobe_reflect=156, lobe_refract=169, background=18, glue_bounce=12, glue_sample=20)
 # DRAM bytes per launch of the render kernel at 3840x2160 from the committed `ncu --set full` capture
-# (profiles/r01_ncu_wavefront.md, r01-j: dram__bytes_read.sum 129.6 MB + dram__bytes_write.sum 115.8 MB; the accumulator
+# (profiles/r01_ncu_wavefront.md, r01-k: dram__bytes_read.sum 129.1 MB + dram__bytes_write.sum 114.1 MB; the accumulator
 # read-modify-write is 265.4 MB algorithmic — part of the writes is still dirty in L2 when the kernel ends — and the sample
 # blocks of the tail pixels add 44 MB of stores).  Independent of spp.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 129641728 + 115766784
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 129124608 + 114142720
 
 
 def flops_per_sample(c: dict) -> float:
