@@ -11,7 +11,7 @@ fn main() {
     let lib = out.join("libptb200.so");
     let status = Command::new(&nvcc)
         .args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-prec-div=false", "-prec-sqrt=false", "-shared", "-Xcompiler", "-fPIC", "-o"])
+               "-prec-div=false", "-prec-sqrt=false", "-ftz=true", "-shared", "-Xcompiler", "-fPIC", "-o"])
         .arg(&lib)
         .arg(csrc.join("ptb_api.cu"))
         .status()

@@ -24,9 +24,10 @@ VARIANTS = [
     #   env PTB200_NO_RESOLVED_MATERIALS=1                           generic shade path (no material table)
     #   PTB_FULL_DIV                                                 f32 quotients as div.full (`a / b`) instead of rcp + mul
     ("default", [], {}),
-    ("t896_1792", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL_RM=1792"], {}),
-    ("t1024_2048", ["-DPTB_WF_THREADS_RM=1024", "-DPTB_WF_POOL_RM=2048"], {}),
-    ("t640_2560", ["-DPTB_WF_THREADS_RM=640", "-DPTB_WF_POOL_RM=2560", "-DPTB_WF_SCENE_BYTES_RM=4096"], {}),
+    ("generic_shade", [], {"PTB200_NO_RESOLVED_MATERIALS": "1"}),
+    ("full_div", ["-DPTB_FULL_DIV"], {}),
+    ("no_tail", ["-DPTB_WF_NO_TAIL"], {}),
+    ("chunk256", ["-DPTB_CHUNK=256"], {}),
 ]
 
 
