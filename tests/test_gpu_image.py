@@ -629,3 +629,31 @@ def test_wavefront_tail_blocks_match_whole_pixels(rp, scene, oracle_demo, wh_spp
     if W * H * S <= 200 * 150 * 16:
         ref, _, _, _ = oracle_demo.render(W, H, S)
         assert (pix_rel(imgs[0], ref) < 1e-4).mean() >= 0.99
+
+
+def test_non_spherical_light_types_are_inert_like_the_reference(rp, po):
+    """LightType::Rectangular / Distant exist in the reference (globals.rs:69-73) but Tracer::sample_light only implements the
+    spherical arm (tracer.rs:217 `_ => {}`: direction and normal stay zero, so the cull at tracer.rs:148 drops the sample) and
+    Scene::sample_lights only intersects spherical lights (scene.rs:69).  They still count in number_of_lights(): the uniform
+    light pick lands on them and the spherical light's emission is scaled by the full count (tracer.rs:137-139, 214)."""
+    e = rp.AnalyticalScene.new().device_export()
+    rect = rp.AnalyticalLight.spherical(rp.F3(-2.0, 2.5, 1.0), 0.8, rp.F3(6, 5, 4)); rect.light.light_type = rp._abi.PTB_LIGHT_RECTANGULAR
+    dist = rp.AnalyticalLight.spherical(rp.F3(0.0, 4.0, -1.0), 0.5, rp.F3(2, 2, 9)); dist.light.light_type = rp._abi.PTB_LIGHT_DISTANT
+    e.lights = [rect, e.lights[0], dist]
+    W, H, S = 160, 100, 4
+    ref, _, _, oc = po.OracleScene(e).render(W, H, S, counters=True)
+    assert oc["end_emitter"] >= 0
+    for integ in (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_STREAM):
+        pt = rp.Tracer.new(rp.ExportedScene(e), integrator=integ, collect_counters=True)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        c = pt.counters()
+        pt.close()
+        rel = pix_rel(buf.pixels, ref)
+        assert (rel < 1e-4).mean() >= 0.99, (integ, (rel < 1e-4).mean())
+        for k in ("closest_hit", "any_hit", "shade", "nee_contrib", "end_sky", "end_emitter"):
+            assert abs(c[k] - oc[k]) <= max(5, 1e-3 * W * H * S), (integ, k, c[k], oc[k])
+    # a third of the light picks land on the spherical light: fewer shadow rays than with that light alone
+    only = rp.AnalyticalScene.new().device_export()
+    _, _, _, oc1 = po.OracleScene(only).render(W, H, S, counters=True)
+    assert oc["any_hit"] < 0.5 * oc1["any_hit"]
