@@ -1181,8 +1181,9 @@ PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const 
 // it if the ray turns out unoccluded — the same additions in the same order, without keeping the shading context alive
 // across kernels.  flags: bits 0..3 = lobes evaluated towards the light, bit 4 = pdf > 0 (the sample can contribute).
 struct NoSink { template <class V> PTB_DEV void operator()(V, uint32_t) const {} };
-// UNROLL: two copies of the lobe code, one per pass (the staged kernel that can afford the code size: +5 % there — the
-// compiler overlaps the independent passes; the fused kernel is instruction-cache bound and keeps the single copy).
+// UNROLL: two copies of the lobe code, one per pass: the compiler overlaps the independent passes (+5 % in the resolved-material
+// wavefront kernel, +4.5 % in the fused kernel on the demo scene, -1 % on the depth-16 stress scene; no effect in the streaming
+// shade kernel, which keeps the single copy).  The single copy dates from the 142 KB fused kernel that was instruction-cache bound.
 template <class R, bool COUNT, bool DEFER = false, class Sink = NoSink, bool UNROLL = false>
 PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat, const ShadeSetup<R>& su, bool nee, const LightSample<R>& ls,
                           R light_area, const R* u, PathCounters* pc, const Sink& sink = Sink()) {
@@ -1254,7 +1255,7 @@ PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>
         if (COUNT) pc->any_hit++;
         nee = !any_hit<R, BVH>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
     }
-    return shade_finish<R, COUNT>(s, p, mat, su, nee, ns.ls, ns.light_area, u, pc);
+    return shade_finish<R, COUNT, false, NoSink, true>(s, p, mat, su, nee, ns.ls, ns.light_area, u, pc);
 }
 
 // ------------------------------------------------------------------------------------------------
