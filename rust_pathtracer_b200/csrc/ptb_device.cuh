@@ -46,6 +46,15 @@ PTB_DEV double div_rn(double a, double b) { return a / b; }
 // sin/cos of an angle known to lie in [0, 2*pi] (every call site passes TWO_PI * u, u in [0,1)):
 // quadrant reduction with a three-term Cody-Waite pi/2 and the Cephes sinf/cosf minimax kernels on
 // [-pi/4, pi/4]; ~1 ulp, no large-argument slow path (sincosf's Payne-Hanek tail is dead code here).
+#ifdef PTB_MUFU_SINCOS
+// MUFU.SIN / MUFU.COS on the argument shifted into [-pi, pi) (sin x = -sin(x - pi), cos x = -cos(x - pi)): max abs error
+// 2^-21.4 = 3.6e-7 there — inside the 1e-5 parity budget, outside the ~1 ulp of the minimax kernel below
+PTB_DEV void m_sincos(float x, float* s, float* c) {
+    float sn, cs;
+    __sincosf(x - 3.14159265358979323846f, &sn, &cs);
+    *s = -sn; *c = -cs;
+}
+#else
 PTB_DEV void m_sincos(float x, float* s, float* c) {
     float kf = rintf(x * 0.636619772f);
     float r = fmaf(kf, -1.5703125f, x);
@@ -60,6 +69,7 @@ PTB_DEV void m_sincos(float x, float* s, float* c) {
     *s = (k & 2) ? -a : a;
     *c = ((k + 1) & 2) ? -b : b;
 }
+#endif
 PTB_DEV void m_sincos(double a, double* s, double* c) { sincos(a, s, c); }
 template <class R> PTB_DEV R m_clamp(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); }  // f32::clamp
 

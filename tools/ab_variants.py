@@ -23,11 +23,12 @@ VARIANTS = [
     #   PTB_WF_NO_TAIL, PTB_WF_TAIL_LOG2, PTB_NO_FILM_FMA            tail items off / block count, IEEE film quotients
     #   env PTB200_NO_RESOLVED_MATERIALS=1                           generic shade path (no material table)
     #   PTB_FULL_DIV                                                 f32 quotients as div.full (`a / b`) instead of rcp + mul
+    #   PTB_MUFU_SINCOS                                              sin / cos on MUFU.SIN / MUFU.COS (3.6e-7 abs) instead of the ~1 ulp minimax kernel
     ("default", [], {}),
     ("generic_shade", [], {"PTB200_NO_RESOLVED_MATERIALS": "1"}),
     ("full_div", ["-DPTB_FULL_DIV"], {}),
     ("no_tail", ["-DPTB_WF_NO_TAIL"], {}),
-    ("chunk256", ["-DPTB_CHUNK=256"], {}),
+    ("mufu_sincos", ["-DPTB_MUFU_SINCOS"], {}),
 ]
 
 
