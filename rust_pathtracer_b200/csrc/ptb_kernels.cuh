@@ -56,7 +56,7 @@ constexpr uint32_t FUSED_CHUNK = PTB_CHUNK;
 // place (next sample of their pixel, or a new pixel from the warp's tile), so the warp stays full
 // until the frame runs out of pixels: termination divergence — the reference's early `break`s,
 // 84 % of paths end on the sky within two bounces — costs nothing, and there is no path state in
-// HBM at all.  Pixels are handed out tile by tile (16x16) through one global atomic per tile;
+// HBM at all.  Pixels are handed out in 16x16-tile order, FUSED_CHUNK (two tile rows) per global atomic;
 // within a warp they are distributed with ballot/popc prefix ranks.  Every pixel's samples are
 // summed in sample order by one lane, so the image is bit-reproducible run to run.
 template <class R, bool COUNT, bool BVH>
