@@ -330,6 +330,11 @@ int  ptb_test_finalize_f32(ptb_tracer* t, size_t n, uint32_t material_index, con
                            const float* dir3, const float* hit_dist, const float* normal3,
                            float* rough_out, float* ccrough_out, float* ax_out, float* ay_out,
                            float* eta_out, float* ffnormal3_out, float* fhp3_out);
+/* HOST-ONLY: the wavefront integrator computes the film coordinates x / W and y / H of tracer.rs:34-46 (IEEE divisions in
+ * the reference) as a correctly rounded reciprocal plus one FMA correction step, but only after checking on the host that this
+ * is bit-identical to the IEEE quotient for EVERY column and row of the frame size; otherwise it divides.  This entry point
+ * returns that verdict (1 = every quotient exact) and the number of columns / rows whose corrected quotient differs. */
+int  ptb_test_film_quotients_f32(uint32_t width, uint32_t height, uint32_t* all_exact_out, uint32_t* mismatches_out);
 /* HOST-ONLY (no device, no tracer): the entry of the resolved-material table that ptb_set_scene_f32 builds for small scenes
  *  for one accepted-primitive chain.  `chain` = material indices of the accepted primitives in test order
  * (one index for scenes whose materials assign every field); `checker_odd` = which checker cell supplies the albedo.

@@ -92,7 +92,7 @@ SYMBOLS = [
     "ptb_last_render_ms",
     "ptb_test_sphere_hit_f32", "ptb_test_plane_hit_f32", "ptb_test_gen_ray_f32", "ptb_test_closest_hit_f32",
     "ptb_test_any_hit_f32", "ptb_test_background_f32", "ptb_test_sample_light_f32", "ptb_test_finalize_f32",
-    "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32", "ptb_test_resolved_material_f32",
+    "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32", "ptb_test_resolved_material_f32", "ptb_test_film_quotients_f32",
 ]
 PTB_RMAT_FLOATS = 35
 
@@ -140,6 +140,7 @@ def load():
     lib.ptb_download_f64.argtypes = [C.c_void_p, C.c_void_p]
     lib.ptb_frames.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.ptb_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+    lib.ptb_test_film_quotients_f32.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.ptb_test_resolved_material_f32.argtypes = [C.POINTER(TYPES["f32"]["Scene"]), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
     lib.ptb_peer_slots_create.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p]
     lib.ptb_peer_slots_open.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]

@@ -922,6 +922,18 @@ int ptb_convert_pixels_to_u8_at_f32(ptb_tracer* t, const float* rgba, uint32_t w
 int ptb_convert_pixels_to_u8_at_f64(ptb_tracer* t, const double* rgba, uint32_t w, uint32_t h, uint8_t* frame, uint32_t x, uint32_t y, uint32_t fw,
                                     uint32_t fh) { return convert_pixels_at_impl<double>(t, rgba, w, h, frame, x, y, fw, fh); }
 
+int ptb_test_film_quotients_f32(uint32_t W, uint32_t H, uint32_t* all_exact, uint32_t* mismatches) {
+    if (!all_exact || !mismatches) return fail(PTB_E_INVALID, "null argument");
+    uint32_t bad = 0;
+    if (W && H && W < (1u << 24) && H < (1u << 24)) {
+        const float wf = (float)W, hf = (float)H, rw = 1.0f / wf, rh = 1.0f / hf;
+        for (uint32_t x = 0; x < W; ++x) bad += div_by_fma((float)x, wf, rw) != (float)x / wf;
+        for (uint32_t y = 1; y <= H; ++y) bad += div_by_fma((float)y, hf, rh) != (float)y / hf;
+    }
+    *mismatches = bad;
+    *all_exact = film_coords_fma_exact(W, H) ? 1u : 0u;      // what wavefront_render decides
+    return PTB_OK;
+}
 int ptb_test_resolved_material_f32(const ptb_scene_f32* sc, const uint32_t* chain, uint32_t chain_len, uint32_t checker_odd, float* out) {
     if (!sc || !chain || !out || chain_len == 0) return fail(PTB_E_INVALID, "null argument or empty chain");
     std::vector<DMaterial<float>> mats(chain_len);

@@ -154,3 +154,32 @@ def test_resolved_material_chain_replays_the_cumulative_assignment(rp, demo_expo
     only_floor = _resolved(rp, e, [floor], 0)
     assert np.all(only_floor["rgb"] == np.float32(0.25)) and only_floor["metallic"] == 0.0 and only_floor["lobe_class"] == 1
     assert only_floor["eta_enter"] == np.float32(1.0) / np.float32(1.45) and only_floor["eta_exit"] == np.float32(1.45)
+
+
+def test_film_quotients_by_fma_are_exact_or_declined(rp):
+    """Host half of the division-free film coordinates (wavefront integrator): the verdict `all_exact` must be true exactly when
+    no column / row quotient differs from the IEEE one, and the common frame sizes take the fast path."""
+    lib = rp._abi.load()
+    ok, bad = C.c_uint32(), C.c_uint32()
+    sizes = [(800, 600), (960, 540), (1280, 720), (1920, 1080), (3840, 2160), (7680, 4320), (1, 1), (37, 19), (97, 61), (4099, 3001),
+             (12345, 6789), (65535, 3)]
+    n_fast = 0
+    for (w, h) in sizes:
+        rp._abi.check(lib.ptb_test_film_quotients_f32(w, h, C.byref(ok), C.byref(bad)))
+        assert (ok.value == 1) == (bad.value == 0), (w, h, ok.value, bad.value)
+        n_fast += ok.value
+        # independent check of the claim in numpy: q = RN(x * RN(1/W)); r = x - q*W exactly; q' = RN(q + r * RN(1/W))
+        x = np.arange(w, dtype=np.float32)
+        rw = np.float32(1.0) / np.float32(w)
+        q = x * rw
+        r = (x.astype(np.float64) - q.astype(np.float64) * np.float64(w)).astype(np.float32)          # exact: |r| is tiny and representable
+        q2 = (q.astype(np.float64) + r.astype(np.float64) * np.float64(rw)).astype(np.float32)        # one rounding (the f64 sum is exact enough)
+        mism = int((q2 != x / np.float32(w)).sum())
+        if ok.value:
+            assert mism == 0, (w, h, mism)
+    for (w, h) in [(800, 600), (1920, 1080), (3840, 2160)]:
+        rp._abi.check(lib.ptb_test_film_quotients_f32(w, h, C.byref(ok), C.byref(bad)))
+        assert ok.value == 1, (w, h, bad.value)
+    assert n_fast >= len(sizes) - 2
+    rp._abi.check(lib.ptb_test_film_quotients_f32(1 << 24, 10, C.byref(ok), C.byref(bad)))
+    assert ok.value == 0                                      # beyond the exactly representable integers: declined
