@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 1
+#define PTB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------ */
 enum {
@@ -224,6 +224,18 @@ int  ptb_upload_f64(ptb_tracer* t, const double* pixels_rgba, uint64_t frames);
 /* device accumulators -> mean image, alpha = 1 where any sample landed (tracer.rs:59,105) */
 int  ptb_download_f32(ptb_tracer* t, float*  pixels_rgba);
 int  ptb_download_f64(ptb_tracer* t, double* pixels_rgba);
+/* The same download without blocking the caller: the mean image is resolved on the tracer's stream and copied to the host on a
+ * side stream, so the copy of step k overlaps the tracing of step k+1 (bench.py's e2e arm; a progressive viewer does the same).
+ * `pixels_rgba` must stay valid — and should be page-locked, ptb_pin_host — until ptb_wait_download returns.  Two downloads may be
+ * in flight; a third waits for the first.  No reference counterpart: the reference's render() is synchronous (tracer.rs:22). */
+int  ptb_download_async_f32(ptb_tracer* t, float*  pixels_rgba);
+int  ptb_download_async_f64(ptb_tracer* t, double* pixels_rgba);
+int  ptb_wait_download(ptb_tracer* t);
+/* Page-lock / release caller-owned host memory (cudaHostRegister, portable) so that uploads and downloads run as DMA.  Opt-in and
+ * owned by the caller: unpin BEFORE freeing the memory.  The host wrappers do this for ColorBuffer.pixels (pin on first render,
+ * unpin in the buffer's destructor).  Already-pinned / not-pinned buffers are not an error. */
+int  ptb_pin_host(void* host_ptr, size_t bytes);
+int  ptb_unpin_host(void* host_ptr);
 /* frames accumulated so far (ColorBuffer.frames) */
 int  ptb_frames(ptb_tracer* t, uint64_t* frames);
 
@@ -236,14 +248,22 @@ int  ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base);
  * is 0 the accumulators are cleared, otherwise the host pixels are uploaded first (they are the
  * source of truth: `pixels` and `frames` are public fields the app may edit between calls);
  * then ONE sample per pixel is traced with sample index frames_before and the running mean is
- * written back to `pixels_rgba_inout`.  Synchronous.  The buffer is page-locked (cudaHostRegister)
- * the first time it is seen and stays so until another buffer is passed or the tracer is destroyed
- * — destroy the tracer (or pass a different buffer) before freeing it.  Throughput-minded callers
- * keep the image device-resident instead: ptb_render + ptb_download. */
+ * written back to `pixels_rgba_inout`.  Synchronous.  Page-lock the buffer with ptb_pin_host for DMA-speed
+ * copies (the host wrappers do).  Throughput-minded callers keep the image device-resident instead:
+ * ptb_render + ptb_download. */
 int  ptb_render_frame_f32(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,
                           float* pixels_rgba_inout);
 int  ptb_render_frame_f64(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,
                           double* pixels_rgba_inout);
+/* The same call with flags.  PTB_FRAME_HOST_UNCHANGED: the caller vouches that `pixels_rgba_inout` still holds exactly what this
+ * tracer's previous render_frame wrote there (a wrapper knows this from a dirty flag on its ColorBuffer).  If in addition the
+ * buffer address, the frame count and the device image are what that call left behind, the H2D upload — half of the PCIe traffic
+ * of the drop-in loop (renderer/src/main.rs:113-122) — is skipped; otherwise the flag is ignored and the pixels are uploaded. */
+enum { PTB_FRAME_HOST_UNCHANGED = 1u << 0 };
+int  ptb_render_frame_ex_f32(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,
+                             float* pixels_rgba_inout, uint32_t flags);
+int  ptb_render_frame_ex_f64(ptb_tracer* t, uint32_t width, uint32_t height, uint64_t frames_before,
+                             double* pixels_rgba_inout, uint32_t flags);
 int  ptb_synchronize(ptb_tracer* t);
 
 /* ColorBuffer::convert_to_u8, buffer.rs:55-64, of the current mean image (device kernel + D2H) */
@@ -335,6 +355,11 @@ int  ptb_test_finalize_f32(ptb_tracer* t, size_t n, uint32_t material_index, con
  * is bit-identical to the IEEE quotient for EVERY column and row of the frame size; otherwise it divides.  This entry point
  * returns that verdict (1 = every quotient exact) and the number of columns / rows whose corrected quotient differs. */
 int  ptb_test_film_quotients_f32(uint32_t width, uint32_t height, uint32_t* all_exact_out, uint32_t* mismatches_out);
+/* HOST-ONLY: builds the sphere BVH the way ptb_set_scene_* does and reports its depth, node count and largest leaf.  The device
+ * traversal keeps a fixed 40-entry stack; the builder falls back to median splits before a chain of SAH splits could exceed it
+ * (tests/test_host.py feeds it adversarial size distributions). */
+int  ptb_test_bvh_build_f32(const ptb_sphere_f32* spheres, uint32_t n_spheres, uint32_t* depth_out, uint32_t* nodes_out,
+                            uint32_t* max_leaf_out);
 /* HOST-ONLY (no device, no tracer): the entry of the resolved-material table that ptb_set_scene_f32 builds for small scenes
  *  for one accepted-primitive chain.  `chain` = material indices of the accepted primitives in test order
  * (one index for scenes whose materials assign every field); `checker_odd` = which checker cell supplies the albedo.

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-PTB_ABI_VERSION = 1
+PTB_ABI_VERSION = 2
 
 # status codes
 PTB_OK, PTB_E_INVALID, PTB_E_NO_DEVICE, PTB_E_CUDA, PTB_E_NO_SCENE, PTB_E_PRECISION, PTB_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
@@ -19,6 +19,7 @@ PTB_BG_CONSTANT, PTB_BG_GRADIENT_Y = 0, 1
 PTB_SCENE_ANYHIT_IGNORES_MAX_DIST, PTB_SCENE_FORCE_BVH, PTB_SCENE_NO_BVH = 1, 2, 4
 PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT, PTB_INTEGRATOR_STREAM = 0, 1, 2, 3
 PTB_PEER_HANDLE_BYTES = 64
+PTB_FRAME_HOST_UNCHANGED = 1
 
 PTB_MAT_RGB, PTB_MAT_EMISSION, PTB_MAT_ANISOTROPIC, PTB_MAT_METALLIC = 1 << 0, 1 << 1, 1 << 2, 1 << 3
 PTB_MAT_ROUGHNESS, PTB_MAT_SUBSURFACE, PTB_MAT_SPECULAR_TINT, PTB_MAT_SHEEN = 1 << 4, 1 << 5, 1 << 6, 1 << 7
@@ -85,14 +86,15 @@ SYMBOLS = [
     "ptb_create", "ptb_destroy", "ptb_abi_version", "ptb_last_error", "ptb_device_count", "ptb_set_stream",
     "ptb_set_scene_f32", "ptb_set_scene_f64", "ptb_resize", "ptb_bind_accumulator", "ptb_clear",
     "ptb_upload_f32", "ptb_upload_f64", "ptb_download_f32", "ptb_download_f64", "ptb_frames",
-    "ptb_render", "ptb_render_frame_f32", "ptb_render_frame_f64", "ptb_synchronize",
+    "ptb_render", "ptb_render_frame_f32", "ptb_render_frame_f64", "ptb_render_frame_ex_f32", "ptb_render_frame_ex_f64", "ptb_synchronize",
+    "ptb_download_async_f32", "ptb_download_async_f64", "ptb_wait_download", "ptb_pin_host", "ptb_unpin_host",
     "ptb_peer_slots_create", "ptb_peer_slots_open", "ptb_peer_set_target", "ptb_peer_sum", "ptb_peer_slots_close",
     "ptb_convert_to_u8", "ptb_convert_to_u8_at", "ptb_convert_pixels_to_u8_f32", "ptb_convert_pixels_to_u8_f64",
     "ptb_convert_pixels_to_u8_at_f32", "ptb_convert_pixels_to_u8_at_f64", "ptb_get_counters", "ptb_reset_counters", "ptb_launch_count",
     "ptb_last_render_ms",
     "ptb_test_sphere_hit_f32", "ptb_test_plane_hit_f32", "ptb_test_gen_ray_f32", "ptb_test_closest_hit_f32",
     "ptb_test_any_hit_f32", "ptb_test_background_f32", "ptb_test_sample_light_f32", "ptb_test_finalize_f32",
-    "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32", "ptb_test_resolved_material_f32", "ptb_test_film_quotients_f32",
+    "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32", "ptb_test_resolved_material_f32", "ptb_test_film_quotients_f32", "ptb_test_bvh_build_f32",
 ]
 PTB_RMAT_FLOATS = 35
 
@@ -141,6 +143,7 @@ def load():
     lib.ptb_frames.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.ptb_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
     lib.ptb_test_film_quotients_f32.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.ptb_test_bvh_build_f32.argtypes = [C.POINTER(TYPES["f32"]["Sphere"]), C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
     lib.ptb_test_resolved_material_f32.argtypes = [C.POINTER(TYPES["f32"]["Scene"]), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
     lib.ptb_peer_slots_create.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p]
     lib.ptb_peer_slots_open.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
@@ -149,6 +152,13 @@ def load():
     lib.ptb_peer_slots_close.argtypes = [C.c_void_p]
     lib.ptb_render_frame_f32.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     lib.ptb_render_frame_f64.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
+    lib.ptb_render_frame_ex_f32.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32]
+    lib.ptb_render_frame_ex_f64.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32]
+    lib.ptb_download_async_f32.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ptb_download_async_f64.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ptb_wait_download.argtypes = [C.c_void_p]
+    lib.ptb_pin_host.argtypes = [C.c_void_p, C.c_size_t]
+    lib.ptb_unpin_host.argtypes = [C.c_void_p]
     lib.ptb_synchronize.argtypes = [C.c_void_p]
     lib.ptb_convert_to_u8.argtypes = [C.c_void_p, C.c_void_p]
     lib.ptb_convert_to_u8_at.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]

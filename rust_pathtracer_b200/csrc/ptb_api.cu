@@ -94,19 +94,20 @@ struct ptb_tracer {
     uint32_t peer_slots = 0;
     size_t peer_frame_bytes = 0;
     void* flush_dst = nullptr;      // current target of ptb_render's per-pixel partial sums (NULL: add to the accumulators)
-    // drop-in path: the caller's ColorBuffer.pixels, page-locked on first use so that the per-call H2D + D2H run as DMA
-    void* pinned_host = nullptr;
-    size_t pinned_bytes = 0;
+    // drop-in path: host buffer that holds exactly the device image as of `host_clean_frames` frames, because this tracer's
+    // last render_frame / download wrote it (NULL: unknown).  With PTB_FRAME_HOST_UNCHANGED the caller vouches that it has
+    // not touched the buffer since, and the upload of the next render_frame is skipped.
+    const void* host_clean = nullptr;
+    uint64_t host_clean_frames = 0;
+    // asynchronous download (ptb_download_async_*): side stream + events, so the copy of step k overlaps the trace of step k+1
+    cudaStream_t dl_stream = nullptr;
+    cudaEvent_t dl_ready = nullptr;
+    cudaEvent_t dl_free[2] = {nullptr, nullptr};   // the D2H copy out of dl_staging[k] has completed
+    bool dl_used[2] = {false, false};
+    void* dl_staging[2] = {nullptr, nullptr};
+    size_t dl_staging_bytes = 0;
+    uint32_t dl_parity = 0;
 };
-
-// Page-lock the host buffer `render_frame` is called with (the same `ColorBuffer.pixels` every frame in the reference's
-// loop, renderer/src/main.rs:113-122).  Failure is not an error: the copies then go through the driver's staging path.
-static void pin_host_buffer(ptb_tracer* t, void* p, size_t bytes) {
-    if (t->pinned_host == p && t->pinned_bytes == bytes) return;
-    if (t->pinned_host) { cudaHostUnregister(t->pinned_host); t->pinned_host = nullptr; t->pinned_bytes = 0; }
-    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) { t->pinned_host = p; t->pinned_bytes = bytes; }
-    else cudaGetLastError();
-}
 
 static size_t real_size(const ptb_tracer* t) { return (size_t)t->precision; }
 
@@ -128,7 +129,14 @@ struct BvhBuilder {
     std::vector<float> pcen;   // 3 per prim
     std::vector<uint32_t> prim;
     std::vector<BvhNode> nodes;
-    void build_node(uint32_t ni, uint32_t first, uint32_t count) {
+    // The device traversal keeps a fixed stack of BVH_STACK entries (ptb_device.cuh) and pushes at most one entry per level,
+    // so the tree may not be deeper than that.  Binned SAH on strongly non-uniform inputs can produce long chains; once the
+    // levels a balanced subtree of `count` primitives still needs would no longer fit, the split falls back to the median
+    // along the widest centroid axis, which halves `count` at every level and so keeps the bound.
+    uint32_t max_depth = 0;
+    static uint32_t ceil_log2(uint32_t n) { uint32_t l = 0; while ((1u << l) < n) ++l; return l; }
+    void build_node(uint32_t ni, uint32_t first, uint32_t count, uint32_t depth = 0) {
+        max_depth = std::max(max_depth, depth);
         Box nb = box_empty(), cb = box_empty();
         for (uint32_t i = first; i < first + count; ++i) {
             box_grow(nb, pbox[prim[i]]);
@@ -165,7 +173,14 @@ struct BvhBuilder {
         // no useful split for a small node: keep it as a leaf
         if (count <= 4 && (best_axis < 0 || best_cost >= box_area(nb) * count)) { make_leaf(); return; }
         uint32_t mid;
-        if (best_axis >= 0) {
+        const bool force_median = depth + ceil_log2(count) + 2u >= (uint32_t)BVH_STACK;
+        if (force_median) {
+            int ax = 0;
+            for (int k = 1; k < 3; ++k) if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+            mid = first + count / 2;
+            std::nth_element(prim.begin() + first, prim.begin() + mid, prim.begin() + first + count,
+                             [&](uint32_t a, uint32_t b) { return pcen[3 * a + ax] < pcen[3 * b + ax]; });
+        } else if (best_axis >= 0) {
             float ext = cb.hi[best_axis] - cb.lo[best_axis];
             float scale = NB / ext;
             auto it = std::partition(prim.begin() + first, prim.begin() + first + count, [&](uint32_t p) {
@@ -182,8 +197,8 @@ struct BvhBuilder {
         nodes.push_back(BvhNode{});
         nodes[ni].left_or_first = left;
         nodes[ni].count = 0;
-        build_node(left, first, mid - first);
-        build_node(left + 1, mid, first + count - mid);
+        build_node(left, first, mid - first, depth + 1);
+        build_node(left + 1, mid, first + count - mid, depth + 1);
     }
 };
 }  // namespace
@@ -311,6 +326,29 @@ template <class R, class PodMaterial> static DMaterial<R> resolve_pod_material(c
     return o;
 }
 
+// BVH over n spheres (binned SAH, f32 bounds rounded outward); returns the depth of the tree
+template <class CenterOf, class RadiusOf>
+static uint32_t build_bvh(size_t n, CenterOf center_of, RadiusOf radius_of, std::vector<BvhNode>& nodes_out, std::vector<uint32_t>& prim_out) {
+    BvhBuilder b;
+    b.pbox.resize(n); b.pcen.resize(3 * n); b.prim.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            double c = center_of(i, k), r = std::fabs(radius_of(i));
+            float lo = (float)(c - r), hi = (float)(c + r);
+            lo = std::nextafterf(lo - std::fabs(lo) * 1e-6f, -3e38f);
+            hi = std::nextafterf(hi + std::fabs(hi) * 1e-6f, 3e38f);
+            b.pbox[i].lo[k] = lo; b.pbox[i].hi[k] = hi; b.pcen[3 * i + k] = (float)c;
+        }
+        b.prim[i] = (uint32_t)i;
+    }
+    b.nodes.reserve(2 * n + 1);
+    b.nodes.push_back(BvhNode{});
+    b.build_node(0, 0, (uint32_t)n);
+    nodes_out.swap(b.nodes);
+    prim_out.swap(b.prim);
+    return b.max_depth;
+}
+
 template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb, const typename PodTypes<R>::scene* sc) {
     if (!t || !sc) return fail(PTB_E_INVALID, "null tracer or scene");
     if ((sc->n_spheres && !sc->spheres) || (sc->n_planes && !sc->planes) || (sc->n_materials && !sc->materials) ||
@@ -359,29 +397,11 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     }
 
     // BVH over the spheres, and over the spherical lights when there are many (binned SAH, f32 bounds rounded outward)
-    auto build_bvh = [](size_t n, auto center_of, auto radius_of, std::vector<BvhNode>& nodes_out, std::vector<uint32_t>& prim_out) {
-        BvhBuilder b;
-        b.pbox.resize(n); b.pcen.resize(3 * n); b.prim.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            for (int k = 0; k < 3; ++k) {
-                double c = center_of(i, k), r = std::fabs(radius_of(i));
-                float lo = (float)(c - r), hi = (float)(c + r);
-                lo = std::nextafterf(lo - std::fabs(lo) * 1e-6f, -3e38f);
-                hi = std::nextafterf(hi + std::fabs(hi) * 1e-6f, 3e38f);
-                b.pbox[i].lo[k] = lo; b.pbox[i].hi[k] = hi; b.pcen[3 * i + k] = (float)c;
-            }
-            b.prim[i] = (uint32_t)i;
-        }
-        b.nodes.reserve(2 * n + 1);
-        b.nodes.push_back(BvhNode{});
-        b.build_node(0, 0, (uint32_t)n);
-        nodes_out.swap(b.nodes);
-        prim_out.swap(b.prim);
-    };
     std::vector<BvhNode> nodes;
     std::vector<uint32_t> prim;
+    uint32_t bvh_depth = 0, light_bvh_depth = 0;
     auto build_sphere_bvh = [&]() {
-        build_bvh(sc->n_spheres, [&](size_t i, int k) { return (double)sc->spheres[i].center[k]; },
+        bvh_depth = build_bvh(sc->n_spheres, [&](size_t i, int k) { return (double)sc->spheres[i].center[k]; },
                   [&](size_t i) { return (double)sc->spheres[i].radius; }, nodes, prim);
     };
     std::vector<BvhNode> lnodes;
@@ -394,7 +414,7 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         // the light BVH lives in the BVH kernels only: scenes with partial material masks (no sphere BVH possible) keep the linear scan
         if (sph_lights.size() >= 16 && !patch && sc->n_spheres > 0 && !(sc->flags & PTB_SCENE_NO_BVH)) {
             use_bvh = true;
-            build_bvh(sph_lights.size(), [&](size_t i, int k) { return (double)sc->lights[sph_lights[i]].position[k]; },
+            light_bvh_depth = build_bvh(sph_lights.size(), [&](size_t i, int k) { return (double)sc->lights[sph_lights[i]].position[k]; },
                       [&](size_t i) { return (double)sc->lights[sph_lights[i]].radius; }, lnodes, lprim);
             lleaf.resize(lprim.size());
             for (size_t i = 0; i < lprim.size(); ++i) {
@@ -405,6 +425,8 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         }
     }
     if (use_bvh) build_sphere_bvh();
+    if (std::max(bvh_depth, light_bvh_depth) >= (uint32_t)BVH_STACK)
+        return fail(PTB_E_INVALID, "internal: BVH depth %u exceeds the traversal stack (%d)", std::max(bvh_depth, light_bvh_depth), BVH_STACK);
     for (const auto* nv : {&nodes, &lnodes})
         for (const BvhNode& nd : *nv)
             if (nd.count > 7u) return fail(PTB_E_INVALID, "internal: BVH leaf with %u primitives (node references carry 3 count bits)", nd.count);
@@ -587,7 +609,10 @@ void ptb_destroy(ptb_tracer* t) {
     t->wf.release();
     t->st.release();
     if (t->peer_base) { if (t->peer_ipc) cudaIpcCloseMemHandle(t->peer_base); else if (t->peer_owner) cudaFree(t->peer_base); }
-    if (t->pinned_host) { cudaHostUnregister(t->pinned_host); cudaGetLastError(); }
+    if (t->dl_stream) { cudaStreamSynchronize(t->dl_stream); cudaStreamDestroy(t->dl_stream); }
+    if (t->dl_ready) cudaEventDestroy(t->dl_ready);
+    for (cudaEvent_t e : t->dl_free) if (e) cudaEventDestroy(e);
+    for (void* p : t->dl_staging) if (p) cudaFree(p);
     if (t->own_accum && t->accum) cudaFree(t->accum);
     if (t->staging) cudaFree(t->staging);
     if (t->work_counter) cudaFree(t->work_counter);
@@ -608,9 +633,35 @@ int ptb_set_stream(ptb_tracer* t, void* cuda_stream) {
     return PTB_OK;
 }
 
+// A tracer may move between the two instantiations of `F` (lib.rs:5-6).  Everything sized in reals belongs to the old
+// precision: the accumulators, the staging image, the frame count, the peer slots.  They are dropped (the next
+// ptb_resize / ptb_render_frame allocates them anew); an accumulator the CALLER owns, or mapped peer slots, cannot be
+// re-typed behind the caller's back, so the switch is refused there.
+static int precision_change(ptb_tracer* t, int new_precision) {
+    if (t->precision == 0 || t->precision == new_precision) return PTB_OK;
+    if (t->accum && !t->own_accum)
+        return fail(PTB_E_PRECISION, "an external accumulator of f%d values is bound; unbind it (ptb_bind_accumulator NULL) before switching precision",
+                    t->precision * 8);
+    if (t->peer_base) return fail(PTB_E_PRECISION, "peer slots of the f%d frame exist; ptb_peer_slots_close before switching precision", t->precision * 8);
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->stream));
+    if (t->accum) cudaFree(t->accum);
+    if (t->staging) cudaFree(t->staging);
+    t->accum = nullptr; t->own_accum = false; t->accum_bytes = 0;
+    t->staging = nullptr; t->staging_bytes = 0;
+    if (t->dl_stream) cudaStreamSynchronize(t->dl_stream);
+    for (int k = 0; k < 2; ++k) { if (t->dl_staging[k]) cudaFree(t->dl_staging[k]); t->dl_staging[k] = nullptr; t->dl_used[k] = false; }
+    t->dl_staging_bytes = 0;
+    t->W = t->H = 0; t->frames = 0; t->flush_dst = nullptr; t->timed = false;
+    t->host_clean = nullptr;
+    return PTB_OK;
+}
+
 int ptb_set_scene_f32(ptb_tracer* t, const ptb_scene_f32* sc) {
     if (!t || !sc) return fail(PTB_E_INVALID, "null tracer or scene");
-    int r = set_scene_impl<float>(t, t->s32, sc);
+    int r = precision_change(t, 4);
+    if (r != PTB_OK) return r;
+    r = set_scene_impl<float>(t, t->s32, sc);
     if (r != PTB_OK) return r;
     t->s64.release();
     t->precision = 4;
@@ -623,7 +674,9 @@ int ptb_set_scene_f32(ptb_tracer* t, const ptb_scene_f32* sc) {
 }
 int ptb_set_scene_f64(ptb_tracer* t, const ptb_scene_f64* sc) {
     if (!t || !sc) return fail(PTB_E_INVALID, "null tracer or scene");
-    int r = set_scene_impl<double>(t, t->s64, sc);
+    int r = precision_change(t, 8);
+    if (r != PTB_OK) return r;
+    r = set_scene_impl<double>(t, t->s64, sc);
     if (r != PTB_OK) return r;
     t->s32.release();
     t->precision = 8;
@@ -642,6 +695,16 @@ static int need_scene(ptb_tracer* t, int precision) {
     return PTB_OK;
 }
 
+// Frames are handed out as 16x16-pixel tiles of 256 work items with 32-bit item indices (RenderArgs::n_items), the wavefront
+// integrator appends up to grid x pool x 8 tail items, and its slots pack a pixel's column and row into 16 bits each.
+static int check_frame_size(uint32_t width, uint32_t height) {
+    if (!width || !height || (uint64_t)width * height > (1ull << 31)) return fail(PTB_E_INVALID, "bad frame size %ux%u", width, height);
+    const uint64_t padded = (uint64_t)((width + 15u) / 16u) * ((height + 15u) / 16u) * 256u;
+    if (padded > 0xffffffffull - (1ull << 26))
+        return fail(PTB_E_INVALID, "frame %ux%u pads to %llu work items; the hand-out counter is 32 bits wide", width, height, (unsigned long long)padded);
+    return PTB_OK;
+}
+
 static int ensure_staging(ptb_tracer* t, size_t bytes) {
     if (t->staging_bytes >= bytes) return PTB_OK;
     if (t->staging) cudaFree(t->staging);
@@ -657,15 +720,18 @@ int ptb_clear(ptb_tracer* t) {
     CU(cudaSetDevice(t->device));
     CU(cudaMemsetAsync(t->accum, 0, t->accum_bytes, t->stream));
     t->frames = 0;
+    t->host_clean = nullptr;
     return PTB_OK;
 }
 
 int ptb_resize(ptb_tracer* t, uint32_t width, uint32_t height) {
     int r = need_scene(t, 0);
     if (r) return r;
-    if (!width || !height || (uint64_t)width * height > (1ull << 31)) return fail(PTB_E_INVALID, "bad frame size %ux%u", width, height);
+    if ((r = check_frame_size(width, height))) return r;
     CU(cudaSetDevice(t->device));
     CU(cudaStreamSynchronize(t->stream));
+    t->flush_dst = nullptr;            // peer slots are sized for the old frame: ptb_peer_set_target must be called again
+    t->host_clean = nullptr;
     if (t->own_accum && t->accum) cudaFree(t->accum);
     t->accum = nullptr; t->own_accum = false;
     t->accum_bytes = (size_t)width * height * 4 * real_size(t);
@@ -680,9 +746,11 @@ int ptb_bind_accumulator(ptb_tracer* t, void* device_ptr, uint32_t width, uint32
     int r = need_scene(t, 0);
     if (r) return r;
     if (!device_ptr) return ptb_resize(t, width, height);
-    if (!width || !height) return fail(PTB_E_INVALID, "bad frame size");
+    if ((r = check_frame_size(width, height))) return r;
     CU(cudaSetDevice(t->device));
     CU(cudaStreamSynchronize(t->stream));
+    t->flush_dst = nullptr;
+    t->host_clean = nullptr;
     if (t->own_accum && t->accum) cudaFree(t->accum);
     t->accum = device_ptr; t->own_accum = false;
     t->accum_bytes = (size_t)width * height * 4 * real_size(t);
@@ -707,6 +775,7 @@ template <class R> static int upload_impl(ptb_tracer* t, const R* pixels, uint64
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(t->stream));
     t->frames = frames;
+    t->host_clean = nullptr;
     return PTB_OK;
 }
 extern "C" {
@@ -729,7 +798,53 @@ template <class R> static int download_impl(ptb_tracer* t, R* pixels) {
     CU(cudaStreamSynchronize(t->stream));
     return PTB_OK;
 }
+// Asynchronous variant for callers that keep rendering: the mean image is resolved on the tracer's stream into one of two
+// staging images and copied to the host on a SIDE stream behind an event, so the D2H of step k overlaps the trace of step k+1
+// (the copy engines and the SMs are independent).  A staging image is reused only after its previous copy has completed.
+template <class R> static int download_async_impl(ptb_tracer* t, R* pixels) {
+    if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    CU(cudaSetDevice(t->device));
+    if (!t->dl_stream) {
+        CU(cudaStreamCreateWithFlags(&t->dl_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&t->dl_ready, cudaEventDisableTiming));
+        for (cudaEvent_t& e : t->dl_free) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (t->dl_staging_bytes < t->accum_bytes) {
+        CU(cudaStreamSynchronize(t->dl_stream));
+        for (int k = 0; k < 2; ++k) {
+            if (t->dl_staging[k]) cudaFree(t->dl_staging[k]);
+            t->dl_staging[k] = nullptr; t->dl_used[k] = false;
+        }
+        t->dl_staging_bytes = 0;
+        for (int k = 0; k < 2; ++k) CU(cudaMalloc(&t->dl_staging[k], t->accum_bytes));
+        t->dl_staging_bytes = t->accum_bytes;
+    }
+    const uint32_t k = t->dl_parity;
+    t->dl_parity ^= 1u;
+    if (t->dl_used[k]) CU(cudaStreamWaitEvent(t->stream, t->dl_free[k], 0));
+    using V4 = typename Vec4T<R>::type;
+    const uint32_t n = t->W * t->H;
+    k_resolve<R><<<(n + 255) / 256, 256, 0, t->stream>>>((const V4*)t->accum, (V4*)t->dl_staging[k], n);
+    t->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(t->dl_ready, t->stream));
+    CU(cudaStreamWaitEvent(t->dl_stream, t->dl_ready, 0));
+    CU(cudaMemcpyAsync(pixels, t->dl_staging[k], t->accum_bytes, cudaMemcpyDeviceToHost, t->dl_stream));
+    CU(cudaEventRecord(t->dl_free[k], t->dl_stream));
+    t->dl_used[k] = true;
+    return PTB_OK;
+}
 extern "C" {
+int ptb_download_async_f32(ptb_tracer* t, float* px) { int r = need_scene(t, 4); return r ? r : download_async_impl<float>(t, px); }
+int ptb_download_async_f64(ptb_tracer* t, double* px) { int r = need_scene(t, 8); return r ? r : download_async_impl<double>(t, px); }
+int ptb_wait_download(ptb_tracer* t) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    if (!t->dl_stream) return PTB_OK;
+    CU(cudaSetDevice(t->device));
+    CU(cudaStreamSynchronize(t->dl_stream));
+    return PTB_OK;
+}
 int ptb_download_f32(ptb_tracer* t, float* px) { int r = need_scene(t, 4); return r ? r : download_impl<float>(t, px); }
 int ptb_download_f64(ptb_tracer* t, double* px) { int r = need_scene(t, 8); return r ? r : download_impl<double>(t, px); }
 
@@ -777,6 +892,8 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
     if (r) return r;
     if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
     CU(cudaSetDevice(t->device));
+    if (t->flush_dst && t->peer_frame_bytes != (size_t)t->W * t->H * 16)
+        return fail(PTB_E_INVALID, "frame size changed since the peer slots were created");
     if (spp == 0) {
         // nothing to trace; with a peer target the slot must still read as "no samples" for this step
         if (t->flush_dst) CU(cudaMemsetAsync(t->flush_dst, 0, t->peer_frame_bytes, t->stream));
@@ -790,9 +907,13 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
     if (integ == PTB_INTEGRATOR_AUTO) {
         if (t->precision != 4) integ = PTB_INTEGRATOR_FUSED;
         else integ = (t->s32.d.use_bvh && t->s32.d.n_spheres >= 4096u) ? PTB_INTEGRATOR_STREAM : PTB_INTEGRATOR_WAVEFRONT;
+        // the wavefront slots pack (column, row) into 16 bits each: wider or taller frames go to the fused integrator
+        if (integ == PTB_INTEGRATOR_WAVEFRONT && (t->W > 65535u || t->H > 65535u)) integ = PTB_INTEGRATOR_FUSED;
     }
     if (integ == PTB_INTEGRATOR_WAVEFRONT) {
         if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the wavefront integrator is built for f32 only");
+        if (t->W > 65535u || t->H > 65535u)
+            return fail(PTB_E_UNSUPPORTED, "the wavefront integrator packs pixel coordinates into 16 bits: frame %ux%u has a side over 65535", t->W, t->H);
         r = wavefront_render(t->wf, t->s32.d, t->accum, t->flush_dst, t->W, t->H, spp, sample_base, t->cfg, t->stream, t->sm_count, t->counters,
                              t->work_counter, t->ev0, t->ev1, &t->launches, g_err);
         if (r) return r;
@@ -808,6 +929,7 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
         if (r) return r;
     }
     t->frames += spp;
+    t->host_clean = nullptr;
     return PTB_OK;
 }
 
@@ -819,21 +941,47 @@ int ptb_synchronize(ptb_tracer* t) {
 }
 
 }  // extern "C"
-template <class R> static int render_frame_impl(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t frames_before, R* pixels) {
+template <class R> static int render_frame_impl(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t frames_before, R* pixels, uint32_t flags) {
     if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
+    if (flags & ~(uint32_t)PTB_FRAME_HOST_UNCHANGED) return fail(PTB_E_INVALID, "unknown render_frame flags 0x%x", flags);
     int r;
     if (w != t->W || h != t->H || !t->accum) { if ((r = ptb_resize(t, w, h))) return r; }
-    pin_host_buffer(t, pixels, (size_t)w * h * 4 * sizeof(R));
     // the host buffer is the source of truth, exactly as in the reference where `pixels` and `frames`
-    // are public fields the app may edit between calls
+    // are public fields the app may edit between calls — unless the caller vouches that it still holds what
+    // this tracer wrote last (same buffer, same frame count, device image untouched since): then the upload is redundant
+    const bool resident = (flags & PTB_FRAME_HOST_UNCHANGED) && t->host_clean == (const void*)pixels && t->host_clean_frames == frames_before &&
+                          t->frames == frames_before;
     if (frames_before == 0) { if ((r = ptb_clear(t))) return r; }
-    else { if ((r = upload_impl<R>(t, pixels, frames_before))) return r; }
+    else if (!resident) { if ((r = upload_impl<R>(t, pixels, frames_before))) return r; }
+    t->host_clean = nullptr;
     if ((r = ptb_render(t, 1, frames_before))) return r;
-    return download_impl<R>(t, pixels);
+    if ((r = download_impl<R>(t, pixels))) return r;
+    t->host_clean = pixels; t->host_clean_frames = t->frames;
+    return PTB_OK;
 }
 extern "C" {
-int ptb_render_frame_f32(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, float* px) { int r = need_scene(t, 4); return r ? r : render_frame_impl<float>(t, w, h, fb, px); }
-int ptb_render_frame_f64(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, double* px) { int r = need_scene(t, 8); return r ? r : render_frame_impl<double>(t, w, h, fb, px); }
+int ptb_render_frame_f32(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, float* px) { int r = need_scene(t, 4); return r ? r : render_frame_impl<float>(t, w, h, fb, px, 0); }
+int ptb_render_frame_f64(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, double* px) { int r = need_scene(t, 8); return r ? r : render_frame_impl<double>(t, w, h, fb, px, 0); }
+int ptb_render_frame_ex_f32(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, float* px, uint32_t flags) { int r = need_scene(t, 4); return r ? r : render_frame_impl<float>(t, w, h, fb, px, flags); }
+int ptb_render_frame_ex_f64(ptb_tracer* t, uint32_t w, uint32_t h, uint64_t fb, double* px, uint32_t flags) { int r = need_scene(t, 8); return r ? r : render_frame_impl<double>(t, w, h, fb, px, flags); }
+
+// Page-locking of caller-owned host memory is the CALLER's decision and lifetime (a registration cached inside the library
+// would outlive a freed buffer and alias the next allocation at the same address).  Portable: valid for every device.
+int ptb_pin_host(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(PTB_E_INVALID, "ptb_pin_host: null buffer");
+    if (ptb_device_count() <= 0) return fail(PTB_E_NO_DEVICE, "no CUDA device visible");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return PTB_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PTB_E_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    return PTB_OK;
+}
+int ptb_unpin_host(void* p) {
+    if (!p) return fail(PTB_E_INVALID, "ptb_unpin_host: null buffer");
+    cudaError_t e = cudaHostUnregister(p);
+    cudaGetLastError();            // never leave a sticky last-error for the next launch check
+    if (e != cudaSuccess && e != cudaErrorHostMemoryNotRegistered) return fail(PTB_E_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    return PTB_OK;
+}
 
 int ptb_convert_to_u8(ptb_tracer* t, uint8_t* rgba8) {
     int r = need_scene(t, 0);
@@ -932,6 +1080,18 @@ int ptb_test_film_quotients_f32(uint32_t W, uint32_t H, uint32_t* all_exact, uin
     }
     *mismatches = bad;
     *all_exact = film_coords_fma_exact(W, H) ? 1u : 0u;      // what wavefront_render decides
+    return PTB_OK;
+}
+int ptb_test_bvh_build_f32(const ptb_sphere_f32* spheres, uint32_t n, uint32_t* depth_out, uint32_t* nodes_out, uint32_t* max_leaf_out) {
+    if (!spheres || !n || !depth_out || !nodes_out || !max_leaf_out) return fail(PTB_E_INVALID, "null argument");
+    std::vector<BvhNode> nodes;
+    std::vector<uint32_t> prim;
+    *depth_out = build_bvh(n, [&](size_t i, int k) { return (double)spheres[i].center[k]; }, [&](size_t i) { return (double)spheres[i].radius; }, nodes, prim);
+    *nodes_out = (uint32_t)nodes.size();
+    uint32_t ml = 0, covered = 0;
+    for (const BvhNode& nd : nodes) { ml = std::max(ml, nd.count); covered += nd.count; }
+    *max_leaf_out = ml;
+    if (covered != n) return fail(PTB_E_INVALID, "internal: BVH leaves cover %u of %u primitives", covered, n);
     return PTB_OK;
 }
 int ptb_test_resolved_material_f32(const ptb_scene_f32* sc, const uint32_t* chain, uint32_t chain_len, uint32_t checker_odd, float* out) {
@@ -1039,6 +1199,7 @@ int ptb_peer_sum(ptb_tracer* t, uint32_t parity) {
     const float4* slots = (const float4*)((char*)t->peer_base + (size_t)parity * t->peer_slots * t->peer_frame_bytes);
     k_peer_sum<<<(n + 255) / 256, 256, 0, t->stream>>>((float4*)t->accum, slots, t->peer_slots, n);
     t->launches++;
+    t->host_clean = nullptr;
     CU(cudaGetLastError());
     return PTB_OK;
 }

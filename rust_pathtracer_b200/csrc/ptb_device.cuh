@@ -34,7 +34,15 @@ PTB_DEV double m_max(double a, double b) { return fmax(a, b); }
 // powf as exp2(b*log2(a)) on the two MUFU instructions directly (lg2.approx / ex2.approx.ftz, no denormal pre-scaling:
 // every base on this path is a colour or a squared roughness >= 1e-6): ~3 ulp for the |b*log2(a)| <= 20 this path produces,
 // a fraction of the size of powf's special-case tree.  a == 0 -> 0, a < 0 -> NaN, a == 1 -> 1, as powf.
+// PTB_IEEE: measurement build (tools/function_parity.py, profiles/r02_function_parity.md) — every deliberate approximation of
+// the shipped build is replaced by the correctly rounded / libm operation (and the build adds -prec-div=true -prec-sqrt=true
+// -ftz=false -fmad=false), so that what remains between it and the oracle is CUDA-libm-vs-glibc rounding alone.  The difference
+// between the two builds' error tables is the cost of the approximations; what both share is the conditioning of the formulas.
+#ifdef PTB_IEEE
+PTB_DEV float m_pow(float a, float b) { return powf(a, b); }
+#else
 PTB_DEV float m_pow(float a, float b) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b * __log2f(a))); return r; }
+#endif
 PTB_DEV double m_pow(double a, double b) { return pow(a, b); }
 PTB_DEV float m_log2(float a) { return log2f(a); }
 PTB_DEV double m_log2(double a) { return log2(a); }
@@ -46,7 +54,9 @@ PTB_DEV double div_rn(double a, double b) { return a / b; }
 // sin/cos of an angle known to lie in [0, 2*pi] (every call site passes TWO_PI * u, u in [0,1)):
 // quadrant reduction with a three-term Cody-Waite pi/2 and the Cephes sinf/cosf minimax kernels on
 // [-pi/4, pi/4]; ~1 ulp, no large-argument slow path (sincosf's Payne-Hanek tail is dead code here).
-#ifdef PTB_MUFU_SINCOS
+#if defined(PTB_IEEE)
+PTB_DEV void m_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+#elif defined(PTB_MUFU_SINCOS)
 // MUFU.SIN / MUFU.COS on the argument shifted into [-pi, pi) (sin x = -sin(x - pi), cos x = -cos(x - pi)): max abs error
 // 2^-21.4 = 3.6e-7 there — inside the 1e-5 parity budget, outside the ~1 ulp of the minimax kernel below
 PTB_DEV void m_sincos(float x, float* s, float* c) {
@@ -107,22 +117,33 @@ template <class R> PTB_DEV R length(V3<R> a) { return m_sqrt(dot(a, a)); }
 // F3 / scalar and normalize (fx.rs:306-313: three divides by sqrt).  f32: one reciprocal (MUFU.RCP /
 // MUFU.RSQ, <= 2 ulp) and three multiplies — a handful of instructions instead of three division
 // sequences; f64 keeps IEEE division.
+#ifdef PTB_IEEE
+PTB_DEV float m_rcp(float x) { return __fdiv_rn(1.0f, x); }
+#else
 PTB_DEV float m_rcp(float x) { return __fdividef(1.0f, x); }
+#endif
 PTB_DEV double m_rcp(double x) { return 1.0 / x; }
 // f32 quotient as MUFU.RCP + FMUL (div.approx: <= 2 ulp for 2^-126 <= |b| <= 2^126, the same error class as the
 // div.full.f32 that `a / b` compiles to under -prec-div=false).  div.full spends two range compares and a predicated
 // rescaling multiply per operand on denominators outside that range — 8 issue slots per quotient, a quarter of the shading
 // stage's instructions — and no denominator of this path gets there without the reference's own result being inf / NaN
 // already (lobe weight sums, roughness products, cosines, squared distances, pdfs).  f64 keeps IEEE division.
-#ifdef PTB_FULL_DIV
+#if defined(PTB_IEEE)
+PTB_DEV float m_div(float a, float b) { return __fdiv_rn(a, b); }
+#elif defined(PTB_FULL_DIV)
 PTB_DEV float m_div(float a, float b) { return a / b; }
 #else
 PTB_DEV float m_div(float a, float b) { return __fdividef(a, b); }
 #endif
 PTB_DEV double m_div(double a, double b) { return a / b; }
+#ifdef PTB_IEEE
+PTB_DEV V3<float> div_s(V3<float> a, float s) { return V3<float>(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)); }
+PTB_DEV V3<float> normalize(V3<float> a) { return div_s(a, __fsqrt_rn(dot(a, a))); }     // fx.rs:306-313
+#else
 PTB_DEV V3<float> div_s(V3<float> a, float s) { float r = m_rcp(s); return V3<float>(a.x * r, a.y * r, a.z * r); }
-PTB_DEV V3<double> div_s(V3<double> a, double s) { return V3<double>(a.x / s, a.y / s, a.z / s); }
 PTB_DEV V3<float> normalize(V3<float> a) { float r = rsqrtf(dot(a, a)); return V3<float>(a.x * r, a.y * r, a.z * r); }
+#endif
+PTB_DEV V3<double> div_s(V3<double> a, double s) { return V3<double>(a.x / s, a.y / s, a.z / s); }
 PTB_DEV V3<double> normalize(V3<double> a) { return div_s(a, length(a)); }
 template <class R> PTB_DEV V3<R> mix3(V3<R> a, V3<R> b, R v) {                          // math.rs:33-39
     R w = R(1) - v;
@@ -479,6 +500,8 @@ PTB_DEV BvhNode load_node(const BvhNode* p) {
 // distance and skipped on pop if the closest hit found meanwhile is nearer).  ANY = shadow-ray mode:
 // first hit within max_dist returns.  Closest mode keeps the reference's tie rule (ascending index,
 // strict `d < dist` => the lowest sphere index wins equal distances).  Returns the sphere index or -1.
+// traversal stack entries; the host builder bounds the tree depth by this (BvhBuilder::build_node, ptb_api.cu)
+constexpr int BVH_STACK = 40;
 template <class R, bool ANY>
 PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __restrict__ leaf_spheres, const uint32_t* __restrict__ leaf_prim,
                          V3<R> o, V3<R> d, R& best_t) {
@@ -486,7 +509,7 @@ PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __
     RayF r;
     r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
     r.idx = m_rcp((float)d.x); r.idy = m_rcp((float)d.y); r.idz = m_rcp((float)d.z);
-    constexpr int STACK = 40;
+    constexpr int STACK = BVH_STACK;
     uint32_t stack_n[STACK];
     float stack_t[STACK];
     int sp = 0;
@@ -779,10 +802,20 @@ template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const Scen
 // Disney BSDF terms (tracer.rs:222-439)
 template <class R> PTB_DEV R power_heuristic(R a, R b) { R t = a * a; return m_div(t, b * b + t); }   // tracer.rs:223-226
 template <class R> PTB_DEV R luminance(V3<R> c) { return R(0.212671) * c.x + R(0.715160) * c.y + R(0.072169) * c.z; }
-PTB_DEV float sat01(float x) { return __saturatef(x); }          // one instruction; differs from f32::clamp only for NaN input
-PTB_DEV double sat01(double x) { return m_clamp(x, 0.0, 1.0); }
+// f32::clamp(0, 1) keeps a NaN input (tracer.rs:289), the hardware's .SAT modifier turns it into 0: the saturating add stays
+// (it is free), and a NaN operand is put back with one compare + select — the reference never filters NaN radiance
+// (SURVEY.md §5), so a poisoned path must stay poisoned here too.
+PTB_DEV float sat01_of_one_minus(float u) {
+#ifdef PTB_SAT_DROPS_NAN
+    return __saturatef(1.0f - u);
+#else
+    const float m = __saturatef(1.0f - u);
+    return u != u ? u : m;
+#endif
+}
+PTB_DEV double sat01_of_one_minus(double u) { return m_clamp(1.0 - u, 0.0, 1.0); }
 template <class R> PTB_DEV R schlick_fresnel(R u) {                                                // tracer.rs:288-292
-    R m = sat01(R(1) - u);
+    R m = sat01_of_one_minus(u);
     R m2 = m * m;
     return m2 * m2 * m;
 }
@@ -870,12 +903,24 @@ template <class R> struct ShadeCtx {
     R lum, wd0, wc0;     // luminance(rgb), diffuse and clearcoat weights before normalisation (tracer.rs:423, 426)
 };
 template <class R> PTB_DEV V3<R> to_local(const ShadeCtx<R>& c, V3<R> w) { return V3<R>(dot(w, c.t), dot(w, c.b), dot(w, c.n)); }
+// The view vector's cosine v.z = dot(v, n) is evaluated like the reference does (three rounded products, two rounded sums —
+// no FMA contraction): sampling the clearcoat lobe at an EXACTLY grazing view (v.z == 0) divides 0 by 0 (smithg(0) = 0 over
+// 4 l.z v.z, tracer.rs:414-418, no v.z guard on the sampling side, tracer.rs:510-520) and poisons the pixel for good — once per
+// ~6e8 samples of the demo scene in the reference's arithmetic.  A contracted dot product practically never lands on an exact
+// zero (the 48-bit products do not cancel), so the fused form would silently lose that behaviour.
+template <class R> PTB_DEV V3<R> to_local_view(const ShadeCtx<R>& c, V3<R> w) {
+#ifdef PTB_CONTRACT_VIEW_COSINE
+    return to_local(c, w);
+#else
+    return V3<R>(dot(w, c.t), dot(w, c.b), dot_rn(w, c.n));
+#endif
+}
 template <class R> PTB_DEV V3<R> to_world(const ShadeCtx<R>& c, V3<R> l) { return l.x * c.t + l.y * c.b + l.z * c.n; }
 
 template <class R> PTB_DEV void shade_ctx_init(ShadeCtx<R>& c, const Mat<R>& m, R eta, V3<R> n, V3<R> v_world) {
     c.n = n;
     onb(n, c.t, c.b);
-    c.v = to_local(c, v_world);
+    c.v = to_local_view(c, v_world);
     c.eta = eta;
     // get_spec_color, tracer.rs:335-341
     R lum = luminance(m.rgb);
@@ -1317,7 +1362,7 @@ PTB_DEV void shade_setup_rm(PathState<float>& p, V3<float> normal, const RMat& r
     ShadeCtx<float>& c = su.c;
     c.n = su.ffn;
     onb(c.n, c.t, c.b);
-    c.v = to_local(c, -p.d);
+    c.v = to_local_view(c, -p.d);
     c.eta = su.eta;
     c.spec_col = V3<float>(rm.spec_col[side][0], rm.spec_col[side][1], rm.spec_col[side][2]);
     c.sheen_col = V3<float>(rm.sheen_col[0], rm.sheen_col[1], rm.sheen_col[2]);

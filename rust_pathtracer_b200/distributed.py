@@ -1,13 +1,19 @@
 """Sample-split multi-GPU driver: one process per GPU, each rank traces a disjoint
-range of global sample indices for the WHOLE image into its own accumulators, and a single NCCL
-sum-reduce over NVLink combines the float4 (sum r, g, b, count) buffers on rank 0.
+range of global sample indices for the WHOLE image, and the per-rank float4 (sum r, g, b, count)
+partial sums are brought together on rank 0.
 
 The counter RNG is keyed on (pixel, global sample index), so the image is independent of the
-number of ranks up to f32 summation order.  There is no other exchange on the path: the reduce
-moves W*H*16 bytes once per batch (132.7 MB at 4K, < 1 ms on NVLink 5), against hundreds of
-milliseconds of tracing, so it is left to NCCL rather than fused into the render kernel
-(DESIGN.md "Multi-GPU").  torch.distributed is plumbing only; with backend "gloo" the same code
-reduces CPU tensors (tests/test_distributed.py).
+number of ranks up to f32 summation order.  Two gathers (DESIGN.md "Multi-GPU"):
+
+* "peer" (default where CUDA IPC + peer access work): the transfer is FUSED INTO THE RENDER KERNEL — each
+  rank's kernel stores every pixel's partial sum of the step straight into a slot buffer in rank 0's
+  memory over NVLink (`ptb_peer_*`); per step only a stream-ordered barrier and one summing kernel on
+  rank 0 remain on the critical path.
+* "nccl" (the north-star baseline, and the fallback): ONE NCCL sum-reduce of the accumulators per step,
+  in place onto rank 0; the other ranks hand their partial sums off and start the next step from zero.
+
+torch.distributed is plumbing only; with backend "gloo" the same code reduces CPU tensors
+(tests/test_distributed.py).
 """
 from __future__ import annotations
 
@@ -128,9 +134,13 @@ class DistributedTracer:
                 self.tracer.peer_sum(self.parity)
             self.parity ^= 1
             return self.accum if self.rank == 0 else None
-        out = self.accum.clone()
-        reduce_accumulators(out, dst)
-        return out if self.rank == dst else None
+        # in place: `dst` keeps the running total (its own cumulative sum + everybody's partial sums of this step); the
+        # other ranks have handed their partial sums off and start the next step from zero — no copy of the 132.7 MB image
+        reduce_accumulators(self.accum, dst)
+        if self.rank != dst:
+            self.accum.zero_()
+            return None
+        return self.accum
 
     def close(self):
         if self.gather == "peer":

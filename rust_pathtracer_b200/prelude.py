@@ -270,17 +270,27 @@ class Scene:
 
 
 class ColorBuffer:
-    """buffer.rs:6-102 — `pixels` is the running MEAN, RGBA interleaved, row 0 = top."""
+    """buffer.rs:6-102 — `pixels` is the running MEAN, RGBA interleaved, row 0 = top.
+
+    `pixels` is a public field in the reference (buffer.rs:9) that the app may edit between render calls, so the tracer treats
+    the host copy as the source of truth and uploads it before every `render()`.  Touching `.pixels` here hands out the
+    writable array and marks the buffer as *escaped* for good (the array may be edited later through that reference); a buffer
+    that never escaped — the reference's own loop only calls `render` and `convert_to_u8`, renderer/src/main.rs:113-122 —
+    lets `Tracer.render` skip the redundant upload (PTB_FRAME_HOST_UNCHANGED).  `read_pixels()` returns a read-only view
+    without escaping."""
 
     def __init__(self, width: int, height: int, precision: str = None, storage: np.ndarray = None):
         self.precision = precision or F
         self.width, self.height = int(width), int(height)
         if storage is not None:      # caller-provided (e.g. page-locked) memory for `pixels`
             assert storage.dtype == _NP[self.precision] and storage.size == self.width * self.height * 4 and storage.flags.c_contiguous
-            self.pixels = storage.reshape(-1)
-            self.pixels[:] = 0
+            self._pixels = storage.reshape(-1)
+            self._pixels[:] = 0
         else:
-            self.pixels = np.zeros(self.width * self.height * 4, dtype=_NP[self.precision])
+            self._pixels = np.zeros(self.width * self.height * 4, dtype=_NP[self.precision])
+        self._own_storage = storage is None
+        self._escaped = False
+        self._unpin = None        # weakref.finalize that releases the page-lock taken on first render
         self.frames = 0
         self._tracer = None       # tracer whose device image mirrors (pixels, frames)
 
@@ -288,9 +298,41 @@ class ColorBuffer:
     def new(width: int, height: int, precision: str = None, storage: np.ndarray = None) -> "ColorBuffer":
         return ColorBuffer(width, height, precision, storage)
 
+    @property
+    def pixels(self) -> np.ndarray:
+        self._escaped = True
+        return self._pixels
+
+    @pixels.setter
+    def pixels(self, value: np.ndarray):
+        value = np.ascontiguousarray(value, dtype=_NP[self.precision]).reshape(-1)
+        assert value.size == self.width * self.height * 4
+        if self._unpin is not None:
+            self._unpin()
+            self._unpin = None
+        self._pixels, self._own_storage, self._escaped = value, True, True
+
+    def read_pixels(self) -> np.ndarray:
+        """read-only view of the running mean (does not mark the buffer as edited)"""
+        v = self._pixels.view()
+        v.flags.writeable = False
+        return v
+
+    def _pin(self, lib) -> None:
+        """Page-lock `pixels` for DMA-speed copies; released when this buffer is collected (the wrapper owns the registration,
+        never the library: ptb_pin_host in include/ptb200.h)."""
+        if self._unpin is not None or not self._own_storage:
+            return
+        import weakref
+        ptr, nbytes = self._pixels.ctypes.data, self._pixels.nbytes
+        if lib.ptb_pin_host(C.c_void_p(ptr), nbytes) == _abi.PTB_OK:
+            self._unpin = weakref.finalize(self, lib.ptb_unpin_host, C.c_void_p(ptr))
+        else:
+            self._unpin = lambda: None      # not an error: copies go through the driver's staging path
+
     def at(self, x: int, y: int):                                   # buffer.rs:29-32
         i = y * self.width * 4 + x * 4
-        return [self.pixels[i], self.pixels[i + 1], self.pixels[i + 2], self.pixels[i + 3]]
+        return [self._pixels[i], self._pixels[i + 1], self._pixels[i + 2], self._pixels[i + 3]]
 
     def _bound_tracer(self):
         if self._tracer is None or not self._tracer._alive():
@@ -306,7 +348,7 @@ class ColorBuffer:
         assert out.size >= self.width * self.height * 4
         t = self._bound_tracer()
         fn = getattr(t._lib, f"ptb_convert_pixels_to_u8_{self.precision}")
-        _abi.check(fn(t._handle(), self.width * self.height, self.pixels.ctypes.data, out.ctypes.data))
+        _abi.check(fn(t._handle(), self.width * self.height, self._pixels.ctypes.data, out.ctypes.data))
 
     def to_u8_vec(self) -> np.ndarray:                              # buffer.rs:37-52
         out = np.zeros(self.width * self.height * 4, dtype=np.uint8)
@@ -317,7 +359,7 @@ class ColorBuffer:
         out = np.frombuffer(frame, dtype=np.uint8) if not isinstance(frame, np.ndarray) else frame
         t = self._bound_tracer()
         fn = getattr(t._lib, f"ptb_convert_pixels_to_u8_at_{self.precision}")
-        _abi.check(fn(t._handle(), self.pixels.ctypes.data, self.width, self.height, out.ctypes.data, at[0], at[1], at[2], at[3]))
+        _abi.check(fn(t._handle(), self._pixels.ctypes.data, self.width, self.height, out.ctypes.data, at[0], at[1], at[2], at[3]))
 
 
 class Tracer:
@@ -379,7 +421,7 @@ class Tracer:
     def _upload(self, buffer: ColorBuffer):
         self._ensure_size(buffer)
         fn = self._lib.ptb_upload_f32 if self.precision == "f32" else self._lib.ptb_upload_f64
-        _abi.check(fn(self._handle(), buffer.pixels.ctypes.data, buffer.frames))
+        _abi.check(fn(self._handle(), buffer._pixels.ctypes.data, buffer.frames))
         buffer._tracer = self
 
     def convert_to_u8(self, out: np.ndarray):
@@ -396,15 +438,20 @@ class Tracer:
         mean), buffer.frames += 1.  `buffer.frames = 0` restarts the accumulation, as in the
         reference."""
         assert buffer.precision == self.precision
-        fn = self._lib.ptb_render_frame_f32 if self.precision == "f32" else self._lib.ptb_render_frame_f64
-        _abi.check(fn(self._handle(), buffer.width, buffer.height, buffer.frames, buffer.pixels.ctypes.data))
+        buffer._pin(self._lib)
+        fn = self._lib.ptb_render_frame_ex_f32 if self.precision == "f32" else self._lib.ptb_render_frame_ex_f64
+        # a buffer whose array never left the wrapper cannot have been edited: the library then skips the upload if the
+        # buffer, the frame count and the device image are still what its previous call left behind
+        flags = _abi.PTB_FRAME_HOST_UNCHANGED if (not buffer._escaped and buffer._tracer is self) else 0
+        _abi.check(fn(self._handle(), buffer.width, buffer.height, buffer.frames, buffer._pixels.ctypes.data, flags))
         self._size = (buffer.width, buffer.height)
         buffer.frames += 1
         buffer._tracer = self
 
-    def render_spp(self, buffer: ColorBuffer, spp: int, download: bool = True) -> None:
+    def render_spp(self, buffer: ColorBuffer, spp: int, download=True) -> None:
         """Extension: `spp` samples per pixel in one device pass (the reference needs `spp` calls).
-        Equivalent to calling render() spp times up to f32 summation order."""
+        Equivalent to calling render() spp times up to f32 summation order.  download: True (blocking), False, or "async"
+        (the copy overlaps whatever is rendered next; `wait_download()` before reading the pixels)."""
         assert buffer.precision == self.precision
         self._ensure_size(buffer)
         if buffer.frames == 0:
@@ -414,12 +461,23 @@ class Tracer:
         _abi.check(self._lib.ptb_render(self._handle(), spp, buffer.frames))
         buffer.frames += spp
         buffer._tracer = self
-        if download:
+        if download == "async":
+            self.download_async(buffer)
+        elif download:
             self.download(buffer)
 
     def download(self, buffer: ColorBuffer) -> None:
         fn = self._lib.ptb_download_f32 if self.precision == "f32" else self._lib.ptb_download_f64
-        _abi.check(fn(self._handle(), buffer.pixels.ctypes.data))
+        _abi.check(fn(self._handle(), buffer._pixels.ctypes.data))
+
+    def download_async(self, buffer: ColorBuffer) -> None:
+        """ptb_download_async_*: resolve on the render stream, D2H on a side stream; `wait_download()` before reading."""
+        buffer._pin(self._lib)
+        fn = self._lib.ptb_download_async_f32 if self.precision == "f32" else self._lib.ptb_download_async_f64
+        _abi.check(fn(self._handle(), buffer._pixels.ctypes.data))
+
+    def wait_download(self) -> None:
+        _abi.check(self._lib.ptb_wait_download(self._handle()))
 
     def synchronize(self) -> None:
         _abi.check(self._lib.ptb_synchronize(self._handle()))

@@ -183,3 +183,53 @@ def test_film_quotients_by_fma_are_exact_or_declined(rp):
     assert n_fast >= len(sizes) - 2
     rp._abi.check(lib.ptb_test_film_quotients_f32(1 << 24, 10, C.byref(ok), C.byref(bad)))
     assert ok.value == 0                                      # beyond the exactly representable integers: declined
+
+
+def test_color_buffer_escape_tracking(rp):
+    """`pixels` is a public field of the reference (buffer.rs:9): once the writable array has been handed out the buffer may
+    have been edited, so Tracer.render() must upload it; a buffer that never escaped may skip the upload."""
+    b = rp.ColorBuffer.new(4, 4)
+    assert not b._escaped
+    v = b.read_pixels()
+    assert not b._escaped and not v.flags.writeable and v.shape == (64,)
+    assert b.at(1, 1) == [0.0, 0.0, 0.0, 0.0] and not b._escaped
+    _ = b.pixels
+    assert b._escaped
+    b2 = rp.ColorBuffer.new(2, 2)
+    b2.pixels = np.arange(16, dtype=np.float32)
+    assert b2._escaped and b2.read_pixels()[5] == 5.0
+
+
+def test_bvh_builder_bounds_depth_on_adversarial_inputs(rp):
+    """binned SAH on strongly non-uniform sizes / positions builds long chains; the device traversal has a fixed
+    40-entry stack, so the builder must switch to median splits before the depth can exceed it (never silently drop subtrees)."""
+    lib = rp._abi.load()
+    S = rp._abi.TYPES["f32"]["Sphere"]
+
+    def build(centers, radii):
+        n = len(radii)
+        arr = (S * n)()
+        for i in range(n):
+            arr[i].center = (C.c_float * 3)(*[float(x) for x in centers[i]]); arr[i].radius = float(radii[i]); arr[i].material = 0
+        d, nn, ml = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        rp._abi.check(lib.ptb_test_bvh_build_f32(arr, n, C.byref(d), C.byref(nn), C.byref(ml)))
+        return d.value, nn.value, ml.value
+
+    rng = np.random.default_rng(5)
+    # uniform field: shallow tree
+    d, nn, ml = build(rng.uniform(-50, 50, (4000, 3)), rng.uniform(0.05, 0.5, 4000))
+    assert d <= 24 and ml <= 7 and nn < 2 * 4000
+    # geometric progression of positions AND sizes: each SAH split peels off one primitive (a chain of depth ~n)
+    n = 600
+    k = np.arange(n)
+    pos = np.stack([1.07 ** k, np.zeros(n), np.zeros(n)], 1)
+    d, nn, ml = build(pos, 0.3 * 1.07 ** k)
+    assert d < 40 and ml <= 7, (d, ml)
+    # nested concentric shells (all centroids coincide) + one far outlier
+    cen = np.zeros((300, 3)); cen[-1] = (1e6, 0, 0)
+    d, nn, ml = build(cen, np.linspace(0.1, 30, 300))
+    assert d < 40 and ml <= 7, (d, ml)
+    # exponentially clustered points on a line, tiny radii
+    pos = np.stack([np.exp(rng.uniform(-20, 20, 5000)), np.zeros(5000), np.zeros(5000)], 1)
+    d, nn, ml = build(pos, np.full(5000, 1e-3))
+    assert d < 40 and ml <= 7, (d, ml)

@@ -24,11 +24,9 @@ VARIANTS = [
     #   env PTB200_NO_RESOLVED_MATERIALS=1                           generic shade path (no material table)
     #   PTB_FULL_DIV                                                 f32 quotients as div.full (`a / b`) instead of rcp + mul
     #   PTB_MUFU_SINCOS                                              sin / cos on MUFU.SIN / MUFU.COS (3.6e-7 abs) instead of the ~1 ulp minimax kernel
+    #   PTB_SAT_DROPS_NAN + PTB_CONTRACT_VIEW_COSINE                  round 1's NaN behaviour (saturate drops NaN, v.z contracted)
     ("default", [], {}),
-    ("generic_shade", [], {"PTB200_NO_RESOLVED_MATERIALS": "1"}),
-    ("full_div", ["-DPTB_FULL_DIV"], {}),
-    ("no_tail", ["-DPTB_WF_NO_TAIL"], {}),
-    ("mufu_sincos", ["-DPTB_MUFU_SINCOS"], {}),
+    ("r1_nan", ["-DPTB_SAT_DROPS_NAN", "-DPTB_CONTRACT_VIEW_COSINE"], {}),
 ]
 
 
