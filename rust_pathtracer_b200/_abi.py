@@ -99,12 +99,23 @@ SYMBOLS = [
 PTB_RMAT_FLOATS = 35
 
 LIB_NAME = "libptb200.so"
-_lib = None
+# The STRICT build of the same sources (-DPTB_IEEE -prec-div=true -prec-sqrt=true -ftz=false -fmad=false): every deliberate
+# approximation of the shipped build replaced by the correctly rounded operation in the reference's operation order.  It is
+# bit-identical to the reference's f32 arithmetic wherever no libm transcendental is involved (profiles/r02_function_parity.md)
+# and exists for parity-critical users and for the tests; `Tracer.new(scene, strict=True)` or PTB200_STRICT=1 selects it.
+STRICT_LIB_NAME = "libptb200_strict.so"
+_libs = {}
 
 
-def lib_path() -> str:
+def strict_default() -> bool:
+    return os.environ.get("PTB200_STRICT", "0") not in ("", "0")
+
+
+def lib_path(strict: bool = False) -> str:
     # PTB200_LIB: developer knob for A/B-ing two builds of the CUDA library (tools/ab_variants.py); it must exist
-    return os.environ.get("PTB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    if os.environ.get("PTB200_LIB") and not strict:
+        return os.environ["PTB200_LIB"]
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), STRICT_LIB_NAME if strict else LIB_NAME)
 
 
 class PtbError(RuntimeError):
@@ -113,12 +124,14 @@ class PtbError(RuntimeError):
         self.code = code
 
 
-def load():
-    """Load libptb200.so (built in-tree by __graft_entry__.build()). Raises if absent — by design."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = lib_path()
+def load(strict: bool = None):
+    """Load libptb200.so / libptb200_strict.so (built in-tree by __graft_entry__.build()). Raises if absent — by design."""
+    if strict is None:
+        strict = strict_default()
+    strict = bool(strict)
+    if strict in _libs:
+        return _libs[strict]
+    path = lib_path(strict)
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: the CUDA extension must be built (python -c 'import __graft_entry__ as g; g.build()'). "
@@ -183,11 +196,11 @@ def load():
         getattr(lib, f"ptb_convert_pixels_to_u8_at_{sfx}").argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp] + [C.c_uint32] * 4
     if lib.ptb_abi_version() != PTB_ABI_VERSION:
         raise RuntimeError("libptb200.so ABI version mismatch")
-    _lib = lib
+    _libs[strict] = lib
     return lib
 
 
-def check(code: int):
+def check(code: int, lib=None):
     if code != PTB_OK:
-        msg = load().ptb_last_error()
+        msg = (lib or load()).ptb_last_error()
         raise PtbError(code, msg.decode() if msg else "")

@@ -17,7 +17,11 @@
 
 #include "../../include/ptb200.h"
 #include "ptb_kernels.cuh"
+#ifdef PTB_WF_V1      // A/B only (tools/ab_variants.py): round 1's two-stage form of the shared-memory wavefront integrator
+#include "ptb_wavefront_v1.cuh"
+#else
 #include "ptb_wavefront.cuh"
+#endif
 #include "ptb_stream.cuh"
 
 using namespace ptb;

@@ -38,13 +38,19 @@ PTB_DEV double m_max(double a, double b) { return fmax(a, b); }
 // the shipped build is replaced by the correctly rounded / libm operation (and the build adds -prec-div=true -prec-sqrt=true
 // -ftz=false -fmad=false), so that what remains between it and the oracle is CUDA-libm-vs-glibc rounding alone.  The difference
 // between the two builds' error tables is the cost of the approximations; what both share is the conditioning of the formulas.
+// glibc's f32 powf / sinf / cosf / log2f (what Rust's f32 methods call on Linux) are correctly rounded on all but a ~1e-6 share of
+// inputs; CUDA's are 1-2 ulp functions.  Evaluating in double and rounding once reproduces the correctly rounded value.
 #ifdef PTB_IEEE
-PTB_DEV float m_pow(float a, float b) { return powf(a, b); }
+PTB_DEV float m_pow(float a, float b) { return (float)pow((double)a, (double)b); }
 #else
 PTB_DEV float m_pow(float a, float b) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b * __log2f(a))); return r; }
 #endif
 PTB_DEV double m_pow(double a, double b) { return pow(a, b); }
+#ifdef PTB_IEEE
+PTB_DEV float m_log2(float a) { return (float)log2((double)a); }
+#else
 PTB_DEV float m_log2(float a) { return log2f(a); }
+#endif
 PTB_DEV double m_log2(double a) { return log2(a); }
 PTB_DEV float m_floor(float a) { return floorf(a); }
 PTB_DEV double m_floor(double a) { return floor(a); }
@@ -55,7 +61,7 @@ PTB_DEV double div_rn(double a, double b) { return a / b; }
 // quadrant reduction with a three-term Cody-Waite pi/2 and the Cephes sinf/cosf minimax kernels on
 // [-pi/4, pi/4]; ~1 ulp, no large-argument slow path (sincosf's Payne-Hanek tail is dead code here).
 #if defined(PTB_IEEE)
-PTB_DEV void m_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+PTB_DEV void m_sincos(float x, float* s, float* c) { double sd, cd; sincos((double)x, &sd, &cd); *s = (float)sd; *c = (float)cd; }
 #elif defined(PTB_MUFU_SINCOS)
 // MUFU.SIN / MUFU.COS on the argument shifted into [-pi, pi) (sin x = -sin(x - pi), cos x = -cos(x - pi)): max abs error
 // 2^-21.4 = 3.6e-7 there — inside the 1e-5 parity budget, outside the ~1 ulp of the minimax kernel below

@@ -64,45 +64,58 @@ constexpr uint32_t WF_POOL_GENERIC = PTB_WF_POOL;       // path slots per CTA
 #define PTB_WF_POOL_RM 2304
 #endif
 constexpr uint32_t WF_POOL_RM = PTB_WF_POOL_RM;
-constexpr int WF_CLASSES = 9;               // queue keys: 8 lobe classes (3 bits, lobe_class_of) + WF_MISS
 constexpr uint32_t WF_MISS = 8;             // the path left the scene: background lookup, done with full warps in stage 2
 
-// per-slot float arrays (SoA: array k occupies words [k*P, (k+1)*P))
-enum { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TX, F_TY, F_TZ, F_RX, F_RY, F_RZ, F_HITDIST, F_PREVPDF, F_AX, F_AY, F_AZ, WF_NF };
-// per-slot u32 arrays.  The last two exist only in the generic instantiation: with a resolved-material table a scene has at
-// most 6 primitives whenever the accepted set matters (U_ACC_LO is enough), and the pixel index is derived from U_PXY.
-enum { U_PXY, U_SIDX, U_FLAGS, U_PRIM, U_ACC_LO, U_ACC_HI, U_PIX, WF_NU };
-constexpr int WF_NU_RM = 5;
-// flags word: bit0 alive, bit1 have_pixel, bit2 done, bits 3..7 sample block (tail items), bits 8..23 bounce, bit 24 tail item
-constexpr uint32_t FL_ALIVE = 1u, FL_PIXEL = 2u, FL_DONE = 4u, FL_BLOCK = 1u << 24, FL_BLOCK_BITS = FL_BLOCK | (31u << 3);
+// per-slot state: five 16-byte vectors (one LDS.128 / STS.128 each) + one packed queue word
+//   ro = (o.xyz, State::hit_dist)        rd = (d.xyz, pixel column | row << 16)
+//   tr = (throughput.xyz, flags)         ra = (radiance.xyz, sample index)
+//   ac = (pixel sum.xyz, hit primitive / accepted set of the pending shading event)
+// flags word: bit0 alive, bit1 have_pixel, bits 3..7 sample block (tail items), bits 8..23 bounce, bit 24 tail item
+constexpr uint32_t FL_ALIVE = 1u, FL_PIXEL = 2u, FL_BLOCK = 1u << 24, FL_BLOCK_BITS = FL_BLOCK | (31u << 3);
 #ifndef PTB_WF_TAIL_LOG2
 #define PTB_WF_TAIL_LOG2 3
 #endif
 constexpr uint32_t WF_TAIL_LOG2_BLOCKS = PTB_WF_TAIL_LOG2;  // the last pixels of a frame are traced as up to 2^this sample blocks each (see wavefront_render)
+constexpr uint32_t WF_REGEN = 9;            // queue key of a slot without a live path: regenerate (next sample / next pixel)
+constexpr uint32_t WF_NKEYS = 10;           // 8 lobe classes, WF_MISS, WF_REGEN
+constexpr uint32_t WF_NOKEY = 0xffffu;      // slot left the queue for good (frame exhausted)
+constexpr uint32_t PRIM_SKY = 0xffffffffu;
 
-template <uint32_t WF_POOL, uint32_t SCENE_BYTES, int NU> struct WfSmemT {
+// GENERIC: scenes with partial material masks may have up to 64 primitives, so the accepted set needs 64 bits of its own
+template <uint32_t WF_POOL, uint32_t SCENE_BYTES, bool GENERIC> struct WfSmemT {
     uint32_t scene[SCENE_BYTES / 4];
-    float f[WF_NF][WF_POOL];
-    uint32_t u[NU][WF_POOL];
-    uint16_t key[WF_POOL];          // lobe class of a queued slot, 0xffff = not queued
-    uint16_t ticket[WF_POOL];       // position inside its class
-    uint16_t order[WF_POOL];        // the shading queue: slot indices, class-ordered
-    uint32_t cnt[WF_CLASSES];       // tickets handed out per class
-    uint32_t off[WF_CLASSES + 1];   // class start offsets; off[WF_CLASSES] = queue length
-    uint32_t n_done;                // slots that can never get work again
-    uint32_t cursor2;               // next 32-entry chunk of the stage-2 queue
+    float4 ro[WF_POOL], rd[WF_POOL], tr[WF_POOL], ra[WF_POOL], ac[WF_POOL];
+    uint32_t acc_lo[GENERIC ? WF_POOL : 1], acc_hi[GENERIC ? WF_POOL : 1];
+    uint32_t kt[WF_POOL];           // queue key << 16 | ticket inside the key (WF_NOKEY: not queued)
+    uint16_t order[WF_POOL];        // the queue: slot indices, key-ordered
+    uint32_t cnt[2][WF_NKEYS + 2];  // tickets handed out per key for the NEXT queue (double-buffered by iteration parity)
+    uint32_t cursor[2];             // next 32-entry chunk of the current queue (double-buffered like cnt)
 };
 
+// One stage per iteration.  Every slot that still has work is in the queue exactly once, ordered by key; warps take 32-entry
+// chunks and run, for their 32 slots,
+//   A  the pending event of the slot's path: background lookup (WF_MISS) or shading (finalize, light sample + shadow ray,
+//      Disney eval with MIS, Disney sample, next ray) — full warps of one lobe class;
+//   B  for lanes whose path has ended (in A, or at an emitter / by roulette in C of the previous iteration): add the radiance to
+//      the pixel sum and regenerate IN PLACE — next sample of the slot's pixel, or a new pixel handed out per warp with
+//      ballot/popc from the global work counter (16x16-tile order), camera ray;
+//   C  closest_hit (incl. lights with the stale hit_dist, MIS-weighted emission on a light hit) for EVERY lane — continuing
+//      and regenerated paths alike, so the intersection code always runs on full warps —, then a ticket for the next queue
+//      under the key of what was hit.
+// Between iterations: one CTA barrier, the counting-sort scatter of the tickets into the next queue (offsets are recomputed
+// by every warp from the 10 counters, no serial section), a second barrier.  Compared with the two-stage form (intersect all
+// slots / sort / shade) a bounce costs one slot visit instead of two — half the state loads / stores and queue bookkeeping —,
+// the previous bounce's pdf never leaves registers, and there are two CTA barriers per iteration instead of four.
+//
 // RM: the scene has a resolved-material table (RMat, ptb_device.cuh) and the host guarantees that the WHOLE blob sits in the
 // shared-memory copy, so every scene read of this instantiation is a shared-memory load (LDS, not a generic LD).
 template <bool COUNT, bool BVH, bool RM>
 __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_render_wavefront(const __grid_constant__ DScene<float> s, const RenderArgs a) {
     using R = float;
     constexpr int WF_THREADS = RM ? WF_THREADS_RM : WF_THREADS_GENERIC;
-    constexpr int WF_WARPS = WF_THREADS / 32;
     static_assert(!(RM && BVH), "the resolved-material table is for scenes that live in shared memory");
     constexpr uint32_t WF_POOL = RM ? WF_POOL_RM : WF_POOL_GENERIC;
-    using WfSmem = WfSmemT<WF_POOL, RM ? WF_SCENE_BYTES_RM : PTB_SMEM_SCENE_BYTES, RM ? WF_NU_RM : (int)WF_NU>;
+    using WfSmem = WfSmemT<WF_POOL, RM ? WF_SCENE_BYTES_RM : PTB_SMEM_SCENE_BYTES, !RM>;
     extern __shared__ __align__(16) unsigned char wf_raw[];
     WfSmem& sm = *reinterpret_cast<WfSmem*>(wf_raw);
     SceneView<R> sv;
@@ -111,7 +124,6 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
     if constexpr (RM) {
         const uint32_t* src = (const uint32_t*)s.blob;
         for (uint32_t i = threadIdx.x; i < s.blob_bytes / 4u; i += WF_THREADS) sm.scene[i] = src[i];
-        __syncthreads();
         const unsigned char* m = reinterpret_cast<const unsigned char*>(sm.scene);
         sv.planes = (const DPlane<R>*)(m + s.off_planes);
         sv.lights = (const DLight<R>*)(m + s.off_lights);
@@ -127,16 +139,25 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
     float4* accum = reinterpret_cast<float4*>(a.accum);
 
     const unsigned FULL = 0xffffffffu;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const R inv_w = a.rcp_w, inv_h = a.rcp_h;     // pixel_size (pinhole.rs:41), correctly rounded on the host
 
-    for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) { sm.u[U_FLAGS][i] = 0; sm.u[U_SIDX][i] = 0; sm.key[i] = 0xffffu; }
-    if (tid < WF_CLASSES) sm.cnt[tid] = 0;
-    if (tid == 0) { sm.n_done = 0; sm.cursor2 = 0; }
+    // the first queue: every slot, key WF_REGEN
+    for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) {
+        sm.ro[i] = make_float4(0.f, 0.f, 0.f, -1.f);
+        sm.rd[i] = make_float4(0.f, 0.f, 1.f, __uint_as_float(0u));
+        sm.tr[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        sm.ra[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        sm.ac[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PRIM_SKY));
+        sm.order[i] = (uint16_t)i;
+        sm.kt[i] = WF_NOKEY << 16;
+    }
+    if (tid < 2u * (WF_NKEYS + 2u)) (&sm.cnt[0][0])[tid] = 0;
+    if (tid < 2u) sm.cursor[tid] = 0;
     __syncthreads();
 
-    uint32_t w_next = 0, w_end = 0;          // warp-uniform cursor into the warp's current 16x16 pixel tile
+    uint32_t n_queue = WF_POOL, par = 0;      // par: which cnt / cursor buffer the CURRENT iteration's consumers use
     PathCounters pc;
     uint32_t n_samples = 0;
     if (COUNT) {
@@ -146,254 +167,215 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
         pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
     }
 
-    while (true) {
-        // ================================ stage 1: generate + intersect ================================
-        // static slot ownership: each warp keeps its own 128 slots, because the pixel-tile cursor (w_next, w_end) lives
-        // in the warp's registers and the tile's remaining pixels must be consumed by the same warp
+    while (n_queue) {
 #pragma unroll 1
-        for (uint32_t base = warp * 32u; base < WF_POOL; base += WF_WARPS * 32u) {
-            const uint32_t i = base + lane;
-            uint32_t fl = sm.u[U_FLAGS][i];
-            uint32_t sidx = sm.u[U_SIDX][i];
-            bool alive = fl & FL_ALIVE, have_pixel = fl & FL_PIXEL, done = fl & FL_DONE;
-            const bool was_done = done;
-            uint32_t pxy = sm.u[U_PXY][i];
-            uint32_t pix;
-            if constexpr (RM) pix = (pxy >> 16) * a.W + (pxy & 0xffffu); else pix = sm.u[U_PIX][i];
+        while (true) {
+            uint32_t chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&sm.cursor[par], 1u);
+            chunk = __shfl_sync(FULL, chunk, 0);
+            if (chunk * 32u >= n_queue) break;
+            const uint32_t j = chunk * 32u + lane;
+            const bool valid = j < n_queue;
+            const uint32_t i = valid ? sm.order[j] : 0u;
+            // ---- load the slot ----
+            PathState<R> p;
+            uint32_t fl = 0, sidx = 0, pxy = 0, prim_bits = PRIM_SKY;
+            uint64_t accepted = 0;
+            p.o = V3<R>(0, 0, 0); p.d = V3<R>(0, 0, 1); p.thr = V3<R>(0, 0, 0); p.rad = V3<R>(0, 0, 0); p.hit_dist = R(-1); p.prev_pdf = 0; p.bounce = 0;
+            if (valid) {
+                const float4 q0 = sm.ro[i], q1 = sm.rd[i], q2 = sm.tr[i], q3 = sm.ra[i];
+                p.o = V3<R>(q0.x, q0.y, q0.z); p.hit_dist = q0.w;
+                p.d = V3<R>(q1.x, q1.y, q1.z); pxy = __float_as_uint(q1.w);
+                p.thr = V3<R>(q2.x, q2.y, q2.z); fl = __float_as_uint(q2.w);
+                p.rad = V3<R>(q3.x, q3.y, q3.z); sidx = __float_as_uint(q3.w);
+                prim_bits = __float_as_uint(sm.ac[i].w);
+                if constexpr (!RM) accepted = (uint64_t)sm.acc_lo[i] | ((uint64_t)sm.acc_hi[i] << 32);
+            }
+            p.bounce = (fl >> 8) & 0xffffu;
+            bool alive = valid && (fl & FL_ALIVE);
+            bool have_pixel = fl & FL_PIXEL;
+            uint32_t pix = (pxy >> 16) * a.W + (pxy & 0xffffu);
 
-            // ---- pixel hand-out (same scheme as the fused integrator) ----
+            // ================================ A: the path's pending event ================================
+            if (alive) {
+                if (prim_bits == PRIM_SKY) {                            // the path left the scene (tracer.rs:66-69)
+                    path_add_sky(s, p);
+                    if (COUNT) pc.end_sky++;
+                    alive = false;
+                } else {
+                    Rng<R> rng(pix, a.sample_base + sidx, a.seed);
+                    R u[8];
+                    bool cont;
+                    if constexpr (RM) {
+                        const int prim = (int)(prim_bits & 0xffffu);
+                        const RMat& rm = rm_lookup(s, sv, rm_keys, rm_table, rm_key_of(s, sv, prim, prim_bits >> 16), p.d);
+                        shade_draws(rng, p.bounce, s.n_lights > 1u || (rm.lobe_class & 4u) != 0u, u);
+                        const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+                        cont = path_shade_rm<COUNT>(s, sv, p, normal, rm, u, &pc);
+                    } else {
+                        const int prim = (int)prim_bits;
+                        Mat<R> mat;
+                        hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+                        shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
+                        const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+                        cont = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, &pc);
+                    }
+                    alive = cont;
+                    if (cont && a.rr_start != 0 && p.bounce >= a.rr_start) {      // Russian-roulette extension (A.12), slot 0 of the new bounce
+                        R u4[4];
+                        rng.block(p.bounce, 0, u4);
+                        if (!russian_roulette_survives(p, u4[0])) { alive = false; if (COUNT) pc.end_rr++; }
+                    }
+                }
+            }
+
+            // ================================ B: finish dead paths, regenerate in place ================================
             // Work items below a.n_whole are whole pixels (all spp samples); the items above are the frame's last a.tail_zt
             // pixels cut into sample blocks, so that the ramp-down at the end of the launch lasts one block, not one pixel.
             // A block's sum goes to a side buffer and k_tail_combine adds the blocks of a pixel in block order: the image
             // stays independent of which slot traced what.
+            bool done = false;
             uint32_t blkbits = fl & FL_BLOCK_BITS;
-            const uint32_t blk = (fl >> 3) & 31u;
-            const uint32_t s_end = (fl & FL_BLOCK) ? ((blk + 1u) * a.spp) >> a.tail_log2b : a.spp;
-            bool want = !alive && !done && (!have_pixel || sidx == s_end);
-            if (want && have_pixel) {
-                if (fl & FL_BLOCK) {
-                    const uint32_t px0 = pxy & 0xffffu, pr0 = pxy >> 16;
-                    const uint32_t pidx = (((pr0 >> 4) * a.tiles_x + (px0 >> 4)) << 8) | ((pr0 & 15u) << 4) | (px0 & 15u);
-                    const uint32_t s_begin = (blk * a.spp) >> a.tail_log2b;
-                    reinterpret_cast<float4*>(a.tail_side)[(pidx - a.n_whole) + blk * a.tail_zt] =
-                        make_float4(sm.f[F_AX][i], sm.f[F_AY][i], sm.f[F_AZ][i], (R)(s_end - s_begin));
-                } else if (a.flush_dst) {       // multi-GPU: this launch's partial sum goes straight into the root GPU's slot (peer store)
-                    reinterpret_cast<float4*>(a.flush_dst)[pix] = make_float4(sm.f[F_AX][i], sm.f[F_AY][i], sm.f[F_AZ][i], (R)a.spp);
-                } else {
-                    float4 v = accum[pix];
-                    v.x += sm.f[F_AX][i]; v.y += sm.f[F_AY][i]; v.z += sm.f[F_AZ][i]; v.w += (R)a.spp;
-                    accum[pix] = v;
+            {
+                V3<R> acc(0, 0, 0);
+                const bool dead = valid && !alive;
+                if (dead) {
+                    const float4 q4 = sm.ac[i];
+                    acc = V3<R>(q4.x + p.rad.x, q4.y + p.rad.y, q4.z + p.rad.z);      // a fresh slot adds 0 to 0
+                    sidx += have_pixel ? 1u : 0u;
                 }
-                have_pixel = false;
-            }
-            unsigned need = __ballot_sync(FULL, want);
-            while (need) {
-                if (w_next == w_end) {
+                const uint32_t blk = (fl >> 3) & 31u;
+                const uint32_t s_end = (fl & FL_BLOCK) ? ((blk + 1u) * a.spp) >> a.tail_log2b : a.spp;
+                bool want = dead && (!have_pixel || sidx == s_end);
+                if (want && have_pixel) {
+                    if (fl & FL_BLOCK) {
+                        const uint32_t px0 = pxy & 0xffffu, pr0 = pxy >> 16;
+                        const uint32_t pidx = (((pr0 >> 4) * a.tiles_x + (px0 >> 4)) << 8) | ((pr0 & 15u) << 4) | (px0 & 15u);
+                        const uint32_t s_begin = (blk * a.spp) >> a.tail_log2b;
+                        reinterpret_cast<float4*>(a.tail_side)[(pidx - a.n_whole) + blk * a.tail_zt] = make_float4(acc.x, acc.y, acc.z, (R)(s_end - s_begin));
+                    } else if (a.flush_dst) {       // multi-GPU: this launch's partial sum goes straight into the root GPU's slot (peer store)
+                        reinterpret_cast<float4*>(a.flush_dst)[pix] = make_float4(acc.x, acc.y, acc.z, (R)a.spp);
+                    } else {
+                        float4 v = accum[pix];
+                        v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += (R)a.spp;
+                        accum[pix] = v;
+                    }
+                    have_pixel = false;
+                }
+                // Hand-out: the lanes that want a pixel reserve exactly as many work items as they are (one warp-aggregated atomic on
+                // the global counter).  Nothing is reserved ahead: with dynamic chunks a warp has no slots of its own that would be
+                // sure to consume a leftover reservation before the queue drains, and an item held back would be a lost pixel.
+                unsigned need = __ballot_sync(FULL, want);
+                while (need) {
+                    const uint32_t n_need = __popc(need);
                     uint32_t b = 0;
-                    if (lane == 0) b = atomicAdd(a.work_counter, FUSED_CHUNK);
+                    if (lane == 0) b = atomicAdd(a.work_counter, n_need);
                     b = __shfl_sync(FULL, b, 0);
-                    if (b >= a.n_items) {
-                        if (want) { done = true; want = false; }
-                        break;
+                    if (want) {
+                        uint32_t idx = b + __popc(need & lt_mask), nb = 0, s0 = 0;
+                        if (idx >= a.n_items) {                                  // frame exhausted: this slot is finished for good
+                            done = true; want = false;
+                        } else {
+                            if (idx >= a.n_whole) {                              // tail item: (pixel, sample block)
+                                const uint32_t k = idx - a.n_whole, b2 = k / a.tail_zt;
+                                idx = a.n_whole + (k - b2 * a.tail_zt);
+                                nb = FL_BLOCK | (b2 << 3);
+                                s0 = (b2 * a.spp) >> a.tail_log2b;
+                            }
+                            const uint32_t tile = idx >> 8, within = idx & 255u;
+                            const uint32_t px = (tile % a.tiles_x) * 16u + (within & 15u);
+                            const uint32_t prow = (tile / a.tiles_x) * 16u + (within >> 4);
+                            if (px < a.W && prow < a.H) {                        // (items of a partial tile outside the frame: take another)
+                                pix = prow * a.W + px; pxy = px | (prow << 16);
+                                have_pixel = true; want = false; sidx = s0; blkbits = nb;
+                                acc = V3<R>(0, 0, 0);
+                            }
+                        }
                     }
-                    w_next = b; w_end = b + FUSED_CHUNK;
+                    need = __ballot_sync(FULL, want);
                 }
-                const uint32_t avail = w_end - w_next;
-                const uint32_t rank = __popc(need & lt_mask);
-                if (want && rank < avail) {
-                    uint32_t idx = w_next + rank, nb = 0, s0 = 0;
-                    if (idx >= a.n_whole) {                                  // tail item: (pixel, sample block)
-                        const uint32_t k = idx - a.n_whole, b2 = k / a.tail_zt;
-                        idx = a.n_whole + (k - b2 * a.tail_zt);
-                        nb = FL_BLOCK | (b2 << 3);
-                        s0 = (b2 * a.spp) >> a.tail_log2b;
-                    }
-                    const uint32_t tile = idx >> 8, within = idx & 255u;
-                    const uint32_t px = (tile % a.tiles_x) * 16u + (within & 15u);
-                    const uint32_t prow = (tile / a.tiles_x) * 16u + (within >> 4);
-                    if (px < a.W && prow < a.H) {
-                        pix = prow * a.W + px; pxy = px | (prow << 16);
-                        have_pixel = true; want = false; sidx = s0; blkbits = nb;
-                        sm.f[F_AX][i] = 0; sm.f[F_AY][i] = 0; sm.f[F_AZ][i] = 0;
-                    }
-                }
-                const uint32_t n_need = __popc(need);
-                w_next += n_need < avail ? n_need : avail;
-                need = __ballot_sync(FULL, want);
-            }
-            if (done && !was_done) atomicAdd(&sm.n_done, 1u);
-
-            // ---- one closest_hit for every live / starting path ----
-            const bool start = !alive && !done;
-            if (alive || start) {
-                PathState<R> p;
-                p.bounce = start ? 0u : (fl >> 8) & 0xffffu;
-                bool dead = false;
-                if (start) {
-                    Rng<R> rng(pix, a.sample_base + sidx, a.seed);
-                    R u4[4];
-                    rng.block(0, 0, u4);
-                    path_begin(s, p, pxy & 0xffffu, pxy >> 16, a.W, a.H, inv_w, inv_h, u4[0], u4[1], a.film_fast != 0u, a.rcp_w, a.rcp_h);
-                    alive = true;
-                    if (COUNT) n_samples++;
-                } else {
-                    p.o = V3<R>(sm.f[F_OX][i], sm.f[F_OY][i], sm.f[F_OZ][i]);
-                    p.d = V3<R>(sm.f[F_DX][i], sm.f[F_DY][i], sm.f[F_DZ][i]);
-                    p.thr = V3<R>(sm.f[F_TX][i], sm.f[F_TY][i], sm.f[F_TZ][i]);
-                    p.rad = V3<R>(sm.f[F_RX][i], sm.f[F_RY][i], sm.f[F_RZ][i]);
-                    p.hit_dist = sm.f[F_HITDIST][i];
-                    p.prev_pdf = sm.f[F_PREVPDF][i];
-                    if (a.rr_start != 0 && p.bounce >= a.rr_start) {
+                if (dead) {
+                    sm.ac[i] = make_float4(acc.x, acc.y, acc.z, __uint_as_float(PRIM_SKY));
+                    if (!done) {                                        // next sample of the slot's pixel
                         Rng<R> rng(pix, a.sample_base + sidx, a.seed);
                         R u4[4];
-                        rng.block(p.bounce, 0, u4);
-                        if (!russian_roulette_survives(p, u4[0])) { dead = true; if (COUNT) pc.end_rr++; }
+                        rng.block(0, 0, u4);
+                        path_begin(s, p, pxy & 0xffffu, pxy >> 16, a.W, a.H, inv_w, inv_h, u4[0], u4[1], a.film_fast != 0u, a.rcp_w, a.rcp_h);
+                        alive = true;
+                        if (COUNT) n_samples++;
                     }
                 }
-                HitCore<R> h;
-                bool sky = false;
-                if (!dead) {
-                    if (p.bounce >= s.depth) {                         // recursion depth 0 (tracer.rs:61)
-                        dead = true;
-                        if (COUNT) pc.end_depth++;
+            }
+
+            // ================================ C: closest_hit for every live path ================================
+            uint32_t key = WF_NOKEY;
+            if (alive) {
+                key = WF_REGEN;
+                uint32_t new_prim = PRIM_SKY;
+                if (p.bounce >= s.depth) {                              // recursion depth 0 (tracer.rs:61)
+                    alive = false;
+                    if (COUNT) pc.end_depth++;
+                } else {
+                    if (COUNT) pc.closest_hit++;
+                    const HitCore<R> h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
+                    p.hit_dist = h.hit_dist;
+                    if (!h.hit) {
+                        key = WF_MISS;                                 // background lookup next iteration, with full warps
+                    } else if (h.is_emitter) {
+                        path_add_emitter<R, BVH>(s, sv, p, h);
+                        alive = false;
+                        if (COUNT) pc.end_emitter++;
                     } else {
-                        if (COUNT) pc.closest_hit++;
-                        h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
-                        p.hit_dist = h.hit_dist;
-                        if (!h.hit) {
-                            sky = true;                                // background is evaluated in stage 2 (compacted)
-                        } else if (h.is_emitter) {
-                            path_add_emitter<R, BVH>(s, sv, p, h);
-                            dead = true;
-                            if (COUNT) pc.end_emitter++;
+                        if constexpr (RM) {
+                            key = rm_table[rm_keys[rm_key_of(s, sv, h.prim, (uint32_t)h.accepted)] & 0xffffu].lobe_class;
+                            new_prim = ((uint32_t)h.prim & 0xffffu) | ((uint32_t)h.accepted << 16);
+                        } else {
+                            key = hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
+                            new_prim = (uint32_t)h.prim;
+                            sm.acc_lo[i] = (uint32_t)h.accepted; sm.acc_hi[i] = (uint32_t)(h.accepted >> 32);
                         }
                     }
                 }
-                if (dead) {
-                    sm.f[F_AX][i] += p.rad.x; sm.f[F_AY][i] += p.rad.y; sm.f[F_AZ][i] += p.rad.z;
-                    sidx++;
-                    alive = false;
-                } else {
-                    // queue for stage 2: ticket inside the path's key (lobe class of the hit material, or WF_MISS)
-                    uint32_t cls;
-                    if constexpr (RM) cls = sky ? WF_MISS : rm_table[rm_keys[rm_key_of(s, sv, h.prim, (uint32_t)h.accepted)] & 0xffffu].lobe_class;
-                    else cls = sky ? WF_MISS : hit_lobe_class<R, BVH>(s, sv, h.prim, h.accepted);
-                    sm.key[i] = (uint16_t)cls;
-                    sm.ticket[i] = (uint16_t)atomicAdd(&sm.cnt[cls], 1u);
-                    sm.u[U_PRIM][i] = sky ? 0xffffffffu : (uint32_t)h.prim;
-                    sm.u[U_ACC_LO][i] = (uint32_t)h.accepted;
-                    if constexpr (!RM) sm.u[U_ACC_HI][i] = (uint32_t)(h.accepted >> 32);
-                    sm.f[F_HITDIST][i] = p.hit_dist;
-                    if (start || a.rr_start != 0) {
-                        sm.f[F_TX][i] = p.thr.x; sm.f[F_TY][i] = p.thr.y; sm.f[F_TZ][i] = p.thr.z;
-                    }
-                    if (start) {
-                        sm.f[F_OX][i] = p.o.x; sm.f[F_OY][i] = p.o.y; sm.f[F_OZ][i] = p.o.z;
-                        sm.f[F_DX][i] = p.d.x; sm.f[F_DY][i] = p.d.y; sm.f[F_DZ][i] = p.d.z;
-                        sm.f[F_RX][i] = 0; sm.f[F_RY][i] = 0; sm.f[F_RZ][i] = 0;
-                        sm.f[F_PREVPDF][i] = 0;
-                    }
-                }
-                fl = (p.bounce << 8);
-            } else {
-                fl = 0;
+                sm.ro[i] = make_float4(p.o.x, p.o.y, p.o.z, p.hit_dist);
+                sm.rd[i] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(pxy));
+                reinterpret_cast<uint32_t*>(&sm.ac[i])[3] = new_prim;
             }
-            sm.u[U_FLAGS][i] = (fl & 0xffff00u) | blkbits | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u) | (done ? FL_DONE : 0u);
-            sm.u[U_SIDX][i] = sidx;
-            if constexpr (!RM) sm.u[U_PIX][i] = pix;
-            sm.u[U_PXY][i] = pxy;
+            if (valid) {
+                fl = (p.bounce << 8) | blkbits | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u);
+                sm.tr[i] = make_float4(p.thr.x, p.thr.y, p.thr.z, __uint_as_float(fl));
+                sm.ra[i] = make_float4(p.rad.x, p.rad.y, p.rad.z, __uint_as_float(sidx));
+                uint32_t ticket = 0;
+                if (key != WF_NOKEY) ticket = atomicAdd(&sm.cnt[par ^ 1u][key], 1u);
+                sm.kt[i] = (key << 16) | ticket;
+            }
         }
         __syncthreads();
 
-        // ================================ sort: tickets -> class-ordered queue ================================
-        if (tid == 0) {
-            // classes with more lobes cost more to shade: queue them first so the dynamic chunking of stage 2
-            // ends on cheap chunks (longest-processing-time-first)
-            const int order_by_cost[WF_CLASSES] = {7, 3, 5, 6, 1, 2, 4, 0, (int)WF_MISS};
+        // ================================ sort: tickets -> key-ordered queue ================================
+        // keys with more lobes cost more to process: queue them first so that the dynamic chunking ends on cheap chunks
+        // (longest-processing-time-first); every thread derives the offsets itself from the ten counters
+        uint32_t off[WF_NKEYS];
+        {
+            const int order_by_cost[WF_NKEYS] = {7, 3, 5, 6, 1, 2, 4, 0, (int)WF_MISS, (int)WF_REGEN};
             uint32_t run = 0;
 #pragma unroll
-            for (int k = 0; k < WF_CLASSES; ++k) { const int c = order_by_cost[k]; sm.off[c] = run; run += sm.cnt[c]; }
-            sm.off[WF_CLASSES] = run;
-            sm.cursor2 = 0;
+            for (int k = 0; k < (int)WF_NKEYS; ++k) { const int c = order_by_cost[k]; off[c] = run; run += sm.cnt[par ^ 1u][c]; }
+            n_queue = run;
         }
-        __syncthreads();
-        const uint32_t n_queue = sm.off[WF_CLASSES];
-        const bool all_done = sm.n_done == WF_POOL;
 #pragma unroll 1
         for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) {
-            const uint32_t k = sm.key[i];
-            if (k != 0xffffu) {
-                sm.order[sm.off[k] + sm.ticket[i]] = (uint16_t)i;
-                sm.key[i] = 0xffffu;
+            const uint32_t kt = sm.kt[i], k = kt >> 16;
+            if (k != WF_NOKEY) {
+                uint32_t o = 0;
+#pragma unroll
+                for (int c = 0; c < (int)WF_NKEYS; ++c) o = (k == (uint32_t)c) ? off[c] : o;
+                sm.order[o + (kt & 0xffffu)] = (uint16_t)i;
+                sm.kt[i] = WF_NOKEY << 16;
             }
         }
-        __syncthreads();
-        if (tid < WF_CLASSES) sm.cnt[tid] = 0;
-        if (n_queue == 0 && all_done) break;
-
-        // ================================ stage 2: shade ================================
-#pragma unroll 1
-        // warps take 32-entry chunks of the queue dynamically (one shared-memory atomic per chunk); expensive lobe
-        // classes are queued first, so the stage ends on cheap chunks
-        while (true) {
-            uint32_t chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&sm.cursor2, 1u);
-            chunk = __shfl_sync(FULL, chunk, 0);
-            if (chunk * 32u >= n_queue) break;
-            const uint32_t j = chunk * 32u + lane;
-            if (j >= n_queue) continue;
-            const uint32_t i = sm.order[j];
-            PathState<R> p;
-            p.o = V3<R>(sm.f[F_OX][i], sm.f[F_OY][i], sm.f[F_OZ][i]);
-            p.d = V3<R>(sm.f[F_DX][i], sm.f[F_DY][i], sm.f[F_DZ][i]);
-            p.thr = V3<R>(sm.f[F_TX][i], sm.f[F_TY][i], sm.f[F_TZ][i]);
-            p.rad = V3<R>(sm.f[F_RX][i], sm.f[F_RY][i], sm.f[F_RZ][i]);
-            p.hit_dist = sm.f[F_HITDIST][i];
-            p.prev_pdf = 0;
-            const uint32_t fl = sm.u[U_FLAGS][i];
-            p.bounce = (fl >> 8) & 0xffffu;
-            const int prim = (int)sm.u[U_PRIM][i];
-            if (prim < 0) {                                             // WF_MISS entry: background, path ends (tracer.rs:66-69)
-                path_add_sky(s, p);
-                if (COUNT) pc.end_sky++;
-                sm.f[F_AX][i] += p.rad.x; sm.f[F_AY][i] += p.rad.y; sm.f[F_AZ][i] += p.rad.z;
-                sm.u[U_SIDX][i] = sm.u[U_SIDX][i] + 1u;
-                sm.u[U_FLAGS][i] = fl & ~FL_ALIVE;
-                continue;
-            }
-            uint64_t accepted = (uint64_t)sm.u[U_ACC_LO][i];
-            uint32_t pix2;
-            if constexpr (RM) { const uint32_t pxy2 = sm.u[U_PXY][i]; pix2 = (pxy2 >> 16) * a.W + (pxy2 & 0xffffu); }
-            else { accepted |= (uint64_t)sm.u[U_ACC_HI][i] << 32; pix2 = sm.u[U_PIX][i]; }
-            const uint32_t sidx = sm.u[U_SIDX][i];
-            Rng<R> rng(pix2, a.sample_base + sidx, a.seed);
-            R u[8];
-            bool cont;
-            if constexpr (RM) {
-                const RMat& rm = rm_lookup(s, sv, rm_keys, rm_table, rm_key_of(s, sv, prim, (uint32_t)accepted), p.d);
-                shade_draws(rng, p.bounce, s.n_lights > 1u || (rm.lobe_class & 4u) != 0u, u);
-                const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-                cont = path_shade_rm<COUNT>(s, sv, p, normal, rm, u, &pc);
-            } else {
-                Mat<R> mat;
-                hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
-                shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
-                const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-                cont = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, &pc);
-            }
-            if (cont) {
-                sm.f[F_OX][i] = p.o.x; sm.f[F_OY][i] = p.o.y; sm.f[F_OZ][i] = p.o.z;
-                sm.f[F_DX][i] = p.d.x; sm.f[F_DY][i] = p.d.y; sm.f[F_DZ][i] = p.d.z;
-                sm.f[F_TX][i] = p.thr.x; sm.f[F_TY][i] = p.thr.y; sm.f[F_TZ][i] = p.thr.z;
-                sm.f[F_RX][i] = p.rad.x; sm.f[F_RY][i] = p.rad.y; sm.f[F_RZ][i] = p.rad.z;
-                sm.f[F_PREVPDF][i] = p.prev_pdf;
-                sm.u[U_FLAGS][i] = (fl & ~0xffff00u) | (p.bounce << 8);
-            } else {
-                sm.f[F_AX][i] += p.rad.x; sm.f[F_AY][i] += p.rad.y; sm.f[F_AZ][i] += p.rad.z;
-                sm.u[U_SIDX][i] = sidx + 1u;
-                sm.u[U_FLAGS][i] = fl & ~FL_ALIVE;
-            }
-        }
+        if (tid < WF_NKEYS) sm.cnt[par][tid] = 0;       // this iteration's consumers are done with it; it collects the tickets of the next one
+        if (tid == 0) sm.cursor[par] = 0;
+        par ^= 1u;
         __syncthreads();
     }
 
@@ -482,7 +464,7 @@ inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* ac
         d.use_bvh ? (count ? k_render_wavefront<true, true, false> : k_render_wavefront<false, true, false>)
         : rm      ? (count ? k_render_wavefront<true, false, true> : k_render_wavefront<false, false, true>)
                   : (count ? k_render_wavefront<true, false, false> : k_render_wavefront<false, false, false>);
-    const size_t smem_bytes = rm ? sizeof(WfSmemT<WF_POOL_RM, WF_SCENE_BYTES_RM, WF_NU_RM>) : sizeof(WfSmemT<WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, (int)WF_NU>);
+    const size_t smem_bytes = rm ? sizeof(WfSmemT<WF_POOL_RM, WF_SCENE_BYTES_RM, false>) : sizeof(WfSmemT<WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, true>);
     const uint32_t WF_POOL = rm ? WF_POOL_RM : WF_POOL_GENERIC;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(wavefront smem): ") + cudaGetErrorString(e); return PTB_E_CUDA; }

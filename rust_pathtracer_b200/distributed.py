@@ -142,6 +142,17 @@ class DistributedTracer:
             return None
         return self.accum
 
+    def step(self, total_spp: int, host_buffer=None):
+        """One progressive step through the host API: trace this rank's share, gather on rank 0 and — there — start the
+        asynchronous download of the running-mean image into `host_buffer.pixels` (ptb_download_async: the copy overlaps the
+        next step's tracing; `tracer.wait_download()` before reading).  All device work goes through the C ABI."""
+        self.render(total_spp)
+        self.reduce(0)
+        if self.rank == 0 and host_buffer is not None:
+            host_buffer.frames = self.samples_done
+            host_buffer._tracer = self.tracer
+            self.tracer.download_async(host_buffer)
+
     def close(self):
         if self.gather == "peer":
             import torch.distributed as dist

@@ -348,7 +348,7 @@ class ColorBuffer:
         assert out.size >= self.width * self.height * 4
         t = self._bound_tracer()
         fn = getattr(t._lib, f"ptb_convert_pixels_to_u8_{self.precision}")
-        _abi.check(fn(t._handle(), self.width * self.height, self._pixels.ctypes.data, out.ctypes.data))
+        t._check(fn(t._handle(), self.width * self.height, self._pixels.ctypes.data, out.ctypes.data))
 
     def to_u8_vec(self) -> np.ndarray:                              # buffer.rs:37-52
         out = np.zeros(self.width * self.height * 4, dtype=np.uint8)
@@ -359,25 +359,27 @@ class ColorBuffer:
         out = np.frombuffer(frame, dtype=np.uint8) if not isinstance(frame, np.ndarray) else frame
         t = self._bound_tracer()
         fn = getattr(t._lib, f"ptb_convert_pixels_to_u8_at_{self.precision}")
-        _abi.check(fn(t._handle(), self._pixels.ctypes.data, self.width, self.height, out.ctypes.data, at[0], at[1], at[2], at[3]))
+        t._check(fn(t._handle(), self._pixels.ctypes.data, self.width, self.height, out.ctypes.data, at[0], at[1], at[2], at[3]))
 
 
 class Tracer:
     """tracer.rs:5-19, 22-123, 629-631."""
 
     def __init__(self, scene: Scene, device: int = 0, precision: str = None, integrator: int = _abi.PTB_INTEGRATOR_AUTO,
-                 seed: int = 0, collect_counters: bool = False, rr_start: int = 0, wave_paths: int = 0, bvh_threshold: int = 0):
+                 seed: int = 0, collect_counters: bool = False, rr_start: int = 0, wave_paths: int = 0, bvh_threshold: int = 0,
+                 strict: bool = None):
         self.eps = 0.005
         self._scene = scene
         self.precision = precision or F
-        self._lib = _abi.load()
+        self.strict = _abi.strict_default() if strict is None else bool(strict)
+        self._lib = _abi.load(self.strict)       # strict: the IEEE / reference-operation-order build of the same kernels
         export = scene.device_export()
         if export is None:
             raise RuntimeError("scene does not implement device_export(); the B200 tracer has no CPU fallback")
         cfg = _abi.Config(device=device, integrator=integrator, seed=seed, rr_start=rr_start, wave_paths=wave_paths,
                           bvh_threshold=bvh_threshold, collect_counters=1 if collect_counters else 0)
         h = C.c_void_p()
-        _abi.check(self._lib.ptb_create(C.byref(cfg), C.byref(h)))
+        self._check(self._lib.ptb_create(C.byref(cfg), C.byref(h)))
         self._ptr = h
         self._size = (0, 0)
         self.sync_scene()
@@ -395,11 +397,14 @@ class Tracer:
         export = self._scene.device_export()
         sc, keep = export.to_c(self.precision)
         fn = self._lib.ptb_set_scene_f32 if self.precision == "f32" else self._lib.ptb_set_scene_f64
-        _abi.check(fn(self._handle(), C.byref(sc)))
+        self._check(fn(self._handle(), C.byref(sc)))
         self.scene_bytes = C.sizeof(sc) + sum(C.sizeof(k) for k in keep)
         self.eps = export.eps
 
     # -- internals ------------------------------------------------------------------------------
+    def _check(self, code: int) -> None:
+        _abi.check(code, self._lib)
+
     def _handle(self):
         if self._ptr is None:
             raise RuntimeError("tracer destroyed")
@@ -410,27 +415,27 @@ class Tracer:
 
     def _device_frames(self) -> int:
         f = C.c_uint64()
-        _abi.check(self._lib.ptb_frames(self._handle(), C.byref(f)))
+        self._check(self._lib.ptb_frames(self._handle(), C.byref(f)))
         return f.value
 
     def _ensure_size(self, buffer: ColorBuffer):
         if self._size != (buffer.width, buffer.height):
-            _abi.check(self._lib.ptb_resize(self._handle(), buffer.width, buffer.height))
+            self._check(self._lib.ptb_resize(self._handle(), buffer.width, buffer.height))
             self._size = (buffer.width, buffer.height)
 
     def _upload(self, buffer: ColorBuffer):
         self._ensure_size(buffer)
         fn = self._lib.ptb_upload_f32 if self.precision == "f32" else self._lib.ptb_upload_f64
-        _abi.check(fn(self._handle(), buffer._pixels.ctypes.data, buffer.frames))
+        self._check(fn(self._handle(), buffer._pixels.ctypes.data, buffer.frames))
         buffer._tracer = self
 
     def convert_to_u8(self, out: np.ndarray):
         """buffer.rs:55-64 of the DEVICE-RESIDENT image (no upload): kernel + D2H of w*h*4 bytes."""
-        _abi.check(self._lib.ptb_convert_to_u8(self._handle(), out.ctypes.data))
+        self._check(self._lib.ptb_convert_to_u8(self._handle(), out.ctypes.data))
 
     def convert_to_u8_at(self, out: np.ndarray, at):
         """buffer.rs:67-102 of the device-resident image into the host frame `out` (at = x, y, frame_w, frame_h)."""
-        _abi.check(self._lib.ptb_convert_to_u8_at(self._handle(), out.ctypes.data, at[0], at[1], at[2], at[3]))
+        self._check(self._lib.ptb_convert_to_u8_at(self._handle(), out.ctypes.data, at[0], at[1], at[2], at[3]))
 
     # -- the hot path ---------------------------------------------------------------------------
     def render(self, buffer: ColorBuffer) -> None:
@@ -443,7 +448,7 @@ class Tracer:
         # a buffer whose array never left the wrapper cannot have been edited: the library then skips the upload if the
         # buffer, the frame count and the device image are still what its previous call left behind
         flags = _abi.PTB_FRAME_HOST_UNCHANGED if (not buffer._escaped and buffer._tracer is self) else 0
-        _abi.check(fn(self._handle(), buffer.width, buffer.height, buffer.frames, buffer._pixels.ctypes.data, flags))
+        self._check(fn(self._handle(), buffer.width, buffer.height, buffer.frames, buffer._pixels.ctypes.data, flags))
         self._size = (buffer.width, buffer.height)
         buffer.frames += 1
         buffer._tracer = self
@@ -455,10 +460,10 @@ class Tracer:
         assert buffer.precision == self.precision
         self._ensure_size(buffer)
         if buffer.frames == 0:
-            _abi.check(self._lib.ptb_clear(self._handle()))
+            self._check(self._lib.ptb_clear(self._handle()))
         elif self._device_frames() != buffer.frames or buffer._tracer is not self:
             self._upload(buffer)
-        _abi.check(self._lib.ptb_render(self._handle(), spp, buffer.frames))
+        self._check(self._lib.ptb_render(self._handle(), spp, buffer.frames))
         buffer.frames += spp
         buffer._tracer = self
         if download == "async":
@@ -468,70 +473,70 @@ class Tracer:
 
     def download(self, buffer: ColorBuffer) -> None:
         fn = self._lib.ptb_download_f32 if self.precision == "f32" else self._lib.ptb_download_f64
-        _abi.check(fn(self._handle(), buffer._pixels.ctypes.data))
+        self._check(fn(self._handle(), buffer._pixels.ctypes.data))
 
     def download_async(self, buffer: ColorBuffer) -> None:
         """ptb_download_async_*: resolve on the render stream, D2H on a side stream; `wait_download()` before reading."""
         buffer._pin(self._lib)
         fn = self._lib.ptb_download_async_f32 if self.precision == "f32" else self._lib.ptb_download_async_f64
-        _abi.check(fn(self._handle(), buffer._pixels.ctypes.data))
+        self._check(fn(self._handle(), buffer._pixels.ctypes.data))
 
     def wait_download(self) -> None:
-        _abi.check(self._lib.ptb_wait_download(self._handle()))
+        self._check(self._lib.ptb_wait_download(self._handle()))
 
     def synchronize(self) -> None:
-        _abi.check(self._lib.ptb_synchronize(self._handle()))
+        self._check(self._lib.ptb_synchronize(self._handle()))
 
     # -- instrumentation ------------------------------------------------------------------------
     def counters(self) -> dict:
         c = _abi.Counters()
-        _abi.check(self._lib.ptb_get_counters(self._handle(), C.byref(c)))
+        self._check(self._lib.ptb_get_counters(self._handle(), C.byref(c)))
         return c.as_dict()
 
     def reset_counters(self) -> None:
-        _abi.check(self._lib.ptb_reset_counters(self._handle()))
+        self._check(self._lib.ptb_reset_counters(self._handle()))
 
     def launch_count(self) -> int:
         n = C.c_uint64()
-        _abi.check(self._lib.ptb_launch_count(self._handle(), C.byref(n)))
+        self._check(self._lib.ptb_launch_count(self._handle(), C.byref(n)))
         return n.value
 
     def last_render_ms(self) -> float:
         ms = C.c_float()
-        _abi.check(self._lib.ptb_last_render_ms(self._handle(), C.byref(ms)))
+        self._check(self._lib.ptb_last_render_ms(self._handle(), C.byref(ms)))
         return ms.value
 
     def set_stream(self, cuda_stream: int) -> None:
-        _abi.check(self._lib.ptb_set_stream(self._handle(), C.c_void_p(cuda_stream)))
+        self._check(self._lib.ptb_set_stream(self._handle(), C.c_void_p(cuda_stream)))
 
     def bind_accumulator(self, device_ptr: int, width: int, height: int) -> None:
-        _abi.check(self._lib.ptb_bind_accumulator(self._handle(), C.c_void_p(device_ptr), width, height))
+        self._check(self._lib.ptb_bind_accumulator(self._handle(), C.c_void_p(device_ptr), width, height))
         self._size = (width, height)
 
     def render_samples(self, spp: int, sample_base: int) -> None:
         """Raw ptb_render: add samples [sample_base, sample_base+spp) to the device accumulators."""
-        _abi.check(self._lib.ptb_render(self._handle(), spp, sample_base))
+        self._check(self._lib.ptb_render(self._handle(), spp, sample_base))
 
     # -- multi-GPU gather over peer memory (ptb_peer_*, include/ptb200.h) --
     def peer_slots_create(self, n_slots: int) -> bytes:
         buf = C.create_string_buffer(_abi.PTB_PEER_HANDLE_BYTES)
-        _abi.check(self._lib.ptb_peer_slots_create(self._handle(), n_slots, buf))
+        self._check(self._lib.ptb_peer_slots_create(self._handle(), n_slots, buf))
         return buf.raw
 
     def peer_slots_open(self, handle: bytes, n_slots: int) -> None:
-        _abi.check(self._lib.ptb_peer_slots_open(self._handle(), C.create_string_buffer(handle, _abi.PTB_PEER_HANDLE_BYTES), n_slots))
+        self._check(self._lib.ptb_peer_slots_open(self._handle(), C.create_string_buffer(handle, _abi.PTB_PEER_HANDLE_BYTES), n_slots))
 
     def peer_set_target(self, slot: int, parity: int = 0) -> None:
-        _abi.check(self._lib.ptb_peer_set_target(self._handle(), slot & 0xffffffff, parity))
+        self._check(self._lib.ptb_peer_set_target(self._handle(), slot & 0xffffffff, parity))
 
     def peer_sum(self, parity: int = 0) -> None:
-        _abi.check(self._lib.ptb_peer_sum(self._handle(), parity))
+        self._check(self._lib.ptb_peer_sum(self._handle(), parity))
 
     def peer_slots_close(self) -> None:
-        _abi.check(self._lib.ptb_peer_slots_close(self._handle()))
+        self._check(self._lib.ptb_peer_slots_close(self._handle()))
 
     def clear(self) -> None:
-        _abi.check(self._lib.ptb_clear(self._handle()))
+        self._check(self._lib.ptb_clear(self._handle()))
 
     def close(self) -> None:
         if getattr(self, "_ptr", None) is not None:

@@ -19,10 +19,10 @@ class DeviceFns:
             def device_export(self_inner):
                 return export
         self.rp = rp
-        self.tracer = rp.Tracer.new(_S(), **tracer_kw)
-        self.lib = rp._abi.load()
+        self.tracer = rp.Tracer.new(_S(), **tracer_kw)      # strict=True: the IEEE build of the same device functions
+        self.lib = self.tracer._lib
         self.h = self.tracer._handle()
-        self.chk = rp._abi.check
+        self.chk = self.tracer._check
 
     def close(self):
         self.tracer.close()

@@ -25,8 +25,13 @@ VARIANTS = [
     #   PTB_FULL_DIV                                                 f32 quotients as div.full (`a / b`) instead of rcp + mul
     #   PTB_MUFU_SINCOS                                              sin / cos on MUFU.SIN / MUFU.COS (3.6e-7 abs) instead of the ~1 ulp minimax kernel
     #   PTB_SAT_DROPS_NAN + PTB_CONTRACT_VIEW_COSINE                  round 1's NaN behaviour (saturate drops NaN, v.z contracted)
+    #   PTB_WF_V1                                                    round 1's two-stage wavefront kernel (ptb_wavefront_v1.cuh)
     ("default", [], {}),
-    ("r1_nan", ["-DPTB_SAT_DROPS_NAN", "-DPTB_CONTRACT_VIEW_COSINE"], {}),
+    ("wf_v1", ["-DPTB_WF_V1"], {}),
+    ("pool2528", ["-DPTB_WF_POOL_RM=2528"], {}),
+    ("pool2048", ["-DPTB_WF_POOL_RM=2048"], {}),
+    ("thr640", ["-DPTB_WF_THREADS_RM=640"], {}),
+    ("thr896", ["-DPTB_WF_THREADS_RM=896"], {}),
 ]
 
 

@@ -17,18 +17,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 VDIR = os.path.join(ROOT, "rust_pathtracer_b200", "variants")
-IEEE_LIB = os.path.join(VDIR, "libptb200_ieee.so")
-IEEE_FLAGS = ["-DPTB_IEEE", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-fmad=false"]
+IEEE_LIB = os.path.join(ROOT, "rust_pathtracer_b200", "libptb200_strict.so")       # built by __graft_entry__.build()
+# two more builds that separate the causes: the shipped approximations WITHOUT FMA contraction, and IEEE operations WITH it
+NOFMA_LIB = os.path.join(VDIR, "libptb200_fast_nofma.so")
+IEEEFMA_LIB = os.path.join(VDIR, "libptb200_ieee_fma.so")
 
 
 def build():
     import __graft_entry__ as g
     os.makedirs(VDIR, exist_ok=True)
-    base = [f for f in g.NVCC_FLAGS if not f.startswith(("-prec-div", "-prec-sqrt", "-ftz"))]
-    cmd = ["nvcc"] + base + IEEE_FLAGS + ["-o", IEEE_LIB, os.path.join(g.CSRC, "ptb_api.cu")]
-    print(" ".join(cmd), flush=True)
-    subprocess.check_call(cmd)
+    procs = []
+    for lib, flags in ((NOFMA_LIB, g.NVCC_FLAGS + ["-fmad=false"]), (IEEEFMA_LIB, [f for f in g.STRICT_FLAGS if f != "-fmad=false"])):
+        cmd = ["nvcc"] + flags + ["-o", lib, os.path.join(g.CSRC, "ptb_api.cu")]
+        print(" ".join(cmd), flush=True)
+        procs.append(subprocess.Popen(cmd))
     g.build()
+    for p in procs:
+        assert p.wait() == 0
 
 
 def one():
@@ -74,7 +79,8 @@ def run():
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
     res = {}
-    for name, lib in (("shipped", os.path.join(ROOT, "rust_pathtracer_b200", "libptb200.so")), ("ieee", IEEE_LIB)):
+    for name, lib in (("shipped", os.path.join(ROOT, "rust_pathtracer_b200", "libptb200.so")), ("ieee", IEEE_LIB), ("fast_nofma", NOFMA_LIB),
+                      ("ieee_fma", IEEEFMA_LIB)):
         if not os.path.exists(lib):
             print(name, "missing:", lib, flush=True)
             continue
@@ -85,16 +91,28 @@ def run():
             continue
         res[name] = json.loads(line[0][5:])
     json.dump(res, open(os.path.join(out_dir, "function_parity.json"), "w"))
-    lines = ["| function | n | shipped max | p99.9 | p99 | p95 | >1e-5 | IEEE max | p99.9 | p99 | >1e-5 | formula floor (oracle f32 vs f64) max / p99.9 / p99 | note |",
-             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    # bounds for tests/test_gpu_function_bounds.py: twice the measured maximum / p99.9 (exactly 0 stays 0: bit-exact is asserted as such)
+    def bound(x):
+        return 0.0 if x == 0 else max(2.0 * x, 2.5e-7)
+    bounds = {tag: {r["name"]: {"max": bound(r["max"]), "p999": bound(r["p999"]), "measured_max": r["max"], "measured_p999": r["p999"], "n": r["n"]}
+                    for r in res.get(src, [])} for tag, src in (("shipped", "shipped"), ("strict", "ieee"))}
+    json.dump(bounds, open(os.path.join(out_dir, "fn_bounds.json"), "w"), indent=1)
+    def extra(name):
+        rows = {r["name"]: r for r in res.get(name, [])}
+        return lambda n: rows.get(n)
+    nofma, ieeefma = extra("fast_nofma"), extra("ieee_fma")
+    lines = ["| function | n | shipped max | p99.9 | p99 | p95 | >1e-5 | IEEE max | p99.9 | p99 | >1e-5 | shipped ops, no FMA: max / p99.9 | IEEE ops + FMA: max / p99.9 | formula floor (oracle f32 vs f64) max / p99.9 / p99 | note |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     ship = res.get("shipped", [])
     ieee = {r["name"]: r for r in res.get("ieee", [])}
     for r in ship:
         i = ieee.get(r["name"])
         fl = r.get("floor")
-        lines.append("| `{}` | {} | {} | {} | {} | {} | {:.2%} | {} | {} | {} | {} | {} | {} |".format(
+        nf, jf = nofma(r["name"]), ieeefma(r["name"])
+        lines.append("| `{}` | {} | {} | {} | {} | {} | {:.2%} | {} | {} | {} | {} | {} | {} | {} | {} |".format(
             r["name"], r["n"], fmt(r["max"]), fmt(r["p999"]), fmt(r["p99"]), fmt(r["p95"]), r["frac_gt_1e5"],
             fmt(i["max"]) if i else "-", fmt(i["p999"]) if i else "-", fmt(i["p99"]) if i else "-", f"{i['frac_gt_1e5']:.2%}" if i else "-",
+            f"{fmt(nf['max'])} / {fmt(nf['p999'])}" if nf else "-", f"{fmt(jf['max'])} / {fmt(jf['p999'])}" if jf else "-",
             f"{fmt(fl['max'])} / {fmt(fl['p999'])} / {fmt(fl['p99'])}" if fl else "-", r["note"]))
     open(os.path.join(out_dir, "function_parity.md"), "w").write("\n".join(lines) + "\n")
     print("\n".join(lines), flush=True)
