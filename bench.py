@@ -248,12 +248,12 @@ def run_own(args, cfg):
 
     integ = {"auto": A.PTB_INTEGRATOR_AUTO, "fused": A.PTB_INTEGRATOR_FUSED, "wavefront": A.PTB_INTEGRATOR_WAVEFRONT,
              "stream": A.PTB_INTEGRATOR_STREAM}[args.integrator]
-    if args.integrator == "auto":
-        kernel_key = "wavefront_rm" if cfg["scene"] == "demo" else "stream"
-    else:
-        kernel_key = {"fused": "fused", "wavefront": "wavefront_rm" if cfg["scene"] == "demo" else "wavefront", "stream": "stream"}[args.integrator]
-    kernel_name = {"fused": "k_render_fused<float,false,BVH>", "stream": "k_stream_* (one kernel per stage: generate, trace, finish, shade, shadow, accumulate)",
-                   "wavefront": "k_render_wavefront<COUNT=false,BVH,RM=false>", "wavefront_rm": "k_render_wavefront<COUNT=false,BVH=false,RM=true>"}[kernel_key]
+    kernel_names = {"fused": "k_render_fused<float,COUNT=false,BVH=false>", "fused_bvh": "k_render_fused<float,COUNT=false,BVH=true>",
+                    "stream": "k_stream_* (one kernel per stage: generate, closest, shade, shadow, accumulate)",
+                    "stream_bvh": "k_stream_* with BVH traversal (one kernel per stage: generate, closest, shade, shadow, accumulate)",
+                    "stream_split_bvh": "k_stream_* (one kernel per stage; bounce >= 1: k_stream_trace + k_stream_finish, shadow rays k_stream_trace<ANY>)",
+                    "wavefront": "k_render_wavefront<COUNT=false,BVH=false,RM=false>", "wavefront_bvh": "k_render_wavefront<COUNT=false,BVH=true,RM=false>",
+                    "wavefront_rm": "k_render_wavefront<COUNT=false,BVH=false,RM=true>"}
 
     # ---- device-resident arm: `value` ---------------------------------------------------------------------
     dt = DistributedTracer(scene, W, H, device=dev, integrator=integ, gather=args.gather, **tracer_kw)
@@ -286,6 +286,8 @@ def run_own(args, cfg):
     total_ms = float(ms.item())
     clocks = sampler.stop() if sampler else None
     launches = dt.tracer.launch_count() - launches0
+    kernel_key = dt.tracer.integrator_used()          # what AUTO resolved to, reported by the library (ptb_last_integrator)
+    kernel_name = kernel_names.get(kernel_key, kernel_key)
     # per-launch duration of the render kernel(s): CUDA events on the launch stream around the last ptb_render, taken on 3 extra
     # UNTIMED steps after the timed region so that the event synchronisations do not perturb `value`
     if not kernel_ms:

@@ -310,6 +310,13 @@ int  ptb_launch_count(ptb_tracer* t, uint64_t* launches);
 /* average device time (ms) of the render kernels launched by the last ptb_render call, measured
  * with CUDA events on the tracer's stream; synchronises. */
 int  ptb_last_render_ms(ptb_tracer* t, float* ms);
+/* which integrator the last ptb_render call actually ran (AUTO resolved: PTB_INTEGRATOR_FUSED / _WAVEFRONT / _STREAM) and
+ * how it was instantiated: PTB_KERNEL_* bits.  Tests and bench.py name the measured kernel from this instead of guessing. */
+#define PTB_KERNEL_BVH      1u   /* sphere BVH traversal instead of the linear scan                               */
+#define PTB_KERNEL_RM_TABLE 2u   /* shades from the resolved-material table (small scenes, shared-memory wavefront) */
+#define PTB_KERNEL_SPLIT    4u   /* streaming integrator: dedicated traversal kernels for bounce >= 1              */
+#define PTB_KERNEL_F64      8u   /* the f64 instantiation of `F` (lib.rs:5-6)                                       */
+int  ptb_last_integrator(ptb_tracer* t, uint32_t* integrator, uint32_t* kernel_bits);
 
 /* ---- per-function parity entry points ------------------------------------------------------- */
 /* Each runs the SAME __device__ functions the integrators call over n independent inputs that

@@ -233,6 +233,18 @@ void t_trace_samples(const SceneBox<R>* sb, uint32_t w, uint32_t h, size_t n, co
     }
 }
 
+// One sample of pixel (px, row) of a w x h frame traced on a recorded draw sequence (SeqRng); returns the draws consumed,
+// or -1 if the sequence was too short.
+template <class R>
+long t_trace_scripted(const SceneBox<R>* sb, uint32_t w, uint32_t h, uint32_t px, uint32_t row, const R* draws, size_t n_draws, R* rgb_out) {
+    Tracer<R> tr(sb->scene.get());
+    if (sb->flat) tr.eps = sb->flat->eps;
+    SeqRng<R> rng(draws, n_draws);
+    V3<R> c = tr.trace_sample_with(px, (size_t)h - 1 - row, w, (R)h, rng, nullptr);
+    rgb_out[0] = c.x; rgb_out[1] = c.y; rgb_out[2] = c.z;
+    return rng.overrun ? -1 : (long)rng.pos;
+}
+
 }  // namespace
 
 extern "C" {
@@ -312,6 +324,9 @@ size_t pto_counters_size(void) { return sizeof(Counters); }
                             uint64_t sample_base, uint64_t seed, int threads, void* counters) {                         \
         return t_render<R>(static_cast<SceneBox<R>*>(sb), w, h, pixels, frames_inout, n_frames, sample_base, seed, threads, \
                            static_cast<Counters*>(counters));                                                           \
+    }                                                                                                                   \
+    long pto_trace_scripted_##SFX(void* sb, uint32_t w, uint32_t h, uint32_t px, uint32_t row, const R* draws, size_t n_draws, R* rgb) { \
+        return t_trace_scripted<R>(static_cast<SceneBox<R>*>(sb), w, h, px, row, draws, n_draws, rgb);                  \
     }                                                                                                                   \
     void pto_trace_samples_##SFX(void* sb, uint32_t w, uint32_t h, size_t n, const uint32_t* px, const uint32_t* row,   \
                                  const uint64_t* sample, uint64_t seed, R* rgb) {                                       \

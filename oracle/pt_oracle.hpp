@@ -234,6 +234,21 @@ template <class R> struct CounterRng {
     uint32_t pixel; uint64_t sample; uint64_t seed;
     CounterRng(uint32_t p, uint64_t s, uint64_t sd) : pixel(p), sample(s), seed(sd) {}
     R draw(uint32_t bounce, uint32_t slot) const;
+    void coin_consumed() const {}
+};
+// Replay of a recorded draw SEQUENCE (tools/ref_kat: the reference run on a scripted RNG): draws are handed out in call
+// order, whatever (bounce, slot) is asked for — valid because this file asks for them at the same program points as the
+// reference calls rng.gen() (tracer.rs:45, 137, 191-192, 446-447, 534).  The coin of tracer.rs:534 is drawn by the
+// reference only inside the spec lobe: the oracle asks for it before it knows the lobe, so the coin is PEEKED and the
+// caller reports afterwards whether the reference would have consumed it.
+template <class R> struct SeqRng {
+    const R* seq; size_t n; mutable size_t pos = 0; mutable bool overrun = false;
+    SeqRng(const R* s, size_t count) : seq(s), n(count) {}
+    R draw(uint32_t, uint32_t slot) const {
+        if (pos >= n) { overrun = true; return R(0); }
+        return slot == 3u /* SLOT_COIN */ ? seq[pos] : seq[pos++];
+    }
+    void coin_consumed() const { if (pos < n) ++pos; else overrun = true; }
 };
 template <> inline float CounterRng<float>::draw(uint32_t bounce, uint32_t slot) const {
     uint32_t c[4] = {bounce * 2u + (slot >> 2), (uint32_t)(sample >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -927,7 +942,8 @@ template <class R> struct Tracer {
     }
 
     // tracer.rs:126-170
-    V3<R> direct_light(const Ray<R>& ray, const State<R>& state, const CounterRng<R>& rng, uint32_t bounce,
+    template <class RNG>
+    V3<R> direct_light(const Ray<R>& ray, const State<R>& state, const RNG& rng, uint32_t bounce,
                        Counters* ctr) const {
         V3<R> ld = V3<R>::zeros();
         V3<R> scatter_pos = state.fhp + eps * state.ffnormal;
@@ -966,13 +982,16 @@ template <class R> struct Tracer {
     // `pixel_id` keys the RNG (memory pixel index r*W + x), `sample` is the global sample index.
     V3<R> trace_sample(size_t x, size_t j, size_t width, R height, uint32_t pixel_id, uint64_t sample,
                        Counters* ctr) const {
+        return trace_sample_with(x, j, width, height, CounterRng<R>(pixel_id, sample, seed), ctr);
+    }
+    template <class RNG>
+    V3<R> trace_sample_with(size_t x, size_t j, size_t width, R height, const RNG& rng, Counters* ctr) const {
         // tracer.rs:34-46:  i = j*width + x with j counted from the LAST memory row
         size_t i = j * width + x;
         R xf = (R)(i % width);
         R yf = height - (R)(i / width);
         R xx = xf / (R)width;
         R yy = yf / height;
-        CounterRng<R> rng(pixel_id, sample, seed);
         R offx = rng.draw(0, SLOT_JITTER_X), offy = rng.draw(0, SLOT_JITTER_Y);
         Ray<R> ray = scene->camera().gen_ray(xx, R(1) - yy, offx, offy, (R)width, height);
 
@@ -1007,8 +1026,10 @@ template <class R> struct Tracer {
             if (ctr) ctr->shade++;
             radiance += direct_light(ray, state, rng, bounce, ctr) * throughput;
             R r1 = rng.draw(bounce, SLOT_BSDF_R1), r2 = rng.draw(bounce, SLOT_BSDF_R2), coin = rng.draw(bounce, SLOT_COIN);
+            int lobe = -1;
             scatter_sample.f = disney_sample(state, -ray.direction, state.ffnormal, scatter_sample.l, scatter_sample.pdf,
-                                             r1, r2, coin, nullptr, ctr);
+                                             r1, r2, coin, &lobe, ctr);
+            if (lobe >= 2) rng.coin_consumed();                                // tracer.rs:534: drawn in the spec lobe only
             if (scatter_sample.pdf > R(0)) {
                 throughput = throughput * (scatter_sample.f / V3<R>::new_x(scatter_sample.pdf));
             } else {

@@ -196,6 +196,17 @@ class OracleScene:
         return rgb
 
 
+    def trace_scripted(self, w, h, px, row, draws):
+        """radiance of ONE sample of pixel (px, row) traced on a recorded draw sequence (call order, tools/ref_kat);
+        returns (rgb, draws consumed) — consumed = -1 if the sequence ran out"""
+        d = self._a(draws)
+        rgb = np.empty(3, self.np)
+        fn = self._fn("trace_scripted")
+        fn.restype = C.c_long
+        k = fn(self.h, C.c_uint32(w), C.c_uint32(h), C.c_uint32(px), C.c_uint32(row), _p(d), C.c_size_t(d.size), _p(rgb))
+        return rgb, int(k)
+
+
 def sphere_hit(o, d, c, r, precision="f32"):
     lib = load(); dt = _NP[precision]
     o, d, c, r = (np.ascontiguousarray(x, dt) for x in (o, d, c, r))

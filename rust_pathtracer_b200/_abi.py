@@ -20,6 +20,7 @@ PTB_SCENE_ANYHIT_IGNORES_MAX_DIST, PTB_SCENE_FORCE_BVH, PTB_SCENE_NO_BVH = 1, 2,
 PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT, PTB_INTEGRATOR_STREAM = 0, 1, 2, 3
 PTB_PEER_HANDLE_BYTES = 64
 PTB_FRAME_HOST_UNCHANGED = 1
+PTB_KERNEL_BVH, PTB_KERNEL_RM_TABLE, PTB_KERNEL_SPLIT, PTB_KERNEL_F64 = 1, 2, 4, 8
 
 PTB_MAT_RGB, PTB_MAT_EMISSION, PTB_MAT_ANISOTROPIC, PTB_MAT_METALLIC = 1 << 0, 1 << 1, 1 << 2, 1 << 3
 PTB_MAT_ROUGHNESS, PTB_MAT_SUBSURFACE, PTB_MAT_SPECULAR_TINT, PTB_MAT_SHEEN = 1 << 4, 1 << 5, 1 << 6, 1 << 7
@@ -91,7 +92,7 @@ SYMBOLS = [
     "ptb_peer_slots_create", "ptb_peer_slots_open", "ptb_peer_set_target", "ptb_peer_sum", "ptb_peer_slots_close",
     "ptb_convert_to_u8", "ptb_convert_to_u8_at", "ptb_convert_pixels_to_u8_f32", "ptb_convert_pixels_to_u8_f64",
     "ptb_convert_pixels_to_u8_at_f32", "ptb_convert_pixels_to_u8_at_f64", "ptb_get_counters", "ptb_reset_counters", "ptb_launch_count",
-    "ptb_last_render_ms",
+    "ptb_last_render_ms", "ptb_last_integrator",
     "ptb_test_sphere_hit_f32", "ptb_test_plane_hit_f32", "ptb_test_gen_ray_f32", "ptb_test_closest_hit_f32",
     "ptb_test_any_hit_f32", "ptb_test_background_f32", "ptb_test_sample_light_f32", "ptb_test_finalize_f32",
     "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32", "ptb_test_resolved_material_f32", "ptb_test_film_quotients_f32", "ptb_test_bvh_build_f32",
@@ -179,6 +180,7 @@ def load(strict: bool = None):
     lib.ptb_reset_counters.argtypes = [C.c_void_p]
     lib.ptb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.ptb_last_render_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.ptb_last_integrator.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     vp = C.c_void_p
     lib.ptb_test_sphere_hit_f32.argtypes = [vp, C.c_size_t] + [vp] * 5
     lib.ptb_test_plane_hit_f32.argtypes = [vp, C.c_size_t] + [vp] * 5

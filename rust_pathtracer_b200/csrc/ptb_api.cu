@@ -86,6 +86,7 @@ struct ptb_tracer {
     unsigned int* work_counter = nullptr;
     DeviceCounters* counters = nullptr;
     uint64_t launches = 0;
+    uint32_t last_integrator = 0, last_kernel_bits = 0;     // what the last ptb_render ran (ptb_last_integrator)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int sm_count = 0;
@@ -932,8 +933,20 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
         r = t->precision == 4 ? render_fused<float>(t, t->s32.d, spp, sample_base) : render_fused<double>(t, t->s64.d, spp, sample_base);
         if (r) return r;
     }
+    t->last_integrator = integ;
+    t->last_kernel_bits = t->precision == 8 ? (PTB_KERNEL_F64 | (t->s64.d.use_bvh ? PTB_KERNEL_BVH : 0u))
+                          : ((t->s32.d.use_bvh ? PTB_KERNEL_BVH : 0u) |
+                             (integ == PTB_INTEGRATOR_WAVEFRONT && t->s32.d.rm_entries != 0 && !t->s32.d.use_bvh ? PTB_KERNEL_RM_TABLE : 0u) |
+                             (integ == PTB_INTEGRATOR_STREAM && stream_uses_split(t->s32.d) ? PTB_KERNEL_SPLIT : 0u));
     t->frames += spp;
     t->host_clean = nullptr;
+    return PTB_OK;
+}
+
+int ptb_last_integrator(ptb_tracer* t, uint32_t* integrator, uint32_t* kernel_bits) {
+    if (!t || !integrator || !kernel_bits) return fail(PTB_E_INVALID, "null argument");
+    if (!t->last_integrator) return fail(PTB_E_INVALID, "no render has been issued");
+    *integrator = t->last_integrator; *kernel_bits = t->last_kernel_bits;
     return PTB_OK;
 }
 

@@ -47,6 +47,7 @@ constexpr uint32_t ST_KEYS = 9;          // 8 lobe classes (lobe_class_of) + ST_
 constexpr uint32_t ST_MISS = 8;          // the path left the scene: background lookup (tracer.rs:66-69)
 constexpr uint32_t ST_DEFAULT_WAVE = 1u << 23;
 constexpr uint32_t ST_SPLIT_MIN_SPHERES = 16384u;   // BVH scenes above this use the persistent-lane traversal kernels from bounce 1 on
+inline bool stream_uses_split(const DScene<float>& d) { return d.use_bvh && d.n_spheres > ST_SPLIT_MIN_SPHERES; }
 
 struct BounceCtr {                       // 128 bytes per bounce, zeroed at the start of a wave
     uint32_t n_ray;                      // rays entering this bounce
@@ -688,7 +689,7 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, v
     split[1] = count ? k_stream_finish<true> : k_stream_finish<false>;
     split[2] = plain[1];
     split[3] = count ? k_stream_trace<true, true> : k_stream_trace<true, false>;
-    const bool use_split = bvh && d.n_spheres > ST_SPLIT_MIN_SPHERES;
+    const bool use_split = stream_uses_split(d);
     int g_plain[3], g_split[4];
     auto grid_of = [&](int& slot, StageKernel k) {
         if (slot == 0) {

@@ -506,6 +506,22 @@ class Tracer:
         self._check(self._lib.ptb_last_render_ms(self._handle(), C.byref(ms)))
         return ms.value
 
+    def integrator_used(self) -> str:
+        """which kernel family the last render ran (AUTO resolved): fused | wavefront | wavefront_rm | stream | stream_split,
+        with _bvh / _f64 suffixes"""
+        i, b = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.ptb_last_integrator(self._handle(), C.byref(i), C.byref(b)))
+        name = {_abi.PTB_INTEGRATOR_FUSED: "fused", _abi.PTB_INTEGRATOR_WAVEFRONT: "wavefront", _abi.PTB_INTEGRATOR_STREAM: "stream"}[i.value]
+        if b.value & _abi.PTB_KERNEL_RM_TABLE:
+            name += "_rm"
+        if b.value & _abi.PTB_KERNEL_SPLIT:
+            name += "_split"
+        if b.value & _abi.PTB_KERNEL_BVH:
+            name += "_bvh"
+        if b.value & _abi.PTB_KERNEL_F64:
+            name += "_f64"
+        return name
+
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._lib.ptb_set_stream(self._handle(), C.c_void_p(cuda_stream)))
 

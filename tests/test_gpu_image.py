@@ -657,3 +657,31 @@ def test_non_spherical_light_types_are_inert_like_the_reference(rp, po):
     only = rp.AnalyticalScene.new().device_export()
     _, _, _, oc1 = po.OracleScene(only).render(W, H, S, counters=True)
     assert oc["any_hit"] < 0.5 * oc1["any_hit"]
+
+
+@pytest.mark.parametrize("wh_spp", [(1920, 1080, 2), (3840, 2160, 2), (3840, 2160, 1)])
+@pytest.mark.parametrize("strict", [False, True])
+def test_benchmarked_kernel_full_frame_parity(rp, scene, oracle_demo, wh_spp, strict):
+    """The instantiation bench.py measures (AUTO -> resolved-material wavefront kernel, tail blocks, FMA-corrected film
+    coordinates) at the frame sizes of BASELINE.json configs[1] and configs[2], against the oracle with the shared counter RNG
+    (VERDICT r1 weak #7).  spp = 2 takes the tail-block path (two one-sample blocks for the frame's last pixels), spp = 1 the
+    whole-pixel path; both builds.  Bars: >= 99.9 % of pixels within 1e-4 relative (shipped; measured 99.99 %), >= 99.99 % for the
+    strict build (its residual is CUDA's double-rounded pow / sincos against glibc's), mean luminance within 1e-5."""
+    W, H, S = wh_spp
+    pt = rp.Tracer.new(scene, strict=strict)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render_spp(buf, S)
+    assert buf.frames == S
+    assert pt.integrator_used() == "wavefront_rm"
+    ref, frames, _, _ = oracle_demo.render(W, H, S)
+    assert frames == S
+    px = buf.pixels.reshape(-1, 4)
+    assert np.all(px[:, 3] == 1.0)
+    ok = np.isfinite(px).all(1) & np.isfinite(ref.reshape(-1, 4)).all(1)     # a 0/0 clearcoat sample poisons a pixel on either side
+    assert (~ok).sum() <= 2
+    rel = pix_rel(buf.pixels, ref)[ok]
+    frac = (rel < 1e-4).mean()
+    assert frac >= (0.9999 if strict else 0.999), frac
+    assert np.median(rel) < (1e-7 if strict else 1e-6)
+    assert abs(lum(buf.pixels)[ok].mean() / lum(ref)[ok].mean() - 1) < 1e-5
+    pt.close()
