@@ -17,8 +17,8 @@
 
 #include "../../include/ptb200.h"
 #include "ptb_kernels.cuh"
-#ifdef PTB_WF_V1      // A/B only (tools/ab_variants.py): round 1's two-stage form of the shared-memory wavefront integrator
-#include "ptb_wavefront_v1.cuh"
+#ifdef PTB_WF_ASYNC   // A/B only (tools/ab_variants.py): barrier-free per-key rings — measured slower: desynchronised warps thrash the
+#include "ptb_wavefront_async.cuh"      // instruction cache (no_instruction 0.21 -> 2.6 stall cycles per issue; profiles/r02_ab_variants.txt)
 #else
 #include "ptb_wavefront.cuh"
 #endif

@@ -1386,7 +1386,11 @@ PTB_DEV bool path_shade_rm(const DScene<float>& s, const SceneView<float>& sv, P
         if (COUNT) pc->any_hit++;
         nee = !any_hit<float, false>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
     }
+#ifdef PTB_RM_SINGLE_COPY
+    return shade_finish<float, COUNT, false, NoSink, false>(s, p, rm.m, su, nee, ns.ls, ns.light_area, u, pc);
+#else
     return shade_finish<float, COUNT, false, NoSink, true>(s, p, rm.m, su, nee, ns.ls, ns.light_area, u, pc);
+#endif
 }
 
 // Russian roulette EXTENSION at the start of bounce > 0 (the reference has none, quirk A.12; off in

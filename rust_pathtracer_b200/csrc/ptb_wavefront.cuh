@@ -64,6 +64,9 @@ constexpr uint32_t WF_POOL_GENERIC = PTB_WF_POOL;       // path slots per CTA
 #define PTB_WF_POOL_RM 2304
 #endif
 constexpr uint32_t WF_POOL_RM = PTB_WF_POOL_RM;
+#ifndef PTB_WF_REGEN_DEN
+#define PTB_WF_REGEN_DEN 4u
+#endif
 constexpr uint32_t WF_MISS = 8;             // the path left the scene: background lookup, done with full warps in stage 2
 
 // per-slot state: five 16-byte vectors (one LDS.128 / STS.128 each) + one packed queue word
@@ -236,7 +239,13 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             // stays independent of which slot traced what.
             bool done = false;
             uint32_t blkbits = fl & FL_BLOCK_BITS;
-            {
+            // In place only where B runs on (nearly) full warps: always in WF_MISS / WF_REGEN chunks, and in a shading chunk when at
+            // least 1 / PTB_WF_REGEN_DEN of its paths ended there (pdf <= 0, depth: ~12 % on the demo scene).  Otherwise the few dead
+            // lanes take a WF_REGEN ticket and are regenerated by a full warp next iteration instead of dragging this warp through
+            // the pixel hand-out, Philox and camera-ray code at 4 of 32 lanes.
+            const unsigned dead_mask = __ballot_sync(FULL, valid && !alive);
+            const bool regen_here = (uint32_t)__popc(dead_mask) * PTB_WF_REGEN_DEN >= (uint32_t)__popc(__ballot_sync(FULL, valid));
+            if (regen_here) {
                 V3<R> acc(0, 0, 0);
                 const bool dead = valid && !alive;
                 if (dead) {
@@ -308,9 +317,8 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             }
 
             // ================================ C: closest_hit for every live path ================================
-            uint32_t key = WF_NOKEY;
+            uint32_t key = valid && !done ? WF_REGEN : WF_NOKEY;      // (a lane that is neither alive nor done waits for its regeneration)
             if (alive) {
-                key = WF_REGEN;
                 uint32_t new_prim = PRIM_SKY;
                 if (p.bounce >= s.depth) {                              // recursion depth 0 (tracer.rs:61)
                     alive = false;

@@ -25,13 +25,12 @@ VARIANTS = [
     #   PTB_FULL_DIV                                                 f32 quotients as div.full (`a / b`) instead of rcp + mul
     #   PTB_MUFU_SINCOS                                              sin / cos on MUFU.SIN / MUFU.COS (3.6e-7 abs) instead of the ~1 ulp minimax kernel
     #   PTB_SAT_DROPS_NAN + PTB_CONTRACT_VIEW_COSINE                  round 1's NaN behaviour (saturate drops NaN, v.z contracted)
-    #   PTB_WF_V1                                                    round 1's two-stage wavefront kernel (ptb_wavefront_v1.cuh)
+    #   PTB_WF_ASYNC                                                 barrier-free per-key rings (ptb_wavefront_async.cuh); PTB_WF_REGEN_DEN: in-place regeneration threshold
     ("default", [], {}),
-    ("wf_v1", ["-DPTB_WF_V1"], {}),
-    ("pool2528", ["-DPTB_WF_POOL_RM=2528"], {}),
-    ("pool2048", ["-DPTB_WF_POOL_RM=2048"], {}),
-    ("thr640", ["-DPTB_WF_THREADS_RM=640"], {}),
-    ("thr896", ["-DPTB_WF_THREADS_RM=896"], {}),
+    ("regen_inplace", ["-DPTB_WF_REGEN_DEN=1000u"], {}),
+    ("regen_half", ["-DPTB_WF_REGEN_DEN=2u"], {}),
+    ("regen_eighth", ["-DPTB_WF_REGEN_DEN=8u"], {}),
+    ("async", ["-DPTB_WF_ASYNC"], {}),
 ]
 
 
