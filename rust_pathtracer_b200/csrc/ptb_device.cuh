@@ -1214,10 +1214,12 @@ template <class R> struct NeeSample {
     V3<R> scatter_pos;
 };
 
-template <class R, bool COUNT>
+// ADD_EMISSION = false: the caller has added `emission * throughput` itself (the shared-memory wavefront keeps radiance and
+// throughput out of registers while it shades)
+template <class R, bool COUNT, bool ADD_EMISSION = true>
 PTB_DEV void shade_setup(const DScene<R>& s, PathState<R>& p, V3<R> normal, Mat<R>& mat, ShadeSetup<R>& su, PathCounters* pc) {
     state_finalize(p.o, p.d, p.hit_dist, normal, mat, su.fhp, su.ffn, su.eta);
-    p.rad = p.rad + mat.emission * p.thr;                       // tracer.rs:74
+    if (ADD_EMISSION) p.rad = p.rad + mat.emission * p.thr;     // tracer.rs:74
     if (COUNT) pc->shade++;
     shade_ctx_init(su.c, mat, su.eta, su.ffn, -p.d);
 }
@@ -1305,10 +1307,10 @@ PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat
 }
 
 // the three pieces in one go (fused integrator, shared-memory wavefront)
-template <class R, bool COUNT, bool BVH>
+template <class R, bool COUNT, bool BVH, bool ADD_EMISSION = true>
 PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, Mat<R>& mat, const R* u, PathCounters* pc) {
     ShadeSetup<R> su;
-    shade_setup<R, COUNT>(s, p, normal, mat, su, pc);
+    shade_setup<R, COUNT, ADD_EMISSION>(s, p, normal, mat, su, pc);
     NeeSample<R> ns;
     shade_nee_sample(s, sv, su, u, ns);
     bool nee = false;
@@ -1356,14 +1358,14 @@ PTB_DEV const RMat& rm_lookup(const DScene<float>& s, const SceneView<float>& sv
     return rm_table[e];
 }
 // shade_setup for a table entry
-template <bool COUNT>
+template <bool COUNT, bool ADD_EMISSION = true>
 PTB_DEV void shade_setup_rm(PathState<float>& p, V3<float> normal, const RMat& rm, ShadeSetup<float>& su, PathCounters* pc) {
     su.fhp = p.o + p.hit_dist * p.d;
     const float nd = dot(normal, p.d);
     su.ffn = nd <= 0.0f ? normal : -normal;
     const int side = nd < 0.0f ? 0 : 1;
     su.eta = rm.eta[side];
-    p.rad = p.rad + rm.m.emission * p.thr;                      // tracer.rs:74
+    if (ADD_EMISSION) p.rad = p.rad + rm.m.emission * p.thr;    // tracer.rs:74
     if (COUNT) pc->shade++;
     ShadeCtx<float>& c = su.c;
     c.n = su.ffn;
@@ -1374,11 +1376,11 @@ PTB_DEV void shade_setup_rm(PathState<float>& p, V3<float> normal, const RMat& r
     c.sheen_col = V3<float>(rm.sheen_col[0], rm.sheen_col[1], rm.sheen_col[2]);
     c.lum = rm.lum; c.wd0 = rm.wd0; c.wc0 = rm.wc0;
 }
-template <bool COUNT>
+template <bool COUNT, bool ADD_EMISSION = true>
 PTB_DEV bool path_shade_rm(const DScene<float>& s, const SceneView<float>& sv, PathState<float>& p, V3<float> normal, const RMat& rm, const float* u,
                            PathCounters* pc) {
     ShadeSetup<float> su;
-    shade_setup_rm<COUNT>(p, normal, rm, su, pc);
+    shade_setup_rm<COUNT, ADD_EMISSION>(p, normal, rm, su, pc);
     NeeSample<float> ns;
     shade_nee_sample(s, sv, su, u, ns);
     bool nee = false;

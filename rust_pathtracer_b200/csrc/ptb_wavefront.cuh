@@ -5,27 +5,18 @@
 // Why shared memory: the demo scene costs ~1.4 kFLOP and ~2 bounces per sample.
 // A classic HBM wavefront streams ~1 KB of ray / path state per sample through the queues, which
 // caps it at ~6 Gsamples/s on a 6.5 TB/s part before any arithmetic is done (SURVEY.md §7 "the
-// roofline that actually binds").  One SM can hold 2048 paths x 96 B (or 2304 x 88 B) of state — 221 / 229 KB
+// roofline that actually binds").  One SM can hold 2048 paths x 96 B (or 2496 x 80 B) of state — 221 / 227 KB
 // with the queue arrays and the scene copy —, enough for every stage to run with full warps, so the state
 // never leaves the SM: HBM traffic stays at the 32 B per pixel of the accumulator read-modify-write.
 //
-// One CTA per SM (512 threads and 2048 slots; 768 threads and 2304 slots in the instantiation that shades from
-// the resolved-material table, RMat in ptb_device.cuh) owns the pool.  Each iteration runs two stages over it,
-// separated by CTA barriers, so that ALL warps of the SM execute the same stage code at the same time (small
-// instruction-cache footprint, the fused kernel's main stall):
-//
-//   stage 1  "generate + intersect"  — every slot: a finished slot regenerates in place (next
-//            sample of its pixel, or a new pixel handed out per warp with ballot/popc from a global
-//            tile counter), then camera-ray generation / closest_hit (+ spherical lights with the
-//            stale hit_dist quirk), MIS-weighted emission on a light hit.  Surviving paths enter the
-//            stage-2 queue: they take a ticket in the counter of their key — the LOBE CLASS of the
-//            hit material (which Disney lobes it can express) or WF_MISS (the path left the scene).
-//   sort     a counting sort by key turns the tickets into a compacted, key-ordered index list
-//            (the queue proper), most expensive classes first.
-//   stage 2  "shade" — warps take 32-entry chunks of the queue, so a warp shades paths of one lobe
-//            class: finalize, light sampling + any_hit shadow ray, Disney eval with MIS, Disney
-//            sample, throughput update, next ray (or termination); WF_MISS chunks do the background
-//            lookup with full warps.
+// One CTA per SM (512 threads and 2048 slots; 832 threads and 2496 slots in the instantiation that shades from
+// the resolved-material table, RMat in ptb_device.cuh) owns the pool and iterates over it; every iteration visits each
+// slot once (the kernel's comment below describes the visit: pending event, regeneration, closest_hit) and ends with
+// a counting sort of the slots by the key of what they hit — the LOBE CLASS of the material, WF_MISS, WF_REGEN — so
+// that the next iteration's warps take 32-slot chunks of ONE key.  All warps of the SM run the same code at the same
+// time, which is what keeps the instruction cache effective: a barrier-free variant with per-key rings
+// (ptb_wavefront_async.cuh, A/B only) removes the 8 % of warp cycles spent at the iteration barrier and loses 17 %
+// to instruction fetch (no_instruction 0.21 -> 2.6 stall cycles per issue; profiles/r02_ab_variants.txt).
 //
 // A slot owns one pixel for `spp` consecutive samples and sums them in sample order; the frame's last pixels (one
 // per slot) are cut into sample blocks that k_tail_combine adds in block order (see wavefront_render).  Either way
@@ -38,14 +29,17 @@
 namespace ptb {
 
 // threads per CTA (one CTA per SM).  The generic and BVH instantiations need ~125 registers in the shade stage: 512 threads.
-// With the resolved-material table the material is read from shared memory where it is used and the kernel fits 80
-// registers (8 bytes of spill), so 768 threads = 24 warps hide the stage's dependent-issue and barrier stalls better
-// (measured, 4K demo scene: 512 / 640 / 768 threads = 6067 / 6151 / 6451 Msamples/s; profiles/r01_ab_variants.txt).
+// With the resolved-material table the material is read from shared memory where it is used, and radiance / throughput /
+// sample bookkeeping stay in shared memory while a path is shaded, so the kernel fits 72 registers with 24 bytes of spill:
+// 832 threads = 26 warps.  Warps and pool go together: an iteration hands out pool / 32 chunks, and the last round of
+// chunks leaves warps idle unless that is a multiple of the warp count — 26 warps x 3 rounds = 78 chunks = 2496 slots is
+// what the 227 KB hold (measured at 4K, threads_pool: 512_2048 7622, 576_2304 8095, 640_2560 8454, 704_2112 8506,
+// 768_2304 8489, 832_2496 8693, 896_2304 8492, 896_1792 8243, 1024_2304 8314 Msamples/s; profiles/r02_ab_variants.txt).
 #ifndef PTB_WF_THREADS
 #define PTB_WF_THREADS 512
 #endif
 #ifndef PTB_WF_THREADS_RM
-#define PTB_WF_THREADS_RM 768
+#define PTB_WF_THREADS_RM 832
 #endif
 constexpr int WF_THREADS_GENERIC = PTB_WF_THREADS;
 constexpr int WF_THREADS_RM = PTB_WF_THREADS_RM;
@@ -58,10 +52,9 @@ constexpr uint32_t WF_SCENE_BYTES_RM = PTB_WF_SCENE_BYTES_RM;
 #define PTB_WF_POOL 2048
 #endif
 constexpr uint32_t WF_POOL_GENERIC = PTB_WF_POOL;       // path slots per CTA
-// resolved-material instantiation: 2304 slots = 3 x 768, every warp owns exactly three 32-slot groups in stage 1 (2048 slots
-// left a third of the warps idle for one group in three); the slot state is two words smaller there (see U_* below)
+// resolved-material instantiation: 2496 slots = 78 chunks = 3 rounds of 26 warps (see above)
 #ifndef PTB_WF_POOL_RM
-#define PTB_WF_POOL_RM 2304
+#define PTB_WF_POOL_RM 2496
 #endif
 constexpr uint32_t WF_POOL_RM = PTB_WF_POOL_RM;
 #ifndef PTB_WF_REGEN_DEN
@@ -94,6 +87,18 @@ template <uint32_t WF_POOL, uint32_t SCENE_BYTES, bool GENERIC> struct WfSmemT {
     uint32_t cnt[2][WF_NKEYS + 2];  // tickets handed out per key for the NEXT queue (double-buffered by iteration parity)
     uint32_t cursor[2];             // next 32-entry chunk of the current queue (double-buffered like cnt)
 };
+
+// shared-memory loads that stay where they are written (volatile: neither nvcc nor ptxas hoists them above the shading code)
+PTB_DEV float4 lds128_late(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+PTB_DEV uint32_t lds32_late(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
 
 // One stage per iteration.  Every slot that still has work is in the queue exactly once, ordered by key; warps take 32-entry
 // chunks and run, for their 32 slots,
@@ -180,24 +185,26 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             const uint32_t j = chunk * 32u + lane;
             const bool valid = j < n_queue;
             const uint32_t i = valid ? sm.order[j] : 0u;
-            // ---- load the slot ----
+            // ---- load what the pending event needs: the ray, the hit, the flags ----
+            // Radiance, throughput, pixel and sample index stay in shared memory while the event is evaluated: A works on a unit
+            // throughput and a zero radiance, and what it returns is applied to the slot's values afterwards — `rad + x * thr` and
+            // `thr * (f / pdf)` are the reference's operations on the reference's operands (tracer.rs:67, 89, 94), only the nine
+            // registers are not live across the shading code, which is where the kernel's register pressure peaks.
             PathState<R> p;
-            uint32_t fl = 0, sidx = 0, pxy = 0, prim_bits = PRIM_SKY;
+            uint32_t fl0 = 0, prim_bits = PRIM_SKY, pxy0 = 0;
             uint64_t accepted = 0;
-            p.o = V3<R>(0, 0, 0); p.d = V3<R>(0, 0, 1); p.thr = V3<R>(0, 0, 0); p.rad = V3<R>(0, 0, 0); p.hit_dist = R(-1); p.prev_pdf = 0; p.bounce = 0;
+            p.o = V3<R>(0, 0, 0); p.d = V3<R>(0, 0, 1); p.thr = V3<R>(1, 1, 1); p.rad = V3<R>(0, 0, 0); p.hit_dist = R(-1); p.prev_pdf = 0; p.bounce = 0;
             if (valid) {
-                const float4 q0 = sm.ro[i], q1 = sm.rd[i], q2 = sm.tr[i], q3 = sm.ra[i];
+                const float4 q0 = sm.ro[i], q1 = sm.rd[i];
                 p.o = V3<R>(q0.x, q0.y, q0.z); p.hit_dist = q0.w;
-                p.d = V3<R>(q1.x, q1.y, q1.z); pxy = __float_as_uint(q1.w);
-                p.thr = V3<R>(q2.x, q2.y, q2.z); fl = __float_as_uint(q2.w);
-                p.rad = V3<R>(q3.x, q3.y, q3.z); sidx = __float_as_uint(q3.w);
+                p.d = V3<R>(q1.x, q1.y, q1.z); pxy0 = __float_as_uint(q1.w);
+                fl0 = __float_as_uint(sm.tr[i].w);
                 prim_bits = __float_as_uint(sm.ac[i].w);
                 if constexpr (!RM) accepted = (uint64_t)sm.acc_lo[i] | ((uint64_t)sm.acc_hi[i] << 32);
             }
-            p.bounce = (fl >> 8) & 0xffffu;
-            bool alive = valid && (fl & FL_ALIVE);
-            bool have_pixel = fl & FL_PIXEL;
-            uint32_t pix = (pxy >> 16) * a.W + (pxy & 0xffffu);
+            p.bounce = (fl0 >> 8) & 0xffffu;
+            bool alive = valid && (fl0 & FL_ALIVE);
+            const bool had_event = alive;
 
             // ================================ A: the path's pending event ================================
             if (alive) {
@@ -206,30 +213,56 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                     if (COUNT) pc.end_sky++;
                     alive = false;
                 } else {
-                    Rng<R> rng(pix, a.sample_base + sidx, a.seed);
+                    Rng<R> rng((pxy0 >> 16) * a.W + (pxy0 & 0xffffu), a.sample_base + __float_as_uint(sm.ra[i].w), a.seed);
                     R u[8];
-                    bool cont;
                     if constexpr (RM) {
                         const int prim = (int)(prim_bits & 0xffffu);
                         const RMat& rm = rm_lookup(s, sv, rm_keys, rm_table, rm_key_of(s, sv, prim, prim_bits >> 16), p.d);
+                        if (s.has_emissive) {                           // tracer.rs:74, on the slot's own radiance and throughput
+                            const float4 t4 = sm.tr[i];
+                            float4 r4 = sm.ra[i];
+                            r4.x = r4.x + rm.m.emission.x * t4.x; r4.y = r4.y + rm.m.emission.y * t4.y; r4.z = r4.z + rm.m.emission.z * t4.z;
+                            sm.ra[i] = r4;
+                        }
                         shade_draws(rng, p.bounce, s.n_lights > 1u || (rm.lobe_class & 4u) != 0u, u);
                         const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-                        cont = path_shade_rm<COUNT>(s, sv, p, normal, rm, u, &pc);
+                        alive = path_shade_rm<COUNT, false>(s, sv, p, normal, rm, u, &pc);
                     } else {
                         const int prim = (int)prim_bits;
                         Mat<R> mat;
                         hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+                        if (s.has_emissive) {
+                            const float4 t4 = sm.tr[i];
+                            float4 r4 = sm.ra[i];
+                            r4.x = r4.x + mat.emission.x * t4.x; r4.y = r4.y + mat.emission.y * t4.y; r4.z = r4.z + mat.emission.z * t4.z;
+                            sm.ra[i] = r4;
+                        }
                         shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
                         const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-                        cont = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, &pc);
-                    }
-                    alive = cont;
-                    if (cont && a.rr_start != 0 && p.bounce >= a.rr_start) {      // Russian-roulette extension (A.12), slot 0 of the new bounce
-                        R u4[4];
-                        rng.block(p.bounce, 0, u4);
-                        if (!russian_roulette_survives(p, u4[0])) { alive = false; if (COUNT) pc.end_rr++; }
+                        alive = path_shade<R, COUNT, BVH, false>(s, sv, p, normal, mat, u, &pc);
                     }
                 }
+            }
+            // ---- the rest of the slot; apply what A returned ----
+            uint32_t fl = 0, sidx = 0, pxy = 0;
+            if (valid) {
+                const float4 q2 = lds128_late(&sm.tr[i]), q3 = lds128_late(&sm.ra[i]);
+                V3<R> thr(q2.x, q2.y, q2.z), rad(q3.x, q3.y, q3.z);
+                fl = __float_as_uint(q2.w); sidx = __float_as_uint(q3.w);
+                pxy = lds32_late(reinterpret_cast<const uint32_t*>(&sm.rd[i]) + 3);
+                if (had_event) {
+                    rad = rad + p.rad * thr;                            // background (tracer.rs:67) or next-event estimation (:89); p.rad is 0 without one
+                    thr = thr * p.thr;                                  // throughput * (f / pdf) (:94); unused when the path ended
+                }
+                p.thr = thr; p.rad = rad;
+            }
+            bool have_pixel = fl & FL_PIXEL;
+            uint32_t pix = (pxy >> 16) * a.W + (pxy & 0xffffu);
+            if (alive && a.rr_start != 0 && p.bounce >= a.rr_start) {         // Russian-roulette extension (A.12), slot 0 of the new bounce
+                Rng<R> rng(pix, a.sample_base + sidx, a.seed);
+                R u4[4];
+                rng.block(p.bounce, 0, u4);
+                if (!russian_roulette_survives(p, u4[0])) { alive = false; if (COUNT) pc.end_rr++; }
             }
 
             // ================================ B: finish dead paths, regenerate in place ================================
