@@ -689,3 +689,29 @@ def test_benchmarked_kernel_full_frame_parity(rp, scene, oracle_demo, wh_spp, st
     assert np.median(rel) < (1e-7 if strict else 1e-6)
     assert abs(lum(buf.pixels)[ok].mean() / lum(ref)[ok].mean() - 1) < 1e-5
     pt.close()
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_config4_full_scene_parity(rp, po, strict):
+    """BASELINE.json configs[3] at FULL scale — 100 000 spheres, 64 lights, sphere BVH + light BVH, the integrator AUTO picks for it
+    (streaming wavefront with the dedicated traversal kernels) — against the oracle's linear scan over all spheres, shared counter
+    RNG, 96x54 x 1 spp (the oracle's 2.5e9 sphere tests take ~15 s on 16 cores).  The strict build must put >= 99 % of the pixels
+    within 1e-4; the shipped build's outliers are paths through the field's glass / high-gloss clearcoat lobes
+    (conditioned to ~1e-4 in f32: profiles/r02_function_parity.md), bar 95 %, measured value printed."""
+    sc = rp.sphere_field_scene()
+    W, H, S = 96, 54, 1
+    pt = rp.Tracer.new(sc, strict=strict)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render_spp(buf, S)
+    used = pt.integrator_used()
+    pt.close()
+    assert used == "stream_split_bvh", used
+    ref, frames, secs, _ = po.OracleScene(sc.device_export()).render(W, H, S)
+    ok = np.isfinite(buf.pixels.reshape(-1, 4)).all(1) & np.isfinite(ref.reshape(-1, 4)).all(1)
+    rel = pix_rel(buf.pixels, ref)[ok]
+    frac = (rel < 1e-4).mean()
+    print(f"[config 4 parity] strict={strict}: within 1e-4: {frac:.5f}, bit-identical {(rel == 0).mean():.5f}, median {np.median(rel):.2e}, "
+          f"non-finite {(~ok).sum()}, oracle {secs:.1f} s")
+    assert (~ok).sum() <= 2
+    assert frac >= (0.99 if strict else 0.95), frac
+    assert abs(lum(buf.pixels)[ok].mean() / lum(ref)[ok].mean() - 1) < (1e-4 if strict else 2e-3)
