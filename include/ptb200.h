@@ -92,6 +92,22 @@ enum {
     PTB_SCENE_NO_BVH                  = 1u << 2
 };
 
+/* Signed-distance program (ptb_set_sdf_*): instructions in postfix order.  Primitives push (distance, material), combinators
+ * pop two entries (a below b) and push one.  No reference counterpart: the reference lists "Implement a SDF based example
+ * scene" as open (Readme.md:18) — this is the device form of such a Scene impl, evaluated identically by the oracle. */
+enum {
+    PTB_SDF_SPHERE = 0,       /* |q - p| - a[0]                                                      */
+    PTB_SDF_BOX = 1,          /* box at p, half extents a[0..2], corner radius a[3]                  */
+    PTB_SDF_TORUS = 2,        /* ring of radius a[0] in the xz plane through p, tube radius a[1]     */
+    PTB_SDF_PLANE = 3,        /* dot(q, a[0..2]) + a[3] (unit normal, offset); p unused              */
+    PTB_SDF_UNION = 16,       /* min(a, b), material of the nearer                                   */
+    PTB_SDF_SMOOTH_UNION = 17,/* polynomial smooth minimum with blend radius a[0]                    */
+    PTB_SDF_SUBTRACT = 18,    /* max(a, -b), material of a                                           */
+    PTB_SDF_INTERSECT = 19    /* max(a, b), material of the farther                                  */
+};
+#define PTB_SDF_MAX_NODES 16
+#define PTB_SDF_MAX_STACK 8
+
 /* Integrator selection (ptb_config.integrator). */
 enum {
     PTB_INTEGRATOR_AUTO      = 0, /* wavefront for f32 scenes, fused for f64                        */
@@ -151,6 +167,20 @@ enum {
         REAL scale;                                                                               \
         REAL gamma;                                                                               \
     } ptb_background_##SFX;                                                                       \
+    typedef struct ptb_sdf_node_##SFX {                                                           \
+        uint32_t op;                     /* PTB_SDF_*                                         */  \
+        uint32_t material;               /* primitives: index into the scene's materials      */  \
+        REAL p[3];                       /* primitives: position                              */  \
+        REAL a[4];                       /* parameters, see PTB_SDF_*                         */  \
+    } ptb_sdf_node_##SFX;                                                                         \
+    typedef struct ptb_sdf_##SFX {                                                                \
+        uint32_t n_nodes;                /* <= PTB_SDF_MAX_NODES; 0 removes the program       */  \
+        const ptb_sdf_node_##SFX* nodes;                                                          \
+        REAL hit_eps;                    /* |distance| below which the surface counts as hit  */  \
+        REAL max_dist;                   /* tracing gives up beyond this distance             */  \
+        REAL normal_h;                   /* offset of the four gradient samples               */  \
+        uint32_t max_steps;                                                                       \
+    } ptb_sdf_##SFX;                                                                              \
     /* What the new `Scene::device_export()` trait method returns. */             \
     typedef struct ptb_scene_##SFX {                                                              \
         uint32_t n_spheres, n_planes, n_materials, n_lights;                                      \
@@ -210,6 +240,12 @@ int  ptb_set_stream(ptb_tracer* t, void* cuda_stream);
 /* ---- scene: replaces the dyn Scene callbacks (scene.rs:5-90) with exported data ------------ */
 int  ptb_set_scene_f32(ptb_tracer* t, const ptb_scene_f32* scene);
 int  ptb_set_scene_f64(ptb_tracer* t, const ptb_scene_f64* scene);
+
+/* Attach a signed-distance program to the scene set last (copied; NULL or n_nodes == 0 removes it; ptb_set_scene_* removes it
+ * too).  The body is tested after the planes in Scene::closest_hit order and by any_hit.  Requires materials that assign every
+ * field (set_mask == PTB_MAT_ALL).  Scenes with a program shade through the generic path (no resolved-material table). */
+int  ptb_set_sdf_f32(ptb_tracer* t, const ptb_sdf_f32* sdf);
+int  ptb_set_sdf_f64(ptb_tracer* t, const ptb_sdf_f64* sdf);
 
 /* ---- ColorBuffer on the device (buffer.rs:6-26) -------------------------------------------- */
 /* (Re)allocate the accumulators for a w x h frame and clear them (ColorBuffer::new). */
@@ -344,6 +380,11 @@ int  ptb_test_closest_hit_f32(ptb_tracer* t, size_t n, const float* origin3, con
 /* Scene::any_hit of the exported scene (analytical.rs:130-145) */
 int  ptb_test_any_hit_f32(ptb_tracer* t, size_t n, const float* origin3, const float* dir3,
                           const float* max_dist, uint32_t* hit_out);
+/* the signed-distance program of ptb_set_sdf_f32: value and material at n points; sphere trace (t < 0 encodes a miss), gradient
+ * normal at the hit and material along n rays */
+int  ptb_test_sdf_eval_f32(ptb_tracer* t, size_t n, const float* point3, float* dist_out, uint32_t* material_out);
+int  ptb_test_sdf_trace_f32(ptb_tracer* t, size_t n, const float* origin3, const float* dir3, const float* limit,
+                            float* t_out, float* normal3_out, uint32_t* material_out);
 /* Scene::background (analytical.rs:28-32) */
 int  ptb_test_background_f32(ptb_tracer* t, size_t n, const float* dir3, float* rgb3_out);
 /* Tracer::sample_light, tracer.rs:173-220, light `light_index` of the scene, draws (r1, r2) */

@@ -233,6 +233,20 @@ void t_trace_samples(const SceneBox<R>* sb, uint32_t w, uint32_t h, size_t n, co
     }
 }
 
+// signed-distance program: evaluation and tracing on their own (per-function parity of the extension)
+template <class R> void t_sdf_eval(const SceneBox<R>* sb, size_t n, const R* q, R* dist_out, uint32_t* mat_out) {
+    for (size_t i = 0; i < n; ++i) sb->flat->sdf.eval(ld3(q, n, i), dist_out[i], mat_out[i]);
+}
+template <class R> void t_sdf_trace(const SceneBox<R>* sb, size_t n, const R* o, const R* d, const R* limit, R* t_out, R* normal_out, uint32_t* mat_out) {
+    for (size_t i = 0; i < n; ++i) {
+        Ray<R> ray(ld3(o, n, i), ld3(d, n, i));
+        uint32_t m = 0xffffffffu;
+        const R t = sb->flat->sdf.trace(ray, limit[i], m);
+        t_out[i] = t; mat_out[i] = m;
+        st3(normal_out, n, i, t >= R(0) ? sb->flat->sdf.normal(ray.at(t)) : V3<R>(0, 0, 0));
+    }
+}
+
 // One sample of pixel (px, row) of a w x h frame traced on a recorded draw sequence (SeqRng); returns the draws consumed,
 // or -1 if the sequence was too short.
 template <class R>
@@ -279,6 +293,16 @@ size_t pto_counters_size(void) { return sizeof(Counters); }
         return sb;                                                                                                      \
     }                                                                                                                   \
     void pto_scene_destroy_##SFX(void* sb) { delete static_cast<SceneBox<R>*>(sb); }                                    \
+    int pto_scene_set_sdf_##SFX(void* sb, const ptb_sdf_##SFX* sdf) {                                                   \
+        auto* b = static_cast<SceneBox<R>*>(sb);                                                                        \
+        if (!b->flat) return -1;                                                                                        \
+        b->flat->set_sdf(sdf);                                                                                          \
+        return 0;                                                                                                       \
+    }                                                                                                                   \
+    void pto_sdf_eval_##SFX(void* sb, size_t n, const R* q, R* dist, uint32_t* mat) { t_sdf_eval<R>(static_cast<SceneBox<R>*>(sb), n, q, dist, mat); } \
+    void pto_sdf_trace_##SFX(void* sb, size_t n, const R* o, const R* d, const R* limit, R* t, R* nrm, uint32_t* mat) { \
+        t_sdf_trace<R>(static_cast<SceneBox<R>*>(sb), n, o, d, limit, t, nrm, mat);                                     \
+    }                                                                                                                   \
     void pto_sphere_hit_##SFX(size_t n, const R* o, const R* d, const R* c, const R* r, R* t) { t_sphere_hit<R>(n, o, d, c, r, t); } \
     void pto_plane_hit_##SFX(size_t n, const R* o, const R* d, const R* p, const R* nn, R* t) { t_plane_hit<R>(n, o, d, p, nn, t); } \
     void pto_gen_ray_##SFX(void* sb, size_t n, const R* p2, const R* off2, R w, R h, R* o, R* d) {                      \

@@ -431,11 +431,81 @@ template <class R> struct AnalyticalSceneLiteral : Scene<R> {
 template <class R> struct FlatTypes;
 template <> struct FlatTypes<float> {
     using scene = ptb_scene_f32; using material = ptb_material_f32; using sphere = ptb_sphere_f32;
-    using plane = ptb_plane_f32; using light = ptb_light_f32;
+    using plane = ptb_plane_f32; using light = ptb_light_f32; using sdf = ptb_sdf_f32; using sdf_node = ptb_sdf_node_f32;
 };
 template <> struct FlatTypes<double> {
     using scene = ptb_scene_f64; using material = ptb_material_f64; using sphere = ptb_sphere_f64;
-    using plane = ptb_plane_f64; using light = ptb_light_f64;
+    using plane = ptb_plane_f64; using light = ptb_light_f64; using sdf = ptb_sdf_f64; using sdf_node = ptb_sdf_node_f64;
+};
+
+// Signed-distance program (include/ptb200.h, PTB_SDF_*).  The reference has no SDF scene (Readme.md:18 lists one as open), so
+// this is not a restatement of reference code: it is the CPU statement of the extension the library defines, written once
+// here in plain C++ and checked against the device evaluator operation for operation (tests/test_gpu_sdf.py).
+template <class R> struct SdfProgram {
+    std::vector<typename FlatTypes<R>::sdf_node> nodes;
+    R hit_eps = 0, max_dist = 0, normal_h = 0;
+    uint32_t max_steps = 0;
+    bool empty() const { return nodes.empty(); }
+    static R len2(R x, R y) { return std::sqrt(x * x + y * y); }
+    static R len3(R x, R y, R z) { return std::sqrt(x * x + y * y + z * z); }
+    static R maxr(R a, R b) { return std::fmax(a, b); }
+    static R minr(R a, R b) { return a < b ? a : b; }
+    // (distance, material) at q
+    void eval(const V3<R>& q, R& dist, uint32_t& material) const {
+        R sd[PTB_SDF_MAX_STACK]; uint32_t sm[PTB_SDF_MAX_STACK];
+        int sp = 0;
+        for (const auto& n : nodes) {
+            const R x = q.x - n.p[0], y = q.y - n.p[1], z = q.z - n.p[2];
+            R d; uint32_t m = n.material;
+            switch (n.op) {
+                case PTB_SDF_SPHERE: d = len3(x, y, z) - n.a[0]; break;
+                case PTB_SDF_BOX: {
+                    const R dx = std::fabs(x) - n.a[0], dy = std::fabs(y) - n.a[1], dz = std::fabs(z) - n.a[2];
+                    const R outside = len3(maxr(dx, R(0)), maxr(dy, R(0)), maxr(dz, R(0)));
+                    d = outside + minr(maxr(dx, maxr(dy, dz)), R(0)) - n.a[3];
+                    break;
+                }
+                case PTB_SDF_TORUS: d = len2(len2(x, z) - n.a[0], y) - n.a[1]; break;
+                case PTB_SDF_PLANE: d = q.x * n.a[0] + q.y * n.a[1] + q.z * n.a[2] + n.a[3]; break;
+                default: {
+                    --sp; const R bd = sd[sp]; const uint32_t bm = sm[sp];
+                    --sp; const R ad = sd[sp]; const uint32_t am = sm[sp];
+                    if (n.op == PTB_SDF_UNION) { if (bd < ad) { d = bd; m = bm; } else { d = ad; m = am; } }
+                    else if (n.op == PTB_SDF_INTERSECT) { if (bd > ad) { d = bd; m = bm; } else { d = ad; m = am; } }
+                    else if (n.op == PTB_SDF_SUBTRACT) { d = maxr(ad, -bd); m = am; }
+                    else {
+                        R h = R(0.5) + R(0.5) * ((bd - ad) / n.a[0]);
+                        h = h < R(0) ? R(0) : (h > R(1) ? R(1) : h);
+                        d = ((R(1) - h) * bd + ad * h) - n.a[0] * h * (R(1) - h);
+                        m = h >= R(0.5) ? am : bm;
+                    }
+                }
+            }
+            sd[sp] = d; sm[sp] = m; ++sp;
+        }
+        dist = sd[0]; material = sm[0];
+    }
+    // sphere tracing from t = 0; returns t >= 0 or -1
+    R trace(const Ray<R>& ray, R limit, uint32_t& material) const {
+        const R t_end = minr(limit, max_dist);
+        R t = 0;
+        for (uint32_t i = 0; i < max_steps; ++i) {
+            R d; uint32_t m;
+            eval(V3<R>(ray.origin.x + t * ray.direction.x, ray.origin.y + t * ray.direction.y, ray.origin.z + t * ray.direction.z), d, m);
+            const R a = std::fabs(d);
+            if (a < hit_eps) { material = m; return t; }
+            t = t + a;
+            if (!(t < t_end)) break;
+        }
+        return R(-1);
+    }
+    V3<R> normal(const V3<R>& q) const {
+        const R h = normal_h;
+        R d0, d1, d2, d3; uint32_t m;
+        eval(V3<R>(q.x + h, q.y - h, q.z - h), d0, m); eval(V3<R>(q.x - h, q.y - h, q.z + h), d1, m);
+        eval(V3<R>(q.x - h, q.y + h, q.z - h), d2, m); eval(V3<R>(q.x + h, q.y + h, q.z + h), d3, m);
+        return normalize(V3<R>(((d0 - d1) - d2) + d3, ((d2 + d3) - d0) - d1, ((d1 + d3) - d0) - d2));
+    }
 };
 
 template <class R> struct FlatScene : Scene<R> {
@@ -450,6 +520,14 @@ template <class R> struct FlatScene : Scene<R> {
     uint16_t depth = 4;
     uint32_t flags = 0;
     R eps = R(0.005);
+    SdfProgram<R> sdf;               // optional signed-distance body, tested after the planes (ptb_set_sdf_*)
+
+    void set_sdf(const typename T::sdf* p) {
+        sdf = SdfProgram<R>();
+        if (!p || p->n_nodes == 0) return;
+        sdf.nodes.assign(p->nodes, p->nodes + p->n_nodes);
+        sdf.hit_eps = p->hit_eps; sdf.max_dist = p->max_dist; sdf.normal_h = p->normal_h; sdf.max_steps = p->max_steps;
+    }
 
     explicit FlatScene(const typename T::scene& s) {
         spheres.assign(s.spheres, s.spheres + s.n_spheres);
@@ -546,10 +624,25 @@ template <class R> struct FlatScene : Scene<R> {
                 }
             }
         }
+        if (!sdf.empty()) {
+            uint32_t mi = 0;
+            const R d = sdf.trace(ray, dist, mi);
+            if (d >= R(0) && d < dist) {
+                state.hit_dist = d;
+                state.normal = sdf.normal(ray.at(d));
+                apply_material(state, mi, ray);
+                hit = true;
+                dist = d;
+            }
+        }
         if (this->sample_lights(ray, state, light_sample, lights)) hit = true;
         return hit;
     }
     bool any_hit(const Ray<R>& ray, R max_dist) const override {
+        if (!sdf.empty()) {
+            uint32_t mi;
+            if (sdf.trace(ray, max_dist, mi) >= R(0)) return true;
+        }
         const bool ignore = (flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
         R d;
         for (const auto& s : spheres)

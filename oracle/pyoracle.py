@@ -80,6 +80,10 @@ class OracleScene:
             sc, keep = export.to_c(precision)
             self._keep = (sc, keep)
             self.h = C.c_void_p(getattr(self.lib, f"pto_scene_flat_{precision}")(C.byref(sc)))
+            if getattr(export, "sdf", None) is not None and export.sdf.nodes:
+                sd, sd_keep = export.sdf.to_c(precision)
+                self._keep = (sc, keep, sd, sd_keep)
+                assert getattr(self.lib, f"pto_scene_set_sdf_{precision}")(self.h, C.byref(sd)) == 0
 
     def close(self):
         if self.h:
@@ -195,6 +199,20 @@ class OracleScene:
         self._fn("trace_samples")(self.h, C.c_uint32(w), C.c_uint32(h), C.c_size_t(n), _p(px), _p(row), _p(sample), C.c_uint64(seed), _p(rgb))
         return rgb
 
+
+    def sdf_eval(self, q):
+        q = self._a(q)
+        n = q.shape[1]
+        dist, mat = np.empty(n, self.np), np.empty(n, np.uint32)
+        self._fn("sdf_eval")(self.h, C.c_size_t(n), _p(q), _p(dist), _p(mat))
+        return dist, mat
+
+    def sdf_trace(self, o, d, limit):
+        o, d, limit = self._a(o), self._a(d), self._a(limit)
+        n = o.shape[1]
+        t, nrm, mat = np.empty(n, self.np), np.empty((3, n), self.np), np.empty(n, np.uint32)
+        self._fn("sdf_trace")(self.h, C.c_size_t(n), _p(o), _p(d), _p(limit), _p(t), _p(nrm), _p(mat))
+        return dict(t=t, normal=nrm, material=mat)
 
     def trace_scripted(self, w, h, px, row, draws):
         """radiance of ONE sample of pixel (px, row) traced on a recorded draw sequence (call order, tools/ref_kat);

@@ -7,9 +7,10 @@ a `Tracer` does not.
 """
 from . import _abi
 from .prelude import (F, I, F3, AnalyticalLight, Background, Camera3D, ColorBuffer, DeviceScene, Light, Material, Pinhole, Plane,
-                      Scene, Sphere, Tracer)
-from .scenes import AnalyticalScene, ExportedScene, divergence_stress_scene, sphere_field_scene
+                      Scene, SdfNode, SdfProgram, Sphere, Tracer)
+from .scenes import AnalyticalScene, ExportedScene, divergence_stress_scene, sdf_demo_scene, sphere_field_scene
 
 __all__ = ["F", "I", "F3", "AnalyticalLight", "Background", "Camera3D", "ColorBuffer", "DeviceScene", "Light", "Material", "Pinhole",
-           "Plane", "Scene", "Sphere", "Tracer", "AnalyticalScene", "ExportedScene", "divergence_stress_scene", "sphere_field_scene",
+           "Plane", "Scene", "SdfNode", "SdfProgram", "Sphere", "Tracer", "AnalyticalScene", "ExportedScene", "divergence_stress_scene", "sdf_demo_scene",
+           "sphere_field_scene",
            "_abi"]

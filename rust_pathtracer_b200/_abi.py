@@ -20,6 +20,9 @@ PTB_SCENE_ANYHIT_IGNORES_MAX_DIST, PTB_SCENE_FORCE_BVH, PTB_SCENE_NO_BVH = 1, 2,
 PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT, PTB_INTEGRATOR_STREAM = 0, 1, 2, 3
 PTB_PEER_HANDLE_BYTES = 64
 PTB_FRAME_HOST_UNCHANGED = 1
+PTB_SDF_SPHERE, PTB_SDF_BOX, PTB_SDF_TORUS, PTB_SDF_PLANE = 0, 1, 2, 3
+PTB_SDF_UNION, PTB_SDF_SMOOTH_UNION, PTB_SDF_SUBTRACT, PTB_SDF_INTERSECT = 16, 17, 18, 19
+PTB_SDF_MAX_NODES, PTB_SDF_MAX_STACK = 16, 8
 PTB_KERNEL_BVH, PTB_KERNEL_RM_TABLE, PTB_KERNEL_SPLIT, PTB_KERNEL_F64 = 1, 2, 4, 8
 
 PTB_MAT_RGB, PTB_MAT_EMISSION, PTB_MAT_ANISOTROPIC, PTB_MAT_METALLIC = 1 << 0, 1 << 1, 1 << 2, 1 << 3
@@ -59,7 +62,15 @@ def _declare(real):
                     ("camera", Camera), ("background", Background),
                     ("depth", C.c_uint32), ("flags", C.c_uint32), ("eps", real)]
 
-    return dict(Material=Material, Sphere=Sphere, Plane=Plane, Light=Light, Camera=Camera, Background=Background, Scene=Scene)
+    class SdfNode(C.Structure):
+        _fields_ = [("op", C.c_uint32), ("material", C.c_uint32), ("p", real * 3), ("a", real * 4)]
+
+    class Sdf(C.Structure):
+        _fields_ = [("n_nodes", C.c_uint32), ("nodes", C.POINTER(SdfNode)), ("hit_eps", real), ("max_dist", real), ("normal_h", real),
+                    ("max_steps", C.c_uint32)]
+
+    return dict(Material=Material, Sphere=Sphere, Plane=Plane, Light=Light, Camera=Camera, Background=Background, Scene=Scene,
+                SdfNode=SdfNode, Sdf=Sdf)
 
 
 TYPES = {"f32": _declare(C.c_float), "f64": _declare(C.c_double)}
@@ -85,7 +96,7 @@ class Counters(C.Structure):
 # every symbol include/ptb200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     "ptb_create", "ptb_destroy", "ptb_abi_version", "ptb_last_error", "ptb_device_count", "ptb_set_stream",
-    "ptb_set_scene_f32", "ptb_set_scene_f64", "ptb_resize", "ptb_bind_accumulator", "ptb_clear",
+    "ptb_set_scene_f32", "ptb_set_scene_f64", "ptb_set_sdf_f32", "ptb_set_sdf_f64", "ptb_resize", "ptb_bind_accumulator", "ptb_clear",
     "ptb_upload_f32", "ptb_upload_f64", "ptb_download_f32", "ptb_download_f64", "ptb_frames",
     "ptb_render", "ptb_render_frame_f32", "ptb_render_frame_f64", "ptb_render_frame_ex_f32", "ptb_render_frame_ex_f64", "ptb_synchronize",
     "ptb_download_async_f32", "ptb_download_async_f64", "ptb_wait_download", "ptb_pin_host", "ptb_unpin_host",
@@ -94,7 +105,7 @@ SYMBOLS = [
     "ptb_convert_pixels_to_u8_at_f32", "ptb_convert_pixels_to_u8_at_f64", "ptb_get_counters", "ptb_reset_counters", "ptb_launch_count",
     "ptb_last_render_ms", "ptb_last_integrator",
     "ptb_test_sphere_hit_f32", "ptb_test_plane_hit_f32", "ptb_test_gen_ray_f32", "ptb_test_closest_hit_f32",
-    "ptb_test_any_hit_f32", "ptb_test_background_f32", "ptb_test_sample_light_f32", "ptb_test_finalize_f32",
+    "ptb_test_any_hit_f32", "ptb_test_sdf_eval_f32", "ptb_test_sdf_trace_f32", "ptb_test_background_f32", "ptb_test_sample_light_f32", "ptb_test_finalize_f32",
     "ptb_test_disney_eval_f32", "ptb_test_disney_sample_f32", "ptb_test_rng_f32", "ptb_test_resolved_material_f32", "ptb_test_film_quotients_f32", "ptb_test_bvh_build_f32",
 ]
 PTB_RMAT_FLOATS = 35
@@ -187,6 +198,10 @@ def load(strict: bool = None):
     lib.ptb_test_gen_ray_f32.argtypes = [vp, C.c_size_t, vp, vp, C.c_float, C.c_float, vp, vp]
     lib.ptb_test_closest_hit_f32.argtypes = [vp, C.c_size_t] + [vp] * 10
     lib.ptb_test_any_hit_f32.argtypes = [vp, C.c_size_t] + [vp] * 4
+    lib.ptb_test_sdf_eval_f32.argtypes = [vp, C.c_size_t] + [vp] * 3
+    lib.ptb_test_sdf_trace_f32.argtypes = [vp, C.c_size_t] + [vp] * 6
+    lib.ptb_set_sdf_f32.argtypes = [vp, vp]
+    lib.ptb_set_sdf_f64.argtypes = [vp, vp]
     lib.ptb_test_background_f32.argtypes = [vp, C.c_size_t, vp, vp]
     lib.ptb_test_sample_light_f32.argtypes = [vp, C.c_size_t, C.c_uint32] + [vp] * 8
     lib.ptb_test_finalize_f32.argtypes = [vp, C.c_size_t, C.c_uint32] + [vp] * 11

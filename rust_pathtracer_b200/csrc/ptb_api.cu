@@ -53,6 +53,7 @@ template <class R> struct SceneBuffers {
     size_t cap_lbvh = 0, cap_lprim = 0, cap_lspheres = 0;
     size_t cap_blob = 0, cap_bvh = 0, cap_prim = 0, cap_spheres = 0;   // allocations are reused across set_scene calls:
     size_t bytes = 0;                                                  // cudaFree would synchronise the whole device
+    uint32_t rm_entries_built = 0;                                     // resolved-material entries in the blob (d.rm_entries is 0 while a signed-distance program is attached)
     void release() {
         for (void** p : {&blob, &bvh, &bvh_prim, &bvh_spheres, &lbvh, &lbvh_prim, &lbvh_spheres}) {
             if (*p) cudaFree(*p);
@@ -291,8 +292,8 @@ constexpr uint32_t RM_MAX_PATCH_PRIMS = 6;      // partial-mask scenes: one key 
 // ------------------------------------------------------------------------------------------------
 // scene upload
 template <class R> struct PodTypes;
-template <> struct PodTypes<float> { using scene = ptb_scene_f32; using material = ptb_material_f32; };
-template <> struct PodTypes<double> { using scene = ptb_scene_f64; using material = ptb_material_f64; };
+template <> struct PodTypes<float> { using scene = ptb_scene_f32; using material = ptb_material_f32; using sdf = ptb_sdf_f32; };
+template <> struct PodTypes<double> { using scene = ptb_scene_f64; using material = ptb_material_f64; using sdf = ptb_sdf_f64; };
 
 template <class T> static cudaError_t upload_vec(void** dst, size_t& cap, const std::vector<T>& v, cudaStream_t st, size_t& bytes) {
     size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
@@ -456,6 +457,8 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     blob.resize((blob.size() + 31) & ~size_t(31));
     // resolved-material table: small f32 scenes whose whole blob (table included) fits the shared-memory scene copy
     d.off_rm_keys = d.off_rm_table = d.rm_entries = 0;
+    d.n_sdf = 0;                                    // a new scene drops the signed-distance program (ptb_set_sdf_*)
+    sb.rm_entries_built = 0;
     if constexpr (std::is_same<R, float>::value) {
         const uint32_t n_prims = sc->n_spheres + sc->n_planes;
         const char* off_env = getenv("PTB200_NO_RESOLVED_MATERIALS");     // A/B switch for profiling the generic shade path
@@ -485,6 +488,7 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
                 d.off_rm_keys = append(keys.data(), keys.size() * sizeof(uint32_t));
                 d.off_rm_table = append(table.data(), table.size() * sizeof(RMat));
                 d.rm_entries = (uint32_t)table.size();
+                sb.rm_entries_built = d.rm_entries;
                 blob.resize((blob.size() + 31) & ~size_t(31));
             }
         }
@@ -691,6 +695,57 @@ int ptb_set_scene_f64(ptb_tracer* t, const ptb_scene_f64* sc) {
     c.fov = sc->camera.fov;
     refresh_camera(t);
     return PTB_OK;
+}
+
+}  // extern "C"
+// Signed-distance program: validated (postfix stack discipline, material indices, parameters) and copied into the scene
+// descriptor the kernels receive as their parameter.
+template <class R> static int set_sdf_impl(ptb_tracer* t, SceneBuffers<R>& sb, const typename PodTypes<R>::sdf* sdf) {
+    DScene<R>& d = sb.d;
+    if (!sdf || sdf->n_nodes == 0) { d.n_sdf = 0; d.rm_entries = sb.rm_entries_built; return PTB_OK; }
+    if (!sdf->nodes) return fail(PTB_E_INVALID, "sdf: nodes is NULL");
+    if (sdf->n_nodes > PTB_SDF_MAX_NODES) return fail(PTB_E_INVALID, "sdf: %u nodes, at most %d", sdf->n_nodes, PTB_SDF_MAX_NODES);
+    if (d.patch_materials) return fail(PTB_E_UNSUPPORTED, "sdf: scenes with a signed-distance program need PTB_MAT_ALL on every material");
+    if (!(sdf->hit_eps > R(0)) || !(sdf->max_dist > R(0)) || !(sdf->normal_h > R(0)) || sdf->max_steps == 0)
+        return fail(PTB_E_INVALID, "sdf: hit_eps, max_dist, normal_h and max_steps must be positive");
+    int depth = 0;
+    for (uint32_t i = 0; i < sdf->n_nodes; ++i) {
+        const auto& n = sdf->nodes[i];
+        if (n.op <= PTB_SDF_PLANE) {
+            if (n.material >= d.n_materials) return fail(PTB_E_INVALID, "sdf node %u: material index out of range", i);
+            if (++depth > PTB_SDF_MAX_STACK) return fail(PTB_E_INVALID, "sdf node %u: the program needs more than %d stack entries", i, PTB_SDF_MAX_STACK);
+        } else if (n.op >= PTB_SDF_UNION && n.op <= PTB_SDF_INTERSECT) {
+            if (depth < 2) return fail(PTB_E_INVALID, "sdf node %u: combinator with fewer than two operands on the stack", i);
+            if (n.op == PTB_SDF_SMOOTH_UNION && !(n.a[0] > R(0))) return fail(PTB_E_INVALID, "sdf node %u: smooth union needs a positive blend radius", i);
+            --depth;
+        } else {
+            return fail(PTB_E_INVALID, "sdf node %u: unknown op %u", i, n.op);
+        }
+    }
+    if (depth != 1) return fail(PTB_E_INVALID, "sdf: the program leaves %d values on the stack, expected 1", depth);
+    for (uint32_t i = 0; i < sdf->n_nodes; ++i) {
+        const auto& n = sdf->nodes[i];
+        DSdfNode<R>& o = d.sdf[i];
+        o.op = n.op; o.material = n.material;
+        for (int k = 0; k < 3; ++k) o.p[k] = n.p[k];
+        for (int k = 0; k < 4; ++k) o.a[k] = n.a[k];
+    }
+    d.n_sdf = sdf->n_nodes; d.sdf_max_steps = sdf->max_steps;
+    d.sdf_hit_eps = sdf->hit_eps; d.sdf_max_dist = sdf->max_dist; d.sdf_normal_h = sdf->normal_h;
+    d.rm_entries = 0;            // the material at a hit on the body comes from the program: generic shade path
+    (void)t;
+    return PTB_OK;
+}
+extern "C" {
+int ptb_set_sdf_f32(ptb_tracer* t, const ptb_sdf_f32* sdf) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    if (t->precision != 4) return fail(t->precision ? PTB_E_PRECISION : PTB_E_NO_SCENE, "ptb_set_sdf_f32 needs an f32 scene (ptb_set_scene_f32 first)");
+    return set_sdf_impl<float>(t, t->s32, sdf);
+}
+int ptb_set_sdf_f64(ptb_tracer* t, const ptb_sdf_f64* sdf) {
+    if (!t) return fail(PTB_E_INVALID, "null tracer");
+    if (t->precision != 8) return fail(t->precision ? PTB_E_PRECISION : PTB_E_NO_SCENE, "ptb_set_sdf_f64 needs an f64 scene (ptb_set_scene_f64 first)");
+    return set_sdf_impl<double>(t, t->s64, sdf);
 }
 
 static int need_scene(ptb_tracer* t, int precision) {
@@ -914,7 +969,11 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
         else integ = (t->s32.d.use_bvh && t->s32.d.n_spheres >= 4096u) ? PTB_INTEGRATOR_STREAM : PTB_INTEGRATOR_WAVEFRONT;
         // the wavefront slots pack (column, row) into 16 bits each: wider or taller frames go to the fused integrator
         if (integ == PTB_INTEGRATOR_WAVEFRONT && (t->W > 65535u || t->H > 65535u)) integ = PTB_INTEGRATOR_FUSED;
+        // signed-distance programs are compiled into the fused kernels and the generic (non-BVH) shared-memory wavefront kernel only
+        if (t->precision == 4 && t->s32.d.n_sdf && (integ == PTB_INTEGRATOR_STREAM || t->s32.d.use_bvh)) integ = PTB_INTEGRATOR_FUSED;
     }
+    if (t->precision == 4 && t->s32.d.n_sdf && (integ == PTB_INTEGRATOR_STREAM || (integ == PTB_INTEGRATOR_WAVEFRONT && t->s32.d.use_bvh)))
+        return fail(PTB_E_UNSUPPORTED, "scenes with a signed-distance program run on the fused integrator or, without a sphere BVH, on the shared-memory wavefront");
     if (integ == PTB_INTEGRATOR_WAVEFRONT) {
         if (t->precision != 4) return fail(PTB_E_UNSUPPORTED, "the wavefront integrator is built for f32 only");
         if (t->W > 65535u || t->H > 65535u)
@@ -1314,6 +1373,26 @@ int ptb_test_any_hit_f32(ptb_tracer* t, size_t n, const float* o, const float* d
     auto* qh = dv.out<uint32_t>(n);
     k_test_any_hit<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, po, pd, pm, qh);
     dv.back(hit, qh, n);
+    TEST_END()
+}
+int ptb_test_sdf_eval_f32(ptb_tracer* t, size_t n, const float* q, float* dist, uint32_t* mat) {
+    TEST_BEGIN(true)
+    if (!t->s32.d.n_sdf) return fail(PTB_E_INVALID, "no signed-distance program set (ptb_set_sdf_f32)");
+    auto* pq = dv.in(q, 3 * n);
+    auto* qd = dv.out<float>(n);
+    auto* qm = dv.out<uint32_t>(n);
+    k_test_sdf_eval<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, pq, qd, qm);
+    dv.back(dist, qd, n); dv.back(mat, qm, n);
+    TEST_END()
+}
+int ptb_test_sdf_trace_f32(ptb_tracer* t, size_t n, const float* o, const float* d, const float* limit, float* t_out, float* nrm, uint32_t* mat) {
+    TEST_BEGIN(true)
+    if (!t->s32.d.n_sdf) return fail(PTB_E_INVALID, "no signed-distance program set (ptb_set_sdf_f32)");
+    auto *po = dv.in(o, 3 * n), *pd = dv.in(d, 3 * n), *pl = dv.in(limit, n);
+    auto *qt = dv.out<float>(n), *qn = dv.out<float>(3 * n);
+    auto* qm = dv.out<uint32_t>(n);
+    k_test_sdf_trace<float><<<grid_for(n), 128, 0, t->stream>>>(t->s32.d, n, po, pd, pl, qt, qn, qm);
+    dv.back(t_out, qt, n); dv.back(nrm, qn, 3 * n); dv.back(mat, qm, n);
     TEST_END()
 }
 int ptb_test_background_f32(ptb_tracer* t, size_t n, const float* d, float* rgb) {

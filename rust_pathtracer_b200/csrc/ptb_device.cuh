@@ -250,6 +250,10 @@ template <class R> struct alignas(4 * sizeof(R)) DSphere { R cx, cy, cz, r; };  
 template <class R> struct DPlane { R px, py, pz, nx, ny, nz; };
 template <class R> struct DLight { R px, py, pz, radius, ex, ey, ez, area; uint32_t type, pad[3]; };
 
+// One instruction of the signed-distance program, in postfix order (ptb_sdf_node_*, include/ptb200.h): primitives push
+// (distance, material), combinators pop two entries and push one.
+template <class R> struct DSdfNode { uint32_t op, material; R p[3]; R a[4]; };
+
 // 32-byte BVH node over spheres (f32 bounds even for the f64 build; bounds are conservative).
 struct alignas(32) BvhNode {
     float lo[3]; uint32_t left_or_first;   // inner: left child index (right = left + 1); leaf: first prim
@@ -285,6 +289,11 @@ template <class R> struct DScene {
     uint32_t bg_kind;
     R bg_a[3], bg_b[3], bg_scale, bg_gamma;
     R n_lights_f;                       // number_of_lights() as F (tracer.rs:138,214)
+    // signed-distance program (ptb_set_sdf_*): one more "primitive", tested after the planes.  The nodes live in the kernel
+    // parameter (constant bank): every lane reads the same node at the same time, which is what that path is fast at.
+    uint32_t n_sdf, sdf_max_steps;
+    R sdf_hit_eps, sdf_max_dist, sdf_normal_h;
+    DSdfNode<R> sdf[PTB_SDF_MAX_NODES];
 };
 
 // Scene arrays as the kernels read them.  The host packs [planes | lights | plane_material | spheres |
@@ -433,6 +442,75 @@ template <class R> PTB_DEV R isect_plane(V3<R> o, V3<R> d, V3<R> p, V3<R> n) {
     }
     return R(-1);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Signed-distance scenes (the reference's stated motivation, Readme.md:18,76-84, and its open "SDF based
+// example scene" todo).  The reference has no SDF code, so there is nothing to restate: the semantics below are this library's
+// extension of the Scene contract (scene.rs:12-16: closest_hit fills hit_dist / normal / material, any_hit answers shadow
+// rays) and oracle/pt_oracle.hpp evaluates the identical program with the identical operation order.  All of it is
+// add / mul / min / max / sqrt — no transcendental — so the strict build reproduces the oracle bit for bit.
+template <class R> struct SdfSample { R d; uint32_t material; };
+template <class R> PTB_DEV R sdf_len2(R x, R y) { return m_sqrt(x * x + y * y); }
+template <class R> PTB_DEV R sdf_len3(R x, R y, R z) { return m_sqrt(x * x + y * y + z * z); }
+template <class R> PTB_DEV R m_min(R a, R b) { return a < b ? a : b; }
+template <class R> PTB_DEV SdfSample<R> sdf_eval(const DScene<R>& s, V3<R> q) {
+    SdfSample<R> st[PTB_SDF_MAX_STACK];
+    int sp = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < s.n_sdf; ++i) {
+        const DSdfNode<R>& n = s.sdf[i];
+        const R x = q.x - n.p[0], y = q.y - n.p[1], z = q.z - n.p[2];
+        SdfSample<R> v;
+        v.material = n.material;
+        switch (n.op) {
+            case PTB_SDF_SPHERE: v.d = sdf_len3(x, y, z) - n.a[0]; break;
+            case PTB_SDF_BOX: {                             // half extents a[0..2], corner radius a[3]
+                const R dx = m_abs(x) - n.a[0], dy = m_abs(y) - n.a[1], dz = m_abs(z) - n.a[2];
+                const R outside = sdf_len3(m_max(dx, R(0)), m_max(dy, R(0)), m_max(dz, R(0)));
+                v.d = outside + m_min(m_max(dx, m_max(dy, dz)), R(0)) - n.a[3];
+                break;
+            }
+            case PTB_SDF_TORUS: v.d = sdf_len2(sdf_len2(x, z) - n.a[0], y) - n.a[1]; break;       // ring of radius a[0] in the xz plane, tube a[1]
+            case PTB_SDF_PLANE: v.d = q.x * n.a[0] + q.y * n.a[1] + q.z * n.a[2] + n.a[3]; break;   // unit normal a[0..2], offset a[3]
+            default: {                                      // combinators: b = top of stack, a = the entry below it
+                const SdfSample<R> b = st[--sp], a = st[--sp];
+                if (n.op == PTB_SDF_UNION) v = b.d < a.d ? b : a;
+                else if (n.op == PTB_SDF_INTERSECT) v = b.d > a.d ? b : a;
+                else if (n.op == PTB_SDF_SUBTRACT) { v.d = m_max(a.d, -b.d); v.material = a.material; }
+                else {                                      // PTB_SDF_SMOOTH_UNION, blend radius a[0] (polynomial smooth minimum)
+                    const R h = m_clamp(R(0.5) + R(0.5) * div_rn(b.d - a.d, n.a[0]), R(0), R(1));
+                    v.d = ((R(1) - h) * b.d + a.d * h) - n.a[0] * h * (R(1) - h);
+                    v.material = h >= R(0.5) ? a.material : b.material;
+                }
+            }
+        }
+        st[sp++] = v;
+    }
+    return st[0];
+}
+// Sphere tracing from t = 0: steps of |distance| (a ray that starts inside a transmissive body walks out to the surface), hit
+// when |distance| < sdf_hit_eps, given up beyond min(limit, sdf_max_dist) or after sdf_max_steps.  Returns t >= 0 or -1.
+template <class R> PTB_DEV R sdf_trace(const DScene<R>& s, V3<R> o, V3<R> d, R limit, uint32_t& material) {
+    const R t_end = m_min(limit, s.sdf_max_dist);
+    R t = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < s.sdf_max_steps; ++i) {
+        const SdfSample<R> v = sdf_eval(s, V3<R>(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z));
+        const R a = m_abs(v.d);
+        if (a < s.sdf_hit_eps) { material = v.material; return t; }
+        t = t + a;
+        if (!(t < t_end)) break;
+    }
+    return R(-1);
+}
+// gradient by four samples on a tetrahedron around the hit point
+template <class R> PTB_DEV V3<R> sdf_normal(const DScene<R>& s, V3<R> q) {
+    const R h = s.sdf_normal_h;
+    const R d0 = sdf_eval(s, V3<R>(q.x + h, q.y - h, q.z - h)).d, d1 = sdf_eval(s, V3<R>(q.x - h, q.y - h, q.z + h)).d;
+    const R d2 = sdf_eval(s, V3<R>(q.x - h, q.y + h, q.z - h)).d, d3 = sdf_eval(s, V3<R>(q.x + h, q.y + h, q.z + h)).d;
+    return normalize(V3<R>(((d0 - d1) - d2) + d3, ((d2 + d3) - d0) - d1, ((d1 + d3) - d0) - d2));
+}
+template <class R> PTB_DEV uint32_t sdf_prim(const DScene<R>& s) { return s.n_spheres + s.n_planes; }   // its index in test order
 
 // camera/pinhole.rs:38-61 (invariants hoisted into DScene by the host); p = film position,
 // off = jitter, inv_w/inv_h = pixel_size
@@ -607,7 +685,8 @@ PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o
 }
 
 // the rest of closest_hit given the sphere result: planes, then Scene::sample_lights
-template <class R, bool BVH>
+// SDF = false compiles the signed-distance test out (instantiations whose scenes cannot carry a program)
+template <class R, bool BVH, bool SDF = true>
 PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, int best, R dist,
                                       uint64_t accepted) {
     HitCore<R> h;
@@ -620,6 +699,13 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
         if (t >= R(0) && t < dist) {                   // analytical.rs:101-103
             dist = t; best = (int)(s.n_spheres + i); accepted |= (1ull << ((s.n_spheres + i) & 63u));
         }
+    }
+    if (SDF && s.n_sdf) {                               // the signed-distance body: one more primitive after the planes
+        uint32_t mi = 0;
+        const R t = sdf_trace(s, o, d, dist, mi);
+        // (scenes with a signed-distance program assign whole materials — ptb_set_sdf_* checks it —, so the accepted set is
+        //  not needed and the word carries the material the program returned at the hit)
+        if (t >= R(0) && t < dist) { dist = t; best = (int)sdf_prim(s); accepted = (uint64_t)mi; }
     }
     h.prim = best; h.accepted = accepted;
     if (best >= 0) { h.hit = true; h.geom = true; h.hit_dist = dist; }
@@ -661,22 +747,23 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
 }
 
 // normal of primitive `prim` at distance t along (o, d): analytical.rs:45-46 (sphere), :105 (plane)
-template <class R, bool BVH>
+template <class R, bool BVH, bool SDF = true>
 PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in) {
     int best;
     R dist;
     uint64_t accepted;
     closest_spheres<R, BVH>(s, sv, o, d, best, dist, accepted);
-    return closest_hit_finish<R, BVH>(s, sv, o, d, hit_dist_in, best, dist, accepted);
+    return closest_hit_finish<R, BVH, SDF>(s, sv, o, d, hit_dist_in, best, dist, accepted);
 }
 
-template <class R, bool BVH>
+template <class R, bool BVH, bool SDF = true>
 PTB_DEV V3<R> hit_normal(const DScene<R>& s, const SceneView<R>& sv, int prim, V3<R> o, V3<R> d, R t) {
     if ((uint32_t)prim < s.n_spheres) {
         DSphere<R> sp = BVH ? s.spheres[prim] : sv.spheres[prim];
         V3<R> hp = o + t * d;
         return normalize(hp - V3<R>(sp.cx, sp.cy, sp.cz));
     }
+    if (SDF && (uint32_t)prim == sdf_prim(s)) return sdf_normal(s, o + t * d);
     DPlane<R> pl = sv.planes[prim - s.n_spheres];
     return V3<R>(pl.nx, pl.ny, pl.nz);
 }
@@ -690,7 +777,7 @@ template <class R, bool BVH> PTB_DEV uint32_t prim_material(const DScene<R>& s, 
 // the reference's assignment order replayed over the accepted primitives (see PTB_MAT_* in ptb200.h)
 template <class R, bool BVH>
 PTB_DEV uint32_t hit_material(const DScene<R>& s, const SceneView<R>& sv, int prim, uint64_t accepted, V3<R> d, Mat<R>& mat) {
-    const uint32_t mi = prim_material<R, BVH>(s, sv, prim);
+    const uint32_t mi = (s.n_sdf && (uint32_t)prim == sdf_prim(s)) ? (uint32_t)accepted : prim_material<R, BVH>(s, sv, prim);
     if (BVH || !s.patch_materials) {
         mat_load(mat, BVH ? s.materials[mi] : sv.materials[mi], d);
     } else {
@@ -718,7 +805,7 @@ template <class R> PTB_DEV uint32_t lobe_class_of(R metallic, R spec_trans, R cl
 template <class R, bool BVH>
 PTB_DEV uint32_t hit_lobe_class(const DScene<R>& s, const SceneView<R>& sv, int prim, uint64_t accepted) {
     if (BVH || !s.patch_materials) {
-        const uint32_t mi = prim_material<R, BVH>(s, sv, prim);
+        const uint32_t mi = (s.n_sdf && (uint32_t)prim == sdf_prim(s)) ? (uint32_t)accepted : prim_material<R, BVH>(s, sv, prim);
         const DMaterial<R>& dm = BVH ? s.materials[mi] : sv.materials[mi];
         return lobe_class_of(dm.metallic, dm.spec_trans, dm.clearcoat);
     }
@@ -763,6 +850,9 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
             if ((uint32_t)c.prim < s.n_spheres) {
                 DSphere<R> sp = BVH ? s.spheres[c.prim] : sv.spheres[c.prim];
                 tg = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
+            } else if ((uint32_t)c.prim == sdf_prim(s)) {
+                uint32_t mi;
+                tg = sdf_trace(s, o, d, Const<R>::MAXV, mi);
             } else {
                 DPlane<R> pl = sv.planes[c.prim - s.n_spheres];
                 tg = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
@@ -790,7 +880,7 @@ template <class R, bool BVH> PTB_DEV bool any_hit_spheres(const DScene<R>& s, co
         return false;
     }
 }
-template <class R> PTB_DEV bool any_hit_planes(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+template <class R, bool SDF = true> PTB_DEV bool any_hit_planes(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
     const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
 #pragma unroll 1
     for (uint32_t i = 0; i < s.n_planes; ++i) {
@@ -798,10 +888,14 @@ template <class R> PTB_DEV bool any_hit_planes(const DScene<R>& s, const SceneVi
         R t = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
         if (t >= R(0) && (ignore || t < max_dist)) return true;
     }
+    if (SDF && s.n_sdf) {                               // the signed-distance body (always honours max_dist)
+        uint32_t mi;
+        if (sdf_trace(s, o, d, max_dist, mi) >= R(0)) return true;
+    }
     return false;
 }
-template <class R, bool BVH> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
-    return any_hit_spheres<R, BVH>(s, sv, o, d, max_dist) || any_hit_planes(s, sv, o, d, max_dist);
+template <class R, bool BVH, bool SDF = true> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+    return any_hit_spheres<R, BVH>(s, sv, o, d, max_dist) || any_hit_planes<R, SDF>(s, sv, o, d, max_dist);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1307,7 +1401,7 @@ PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat
 }
 
 // the three pieces in one go (fused integrator, shared-memory wavefront)
-template <class R, bool COUNT, bool BVH, bool ADD_EMISSION = true>
+template <class R, bool COUNT, bool BVH, bool ADD_EMISSION = true, bool SDF = true>
 PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, Mat<R>& mat, const R* u, PathCounters* pc) {
     ShadeSetup<R> su;
     shade_setup<R, COUNT, ADD_EMISSION>(s, p, normal, mat, su, pc);
@@ -1316,7 +1410,7 @@ PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>
     bool nee = false;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;
-        nee = !any_hit<R, BVH>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
+        nee = !any_hit<R, BVH, SDF>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
     }
     return shade_finish<R, COUNT, false, NoSink, true>(s, p, mat, su, nee, ns.ls, ns.light_area, u, pc);
 }
@@ -1386,7 +1480,7 @@ PTB_DEV bool path_shade_rm(const DScene<float>& s, const SceneView<float>& sv, P
     bool nee = false;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;
-        nee = !any_hit<float, false>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
+        nee = !any_hit<float, false, false>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
     }
 #ifdef PTB_RM_SINGLE_COPY
     return shade_finish<float, COUNT, false, NoSink, false>(s, p, rm.m, su, nee, ns.ls, ns.light_area, u, pc);

@@ -303,6 +303,23 @@ __global__ void k_test_any_hit(const __grid_constant__ DScene<R> s, size_t n, co
     if (i >= n) return;
     hit[i] = s.use_bvh ? any_hit<R, true>(s, sv, ld3(o, n, i), ld3(d, n, i), md[i]) : any_hit<R, false>(s, sv, ld3(o, n, i), ld3(d, n, i), md[i]);
 }
+// the signed-distance program on its own: value + material at a point; sphere trace + normal along a ray
+template <class R> __global__ void k_test_sdf_eval(const __grid_constant__ DScene<R> s, size_t n, const R* q, R* dist, uint32_t* mat) {
+    PTB_TEST_PROLOGUE
+    if (i >= n) return;
+    const SdfSample<R> v = sdf_eval(s, ld3(q, n, i));
+    dist[i] = v.d; mat[i] = v.material;
+}
+template <class R>
+__global__ void k_test_sdf_trace(const __grid_constant__ DScene<R> s, size_t n, const R* o, const R* d, const R* limit, R* t_out, R* nrm, uint32_t* mat) {
+    PTB_TEST_PROLOGUE
+    if (i >= n) return;
+    const V3<R> oo = ld3(o, n, i), dd = ld3(d, n, i);
+    uint32_t m = 0xffffffffu;
+    const R t = sdf_trace(s, oo, dd, limit[i], m);
+    t_out[i] = t; mat[i] = m;
+    st3(nrm, n, i, t >= R(0) ? sdf_normal(s, oo + t * dd) : V3<R>(0, 0, 0));
+}
 template <class R> __global__ void k_test_background(const __grid_constant__ DScene<R> s, size_t n, const R* d, R* rgb) {
     PTB_TEST_PROLOGUE
     if (i >= n) return;

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_cons
             const float4 A0 = a.a0[slot], A1 = a.a1[slot];
             const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
             if (COUNT) pc.closest_hit++;
-            const HitCore<R> h = closest_hit_core<R, BVH>(s, sv, o, d, A1.z);
+            const HitCore<R> h = closest_hit_core<R, BVH, false>(s, sv, o, d, A1.z);       // (no signed-distance programs in this integrator)
             key = stream_after_hit<COUNT, BVH>(s, sv, a, slot, d, A1.w, h, pc);
         }
         push_by_key(a, ctr, key, slot);
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_trace(const __grid_consta
                         const float4 S0 = a.s0[my], S1 = a.s1[my];
                         o = V3<R>(S0.x, S0.y, S0.z); d = V3<R>(S1.x, S1.y, S1.z);
                         best_t = ignore_max ? Const<R>::MAXV : S0.w;
-                        if (any_hit_planes(s, sv, o, d, S0.w)) go = false;            // occluded by a plane: nothing to add
+                        if (any_hit_planes<R, false>(s, sv, o, d, S0.w)) go = false;            // occluded by a plane: nothing to add
                     } else {
                         slot = q[my];
                         const float4 A0 = a.a0[slot], A1 = a.a1[slot];
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_finish(const __grid_const
             const float4 A0 = a.a0[slot], A1 = a.a1[slot];
             const uint4 H = a.hit[slot];
             const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
-            const HitCore<R> h = closest_hit_finish<R, true>(s, sv, o, d, A1.z, (int)H.x, __uint_as_float(H.w), 0ull);
+            const HitCore<R> h = closest_hit_finish<R, true, false>(s, sv, o, d, A1.z, (int)H.x, __uint_as_float(H.w), 0ull);
             key = stream_after_hit<COUNT, true>(s, sv, a, slot, d, A1.w, h, pc);
         }
         push_by_key(a, ctr, key, slot);
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
         shade_draws(rng, bounce, s.n_lights > 1u || (key & 4u) != 0u, u);      // the queue key is the lobe class: warp-uniform
         Mat<R> mat;
         hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
-        const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+        const V3<R> normal = hit_normal<R, BVH, false>(s, sv, prim, p.o, p.d, p.hit_dist);
         ShadeSetup<R> su;
         shade_setup<R, COUNT>(s, p, normal, mat, su, &pc);
         if (s.has_emissive) { A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z; a.a3[slot] = A3; }     // tracer.rs:74
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_const
         const uint32_t j = chunk + lane;
         if (j >= n) continue;
         const float4 S0 = a.s0[j], S1 = a.s1[j];
-        const bool occluded = any_hit<R, BVH>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
+        const bool occluded = any_hit<R, BVH, false>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
         if (!occluded) {
             const float4 S2 = a.s2[j];
             const uint32_t flags = __float_as_uint(S2.w);

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                             sm.ra[i] = r4;
                         }
                         shade_draws(rng, p.bounce, s.n_lights > 1u || (rm.lobe_class & 4u) != 0u, u);
-                        const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+                        const V3<R> normal = hit_normal<R, BVH, false>(s, sv, prim, p.o, p.d, p.hit_dist);
                         alive = path_shade_rm<COUNT, false>(s, sv, p, normal, rm, u, &pc);
                     } else {
                         const int prim = (int)prim_bits;
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                             sm.ra[i] = r4;
                         }
                         shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
-                        const V3<R> normal = hit_normal<R, BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-                        alive = path_shade<R, COUNT, BVH, false>(s, sv, p, normal, mat, u, &pc);
+                        const V3<R> normal = hit_normal<R, BVH, !BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+                        alive = path_shade<R, COUNT, BVH, false, !BVH>(s, sv, p, normal, mat, u, &pc);
                     }
                 }
             }
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                     if (COUNT) pc.end_depth++;
                 } else {
                     if (COUNT) pc.closest_hit++;
-                    const HitCore<R> h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
+                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH>(s, sv, p.o, p.d, p.hit_dist);   // signed-distance programs: generic instantiation only
                     p.hit_dist = h.hit_dist;
                     if (!h.hit) {
                         key = WF_MISS;                                 // background lookup next iteration, with full warps

@@ -190,6 +190,72 @@ class Background:
 
 
 @dataclass
+class SdfNode:
+    """One instruction of a signed-distance program in postfix order (ptb_sdf_node_*): primitives push (distance, material),
+    combinators pop two entries and push one."""
+    op: int
+    material: int = 0
+    p: F3 = field(default_factory=lambda: F3(0.0, 0.0, 0.0))
+    a: Sequence[float] = (0.0, 0.0, 0.0, 0.0)
+
+    @staticmethod
+    def sphere(center, radius: float, material: int) -> "SdfNode":
+        return SdfNode(_abi.PTB_SDF_SPHERE, material, _f3(center), (radius, 0.0, 0.0, 0.0))
+
+    @staticmethod
+    def box(center, half_extents, material: int, rounding: float = 0.0) -> "SdfNode":
+        h = tuple(_f3(half_extents))
+        return SdfNode(_abi.PTB_SDF_BOX, material, _f3(center), (h[0], h[1], h[2], rounding))
+
+    @staticmethod
+    def torus(center, ring_radius: float, tube_radius: float, material: int) -> "SdfNode":
+        return SdfNode(_abi.PTB_SDF_TORUS, material, _f3(center), (ring_radius, tube_radius, 0.0, 0.0))
+
+    @staticmethod
+    def plane(normal, offset: float, material: int) -> "SdfNode":
+        n = tuple(_f3(normal))
+        return SdfNode(_abi.PTB_SDF_PLANE, material, F3(0.0, 0.0, 0.0), (n[0], n[1], n[2], offset))
+
+    @staticmethod
+    def union() -> "SdfNode":
+        return SdfNode(_abi.PTB_SDF_UNION)
+
+    @staticmethod
+    def smooth_union(k: float) -> "SdfNode":
+        return SdfNode(_abi.PTB_SDF_SMOOTH_UNION, 0, F3(0.0, 0.0, 0.0), (k, 0.0, 0.0, 0.0))
+
+    @staticmethod
+    def subtract() -> "SdfNode":
+        return SdfNode(_abi.PTB_SDF_SUBTRACT)
+
+    @staticmethod
+    def intersect() -> "SdfNode":
+        return SdfNode(_abi.PTB_SDF_INTERSECT)
+
+
+@dataclass
+class SdfProgram:
+    """A signed-distance body for `DeviceScene.sdf` (ptb_sdf_*): sphere-traced after the planes in closest_hit order."""
+    nodes: List[SdfNode] = field(default_factory=list)
+    hit_eps: float = 1e-4
+    max_dist: float = 100.0
+    normal_h: float = 1e-3
+    max_steps: int = 192
+
+    def to_c(self, precision: str = "f32"):
+        T = _abi.TYPES[precision]
+        real = _abi.REAL[precision]
+        arr = (T["SdfNode"] * max(1, len(self.nodes)))()
+        for i, n in enumerate(self.nodes):
+            arr[i].op = n.op; arr[i].material = n.material
+            arr[i].p = (real * 3)(*tuple(_f3(n.p))); arr[i].a = (real * 4)(*[float(x) for x in n.a])
+        sd = T["Sdf"]()
+        sd.n_nodes = len(self.nodes); sd.nodes = C.cast(arr, C.POINTER(T["SdfNode"]))
+        sd.hit_eps, sd.max_dist, sd.normal_h, sd.max_steps = self.hit_eps, self.max_dist, self.normal_h, self.max_steps
+        return sd, arr
+
+
+@dataclass
 class DeviceScene:
     """What `Scene.device_export()` returns: the scene as data (ptb_scene_f32 / _f64)."""
     spheres: List[Sphere] = field(default_factory=list)
@@ -201,6 +267,7 @@ class DeviceScene:
     depth: int = 4          # Scene::recursion_depth, scene.rs:28-30
     flags: int = 0
     eps: float = 0.005      # tracer.rs:16
+    sdf: Optional[SdfProgram] = None     # signed-distance body (ptb_set_sdf_*), SURVEY.md §8 f2
 
     def to_c(self, precision: str = "f32"):
         """Build the POD struct; returns (scene_struct, keepalive)."""
@@ -399,6 +466,11 @@ class Tracer:
         fn = self._lib.ptb_set_scene_f32 if self.precision == "f32" else self._lib.ptb_set_scene_f64
         self._check(fn(self._handle(), C.byref(sc)))
         self.scene_bytes = C.sizeof(sc) + sum(C.sizeof(k) for k in keep)
+        if export.sdf is not None and export.sdf.nodes:
+            sd, sd_keep = export.sdf.to_c(self.precision)
+            fn = self._lib.ptb_set_sdf_f32 if self.precision == "f32" else self._lib.ptb_set_sdf_f64
+            self._check(fn(self._handle(), C.byref(sd)))
+            self.scene_bytes += C.sizeof(sd) + C.sizeof(sd_keep)
         self.eps = export.eps
 
     # -- internals ------------------------------------------------------------------------------

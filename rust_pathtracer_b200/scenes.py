@@ -10,7 +10,7 @@ from __future__ import annotations
 import math
 
 from . import _abi
-from .prelude import (AnalyticalLight, Background, DeviceScene, F3, Material, Pinhole, Plane, Scene, Sphere)
+from .prelude import (AnalyticalLight, Background, DeviceScene, F3, Material, Pinhole, Plane, Scene, SdfNode, SdfProgram, Sphere)
 
 
 class AnalyticalScene(Scene):
@@ -155,3 +155,28 @@ def divergence_stress_scene(side: int = 64, depth: int = 16, seed: int = 0xD1CE)
     cam.set_fov(70.0)
     return ExportedScene(DeviceScene(spheres=spheres, planes=[Plane(F3(0.0, -1.0, 0.0), F3(0.0, 1.0, 0.0), 0)], materials=mats,
                                      lights=lights, camera=cam, depth=depth, flags=0, eps=0.005))
+
+
+def sdf_demo_scene(depth: int = 4) -> ExportedScene:
+    """The reference's open todo "Implement a SDF based example scene" (Readme.md:18) in device form: a rounded box smoothly
+    joined to a torus with a sphere carved out of it (clearcoat paint), a glass ball and a metal ball — all one signed-distance
+    program —, standing on the demo scene's checker plane under the demo scene's light and sky."""
+    paint = Material(); paint.rgb = F3(0.9, 0.25, 0.1); paint.clearcoat = 1.0; paint.clearcoat_gloss = 0.8; paint.roughness = 0.3
+    metal = Material(); metal.rgb = F3(0.95, 0.9, 0.8); metal.metallic = 1.0; metal.roughness = 0.08
+    glass = Material(); glass.rgb = F3(1.0, 1.0, 1.0); glass.spec_trans = 1.0; glass.roughness = 0.03; glass.ior = 1.45
+    mats = [_checker_plane_material(), paint, metal, glass]
+    prog = SdfProgram(nodes=[
+        SdfNode.box((-0.6, -0.35, 0.0), (0.55, 0.55, 0.55), 1, rounding=0.1),
+        SdfNode.torus((-0.6, 0.35, 0.0), 0.55, 0.16, 1),
+        SdfNode.smooth_union(0.25),
+        SdfNode.sphere((-0.15, 0.15, 0.55), 0.45, 1),
+        SdfNode.subtract(),
+        SdfNode.sphere((1.2, -0.45, 0.3), 0.55, 3),
+        SdfNode.union(),
+        SdfNode.sphere((0.55, -0.7, 1.1), 0.3, 2),
+        SdfNode.union(),
+    ], hit_eps=1e-4, max_dist=60.0, normal_h=1e-3, max_steps=192)
+    cam = Pinhole.new()
+    return ExportedScene(DeviceScene(spheres=[], planes=[Plane(F3(0.0, -1.0, 0.0), F3(0.0, 1.0, 0.0), 0)], materials=mats,
+                                     lights=[AnalyticalLight.spherical(F3(3.0, 2.0, 2.0), 1.0, F3(3.0, 3.0, 3.0))], camera=cam,
+                                     depth=depth, flags=0, eps=0.005, sdf=prog))

@@ -54,6 +54,19 @@ class DeviceFns:
         self.chk(self.lib.ptb_test_closest_hit_f32(self.h, n, _p(o), _p(d), _p(hd), _p(hit), _p(em), _p(hdo), _p(nrm), _p(mat), _p(lpdf), _p(lem)))
         return dict(hit=hit, is_emitter=em, hit_dist=hdo, normal=nrm, material=mat, light_pdf=lpdf, light_emission=lem)
 
+    def sdf_eval(self, q):
+        q = _a(q)
+        n = q.shape[1]; dist = np.empty(n, np.float32); mat = np.empty(n, np.uint32)
+        self.chk(self.lib.ptb_test_sdf_eval_f32(self.h, n, _p(q), _p(dist), _p(mat)))
+        return dist, mat
+
+    def sdf_trace(self, o, d, limit):
+        o, d, limit = _a(o), _a(d), _a(limit)
+        n = o.shape[1]
+        t, nrm, mat = np.empty(n, np.float32), np.empty((3, n), np.float32), np.empty(n, np.uint32)
+        self.chk(self.lib.ptb_test_sdf_trace_f32(self.h, n, _p(o), _p(d), _p(limit), _p(t), _p(nrm), _p(mat)))
+        return dict(t=t, normal=nrm, material=mat)
+
     def any_hit(self, o, d, md):
         o, d, md = _a(o), _a(d), _a(md)
         n = o.shape[1]; hit = np.empty(n, np.uint32)
