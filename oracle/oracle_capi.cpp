@@ -233,6 +233,26 @@ void t_trace_samples(const SceneBox<R>* sb, uint32_t w, uint32_t h, size_t n, co
     }
 }
 
+template <class R>
+double t_render_chacha(const SceneBox<R>* sb, uint32_t w, uint32_t h, R* pixels, uint64_t* frames_inout, uint32_t n_frames, uint64_t seed, int threads) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+    ColorBuffer<R> buf(w, h);
+    std::copy(pixels, pixels + (size_t)w * h * 4, buf.pixels.begin());
+    buf.frames = (size_t)*frames_inout;
+    Tracer<R> tr(sb->scene.get());
+    if (sb->flat) tr.eps = sb->flat->eps;
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t f = 0; f < n_frames; ++f) tr.render_chacha(buf, seed);
+    auto t1 = std::chrono::steady_clock::now();
+    std::copy(buf.pixels.begin(), buf.pixels.end(), pixels);
+    *frames_inout = buf.frames;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // signed-distance program: evaluation and tracing on their own (per-function parity of the extension)
 template <class R> void t_sdf_eval(const SceneBox<R>* sb, size_t n, const R* q, R* dist_out, uint32_t* mat_out) {
     for (size_t i = 0; i < n; ++i) sb->flat->sdf.eval(ld3(q, n, i), dist_out[i], mat_out[i]);
@@ -278,6 +298,10 @@ void pto_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 }
 
 size_t pto_counters_size(void) { return sizeof(Counters); }
+
+void pto_chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]) {
+    chacha_block(key, counter, stream, rounds, out);
+}
 
 #define PTO_INSTANTIATE(SFX, R)                                                                                         \
     void* pto_scene_literal_##SFX(void) {                                                                               \
@@ -351,6 +375,10 @@ size_t pto_counters_size(void) { return sizeof(Counters); }
     }                                                                                                                   \
     long pto_trace_scripted_##SFX(void* sb, uint32_t w, uint32_t h, uint32_t px, uint32_t row, const R* draws, size_t n_draws, R* rgb) { \
         return t_trace_scripted<R>(static_cast<SceneBox<R>*>(sb), w, h, px, row, draws, n_draws, rgb);                  \
+    }                                                                                                                   \
+    double pto_render_chacha_##SFX(void* sb, uint32_t w, uint32_t h, R* pixels, uint64_t* frames_inout, uint32_t n_frames,\
+                                   uint64_t seed, int threads) {                                                        \
+        return t_render_chacha<R>(static_cast<SceneBox<R>*>(sb), w, h, pixels, frames_inout, n_frames, seed, threads);  \
     }                                                                                                                   \
     void pto_trace_samples_##SFX(void* sb, uint32_t w, uint32_t h, size_t n, const uint32_t* px, const uint32_t* row,   \
                                  const uint64_t* sample, uint64_t seed, R* rgb) {                                       \

@@ -25,6 +25,9 @@
 // (uniform on the 2^-24 grid in [0,1) for f32, 2^-53 for f64) matters.  The oracle and the device
 // share a counter-based Philox4x32-10 stream instead (SURVEY.md §8d "Seeds").
 #pragma once
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstddef>
@@ -250,6 +253,66 @@ template <class R> struct SeqRng {
     }
     void coin_consumed() const { if (pos < n) ++pos; else overrun = true; }
 };
+// ChaCha block function (D. J. Bernstein's original layout: 64-bit block counter in words 12-13, 64-bit stream id in 14-15) and a
+// sequential generator over it.  The reference draws from rand 0.8.5's `thread_rng()` = ChaCha12 (rand_chacha 0.3.1,
+// Cargo.lock:1428-1450), buffered four blocks at a time, and turns a word into an f32 as (w >> 8) * 2^-24 (f64: 53 bits of two
+// words) — this generator reproduces that COST and distribution for the CPU baseline (bench.py cpu_baseline.chacha12); the
+// parity runs use the counter RNG above.  `rounds` = 20 reproduces the RFC 7539 block test vector (tests/test_oracle.py).
+inline void chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]) {
+    uint32_t x[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                      (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t in[16];
+    for (int i = 0; i < 16; ++i) in[i] = x[i];
+    auto rotl = [](uint32_t v, int c) { return (v << c) | (v >> (32 - c)); };
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+    };
+    for (int r = 0; r < rounds; r += 2) {
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
+}
+template <class R> struct ChaCha12Rng {
+    uint32_t key[8];
+    mutable uint64_t counter = 0;
+    mutable uint32_t buf[64];
+    mutable int pos = 64;
+    explicit ChaCha12Rng(uint64_t seed) {
+        // key expansion from a 64-bit seed (splitmix64, like rand's seed_from_u64; the reference seeds from the OS)
+        uint64_t z = seed;
+        for (int i = 0; i < 4; ++i) {
+            z += 0x9E3779B97F4A7C15ull;
+            uint64_t v = z;
+            v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull; v = (v ^ (v >> 27)) * 0x94D049BB133111EBull; v ^= v >> 31;
+            key[2 * i] = (uint32_t)v; key[2 * i + 1] = (uint32_t)(v >> 32);
+        }
+    }
+    uint32_t next_u32() const {
+        if (pos >= 64) {                                            // rand_chacha refills four blocks (256 bytes) at a time
+            for (int b = 0; b < 4; ++b) chacha_block(key, counter++, 0, 12, buf + 16 * b);
+            pos = 0;
+        }
+        return buf[pos++];
+    }
+    R next() const;
+    mutable bool have_coin = false;
+    mutable R coin = 0;
+    // call-order interface of the tracer (see SeqRng): the coin of tracer.rs:534 is drawn only in the spec lobe
+    R draw(uint32_t, uint32_t slot) const {
+        if (slot == 3u) { if (!have_coin) { coin = next(); have_coin = true; } return coin; }
+        return next();
+    }
+    void coin_consumed() const { have_coin = false; }
+};
+template <> inline float ChaCha12Rng<float>::next() const { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
+template <> inline double ChaCha12Rng<double>::next() const {
+    const uint64_t lo = next_u32(), hi = next_u32();
+    return (double)(((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
 template <> inline float CounterRng<float>::draw(uint32_t bounce, uint32_t slot) const {
     uint32_t c[4] = {bounce * 2u + (slot >> 2), (uint32_t)(sample >> 32), (uint32_t)seed, (uint32_t)(seed >> 32)};
     philox4x32_10(c, pixel, (uint32_t)sample);
@@ -1135,6 +1198,39 @@ template <class R> struct Tracer {
         }
         if (!ended && ctr) ctr->end_depth++;
         return radiance;
+    }
+
+    // The same frame loop on per-thread ChaCha12 generators in call order — the reference's RNG cost and call pattern
+    // (`thread_rng()` per pixel is a handle to the thread's generator, tracer.rs:44).  Not reproducible against the counter-RNG
+    // image sample by sample (like the reference against itself); converges to the same image.
+    void render_chacha(ColorBuffer<R>& buffer, uint64_t base_seed) const {
+        const size_t width = buffer.width;
+        const R height = (R)buffer.height;
+        const size_t H = buffer.height;
+        const R mixv = R(1) / (R)(buffer.frames + 1);
+#pragma omp parallel
+        {
+#ifdef _OPENMP
+            const uint64_t tid = (uint64_t)omp_get_thread_num();
+#else
+            const uint64_t tid = 0;
+#endif
+            ChaCha12Rng<R> rng(base_seed * 0x10001ull + tid * 0x9E3779B97F4A7C15ull + buffer.frames);
+#pragma omp for schedule(dynamic, 1)
+            for (long long jj = 0; jj < (long long)H; ++jj) {
+                size_t j = (size_t)jj;
+                size_t row = H - 1 - j;
+                R* line = buffer.pixels.data() + row * width * 4;
+                for (size_t x = 0; x < width; ++x) {
+                    rng.have_coin = false;
+                    V3<R> radiance = trace_sample_with(x, j, width, height, rng, nullptr);
+                    R* pixel = line + x * 4;
+                    R color[4] = {radiance.x, radiance.y, radiance.z, R(1)};
+                    for (int c = 0; c < 4; ++c) pixel[c] = (R(1) - mixv) * pixel[c] + color[c] * mixv;
+                }
+            }
+        }
+        buffer.frames += 1;
     }
 
     // tracer.rs:22-123 — one frame (1 spp) accumulated as a running mean; rows are independent

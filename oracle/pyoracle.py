@@ -44,6 +44,7 @@ def load():
             getattr(_lib, f"pto_scene_flat_{sfx}").argtypes = [C.c_void_p]
             getattr(_lib, f"pto_scene_destroy_{sfx}").argtypes = [C.c_void_p]
             getattr(_lib, f"pto_render_{sfx}").restype = C.c_double
+            getattr(_lib, f"pto_render_chacha_{sfx}").restype = C.c_double
         assert _lib.pto_counters_size() == 8 * len(COUNTER_FIELDS)
     return _lib
 
@@ -192,6 +193,14 @@ class OracleScene:
         cd = {k: int(ctr[i]) for i, k in enumerate(COUNTER_FIELDS)} if counters else None
         return px, fr.value, float(secs), cd
 
+    def render_chacha(self, w, h, n_frames, pixels=None, frames=0, seed=0, threads=0):
+        """the same frame loop drawing from per-thread ChaCha12 generators in call order (the reference's RNG: rand 0.8.5
+        thread_rng) — the CPU baseline closest to the rayon path's cost.  Returns (pixels, frames, seconds)."""
+        px = np.zeros(w * h * 4, self.np) if pixels is None else np.ascontiguousarray(pixels, self.np).copy()
+        fr = C.c_uint64(frames)
+        secs = self._fn("render_chacha")(self.h, C.c_uint32(w), C.c_uint32(h), _p(px), C.byref(fr), C.c_uint32(n_frames), C.c_uint64(seed), C.c_int(threads))
+        return px, fr.value, float(secs)
+
     def trace_samples(self, w, h, px, row, sample, seed=0):
         px = np.ascontiguousarray(px, np.uint32); row = np.ascontiguousarray(row, np.uint32); sample = np.ascontiguousarray(sample, np.uint64)
         n = px.size
@@ -223,6 +232,14 @@ class OracleScene:
         fn.restype = C.c_long
         k = fn(self.h, C.c_uint32(w), C.c_uint32(h), C.c_uint32(px), C.c_uint32(row), _p(d), C.c_size_t(d.size), _p(rgb))
         return rgb, int(k)
+
+
+def chacha_block(key8, counter, stream, rounds):
+    lib = load()
+    k = (C.c_uint32 * 8)(*key8)
+    o = (C.c_uint32 * 16)()
+    lib.pto_chacha_block(k, C.c_uint64(counter), C.c_uint64(stream), C.c_int(rounds), o)
+    return [int(x) for x in o]
 
 
 def sphere_hit(o, d, c, r, precision="f32"):

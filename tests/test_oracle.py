@@ -296,3 +296,28 @@ def test_convert_to_u8_at_bounds(po):
     written = frame[..., 0] == 127
     # x in (1, 5) -> columns 2,3,4; y in (1, 4) -> y = fh - j = 2,3 -> frame rows fh-1-j: j = 4,3 -> rows 1,2
     assert written.sum() == 3 * 2 and written[1:3, 2:5].all()
+
+
+def test_chacha_block_rfc7539_vector(po):
+    """the block function behind the baseline's thread_rng stand-in, pinned by RFC 7539 section 2.3.2 (ChaCha20: same quarter
+    round and layout, 20 rounds; words 12..15 = counter 1, nonce 00000009 0000004a 00000000)"""
+    import struct
+    key = list(struct.unpack("<8I", bytes(range(32))))
+    out = po.chacha_block(key, 1 | (0x09000000 << 32), 0x4A000000, 20)
+    assert out == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3, 0xC7F4D1C7, 0x0368C033, 0x9AAA2204, 0x4E6CD4C3,
+                   0x466482D2, 0x09AA9F07, 0x05D7C214, 0xA2028BD9, 0xD19C12B5, 0xB94E16DE, 0xE883D0CB, 0x4E3C50A2]
+    assert po.chacha_block(key, 1, 0, 12) != po.chacha_block(key, 2, 0, 12)
+
+
+def test_chacha_render_converges_to_the_counter_rng_image(po, oracle_demo):
+    """the ChaCha12 call-order frame loop (bench.py's CPU baseline) renders the same image as the counter-RNG loop"""
+    W, H, S = 96, 54, 48
+    a, fa, _ = oracle_demo.render_chacha(W, H, S, seed=7)
+    b, fb, _, _ = oracle_demo.render(W, H, S)
+    assert fa == fb == S
+    la, lb = a.reshape(-1, 4)[:, :3].mean(), b.reshape(-1, 4)[:, :3].mean()
+    assert abs(la / lb - 1) < 0.01
+    assert np.all(a.reshape(-1, 4)[:, 3] == 1.0)
+    # per-pixel: two independent 48-spp estimates of the same image
+    d = (a - b).reshape(-1, 4)[:, :3]
+    assert np.sqrt((d ** 2).mean()) < 0.08
