@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 2
+#define PTB_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------ */
 enum {

@@ -20,7 +20,7 @@ fn main() {
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=ptb200");
     println!("cargo:rustc-link-lib=dylib=cudart");
-    for f in ["ptb_api.cu", "ptb_device.cuh", "ptb_kernels.cuh", "ptb_wavefront.cuh"] {
+    for f in ["ptb_api.cu", "ptb_device.cuh", "ptb_kernels.cuh", "ptb_wavefront.cuh", "ptb_wavefront_async.cuh", "ptb_stream.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/ptb200.h").display());
