@@ -272,6 +272,11 @@ int  ptb_wait_download(ptb_tracer* t);
  * unpin in the buffer's destructor).  Already-pinned / not-pinned buffers are not an error. */
 int  ptb_pin_host(void* host_ptr, size_t bytes);
 int  ptb_unpin_host(void* host_ptr);
+/* Denoised copy of the mean image (the accumulators are untouched): `iterations` levels (1..8) of an edge-avoiding a-trous
+ * wavelet filter guided by the colour, range weight exp(-|dc|^2 / sigma^2) with sigma halving per level; NaN / inf pixels are
+ * repaired from their finite neighbours.  No reference counterpart: the reference lists a denoiser as open (Readme.md:14). */
+int  ptb_denoise_f32(ptb_tracer* t, uint32_t iterations, float sigma_color, float* pixels_rgba_out);
+int  ptb_denoise_f64(ptb_tracer* t, uint32_t iterations, double sigma_color, double* pixels_rgba_out);
 /* frames accumulated so far (ColorBuffer.frames) */
 int  ptb_frames(ptb_tracer* t, uint64_t* frames);
 

@@ -97,7 +97,7 @@ class Counters(C.Structure):
 SYMBOLS = [
     "ptb_create", "ptb_destroy", "ptb_abi_version", "ptb_last_error", "ptb_device_count", "ptb_set_stream",
     "ptb_set_scene_f32", "ptb_set_scene_f64", "ptb_set_sdf_f32", "ptb_set_sdf_f64", "ptb_resize", "ptb_bind_accumulator", "ptb_clear",
-    "ptb_upload_f32", "ptb_upload_f64", "ptb_download_f32", "ptb_download_f64", "ptb_frames",
+    "ptb_upload_f32", "ptb_upload_f64", "ptb_download_f32", "ptb_download_f64", "ptb_denoise_f32", "ptb_denoise_f64", "ptb_frames",
     "ptb_render", "ptb_render_frame_f32", "ptb_render_frame_f64", "ptb_render_frame_ex_f32", "ptb_render_frame_ex_f64", "ptb_synchronize",
     "ptb_download_async_f32", "ptb_download_async_f64", "ptb_wait_download", "ptb_pin_host", "ptb_unpin_host",
     "ptb_peer_slots_create", "ptb_peer_slots_open", "ptb_peer_set_target", "ptb_peer_sum", "ptb_peer_slots_close",
@@ -166,6 +166,8 @@ def load(strict: bool = None):
     lib.ptb_download_f32.argtypes = [C.c_void_p, C.c_void_p]
     lib.ptb_download_f64.argtypes = [C.c_void_p, C.c_void_p]
     lib.ptb_frames.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.ptb_denoise_f32.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p]
+    lib.ptb_denoise_f64.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]
     lib.ptb_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
     lib.ptb_test_film_quotients_f32.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.ptb_test_bvh_build_f32.argtypes = [C.POINTER(TYPES["f32"]["Sphere"]), C.c_uint32] + [C.POINTER(C.c_uint32)] * 3

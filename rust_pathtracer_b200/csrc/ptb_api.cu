@@ -908,6 +908,37 @@ int ptb_wait_download(ptb_tracer* t) {
 int ptb_download_f32(ptb_tracer* t, float* px) { int r = need_scene(t, 4); return r ? r : download_impl<float>(t, px); }
 int ptb_download_f64(ptb_tracer* t, double* px) { int r = need_scene(t, 8); return r ? r : download_impl<double>(t, px); }
 
+}  // extern "C"
+template <class R> static int denoise_impl(ptb_tracer* t, uint32_t iterations, R sigma_color, R* pixels) {
+    if (!pixels) return fail(PTB_E_INVALID, "pixels is NULL");
+    if (!t->accum) return fail(PTB_E_INVALID, "no frame allocated (ptb_resize)");
+    if (iterations == 0 || iterations > 8 || !(sigma_color > R(0))) return fail(PTB_E_INVALID, "denoise: 1..8 iterations, sigma_color > 0");
+    CU(cudaSetDevice(t->device));
+    int r = ensure_staging(t, 2 * t->accum_bytes);            // two mean images: ping and pong
+    if (r) return r;
+    using V4 = typename Vec4T<R>::type;
+    const uint32_t n = t->W * t->H;
+    V4* a = (V4*)t->staging;
+    V4* b = a + n;
+    k_resolve<R><<<(n + 255) / 256, 256, 0, t->stream>>>((const V4*)t->accum, a, n);
+    t->launches++;
+    const dim3 blk(32, 8), grd((t->W + 31) / 32, (t->H + 7) / 8);
+    R sigma = sigma_color;
+    for (uint32_t i = 0; i < iterations; ++i) {
+        k_atrous<R><<<grd, blk, 0, t->stream>>>(a, b, t->W, t->H, 1 << i, R(1) / (sigma * sigma));
+        t->launches++;
+        std::swap(a, b);
+        sigma *= R(0.5);                                        // the range weight tightens as the footprint grows
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pixels, a, t->accum_bytes, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    return PTB_OK;
+}
+extern "C" {
+int ptb_denoise_f32(ptb_tracer* t, uint32_t iterations, float sigma_color, float* px) { int r = need_scene(t, 4); return r ? r : denoise_impl<float>(t, iterations, sigma_color, px); }
+int ptb_denoise_f64(ptb_tracer* t, uint32_t iterations, double sigma_color, double* px) { int r = need_scene(t, 8); return r ? r : denoise_impl<double>(t, iterations, sigma_color, px); }
+
 int ptb_frames(ptb_tracer* t, uint64_t* frames) {
     if (!t || !frames) return fail(PTB_E_INVALID, "null argument");
     *frames = t->frames;

@@ -193,6 +193,38 @@ template <class R> __global__ void k_unresolve(const typename Vec4T<R>::type* me
     accum[i] = mk4(v.x * frames, v.y * frames, v.z * frames, frames);
 }
 
+// Edge-avoiding a-trous wavelet filter, one level (Dammertz et al. 2010, guided by the colour alone: this path produces no
+// normal / albedo buffers).  5x5 taps of the B3 spline (1/16, 1/4, 3/8, 1/4, 1/16) spread `step` pixels apart, each weighted by
+// exp(-|c_p - c_q|^2 * inv_sigma2); non-finite neighbours are skipped, and a non-finite centre (a pixel the path loop poisoned
+// with 0/0, which the reference never filters) takes the plain spline average of its finite neighbours.  The reference lists a
+// denoiser as open (Readme.md:14): this is the device form of that item, checked against a numpy statement of the same filter.
+template <class R>
+__global__ void k_atrous(const typename Vec4T<R>::type* in, typename Vec4T<R>::type* out, uint32_t W, uint32_t H, int step, R inv_sigma2) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const R k[3] = {R(0.375), R(0.25), R(0.0625)};
+    const auto c = in[(size_t)y * W + x];
+    const bool c_ok = isfinite(c.x) && isfinite(c.y) && isfinite(c.z);
+    R sx = 0, sy = 0, sz = 0, sw = 0;
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = (int)y + dy * step;
+        if (yy < 0 || yy >= (int)H) continue;
+        for (int dx = -2; dx <= 2; ++dx) {
+            const int xx = (int)x + dx * step;
+            if (xx < 0 || xx >= (int)W) continue;
+            const auto q = in[(size_t)yy * W + xx];
+            if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) continue;
+            R w = k[dx < 0 ? -dx : dx] * k[dy < 0 ? -dy : dy];
+            if (c_ok) {
+                const R ex = q.x - c.x, ey = q.y - c.y, ez = q.z - c.z;
+                w *= (R)exp(-(double)((ex * ex + ey * ey + ez * ez) * inv_sigma2));
+            }
+            sx += w * q.x; sy += w * q.y; sz += w * q.z; sw += w;
+        }
+    }
+    out[(size_t)y * W + x] = sw > R(0) ? mk4(div_rn(sx, sw), div_rn(sy, sw), div_rn(sz, sw), c.w) : c;
+}
+
 // multi-GPU gather: accumulators += sum over the n_slots partial-sum buffers of one step, in slot order (deterministic)
 __global__ void k_peer_sum(float4* accum, const float4* slots, uint32_t n_slots, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -547,6 +547,14 @@ class Tracer:
         fn = self._lib.ptb_download_f32 if self.precision == "f32" else self._lib.ptb_download_f64
         self._check(fn(self._handle(), buffer._pixels.ctypes.data))
 
+    def denoise(self, iterations: int = 4, sigma_color: float = 0.35) -> np.ndarray:
+        """a denoised copy of the device-resident mean image (edge-avoiding a-trous wavelet filter, ptb_denoise_*); returns
+        W*H*4 reals, the accumulators stay as they are"""
+        out = np.empty(self._size[0] * self._size[1] * 4, dtype=_NP[self.precision])
+        fn = getattr(self._lib, f"ptb_denoise_{self.precision}")
+        self._check(fn(self._handle(), int(iterations), float(sigma_color), out.ctypes.data))
+        return out
+
     def download_async(self, buffer: ColorBuffer) -> None:
         """ptb_download_async_*: resolve on the render stream, D2H on a side stream; `wait_download()` before reading."""
         buffer._pin(self._lib)
