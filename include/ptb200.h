@@ -110,10 +110,10 @@ enum {
 
 /* Integrator selection (ptb_config.integrator). */
 enum {
-    PTB_INTEGRATOR_AUTO      = 0, /* wavefront for f32 scenes, fused for f64                        */
+    PTB_INTEGRATOR_AUTO      = 0, /* shared-memory wavefront; streaming wavefront for large BVH scenes */
     PTB_INTEGRATOR_FUSED     = 1, /* persistent per-lane path loop with in-register regeneration   */
     PTB_INTEGRATOR_WAVEFRONT = 2, /* SoA path-state queues in shared memory, one stage per kind of
-                                     work, queue sorted by lobe class between stages (f32 only)     */
+                                     work, queue sorted by lobe class between stages (f32 and f64)  */
     PTB_INTEGRATOR_STREAM    = 3  /* SoA ray / path-state queues in HBM, one KERNEL per kind of work
                                      (generate, closest_hit, shade per lobe class, any_hit,
                                      accumulate), ballot/popc compaction between them (f32 only)    */

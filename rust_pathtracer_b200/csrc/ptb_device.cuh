@@ -231,6 +231,7 @@ template <> struct Rng<double> {
 // The draws of a shaded bounce for the f32 staged integrators: slots 4..7 always; slots 2,3 (light pick, coin) only when
 // they can matter — with one light the pick is index 0 whatever the draw ((u * 1) as usize, u < 1), and without a
 // transmission lobe the coin decides nothing (ff = 1 - (1-F) * spec_trans * (1-metallic) = 1 > coin, tracer.rs:532-534).
+PTB_DEV void shade_draws(const Rng<double>& rng, uint32_t bounce, bool, double u[8]) { rng.draws(bounce, u); }
 PTB_DEV void shade_draws(const Rng<float>& rng, uint32_t bounce, bool need_first_block, float u[8]) {
     u[0] = u[1] = u[2] = u[3] = 0.0f;
     if (need_first_block) rng.block(bounce, 0, u);

@@ -32,6 +32,7 @@ struct RenderArgs {
     // film_fast says that the host verified, for EVERY column and row of this frame size, that the FMA-corrected quotient
     // (film_coords_fma) equals the IEEE x / W and y / H of tracer.rs:34-46 bit for bit
     float rcp_w, rcp_h;
+    double rcp_w64, rcp_h64;     // the same pixel size for the f64 instantiation
     uint32_t film_fast;
     // tail items (wavefront integrator): work items [n_whole, n_items) are the frame's last tail_zt pixels (in tile order) cut
     // into 2^tail_log2b sample blocks; item n_whole + b * tail_zt + z is block b of tail pixel z and its sum goes to tail_side

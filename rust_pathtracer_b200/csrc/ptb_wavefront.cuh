@@ -41,6 +41,17 @@ namespace ptb {
 #ifndef PTB_WF_THREADS_RM
 #define PTB_WF_THREADS_RM 832
 #endif
+// f64 (`F = f64`, lib.rs:5-6): a slot is five 32-byte vectors, so the 227 KB hold 1024 of them = 32 chunks.  The shading code
+// would like 255 registers, but warps pay more than spills cost: threads_pool 192_1152 / 256_1024 / 320_960 / 384_1152 /
+// 512_1024 = 879 / 1029 / 1084 / 1166 / 1215 Msamples/s at 4K (128 registers, 2 rounds of 16 warps; the fused f64 kernel: 696)
+#ifndef PTB_WF_THREADS_F64
+#define PTB_WF_THREADS_F64 512
+#endif
+#ifndef PTB_WF_POOL_F64
+#define PTB_WF_POOL_F64 1024
+#endif
+constexpr int WF_THREADS_F64 = PTB_WF_THREADS_F64;
+constexpr uint32_t WF_POOL_F64 = PTB_WF_POOL_F64;
 constexpr int WF_THREADS_GENERIC = PTB_WF_THREADS;
 constexpr int WF_THREADS_RM = PTB_WF_THREADS_RM;
 // shared-memory scene copy of the resolved-material instantiation (the host builds the table only if the blob fits)
@@ -78,9 +89,10 @@ constexpr uint32_t WF_NOKEY = 0xffffu;      // slot left the queue for good (fra
 constexpr uint32_t PRIM_SKY = 0xffffffffu;
 
 // GENERIC: scenes with partial material masks may have up to 64 primitives, so the accepted set needs 64 bits of its own
-template <uint32_t WF_POOL, uint32_t SCENE_BYTES, bool GENERIC> struct WfSmemT {
+template <class R, uint32_t WF_POOL, uint32_t SCENE_BYTES, bool GENERIC> struct WfSmemT {
+    using V4 = typename Vec4T<R>::type;
     uint32_t scene[SCENE_BYTES / 4];
-    float4 ro[WF_POOL], rd[WF_POOL], tr[WF_POOL], ra[WF_POOL], ac[WF_POOL];
+    V4 ro[WF_POOL], rd[WF_POOL], tr[WF_POOL], ra[WF_POOL], ac[WF_POOL];
     uint32_t acc_lo[GENERIC ? WF_POOL : 1], acc_hi[GENERIC ? WF_POOL : 1];
     uint32_t kt[WF_POOL];           // queue key << 16 | ticket inside the key (WF_NOKEY: not queued)
     uint16_t order[WF_POOL];        // the queue: slot indices, key-ordered
@@ -88,7 +100,19 @@ template <uint32_t WF_POOL, uint32_t SCENE_BYTES, bool GENERIC> struct WfSmemT {
     uint32_t cursor[2];             // next 32-entry chunk of the current queue (double-buffered like cnt)
 };
 
+// a 32-bit word kept in the .w lane of a vector of reals (bit pattern only: the lane is never used arithmetically)
+PTB_DEV float wf_word(float, uint32_t u) { return __uint_as_float(u); }
+PTB_DEV double wf_word(double, uint32_t u) { return __hiloint2double(0, (int)u); }
+PTB_DEV uint32_t wf_bits(float w) { return __float_as_uint(w); }
+PTB_DEV uint32_t wf_bits(double w) { return (uint32_t)__double2loint(w); }
 // shared-memory loads that stay where they are written (volatile: neither nvcc nor ptxas hoists them above the shading code)
+PTB_DEV double4 lds128_late(const double4* p) {      // (256 bits here)
+    double4 v;
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(a + 16u) : "memory");
+    return v;
+}
 PTB_DEV float4 lds128_late(const float4* p) {
     float4 v;
     asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
@@ -117,13 +141,16 @@ PTB_DEV uint32_t lds32_late(const uint32_t* p) {
 //
 // RM: the scene has a resolved-material table (RMat, ptb_device.cuh) and the host guarantees that the WHOLE blob sits in the
 // shared-memory copy, so every scene read of this instantiation is a shared-memory load (LDS, not a generic LD).
-template <bool COUNT, bool BVH, bool RM>
-__global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_render_wavefront(const __grid_constant__ DScene<float> s, const RenderArgs a) {
-    using R = float;
-    constexpr int WF_THREADS = RM ? WF_THREADS_RM : WF_THREADS_GENERIC;
+template <class R> __host__ __device__ constexpr int wf_threads(bool rm) { return sizeof(R) == 8 ? WF_THREADS_F64 : (rm ? WF_THREADS_RM : WF_THREADS_GENERIC); }
+template <class R> __host__ __device__ constexpr uint32_t wf_pool(bool rm) { return sizeof(R) == 8 ? WF_POOL_F64 : (rm ? WF_POOL_RM : WF_POOL_GENERIC); }
+template <class R, bool COUNT, bool BVH, bool RM>
+__global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const __grid_constant__ DScene<R> s, const RenderArgs a) {
+    constexpr int WF_THREADS = wf_threads<R>(RM);
     static_assert(!(RM && BVH), "the resolved-material table is for scenes that live in shared memory");
-    constexpr uint32_t WF_POOL = RM ? WF_POOL_RM : WF_POOL_GENERIC;
-    using WfSmem = WfSmemT<WF_POOL, RM ? WF_SCENE_BYTES_RM : PTB_SMEM_SCENE_BYTES, !RM>;
+    static_assert(!RM || sizeof(R) == 4, "the resolved-material table is built in f32");
+    constexpr uint32_t WF_POOL = wf_pool<R>(RM);
+    using V4 = typename Vec4T<R>::type;
+    using WfSmem = WfSmemT<R, WF_POOL, RM ? WF_SCENE_BYTES_RM : PTB_SMEM_SCENE_BYTES, !RM>;
     extern __shared__ __align__(16) unsigned char wf_raw[];
     WfSmem& sm = *reinterpret_cast<WfSmem*>(wf_raw);
     SceneView<R> sv;
@@ -144,20 +171,20 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
     } else {
         sv = stage_scene(s, sm.scene, PTB_SMEM_SCENE_BYTES);
     }
-    float4* accum = reinterpret_cast<float4*>(a.accum);
+    V4* accum = reinterpret_cast<V4*>(a.accum);
 
     const unsigned FULL = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const R inv_w = a.rcp_w, inv_h = a.rcp_h;     // pixel_size (pinhole.rs:41), correctly rounded on the host
+    const R inv_w = sizeof(R) == 8 ? (R)a.rcp_w64 : (R)a.rcp_w, inv_h = sizeof(R) == 8 ? (R)a.rcp_h64 : (R)a.rcp_h;     // pixel_size (pinhole.rs:41), correctly rounded on the host
 
     // the first queue: every slot, key WF_REGEN
     for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) {
-        sm.ro[i] = make_float4(0.f, 0.f, 0.f, -1.f);
-        sm.rd[i] = make_float4(0.f, 0.f, 1.f, __uint_as_float(0u));
-        sm.tr[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-        sm.ra[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-        sm.ac[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PRIM_SKY));
+        sm.ro[i] = mk4(R(0), R(0), R(0), R(-1));
+        sm.rd[i] = mk4(R(0), R(0), R(1), wf_word(R(0), 0u));
+        sm.tr[i] = mk4(R(0), R(0), R(0), wf_word(R(0), 0u));
+        sm.ra[i] = mk4(R(0), R(0), R(0), wf_word(R(0), 0u));
+        sm.ac[i] = mk4(R(0), R(0), R(0), wf_word(R(0), PRIM_SKY));
         sm.order[i] = (uint16_t)i;
         sm.kt[i] = WF_NOKEY << 16;
     }
@@ -195,11 +222,11 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             uint64_t accepted = 0;
             p.o = V3<R>(0, 0, 0); p.d = V3<R>(0, 0, 1); p.thr = V3<R>(1, 1, 1); p.rad = V3<R>(0, 0, 0); p.hit_dist = R(-1); p.prev_pdf = 0; p.bounce = 0;
             if (valid) {
-                const float4 q0 = sm.ro[i], q1 = sm.rd[i];
+                const V4 q0 = sm.ro[i], q1 = sm.rd[i];
                 p.o = V3<R>(q0.x, q0.y, q0.z); p.hit_dist = q0.w;
-                p.d = V3<R>(q1.x, q1.y, q1.z); pxy0 = __float_as_uint(q1.w);
-                fl0 = __float_as_uint(sm.tr[i].w);
-                prim_bits = __float_as_uint(sm.ac[i].w);
+                p.d = V3<R>(q1.x, q1.y, q1.z); pxy0 = wf_bits(q1.w);
+                fl0 = wf_bits(sm.tr[i].w);
+                prim_bits = wf_bits(sm.ac[i].w);
                 if constexpr (!RM) accepted = (uint64_t)sm.acc_lo[i] | ((uint64_t)sm.acc_hi[i] << 32);
             }
             p.bounce = (fl0 >> 8) & 0xffffu;
@@ -213,14 +240,14 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                     if (COUNT) pc.end_sky++;
                     alive = false;
                 } else {
-                    Rng<R> rng((pxy0 >> 16) * a.W + (pxy0 & 0xffffu), a.sample_base + __float_as_uint(sm.ra[i].w), a.seed);
+                    Rng<R> rng((pxy0 >> 16) * a.W + (pxy0 & 0xffffu), a.sample_base + wf_bits(sm.ra[i].w), a.seed);
                     R u[8];
                     if constexpr (RM) {
                         const int prim = (int)(prim_bits & 0xffffu);
                         const RMat& rm = rm_lookup(s, sv, rm_keys, rm_table, rm_key_of(s, sv, prim, prim_bits >> 16), p.d);
                         if (s.has_emissive) {                           // tracer.rs:74, on the slot's own radiance and throughput
-                            const float4 t4 = sm.tr[i];
-                            float4 r4 = sm.ra[i];
+                            const V4 t4 = sm.tr[i];
+                            V4 r4 = sm.ra[i];
                             r4.x = r4.x + rm.m.emission.x * t4.x; r4.y = r4.y + rm.m.emission.y * t4.y; r4.z = r4.z + rm.m.emission.z * t4.z;
                             sm.ra[i] = r4;
                         }
@@ -232,8 +259,8 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                         Mat<R> mat;
                         hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
                         if (s.has_emissive) {
-                            const float4 t4 = sm.tr[i];
-                            float4 r4 = sm.ra[i];
+                            const V4 t4 = sm.tr[i];
+                            V4 r4 = sm.ra[i];
                             r4.x = r4.x + mat.emission.x * t4.x; r4.y = r4.y + mat.emission.y * t4.y; r4.z = r4.z + mat.emission.z * t4.z;
                             sm.ra[i] = r4;
                         }
@@ -246,10 +273,10 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
             // ---- the rest of the slot; apply what A returned ----
             uint32_t fl = 0, sidx = 0, pxy = 0;
             if (valid) {
-                const float4 q2 = lds128_late(&sm.tr[i]), q3 = lds128_late(&sm.ra[i]);
+                const V4 q2 = lds128_late(&sm.tr[i]), q3 = lds128_late(&sm.ra[i]);
                 V3<R> thr(q2.x, q2.y, q2.z), rad(q3.x, q3.y, q3.z);
-                fl = __float_as_uint(q2.w); sidx = __float_as_uint(q3.w);
-                pxy = lds32_late(reinterpret_cast<const uint32_t*>(&sm.rd[i]) + 3);
+                fl = wf_bits(q2.w); sidx = wf_bits(q3.w);
+                pxy = lds32_late(reinterpret_cast<const uint32_t*>(&sm.rd[i].w));
                 if (had_event) {
                     rad = rad + p.rad * thr;                            // background (tracer.rs:67) or next-event estimation (:89); p.rad is 0 without one
                     thr = thr * p.thr;                                  // throughput * (f / pdf) (:94); unused when the path ended
@@ -282,7 +309,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                 V3<R> acc(0, 0, 0);
                 const bool dead = valid && !alive;
                 if (dead) {
-                    const float4 q4 = sm.ac[i];
+                    const V4 q4 = sm.ac[i];
                     acc = V3<R>(q4.x + p.rad.x, q4.y + p.rad.y, q4.z + p.rad.z);      // a fresh slot adds 0 to 0
                     sidx += have_pixel ? 1u : 0u;
                 }
@@ -294,11 +321,11 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                         const uint32_t px0 = pxy & 0xffffu, pr0 = pxy >> 16;
                         const uint32_t pidx = (((pr0 >> 4) * a.tiles_x + (px0 >> 4)) << 8) | ((pr0 & 15u) << 4) | (px0 & 15u);
                         const uint32_t s_begin = (blk * a.spp) >> a.tail_log2b;
-                        reinterpret_cast<float4*>(a.tail_side)[(pidx - a.n_whole) + blk * a.tail_zt] = make_float4(acc.x, acc.y, acc.z, (R)(s_end - s_begin));
+                        reinterpret_cast<V4*>(a.tail_side)[(pidx - a.n_whole) + blk * a.tail_zt] = mk4(acc.x, acc.y, acc.z, (R)(s_end - s_begin));
                     } else if (a.flush_dst) {       // multi-GPU: this launch's partial sum goes straight into the root GPU's slot (peer store)
-                        reinterpret_cast<float4*>(a.flush_dst)[pix] = make_float4(acc.x, acc.y, acc.z, (R)a.spp);
+                        reinterpret_cast<V4*>(a.flush_dst)[pix] = mk4(acc.x, acc.y, acc.z, (R)a.spp);
                     } else {
-                        float4 v = accum[pix];
+                        V4 v = accum[pix];
                         v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += (R)a.spp;
                         accum[pix] = v;
                     }
@@ -337,12 +364,12 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                     need = __ballot_sync(FULL, want);
                 }
                 if (dead) {
-                    sm.ac[i] = make_float4(acc.x, acc.y, acc.z, __uint_as_float(PRIM_SKY));
+                    sm.ac[i] = mk4(acc.x, acc.y, acc.z, wf_word(R(0), PRIM_SKY));
                     if (!done) {                                        // next sample of the slot's pixel
                         Rng<R> rng(pix, a.sample_base + sidx, a.seed);
                         R u4[4];
                         rng.block(0, 0, u4);
-                        path_begin(s, p, pxy & 0xffffu, pxy >> 16, a.W, a.H, inv_w, inv_h, u4[0], u4[1], a.film_fast != 0u, a.rcp_w, a.rcp_h);
+                        path_begin(s, p, pxy & 0xffffu, pxy >> 16, a.W, a.H, inv_w, inv_h, u4[0], u4[1], sizeof(R) == 4 && a.film_fast != 0u, a.rcp_w, a.rcp_h);
                         alive = true;
                         if (COUNT) n_samples++;
                     }
@@ -377,14 +404,14 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
                         }
                     }
                 }
-                sm.ro[i] = make_float4(p.o.x, p.o.y, p.o.z, p.hit_dist);
-                sm.rd[i] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(pxy));
-                reinterpret_cast<uint32_t*>(&sm.ac[i])[3] = new_prim;
+                sm.ro[i] = mk4(p.o.x, p.o.y, p.o.z, p.hit_dist);
+                sm.rd[i] = mk4(p.d.x, p.d.y, p.d.z, wf_word(R(0), pxy));
+                sm.ac[i].w = wf_word(R(0), new_prim);
             }
             if (valid) {
                 fl = (p.bounce << 8) | blkbits | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u);
-                sm.tr[i] = make_float4(p.thr.x, p.thr.y, p.thr.z, __uint_as_float(fl));
-                sm.ra[i] = make_float4(p.rad.x, p.rad.y, p.rad.z, __uint_as_float(sidx));
+                sm.tr[i] = mk4(p.thr.x, p.thr.y, p.thr.z, wf_word(R(0), fl));
+                sm.ra[i] = mk4(p.rad.x, p.rad.y, p.rad.z, wf_word(R(0), sidx));
                 uint32_t ticket = 0;
                 if (key != WF_NOKEY) ticket = atomicAdd(&sm.cnt[par ^ 1u][key], 1u);
                 sm.kt[i] = (key << 16) | ticket;
@@ -449,24 +476,25 @@ struct WavefrontState {
 
 // Adds the sample blocks of every tail pixel in block order (fixed association: the result does not depend on which slot traced
 // which block) to the accumulator, or stores the sum into the peer slot like the render kernel does for whole pixels.
-__global__ void k_tail_combine(const RenderArgs a) {
+template <class R> __global__ void k_tail_combine(const RenderArgs a) {
+    using V4 = typename Vec4T<R>::type;
     const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= a.tail_zt) return;
     const uint32_t idx = a.n_whole + z, tile = idx >> 8, within = idx & 255u;
     const uint32_t px = (tile % a.tiles_x) * 16u + (within & 15u), prow = (tile / a.tiles_x) * 16u + (within >> 4);
     if (px >= a.W || prow >= a.H) return;
-    const float4* side = reinterpret_cast<const float4*>(a.tail_side);
-    float4 sum = side[z];
+    const V4* side = reinterpret_cast<const V4*>(a.tail_side);
+    V4 sum = side[z];
     for (uint32_t b = 1; b < (1u << a.tail_log2b); ++b) {
-        const float4 v = side[z + b * a.tail_zt];
+        const V4 v = side[z + b * a.tail_zt];
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
     }
     const uint32_t pix = prow * a.W + px;
     if (a.flush_dst) {
-        reinterpret_cast<float4*>(a.flush_dst)[pix] = sum;
+        reinterpret_cast<V4*>(a.flush_dst)[pix] = sum;
     } else {
-        float4* accum = reinterpret_cast<float4*>(a.accum);
-        float4 v = accum[pix];
+        V4* accum = reinterpret_cast<V4*>(a.accum);
+        V4 v = accum[pix];
         v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
         accum[pix] = v;
     }
@@ -484,29 +512,42 @@ inline bool film_coords_fma_exact(uint32_t W, uint32_t H) {
 }
 
 // host launcher: one persistent CTA per SM
-inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* accum, void* flush_dst, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
+template <class R>
+inline int wavefront_render(WavefrontState& wf, const DScene<R>& d, void* accum, void* flush_dst, uint32_t W, uint32_t H, uint32_t spp, uint64_t sample_base,
                             const ptb_config& cfg, cudaStream_t stream, int sm_count, DeviceCounters* counters, unsigned int* work_counter,
                             cudaEvent_t ev0, cudaEvent_t ev1, uint64_t* launches, std::string& err) {
+    constexpr bool F32 = sizeof(R) == 4;
+    using V4 = typename Vec4T<R>::type;
     RenderArgs a{};
     a.accum = accum; a.flush_dst = flush_dst; a.W = W; a.H = H; a.spp = spp; a.sample_base = sample_base; a.seed = cfg.seed; a.rr_start = cfg.rr_start;
     a.tiles_x = (W + 15u) / 16u;
     a.n_items = a.tiles_x * ((H + 15u) / 16u) * 256u;
     a.work_counter = work_counter;
     a.counters = counters;
-    if (wf.film_w != W || wf.film_h != H) { wf.film_fast = film_coords_fma_exact(W, H); wf.film_w = W; wf.film_h = H; }
-    a.film_fast = wf.film_fast ? 1u : 0u;
+    if (F32 && (wf.film_w != W || wf.film_h != H)) { wf.film_fast = film_coords_fma_exact(W, H); wf.film_w = W; wf.film_h = H; }
+    a.film_fast = F32 && wf.film_fast ? 1u : 0u;
 #ifdef PTB_NO_FILM_FMA
     a.film_fast = 0u;
 #endif
     a.rcp_w = 1.0f / (float)W; a.rcp_h = 1.0f / (float)H;
+    a.rcp_w64 = 1.0 / (double)W; a.rcp_h64 = 1.0 / (double)H;
     const bool count = cfg.collect_counters != 0;
-    const bool rm = d.rm_entries != 0 && !d.use_bvh;
-    void (*kern)(const DScene<float>, const RenderArgs) =
-        d.use_bvh ? (count ? k_render_wavefront<true, true, false> : k_render_wavefront<false, true, false>)
-        : rm      ? (count ? k_render_wavefront<true, false, true> : k_render_wavefront<false, false, true>)
-                  : (count ? k_render_wavefront<true, false, false> : k_render_wavefront<false, false, false>);
-    const size_t smem_bytes = rm ? sizeof(WfSmemT<WF_POOL_RM, WF_SCENE_BYTES_RM, false>) : sizeof(WfSmemT<WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, true>);
-    const uint32_t WF_POOL = rm ? WF_POOL_RM : WF_POOL_GENERIC;
+    bool rm = false;
+    void (*kern)(const DScene<R>, const RenderArgs);
+    size_t smem_bytes;
+    if constexpr (F32) {
+        rm = d.rm_entries != 0 && !d.use_bvh;
+        kern = d.use_bvh ? (count ? k_render_wavefront<float, true, true, false> : k_render_wavefront<float, false, true, false>)
+               : rm      ? (count ? k_render_wavefront<float, true, false, true> : k_render_wavefront<float, false, false, true>)
+                         : (count ? k_render_wavefront<float, true, false, false> : k_render_wavefront<float, false, false, false>);
+        smem_bytes = rm ? sizeof(WfSmemT<float, WF_POOL_RM, WF_SCENE_BYTES_RM, false>) : sizeof(WfSmemT<float, WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, true>);
+    } else {
+        kern = d.use_bvh ? (count ? k_render_wavefront<double, true, true, false> : k_render_wavefront<double, false, true, false>)
+                         : (count ? k_render_wavefront<double, true, false, false> : k_render_wavefront<double, false, false, false>);
+        smem_bytes = sizeof(WfSmemT<double, WF_POOL_F64, PTB_SMEM_SCENE_BYTES, true>);
+    }
+    const uint32_t WF_POOL = wf_pool<R>(rm);
+    const int threads = wf_threads<R>(rm);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(wavefront smem): ") + cudaGetErrorString(e); return PTB_E_CUDA; }
     wf.configured = true;
@@ -521,7 +562,7 @@ inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* ac
         uint32_t log2b = 1;
         while (log2b < WF_TAIL_LOG2_BLOCKS && (2u << log2b) <= spp) ++log2b;      // at least one sample per block
         const uint32_t zt = std::min<uint32_t>(a.n_items, (((uint32_t)grid * WF_POOL + 255u) / 256u) * 256u);
-        const size_t need = ((size_t)zt << log2b) * sizeof(float4);
+        const size_t need = ((size_t)zt << log2b) * sizeof(V4);
         if (need > wf.tail_side_bytes) {
             if (wf.tail_side) cudaFree(wf.tail_side);
             wf.tail_side = nullptr; wf.tail_side_bytes = 0;
@@ -534,9 +575,9 @@ inline int wavefront_render(WavefrontState& wf, const DScene<float>& d, void* ac
 #endif
     if ((e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess ||
         (e = cudaEventRecord(ev0, stream)) != cudaSuccess) { err = cudaGetErrorString(e); return PTB_E_CUDA; }
-    kern<<<grid, rm ? WF_THREADS_RM : WF_THREADS_GENERIC, smem_bytes, stream>>>(d, a);
+    kern<<<grid, threads, smem_bytes, stream>>>(d, a);
     if ((e = cudaGetLastError()) == cudaSuccess && a.tail_zt) {
-        k_tail_combine<<<(a.tail_zt + 255u) / 256u, 256, 0, stream>>>(a);
+        k_tail_combine<R><<<(a.tail_zt + 255u) / 256u, 256, 0, stream>>>(a);
         e = cudaGetLastError();
         (*launches)++;
     }

@@ -716,3 +716,42 @@ def test_config4_full_scene_parity(rp, po, strict):
     assert (~ok).sum() <= 2
     assert frac >= (0.99 if strict else 0.93), frac
     assert abs(lum(buf.pixels)[ok].mean() / lum(ref)[ok].mean() - 1) < (1e-4 if strict else 2e-3)
+
+
+@pytest.mark.parametrize("wh_spp", [(96, 64, 4), (200, 150, 5), (37, 19, 9)])
+def test_f64_on_the_wavefront_integrator(rp, scene, po, demo_export, wh_spp):
+    """`F = f64` (lib.rs:5-6) on the shared-memory wavefront integrator: same paths as the f64 oracle to
+    1e-9, same image as the fused f64 kernel, tail blocks and odd frame sizes included."""
+    W, H, S = wh_spp
+    imgs = {}
+    for name, integ in (("wave", rp._abi.PTB_INTEGRATOR_WAVEFRONT), ("fused", rp._abi.PTB_INTEGRATOR_FUSED)):
+        pt = rp.Tracer.new(scene, precision="f64", integrator=integ)
+        buf = rp.ColorBuffer.new(W, H, "f64")
+        pt.render_spp(buf, S)
+        assert pt.integrator_used() == ("wavefront_f64" if name == "wave" else "fused_f64")
+        assert buf.frames == S and np.all(buf.pixels.reshape(-1, 4)[:, 3] == 1.0)
+        imgs[name] = buf.pixels.copy()
+        pt.close()
+    ref, _, _, _ = po.OracleScene(demo_export, "f64").render(W, H, S)
+    rel = pix_rel(imgs["wave"], ref)
+    assert (rel < 1e-9).mean() >= 0.99 and np.median(rel) < 1e-13
+    assert (pix_rel(imgs["wave"], imgs["fused"]) < 1e-11).mean() >= 0.995
+
+
+def test_f64_wavefront_on_a_bvh_scene_and_with_a_signed_distance_body(rp, po):
+    sc = _small_field(rp, 800, 2)
+    W, H, S = 96, 54, 2
+    pt = rp.Tracer.new(sc, precision="f64", integrator=rp._abi.PTB_INTEGRATOR_WAVEFRONT)
+    buf = rp.ColorBuffer.new(W, H, "f64")
+    pt.render_spp(buf, S)
+    assert pt.integrator_used() == "wavefront_bvh_f64"
+    pt.close()
+    ref, _, _, _ = po.OracleScene(sc.device_export(), "f64").render(W, H, S)
+    assert (pix_rel(buf.pixels, ref) < 1e-8).mean() >= 0.99
+    sd = rp.sdf_demo_scene()
+    pt = rp.Tracer.new(sd, precision="f64", integrator=rp._abi.PTB_INTEGRATOR_WAVEFRONT)
+    b2 = rp.ColorBuffer.new(W, H, "f64")
+    pt.render_spp(b2, S)
+    pt.close()
+    ref2, _, _, _ = po.OracleScene(sd.device_export(), "f64").render(W, H, S)
+    assert (pix_rel(b2.pixels, ref2) < 1e-7).mean() >= 0.995

@@ -4,36 +4,36 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-template <int ILP>
-__global__ void __launch_bounds__(256) k_fma(float* out, int iters, float a, float b) {
-    float x[ILP];
+template <int ILP, class T>
+__global__ void __launch_bounds__(256) k_fma(T* out, int iters, T a, T b) {
+    T x[ILP];
 #pragma unroll
-    for (int i = 0; i < ILP; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int i = 0; i < ILP; ++i) x[i] = (T)(threadIdx.x + i) * (T)1e-3;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < ILP; ++i) x[i] = fmaf(x[i], a, b);
+        for (int i = 0; i < ILP; ++i) x[i] = fma(x[i], a, b);
     }
-    float s = 0.f;
+    T s = 0;
 #pragma unroll
     for (int i = 0; i < ILP; ++i) s += x[i];
-    if (s == 123.456f) out[0] = s;   // never true; keeps the chain live
+    if (s == (T)123.456) out[0] = s;   // never true; keeps the chain live
 }
 
-extern "C" int fp32_peak(int device, double* tflops_out, double* ms_out, int* sm_count_out) {
+template <class T> static int fma_peak(int device, int iters, double* tflops_out, double* ms_out, int* sm_count_out) {
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    float* out = nullptr;
-    cudaMalloc(&out, 4);
+    T* out = nullptr;
+    cudaMalloc(&out, sizeof(T));
     constexpr int ILP = 16;
-    const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+    const int blocks = sms * 8, threads = 256;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     double best = 0, best_ms = 0;
     for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(e0);
-        k_fma<ILP><<<blocks, threads>>>(out, iters, 1.0000001f, 1e-7f);
+        k_fma<ILP, T><<<blocks, threads>>>(out, iters, (T)1.0000001, (T)1e-7);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) return -2;
         float ms = 0;
@@ -50,3 +50,7 @@ extern "C" int fp32_peak(int device, double* tflops_out, double* ms_out, int* sm
     if (sm_count_out) *sm_count_out = sms;
     return 0;
 }
+
+extern "C" int fp32_peak(int device, double* tflops_out, double* ms_out, int* sm_count_out) { return fma_peak<float>(device, 1 << 15, tflops_out, ms_out, sm_count_out); }
+// the FP64 pipe, for the f64 instantiation of `F` (lib.rs:5-6)
+extern "C" int fp64_peak(int device, double* tflops_out, double* ms_out, int* sm_count_out) { return fma_peak<double>(device, 1 << 12, tflops_out, ms_out, sm_count_out); }
