@@ -266,8 +266,11 @@ PTB_DEV float box_entry_s(float4 lo, float4 hi, const RayS& r, float limit) {
     return (tn <= tf * 1.0001f && tn <= limit) ? tn : 3.0e38f;
 }
 
+#ifndef PTB_ST_TRACE_MIN_BLOCKS
+#define PTB_ST_TRACE_MIN_BLOCKS 1
+#endif
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(ST_THREADS) k_stream_trace(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+__global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_trace(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);       // planes (shadow rays test them first)

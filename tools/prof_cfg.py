@@ -9,3 +9,8 @@ buf = rp.ColorBuffer.new(W, H)
 pt.render_spp(buf, 1, download=False)
 pt.render_spp(buf, spp, download=False)
 print(pt.last_render_ms())
+if os.environ.get("PTB_PROF_COUNT"):
+    ct = rp.Tracer.new(scene, integrator=integ, rr_start=3 if cfg == 5 else 0, collect_counters=True)
+    ct.render_spp(buf, spp, download=False)
+    c = ct.counters()
+    print("RAYS", c["closest_hit"] + c["any_hit"], "SAMPLES", c["samples"])

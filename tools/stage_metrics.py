@@ -1,6 +1,8 @@
 """Per-stage table of the streaming integrator from an ncu metrics pass:
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none --csv --log-file X.csv python tools/prof_cfg.py ...
-usage: python tools/stage_metrics.py X.csv [hbm_peak_gbs]"""
+(round 2: add lts__t_bytes.sum,lts__t_bytes.sum.pct_of_peak_sustained_elapsed,l1tex__t_bytes.sum,l1tex__t_bytes.sum.pct_of_peak_sustained_elapsed
+to the metric list for the L2 / L1TEX columns)
+usage: python tools/stage_metrics.py X.csv [hbm_peak_gbs] [rays_in_the_profiled_pass]"""
 import collections
 import csv
 import re
@@ -46,11 +48,25 @@ for i in ids:
                     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue")):
         a[nm] += d[key] * t_ms
     a["regs"] = d["launch__registers_per_thread"]
+    if "lts__t_bytes.sum" in d:
+        a["l2"] += to_bytes("lts__t_bytes.sum"); a["l1"] += to_bytes("l1tex__t_bytes.sum")
+        a["l2pct"] += d.get("lts__t_bytes.sum.pct_of_peak_sustained_elapsed", 0.0) * t_ms
+        a["l1pct"] += d.get("l1tex__t_bytes.sum.pct_of_peak_sustained_elapsed", 0.0) * t_ms
 T = sum(a["ms"] for a in agg.values())
 print(f"| stage kernel | launches | time ms (share) | regs | occupancy % of 64 warps | lanes / 32 | issue slots % | FMA pipe % | DRAM GB/s (of {peak:.0f}) |")
 print("|---|---|---|---|---|---|---|---|---|")
 for k, a in agg.items():
     print(f"| {k} | {int(a['n'])} | {a['ms']:.2f} ({100 * a['ms'] / T:.0f} %) | {int(a['regs'])} | {a['occ'] / a['ms']:.0f} | {a['lanes'] / a['ms']:.1f} | {a['issue'] / a['ms']:.0f} | "
           f"{a['fma'] / a['ms']:.0f} | {a['bytes'] / a['ms'] / 1e6:.0f} ({100 * a['bytes'] / a['ms'] / 1e6 / peak:.0f} %) |")
+if any(a["l2"] for a in agg.values()):
+    rays = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
+    print("\n| stage kernel | L2 traffic GB/s (% of the L2's peak, ncu) | L1TEX traffic GB/s (% of peak, ncu) | L2 bytes | L1TEX bytes |")
+    print("|---|---|---|---|---|")
+    for k, a in agg.items():
+        print(f"| {k} | {a['l2'] / a['ms'] / 1e6:.0f} ({a['l2pct'] / a['ms']:.0f} %) | {a['l1'] / a['ms'] / 1e6:.0f} ({a['l1pct'] / a['ms']:.0f} %) | {a['l2'] / 1e6:.0f} MB | {a['l1'] / 1e6:.0f} MB |")
+    if rays:
+        tr = [a for k, a in agg.items() if k.startswith("trace") or k in ("closest", "shadow")]
+        print(f"\nintersection kernels (closest, shadow, trace): {sum(a['l1'] for a in tr) / rays:.0f} B of L1TEX and {sum(a['l2'] for a in tr) / rays:.0f} B of L2 traffic per ray "
+              f"({rays / 1e6:.1f} M rays); whole wave {rays / (T * 1e-3) / 1e9:.2f} Grays/s under ncu's serialised, cold-cache launches")
 tot_bytes = sum(a["bytes"] for a in agg.values())
 print(f"\ntotal {T:.2f} ms, {tot_bytes / 1e9:.2f} GB of DRAM traffic = {tot_bytes / T / 1e6:.0f} GB/s average")
