@@ -221,6 +221,8 @@ typedef struct ptb_counters {
     uint64_t end_sky, end_emitter, end_pdf, end_depth, end_rr;
     /* lobe evaluations, inside disney_eval and disney_sample together (tracer.rs:343-419) */
     uint64_t ev_diffuse, ev_clearcoat, ev_reflect, ev_refract;
+    /* sphere-BVH work (0 for scenes without one): inner nodes visited — one visit tests both children — and leaf spheres tested */
+    uint64_t bvh_nodes, bvh_leaf_tests;
 } ptb_counters;
 
 typedef struct ptb_tracer ptb_tracer;

@@ -87,7 +87,7 @@ class Counters(C.Structure):
         "samples", "closest_hit", "any_hit", "shade", "nee_contrib", "eval_calls",
         "lobe_diffuse", "lobe_clearcoat", "lobe_reflect", "lobe_refract",
         "end_sky", "end_emitter", "end_pdf", "end_depth", "end_rr",
-        "ev_diffuse", "ev_clearcoat", "ev_reflect", "ev_refract")]
+        "ev_diffuse", "ev_clearcoat", "ev_reflect", "ev_refract", "bvh_nodes", "bvh_leaf_tests")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -589,7 +589,7 @@ PTB_DEV BvhNode load_node(const BvhNode* p) {
 constexpr int BVH_STACK = 40;
 template <class R, bool ANY>
 PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __restrict__ leaf_spheres, const uint32_t* __restrict__ leaf_prim,
-                         V3<R> o, V3<R> d, R& best_t) {
+                         V3<R> o, V3<R> d, R& best_t, uint32_t* stats = nullptr) {
     int best = -1;
     RayF r;
     r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
@@ -603,6 +603,7 @@ PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __
     uint32_t cur_lf = root.left_or_first, cur_cnt = root.count;
     while (true) {
         if (cur_cnt) {
+            if (stats) stats[1] += cur_cnt;
             for (uint32_t i = 0; i < cur_cnt; ++i) {
                 const DSphere<R> sph = leaf_spheres[cur_lf + i];
                 R t = isect_sphere(o, d, V3<R>(sph.cx, sph.cy, sph.cz), sph.r);
@@ -615,6 +616,7 @@ PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __
                 }
             }
         } else {
+            if (stats) stats[0]++;
             const BvhNode a = load_node(nodes + cur_lf), b = load_node(nodes + cur_lf + 1);
             const float ta = box_entry(a.lo, a.hi, r, (float)best_t), tb = box_entry(b.lo, b.hi, r, (float)best_t);
             const bool ha = ta < 3.0e38f, hb = tb < 3.0e38f;
@@ -644,12 +646,12 @@ PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __
     }
     return best;
 }
-template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t) {
-    return bvh_traverse<R, false>(s.bvh, s.bvh_spheres, s.bvh_prim, o, d, best_t);
+template <class R> PTB_DEV int bvh_closest(const DScene<R>& s, V3<R> o, V3<R> d, R& best_t, uint32_t* stats = nullptr) {
+    return bvh_traverse<R, false>(s.bvh, s.bvh_spheres, s.bvh_prim, o, d, best_t, stats);
 }
-template <class R> PTB_DEV bool bvh_any(const DScene<R>& s, V3<R> o, V3<R> d, R max_dist, bool ignore_max) {
+template <class R> PTB_DEV bool bvh_any(const DScene<R>& s, V3<R> o, V3<R> d, R max_dist, bool ignore_max, uint32_t* stats = nullptr) {
     R limit = ignore_max ? Const<R>::MAXV : max_dist;
-    return bvh_traverse<R, true>(s.bvh, s.bvh_spheres, s.bvh_prim, o, d, limit) >= 0;
+    return bvh_traverse<R, true>(s.bvh, s.bvh_spheres, s.bvh_prim, o, d, limit, stats) >= 0;
 }
 
 // Scene::closest_hit for the exported scene, geometry part (analytical.rs:36-127 + scene.rs:36-86):
@@ -667,12 +669,12 @@ template <class R> struct HitCore {
 
 // sphere part of closest_hit: the closest sphere (index, distance) — the part a dedicated traversal kernel can run
 template <class R, bool BVH>
-PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, int& best, R& dist, uint64_t& accepted) {
+PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, int& best, R& dist, uint64_t& accepted, uint32_t* bvh_stats = nullptr) {
     dist = Const<R>::MAXV;
     best = -1;
     accepted = 0;
     if (BVH) {
-        best = bvh_closest(s, o, d, dist);
+        best = bvh_closest(s, o, d, dist, bvh_stats);
     } else {
 #pragma unroll 1
         for (uint32_t i = 0; i < s.n_spheres; ++i) {
@@ -749,11 +751,11 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
 
 // normal of primitive `prim` at distance t along (o, d): analytical.rs:45-46 (sphere), :105 (plane)
 template <class R, bool BVH, bool SDF = true>
-PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in) {
+PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, uint32_t* bvh_stats = nullptr) {
     int best;
     R dist;
     uint64_t accepted;
-    closest_spheres<R, BVH>(s, sv, o, d, best, dist, accepted);
+    closest_spheres<R, BVH>(s, sv, o, d, best, dist, accepted, bvh_stats);
     return closest_hit_finish<R, BVH, SDF>(s, sv, o, d, hit_dist_in, best, dist, accepted);
 }
 
@@ -867,10 +869,10 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
 
 // Scene::any_hit, analytical.rs:130-145 (+ max_dist unless the scene flag says the impl ignores it), in two parts
 // so that a dedicated traversal kernel can run the sphere part
-template <class R, bool BVH> PTB_DEV bool any_hit_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+template <class R, bool BVH> PTB_DEV bool any_hit_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist, uint32_t* bvh_stats = nullptr) {
     const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
     if constexpr (BVH) {
-        return bvh_any(s, o, d, max_dist, ignore);
+        return bvh_any(s, o, d, max_dist, ignore, bvh_stats);
     } else {
 #pragma unroll 1
         for (uint32_t i = 0; i < s.n_spheres; ++i) {
@@ -895,8 +897,8 @@ template <class R, bool SDF = true> PTB_DEV bool any_hit_planes(const DScene<R>&
     }
     return false;
 }
-template <class R, bool BVH, bool SDF = true> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
-    return any_hit_spheres<R, BVH>(s, sv, o, d, max_dist) || any_hit_planes<R, SDF>(s, sv, o, d, max_dist);
+template <class R, bool BVH, bool SDF = true> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist, uint32_t* bvh_stats = nullptr) {
+    return any_hit_spheres<R, BVH>(s, sv, o, d, max_dist, bvh_stats) || any_hit_planes<R, SDF>(s, sv, o, d, max_dist);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1273,6 +1275,7 @@ template <class R> struct PathState {
 
 struct PathCounters {   // per-thread event counts (only when collect_counters)
     uint32_t closest_hit, any_hit, shade, nee_contrib, eval_calls, lobe[4], end_sky, end_emitter, end_pdf, end_depth, end_rr, ev[4];
+    uint32_t bvh[2];    // sphere-BVH work: [0] inner nodes visited (one visit tests both children), [1] leaf spheres tested
 };
 
 template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, uint32_t x, uint32_t row, uint32_t W, uint32_t H,
@@ -1411,7 +1414,7 @@ PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>
     bool nee = false;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;
-        nee = !any_hit<R, BVH, SDF>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
+        nee = !any_hit<R, BVH, SDF>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT ? pc->bvh : nullptr);   // tracer.rs:150-154
     }
     return shade_finish<R, COUNT, false, NoSink, true>(s, p, mat, su, nee, ns.ls, ns.light_area, u, pc);
 }
@@ -1528,7 +1531,7 @@ PTB_DEV int path_intersect(const DScene<R>& s, const SceneView<R>& sv, PathState
         return 0;
     }
     if (COUNT) pc->closest_hit++;
-    h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist);
+    h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc->bvh : nullptr);
     p.hit_dist = h.hit_dist;
     if (!h.hit) {
         path_add_sky(s, p);

@@ -13,7 +13,7 @@ PTB_DEV double4 mk4(double a, double b, double c, double d) { return make_double
 
 struct DeviceCounters {   // mirrors ptb_counters
     unsigned long long samples, closest_hit, any_hit, shade, nee_contrib, eval_calls, lobe[4], end_sky, end_emitter, end_pdf,
-        end_depth, end_rr, ev[4];
+        end_depth, end_rr, ev[4], bvh_nodes, bvh_leaf_tests;
 };
 
 struct RenderArgs {
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_con
         pc.lobe[0] = pc.lobe[1] = pc.lobe[2] = pc.lobe[3] = 0;
         pc.end_sky = pc.end_emitter = pc.end_pdf = pc.end_depth = pc.end_rr = 0;
         pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
+        pc.bvh[0] = pc.bvh[1] = 0;
     }
     uint32_t n_samples = 0;
 
@@ -172,6 +173,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_con
         atomicAdd(&c->end_pdf, (unsigned long long)pc.end_pdf);
         atomicAdd(&c->end_depth, (unsigned long long)pc.end_depth);
         atomicAdd(&c->end_rr, (unsigned long long)pc.end_rr);
+        atomicAdd(&c->bvh_nodes, (unsigned long long)pc.bvh[0]);
+        atomicAdd(&c->bvh_leaf_tests, (unsigned long long)pc.bvh[1]);
     }
 }
 

@@ -93,6 +93,7 @@ PTB_DEV void pc_clear(PathCounters& pc) {
     pc.lobe[0] = pc.lobe[1] = pc.lobe[2] = pc.lobe[3] = 0;
     pc.end_sky = pc.end_emitter = pc.end_pdf = pc.end_depth = pc.end_rr = 0;
     pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
+    pc.bvh[0] = pc.bvh[1] = 0;
 }
 PTB_DEV void pc_flush(const PathCounters& pc, uint32_t n_samples, DeviceCounters* c) {
     auto add = [](unsigned long long* p, uint32_t v) { if (v) atomicAdd(p, (unsigned long long)v); };
@@ -102,6 +103,7 @@ PTB_DEV void pc_flush(const PathCounters& pc, uint32_t n_samples, DeviceCounters
     for (int i = 0; i < 4; ++i) { add(&c->lobe[i], pc.lobe[i]); add(&c->ev[i], pc.ev[i]); }
     add(&c->end_sky, pc.end_sky); add(&c->end_emitter, pc.end_emitter); add(&c->end_pdf, pc.end_pdf);
     add(&c->end_depth, pc.end_depth); add(&c->end_rr, pc.end_rr);
+    add(&c->bvh_nodes, pc.bvh[0]); add(&c->bvh_leaf_tests, pc.bvh[1]);
 }
 
 // warp-aggregated queue push for the lanes that are converged here (any subset of the warp): one atomic per group
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_cons
             const float4 A0 = a.a0[slot], A1 = a.a1[slot];
             const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
             if (COUNT) pc.closest_hit++;
-            const HitCore<R> h = closest_hit_core<R, BVH, false>(s, sv, o, d, A1.z);       // (no signed-distance programs in this integrator)
+            const HitCore<R> h = closest_hit_core<R, BVH, false>(s, sv, o, d, A1.z, COUNT ? pc.bvh : nullptr);       // (no signed-distance programs in this integrator)
             key = stream_after_hit<COUNT, BVH>(s, sv, a, slot, d, A1.w, h, pc);
         }
         push_by_key(a, ctr, key, slot);
@@ -344,6 +346,7 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
         }
         // ---- one inner node: both children with one 64-byte read, nearer first
         if (active && cur != ST_NONE && (cur & 7u) == 0u) {
+            if (COUNT) pc.bvh[0]++;
             const float4* c = nodes + (size_t)(cur >> 3) * 2u;
             const float4 alo = __ldg(c), ahi = __ldg(c + 1), blo = __ldg(c + 2), bhi = __ldg(c + 3);
             const float ta = box_entry_s(alo, ahi, r, best_t), tb = box_entry_s(blo, bhi, r, best_t);
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
             if (active && pend != 0u) {
                 const uint32_t first = pend >> 3, cnt = pend & 7u;
                 pend = 0u;
+                if (COUNT) pc.bvh[1] += cnt;
                 for (uint32_t i = 0; i < cnt; ++i) {
                     const DSphere<R> sph = leaf_spheres[first + i];
                     const R t = isect_sphere(o, d, V3<R>(sph.cx, sph.cy, sph.cz), sph.r);
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_const
         const uint32_t j = chunk + lane;
         if (j >= n) continue;
         const float4 S0 = a.s0[j], S1 = a.s1[j];
-        const bool occluded = any_hit<R, BVH, false>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w);     // tracer.rs:150-154
+        const bool occluded = any_hit<R, BVH, false>(s, sv, V3<R>(S0.x, S0.y, S0.z), V3<R>(S1.x, S1.y, S1.z), S0.w, COUNT ? pc.bvh : nullptr);     // tracer.rs:150-154
         if (!occluded) {
             const float4 S2 = a.s2[j];
             const uint32_t flags = __float_as_uint(S2.w);

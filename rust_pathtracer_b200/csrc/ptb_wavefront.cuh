@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
         pc.lobe[0] = pc.lobe[1] = pc.lobe[2] = pc.lobe[3] = 0;
         pc.end_sky = pc.end_emitter = pc.end_pdf = pc.end_depth = pc.end_rr = 0;
         pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
+        pc.bvh[0] = pc.bvh[1] = 0;
     }
 
     while (n_queue) {
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                     if (COUNT) pc.end_depth++;
                 } else {
                     if (COUNT) pc.closest_hit++;
-                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH>(s, sv, p.o, p.d, p.hit_dist);   // signed-distance programs: generic instantiation only
+                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc.bvh : nullptr);   // signed-distance programs: generic instantiation only
                     p.hit_dist = h.hit_dist;
                     if (!h.hit) {
                         key = WF_MISS;                                 // background lookup next iteration, with full warps
@@ -462,6 +463,8 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
         atomicAdd(&c->end_pdf, (unsigned long long)pc.end_pdf);
         atomicAdd(&c->end_depth, (unsigned long long)pc.end_depth);
         atomicAdd(&c->end_rr, (unsigned long long)pc.end_rr);
+        atomicAdd(&c->bvh_nodes, (unsigned long long)pc.bvh[0]);
+        atomicAdd(&c->bvh_leaf_tests, (unsigned long long)pc.bvh[1]);
     }
 }
 

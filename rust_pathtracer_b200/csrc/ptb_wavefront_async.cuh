@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
         pc.lobe[0] = pc.lobe[1] = pc.lobe[2] = pc.lobe[3] = 0;
         pc.end_sky = pc.end_emitter = pc.end_pdf = pc.end_depth = pc.end_rr = 0;
         pc.ev[0] = pc.ev[1] = pc.ev[2] = pc.ev[3] = 0;
+        pc.bvh[0] = pc.bvh[1] = 0;
     }
 
 #pragma unroll 1
@@ -433,6 +434,8 @@ __global__ void __launch_bounds__(RM ? WF_THREADS_RM : WF_THREADS_GENERIC, 1) k_
         atomicAdd(&c->end_pdf, (unsigned long long)pc.end_pdf);
         atomicAdd(&c->end_depth, (unsigned long long)pc.end_depth);
         atomicAdd(&c->end_rr, (unsigned long long)pc.end_rr);
+        atomicAdd(&c->bvh_nodes, (unsigned long long)pc.bvh[0]);
+        atomicAdd(&c->bvh_leaf_tests, (unsigned long long)pc.bvh[1]);
     }
 }
 

@@ -416,6 +416,9 @@ def test_stream_bvh_and_rr(rp):
         pt.close()
     assert (pix_rel(img["stream"][0], img["fused"][0]) < 1e-5).mean() > 0.99
     for k in img["fused"][1]:
+        if k.startswith("bvh_"):        # traversal work: absolute tolerances below are per path event, not per node visit
+            assert abs(img["stream"][1][k] - img["fused"][1][k]) <= 5e-3 * img["fused"][1][k], k
+            continue
         assert abs(img["stream"][1][k] - img["fused"][1][k]) <= max(3, 1e-3 * W * H * S), k
     sc = rp.divergence_stress_scene(side=6, depth=16)
     for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
@@ -435,6 +438,9 @@ def test_stream_bvh_and_rr(rp):
         pt.close()
     assert (pix_rel(img["stream"][0], img["fused"][0]) < 1e-5).mean() > 0.99
     for k in img["fused"][1]:
+        if k.startswith("bvh_"):        # the dedicated traversal kernels of large scenes visit the tree in another order
+            assert 0.5 < img["stream"][1][k] / max(1, img["fused"][1][k]) < 2.0, k
+            continue
         assert abs(img["stream"][1][k] - img["fused"][1][k]) <= max(3, 1e-3 * 160 * 90 * 3), k
     pt = rp.Tracer.new(sc, integrator=rp._abi.PTB_INTEGRATOR_STREAM)      # non-counting build: zero-pdf shadow rays pruned
     buf = rp.ColorBuffer.new(160, 90)
@@ -755,3 +761,36 @@ def test_f64_wavefront_on_a_bvh_scene_and_with_a_signed_distance_body(rp, po):
     pt.close()
     ref2, _, _, _ = po.OracleScene(sd.device_export(), "f64").render(W, H, S)
     assert (pix_rel(b2.pixels, ref2) < 1e-7).mean() >= 0.995
+
+
+def test_bvh_work_counters(rp):
+    """ptb_counters.bvh_nodes / bvh_leaf_tests (bench.py's work model for BASELINE configs 4 and 5): the three integrators run the
+    same traversal on scenes below the split threshold, so they must count the same work for the same rays; the dedicated
+    traversal kernels of large scenes (persistent lanes, parked leaves) visit the same tree in another order."""
+    sc = _small_field(rp, 3000, 2)
+    W, H, S = 96, 54, 2
+    got = {}
+    for name, integ in (("fused", rp._abi.PTB_INTEGRATOR_FUSED), ("wave", rp._abi.PTB_INTEGRATOR_WAVEFRONT), ("stream", rp._abi.PTB_INTEGRATOR_STREAM)):
+        pt = rp.Tracer.new(sc, integrator=integ, collect_counters=True)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        got[name] = pt.counters()
+        pt.close()
+    rays = got["fused"]["closest_hit"] + got["fused"]["any_hit"]
+    assert got["fused"]["bvh_nodes"] > 2 * rays and got["fused"]["bvh_leaf_tests"] > 0.2 * rays      # a 3000-sphere tree is ~11 levels deep
+    for name in ("wave", "stream"):
+        for k in ("bvh_nodes", "bvh_leaf_tests"):
+            assert abs(got[name][k] - got["fused"][k]) <= 2e-3 * got["fused"][k], (name, k, got[name][k], got["fused"][k])
+    big = rp.sphere_field_scene(n_spheres=20000, n_lights_side=2)                                  # above ST_SPLIT_MIN_SPHERES
+    pt = rp.Tracer.new(big, collect_counters=True)
+    buf = rp.ColorBuffer.new(W, H)
+    pt.render_spp(buf, S)
+    c = pt.counters()
+    assert pt.integrator_used() == "stream_split_bvh"
+    pt.close()
+    pt = rp.Tracer.new(big, collect_counters=True, integrator=rp._abi.PTB_INTEGRATOR_FUSED)
+    pt.render_spp(buf, S)
+    f = pt.counters()
+    pt.close()
+    assert abs(c["closest_hit"] - f["closest_hit"]) <= 1e-2 * f["closest_hit"]      # (a few paths flip a branch between the two instantiations)
+    assert 0.5 < c["bvh_nodes"] / f["bvh_nodes"] < 2.0 and 0.5 < c["bvh_leaf_tests"] / f["bvh_leaf_tests"] < 2.0
