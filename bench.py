@@ -379,8 +379,10 @@ def run_own(args, cfg):
         host_bufs = [rp.ColorBuffer.new(W, H) for _ in range(2)]            # page-locked by the wrapper on first use (ptb_pin_host)
         step_no = [0]
 
+        pod = et.tracer.prepare_scene()                         # the POD arrays a Rust / C++ host holds; uploaded every step
+
         def e2e_step():
-            et.tracer.sync_scene()                              # H2D: the step's input (the scene description)
+            et.tracer.sync_scene(pod)                           # H2D: the step's input (the scene description)
             et.step(S, host_bufs[step_no[0] & 1])               # trace + gather + (rank 0) asynchronous D2H of the mean image
             step_no[0] += 1
 

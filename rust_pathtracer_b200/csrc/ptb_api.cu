@@ -53,12 +53,16 @@ template <class R> struct SceneBuffers {
     size_t cap_lbvh = 0, cap_lprim = 0, cap_lspheres = 0;
     size_t cap_blob = 0, cap_bvh = 0, cap_prim = 0, cap_spheres = 0;   // allocations are reused across set_scene calls:
     size_t bytes = 0;                                                  // cudaFree would synchronise the whole device
-    uint32_t rm_entries_built = 0;                                     // resolved-material entries in the blob (d.rm_entries is 0 while a signed-distance program is attached)
+    uint32_t rm_entries_built = 0;
+    // the sphere BVH on the device is keyed by the sphere data it was built from: re-exporting a scene whose spheres are unchanged
+    // (ptb_set_scene_* per frame, the way the reference re-reads its scene per ray) re-uploads the arrays but not the tree
+    uint64_t bvh_key = 0; size_t bvh_key_n = 0, bvh_bytes = 0; bool bvh_cached = false;                                     // resolved-material entries in the blob (d.rm_entries is 0 while a signed-distance program is attached)
     void release() {
         for (void** p : {&blob, &bvh, &bvh_prim, &bvh_spheres, &lbvh, &lbvh_prim, &lbvh_spheres}) {
             if (*p) cudaFree(*p);
             *p = nullptr;
         }
+        bvh_cached = false;
         cap_blob = cap_bvh = cap_prim = cap_spheres = cap_lbvh = cap_lprim = cap_lspheres = 0;
         bytes = 0;
     }
@@ -430,7 +434,13 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
             }
         }
     }
-    if (use_bvh) build_sphere_bvh();
+    uint64_t sphere_key = 1469598103934665603ull;          // FNV-1a over the sphere array
+    {
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(spheres.data());
+        for (size_t i = 0, n = spheres.size() * sizeof(DSphere<R>); i < n; ++i) { sphere_key ^= b[i]; sphere_key *= 1099511628211ull; }
+    }
+    const bool reuse_bvh = use_bvh && sb.bvh_cached && sb.bvh_key == sphere_key && sb.bvh_key_n == spheres.size() && sb.bvh && sb.bvh_prim && sb.bvh_spheres;
+    if (use_bvh && !reuse_bvh) build_sphere_bvh();
     if (std::max(bvh_depth, light_bvh_depth) >= (uint32_t)BVH_STACK)
         return fail(PTB_E_INVALID, "internal: BVH depth %u exceeds the traversal stack (%d)", std::max(bvh_depth, light_bvh_depth), BVH_STACK);
     for (const auto* nv : {&nodes, &lnodes})
@@ -496,11 +506,19 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
 
     sb.bytes = 0;
     CU(upload_vec(&sb.blob, sb.cap_blob, blob, t->stream, sb.bytes));
-    CU(upload_vec(&sb.bvh, sb.cap_bvh, nodes, t->stream, sb.bytes));
-    CU(upload_vec(&sb.bvh_prim, sb.cap_prim, prim, t->stream, sb.bytes));
-    std::vector<DSphere<R>> leaf_spheres(prim.size());
-    for (size_t i = 0; i < prim.size(); ++i) leaf_spheres[i] = spheres[prim[i]];
-    CU(upload_vec(&sb.bvh_spheres, sb.cap_spheres, leaf_spheres, t->stream, sb.bytes));
+    if (reuse_bvh) {
+        sb.bytes += sb.bvh_bytes;                       // still resident
+    } else {
+        const size_t before = sb.bytes;
+        CU(upload_vec(&sb.bvh, sb.cap_bvh, nodes, t->stream, sb.bytes));
+        CU(upload_vec(&sb.bvh_prim, sb.cap_prim, prim, t->stream, sb.bytes));
+        std::vector<DSphere<R>> leaf_spheres(prim.size());
+        for (size_t i = 0; i < prim.size(); ++i) leaf_spheres[i] = spheres[prim[i]];
+        CU(upload_vec(&sb.bvh_spheres, sb.cap_spheres, leaf_spheres, t->stream, sb.bytes));
+        CU(cudaStreamSynchronize(t->stream));           // leaf_spheres goes out of scope
+        sb.bvh_bytes = sb.bytes - before;
+        sb.bvh_cached = use_bvh; sb.bvh_key = sphere_key; sb.bvh_key_n = spheres.size();
+    }
     CU(upload_vec(&sb.lbvh, sb.cap_lbvh, lnodes, t->stream, sb.bytes));
     CU(upload_vec(&sb.lbvh_prim, sb.cap_lprim, lprim, t->stream, sb.bytes));
     CU(upload_vec(&sb.lbvh_spheres, sb.cap_lspheres, lleaf, t->stream, sb.bytes));

@@ -459,19 +459,26 @@ class Tracer:
         """Mutable access to the scene; call `sync_scene()` after editing it."""
         return self._scene
 
-    def sync_scene(self) -> None:
-        """Re-export the scene to the device (the reference re-reads the scene every ray)."""
+    def prepare_scene(self):
+        """the scene as the POD structs of include/ptb200.h, built once (a Rust or C++ host holds these arrays anyway; building
+        100 000 ctypes structs is the slow part of `sync_scene` in this Python mirror)"""
         export = self._scene.device_export()
         sc, keep = export.to_c(self.precision)
+        sd = export.sdf.to_c(self.precision) if (export.sdf is not None and export.sdf.nodes) else None
+        return (sc, keep, sd, export.eps)
+
+    def sync_scene(self, prepared=None) -> None:
+        """Re-export the scene to the device (the reference re-reads the scene every ray).  `prepared`: what prepare_scene()
+        returned, to upload the same POD arrays again without rebuilding them."""
+        sc, keep, sd, eps = prepared if prepared is not None else self.prepare_scene()
         fn = self._lib.ptb_set_scene_f32 if self.precision == "f32" else self._lib.ptb_set_scene_f64
         self._check(fn(self._handle(), C.byref(sc)))
         self.scene_bytes = C.sizeof(sc) + sum(C.sizeof(k) for k in keep)
-        if export.sdf is not None and export.sdf.nodes:
-            sd, sd_keep = export.sdf.to_c(self.precision)
+        if sd is not None:
             fn = self._lib.ptb_set_sdf_f32 if self.precision == "f32" else self._lib.ptb_set_sdf_f64
-            self._check(fn(self._handle(), C.byref(sd)))
-            self.scene_bytes += C.sizeof(sd) + C.sizeof(sd_keep)
-        self.eps = export.eps
+            self._check(fn(self._handle(), C.byref(sd[0])))
+            self.scene_bytes += C.sizeof(sd[0]) + C.sizeof(sd[1])
+        self.eps = eps
 
     # -- internals ------------------------------------------------------------------------------
     def _check(self, code: int) -> None:

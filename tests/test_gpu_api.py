@@ -218,3 +218,29 @@ def test_async_download_matches_blocking_download(rp, scene):
     for k in range(3):
         assert np.array_equal(bufs[k].read_pixels(), sync[k]), k
     pt.close()
+
+
+def test_scene_reexport_reuses_the_bvh_only_for_unchanged_spheres(rp):
+    """ptb_set_scene_* keys the device BVH by the sphere data: re-exporting the same scene (bench.py's e2e step does it every step,
+    like the reference re-reads its scene per ray) must not rebuild it, and must rebuild it as soon as one sphere moves."""
+    import time
+    sc = rp.sphere_field_scene(n_spheres=30000, n_lights_side=2)
+    pt = rp.Tracer.new(sc)
+    W, H = 96, 54
+    a = rp.ColorBuffer.new(W, H); pt.render_spp(a, 2)
+    pod = pt.prepare_scene()
+    t0 = time.perf_counter(); pt.sync_scene(pod); t_same = time.perf_counter() - t0
+    b = rp.ColorBuffer.new(W, H); pt.render_spp(b, 2)
+    assert np.array_equal(a.pixels, b.pixels)
+    export = sc.device_export()
+    export.spheres[0].center = rp.F3(0.0, 500.0, 0.0)
+    big = export.spheres[1]; big.center = rp.F3(0.0, 1.5, 6.0); big.radius = 2.5      # a large sphere in front of the camera
+    pod2 = pt.prepare_scene()
+    t0 = time.perf_counter(); pt.sync_scene(pod2); t_changed = time.perf_counter() - t0
+    c = rp.ColorBuffer.new(W, H); pt.render_spp(c, 2)
+    assert not np.array_equal(a.pixels, c.pixels)
+    fresh = rp.Tracer.new(sc)
+    d = rp.ColorBuffer.new(W, H); fresh.render_spp(d, 2)
+    assert np.array_equal(c.pixels, d.pixels)                      # the rebuilt tree is the tree a new tracer builds
+    assert t_same < 0.5 * t_changed, (t_same, t_changed)
+    pt.close(); fresh.close()
