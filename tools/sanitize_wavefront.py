@@ -24,4 +24,21 @@ pt = rp.Tracer.new(rp.divergence_stress_scene(side=8, depth=6), integrator=WF, r
 buf = rp.ColorBuffer.new(96, 54)
 pt.render_spp(buf, 3)
 pt.close()
+# round 2: the f64 instantiation, a signed-distance scene (generic kernel, f32 and f64) and an emissive material (the
+# emission read-modify-write on the slot's radiance before shading)
+pt = rp.Tracer.new(rp.AnalyticalScene.new(), integrator=WF, precision="f64")
+buf = rp.ColorBuffer.new(97, 61, "f64")
+pt.render_spp(buf, 5)
+pt.close()
+for prec in ("f32", "f64"):
+    pt = rp.Tracer.new(rp.sdf_demo_scene(), integrator=WF, precision=prec)
+    buf = rp.ColorBuffer.new(64, 36, prec)
+    pt.render_spp(buf, 2)
+    pt.close()
+ex = rp.AnalyticalScene.new().device_export()
+ex.materials[1].emission = rp.F3(0.5, 0.2, 0.1)
+pt = rp.Tracer.new(rp.ExportedScene(ex), integrator=WF)
+buf = rp.ColorBuffer.new(80, 45)
+pt.render_spp(buf, 3)
+pt.close()
 print("ok")
