@@ -71,8 +71,13 @@ enum {
     PTB_MAT_IOR = 1u << 12, PTB_MAT_ALL = 0x1fffu
 };
 
-/* Light kinds, rust-pathtracer/src/globals.rs:69-73.  Only Spherical is implemented by the
- * reference (tracer.rs:175-217) and by this library. */
+/* Light kinds, rust-pathtracer/src/globals.rs:69-73.  Only Spherical is implemented by the reference (tracer.rs:175-217,
+ * scene.rs:69): by default the other two are inert exactly like there (they still count in number_of_lights()).  With
+ * PTB_SCENE_EXTENDED_LIGHTS they get the semantics of the GLSL project the reference was ported from (the hooks are in place:
+ * `Light.u / v / area`, globals.rs:76-84; the single-sided cull at tracer.rs:148; "no MIS for distant light", tracer.rs:158):
+ *   RECTANGULAR  quad position + s*u + t*v, s, t in [0,1]; emits from the side cross(u, v) points to; sampled uniformly by area,
+ *                pdf = dist^2 / (area * |n.d|); hit by rays (hidden from behind), pdf = t^2 / (area * cos) for the MIS weight
+ *   DISTANT      direction normalize(position), emission constant, pdf 1, area 0 (no MIS), never hit by rays             */
 enum { PTB_LIGHT_RECTANGULAR = 0, PTB_LIGHT_SPHERICAL = 1, PTB_LIGHT_DISTANT = 2 };
 
 /* Background kinds. */
@@ -89,7 +94,9 @@ enum {
     PTB_SCENE_ANYHIT_IGNORES_MAX_DIST = 1u << 0,
     /* Build / use the sphere BVH even for small sphere counts (otherwise: count >= bvh_threshold) */
     PTB_SCENE_FORCE_BVH               = 1u << 1,
-    PTB_SCENE_NO_BVH                  = 1u << 2
+    PTB_SCENE_NO_BVH                  = 1u << 2,
+    /* Rectangular and distant lights are sampled / hit (see PTB_LIGHT_*) instead of being inert like in the reference */
+    PTB_SCENE_EXTENDED_LIGHTS         = 1u << 3
 };
 
 /* Signed-distance program (ptb_set_sdf_*): instructions in postfix order.  Primitives push (distance, material), combinators
@@ -152,7 +159,9 @@ enum {
         REAL position[3];                                                                         \
         REAL radius;                                                                              \
         REAL emission[3];                                                                         \
-        uint32_t type;                   /* PTB_LIGHT_*; only SPHERICAL is sampled            */  \
+        uint32_t type;                   /* PTB_LIGHT_*                                       */  \
+        REAL u[3];                       /* RECTANGULAR: the two edges (globals.rs:80-81)     */  \
+        REAL v[3];                                                                                \
     } ptb_light_##SFX;                                                                            \
     /* camera/pinhole.rs:5-25 (private fields origin/center/fov; fov in degrees, horizontal) */   \
     typedef struct ptb_camera_##SFX {                                                             \

@@ -184,7 +184,7 @@ public:
         }
         for (size_t i = 0; i < li.size(); ++i) {
             const Light& l = e.lights[i].light;
-            li[i] = LI{{l.position.x, l.position.y, l.position.z}, l.radius, {l.emission.x, l.emission.y, l.emission.z}, l.light_type};
+            li[i] = LI{{l.position.x, l.position.y, l.position.z}, l.radius, {l.emission.x, l.emission.y, l.emission.z}, l.light_type, {0, 0, 0}, {0, 0, 0}};
         }
         S s{};
         s.n_spheres = (uint32_t)sp.size(); s.n_planes = (uint32_t)pl.size(); s.n_materials = (uint32_t)ma.size(); s.n_lights = (uint32_t)li.size();

@@ -134,6 +134,7 @@ template <class R> struct Light {
     uint32_t type = PTB_LIGHT_SPHERICAL;
     V3<R> position, emission;
     R radius = 0, area = 0;
+    V3<R> u, v;                         // globals.rs:80-81 (rectangular lights)
     static Light spherical(V3<R> pos, R radius, V3<R> emission) {
         Light l;
         l.type = PTB_LIGHT_SPHERICAL;
@@ -355,9 +356,45 @@ template <class R> struct Scene {
         t_out = t0;
         return true;
     }
+    // PTB_SCENE_EXTENDED_LIGHTS (include/ptb200.h): rectangular / distant lights take the upstream GLSL project's semantics
+    // instead of being inert like in the reference.  Not reference code: the CPU statement of the library's extension.
+    virtual bool extended_lights() const { return false; }
+    // ray against a rectangular light: hidden from behind; t and the cosine at the quad
+    static bool light_rect(const Ray<R>& ray, const Light<R>& L, R& t_out, R& cos_out) {
+        const V3<R> n = normalize(cross(L.u, L.v));
+        const R dn = dot(n, ray.direction);
+        if (!(dn < R(0))) return false;
+        const R t = dot(n, L.position - ray.origin) / dn;
+        if (!(t > R(0))) return false;
+        const V3<R> w = (ray.origin + t * ray.direction) - L.position;
+        const R a1 = dot(L.u, w) / dot(L.u, L.u), a2 = dot(L.v, w) / dot(L.v, L.v);
+        if (a1 < R(0) || a1 > R(1) || a2 < R(0) || a2 > R(1)) return false;
+        t_out = t; cos_out = -dn;
+        return true;
+    }
     // scene.rs:36-86 — default method; `dist` starts from the (possibly stale) state.hit_dist
     bool sample_lights(const Ray<R>& ray, State<R>& state, LightSampleRec<R>& light_sample,
                        const std::vector<Light<R>>& lights) const {
+        bool hit = sample_lights_spherical(ray, state, light_sample, lights);
+        if (extended_lights() && state.hit_dist > R(0)) {         // quads after the spheres, nearest wins (extension)
+            R dist = state.hit_dist;
+            for (const Light<R>& light : lights) {
+                if (light.type != PTB_LIGHT_RECTANGULAR) continue;
+                R d, c;
+                if (light_rect(ray, light, d, c) && d < dist) {
+                    dist = d;
+                    light_sample.pdf = (dist * dist) / (light.area * c);
+                    light_sample.emission = light.emission;
+                    state.is_emitter = true;
+                    state.hit_dist = d;
+                    hit = true;
+                }
+            }
+        }
+        return hit;
+    }
+    bool sample_lights_spherical(const Ray<R>& ray, State<R>& state, LightSampleRec<R>& light_sample,
+                                 const std::vector<Light<R>>& lights) const {
         bool hit = false;
         R dist = state.hit_dist;
         for (const Light<R>& light : lights) {
@@ -601,6 +638,13 @@ template <class R> struct FlatScene : Scene<R> {
             Light<R> L = Light<R>::spherical(V3<R>(l.position[0], l.position[1], l.position[2]), l.radius,
                                              V3<R>(l.emission[0], l.emission[1], l.emission[2]));
             L.type = l.type;
+            L.u = V3<R>(l.u[0], l.u[1], l.u[2]); L.v = V3<R>(l.v[0], l.v[1], l.v[2]);
+            if (l.type == PTB_LIGHT_RECTANGULAR) {
+                const R cx = l.u[1] * l.v[2] - l.u[2] * l.v[1], cy = l.u[2] * l.v[0] - l.u[0] * l.v[2], cz = l.u[0] * l.v[1] - l.u[1] * l.v[0];
+                L.area = std::sqrt(cx * cx + cy * cy + cz * cz);
+            } else if (l.type == PTB_LIGHT_DISTANT) {
+                L.area = R(0);
+            }
             lights.push_back(L);
         }
         pinhole.origin = V3<R>(s.camera.origin[0], s.camera.origin[1], s.camera.origin[2]);
@@ -617,6 +661,7 @@ template <class R> struct FlatScene : Scene<R> {
     }
     const Pinhole<R>& camera() const override { return pinhole; }
     uint16_t recursion_depth() const override { return depth; }
+    bool extended_lights() const override { return (flags & PTB_SCENE_EXTENDED_LIGHTS) != 0; }
     V3<R> background(const Ray<R>& ray) const override {
         if (bg_kind == PTB_BG_GRADIENT_Y) {
             R t = R(0.5) * (ray.direction.y + R(1));
@@ -1076,7 +1121,25 @@ template <class R> struct Tracer {
 
     // tracer.rs:173-220 — (r1, r2) are the draws at 191-192
     void sample_light(const Light<R>& light, const V3<R>& scatter_pos, LightSampleRec<R>& light_sample, R r1, R r2) const {
-        if (light.type != PTB_LIGHT_SPHERICAL) return;                        // tracer.rs:217
+        if (light.type != PTB_LIGHT_SPHERICAL) {
+            if (!scene->extended_lights()) return;                            // tracer.rs:217 `_ => {}`
+            light_sample.emission = (R)scene->number_of_lights() * light.emission;
+            if (light.type == PTB_LIGHT_RECTANGULAR) {                        // extension: uniform by area
+                V3<R> surf = (light.position + r1 * light.u) + r2 * light.v;
+                light_sample.direction = surf - scatter_pos;
+                light_sample.dist = length(light_sample.direction);
+                R dist_sq = light_sample.dist * light_sample.dist;
+                light_sample.direction /= V3<R>::new_x(light_sample.dist);
+                light_sample.normal = normalize(cross(light.u, light.v));
+                light_sample.pdf = dist_sq / (light.area * std::fabs(dot(light_sample.normal, light_sample.direction)));
+            } else {                                                          // distant
+                light_sample.direction = normalize(light.position);
+                light_sample.normal = normalize(scatter_pos - light.position);
+                light_sample.dist = std::numeric_limits<R>::max();
+                light_sample.pdf = R(1);
+            }
+            return;
+        }
         V3<R> sphere_center_to_surface = scatter_pos - light.position;
         R dist_to_sphere_center = length(sphere_center_to_surface);
         // uniform_sample_hemisphere, tracer.rs:178-182

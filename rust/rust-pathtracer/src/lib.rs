@@ -85,7 +85,8 @@ impl DeviceScene {
     /// a spherical light; the library derives `area = 4 pi r^2` in `F` (light.rs:22)
     pub fn light(l: &AnalyticalLight) -> abi::Light {
         let p = l.light.position; let e = l.light.emission;
-        abi::Light { position: [p.x, p.y, p.z], radius: l.light.radius, emission: [e.x, e.y, e.z],
+        let (u, v) = (l.light.u, l.light.v);
+        abi::Light { position: [p.x, p.y, p.z], radius: l.light.radius, emission: [e.x, e.y, e.z], u: [u.x, u.y, u.z], v: [v.x, v.y, v.z],
                      type_: match l.light.light_type { LightType::Rectangular => sys::PTB_LIGHT_RECTANGULAR, LightType::Spherical => sys::PTB_LIGHT_SPHERICAL,
                                                         LightType::Distant => sys::PTB_LIGHT_DISTANT } }
     }

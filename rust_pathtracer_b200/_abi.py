@@ -19,6 +19,7 @@ PTB_BG_CONSTANT, PTB_BG_GRADIENT_Y = 0, 1
 PTB_SCENE_ANYHIT_IGNORES_MAX_DIST, PTB_SCENE_FORCE_BVH, PTB_SCENE_NO_BVH = 1, 2, 4
 PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT, PTB_INTEGRATOR_STREAM = 0, 1, 2, 3
 PTB_PEER_HANDLE_BYTES = 64
+PTB_SCENE_EXTENDED_LIGHTS = 1 << 3
 PTB_FRAME_HOST_UNCHANGED = 1
 PTB_SDF_SPHERE, PTB_SDF_BOX, PTB_SDF_TORUS, PTB_SDF_PLANE = 0, 1, 2, 3
 PTB_SDF_UNION, PTB_SDF_SMOOTH_UNION, PTB_SDF_SUBTRACT, PTB_SDF_INTERSECT = 16, 17, 18, 19
@@ -47,7 +48,7 @@ def _declare(real):
         _fields_ = [("point", real * 3), ("normal", real * 3), ("material", C.c_uint32)]
 
     class Light(C.Structure):
-        _fields_ = [("position", real * 3), ("radius", real), ("emission", real * 3), ("type", C.c_uint32)]
+        _fields_ = [("position", real * 3), ("radius", real), ("emission", real * 3), ("type", C.c_uint32), ("u", real * 3), ("v", real * 3)]
 
     class Camera(C.Structure):
         _fields_ = [("origin", real * 3), ("center", real * 3), ("fov", real)]

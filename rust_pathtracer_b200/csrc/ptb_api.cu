@@ -403,7 +403,14 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         o.px = l.position[0]; o.py = l.position[1]; o.pz = l.position[2]; o.radius = l.radius;
         o.ex = l.emission[0]; o.ey = l.emission[1]; o.ez = l.emission[2];
         o.area = R(4) * PI_R * l.radius * l.radius;   // light.rs:22
-        o.type = l.type; o.pad[0] = o.pad[1] = o.pad[2] = 0;
+        o.type = l.type; o.pad = 0;
+        o.ux = l.u[0]; o.uy = l.u[1]; o.uz = l.u[2]; o.vx = l.v[0]; o.vy = l.v[1]; o.vz = l.v[2];
+        if (l.type == PTB_LIGHT_RECTANGULAR) {          // |cross(u, v)|, in R with this operation order (the oracle's)
+            const R cx = l.u[1] * l.v[2] - l.u[2] * l.v[1], cy = l.u[2] * l.v[0] - l.u[0] * l.v[2], cz = l.u[0] * l.v[1] - l.u[1] * l.v[0];
+            o.area = std::sqrt(cx * cx + cy * cy + cz * cz);
+        } else if (l.type == PTB_LIGHT_DISTANT) {
+            o.area = R(0);                              // no MIS for distant lights (tracer.rs:158)
+        }
     }
 
     // BVH over the spheres, and over the spherical lights when there are many (binned SAH, f32 bounds rounded outward)
@@ -544,6 +551,8 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
             d.light_hi[k] = std::max(d.light_hi[k], std::nextafterf((float)(c[k] + r), 3e38f));
         }
     }
+    d.n_rect_lights = 0;
+    for (const auto& l : lights) if (l.type == PTB_LIGHT_RECTANGULAR) d.n_rect_lights++;
     d.use_bvh = use_bvh; d.patch_materials = patch;
     d.depth = sc->depth; d.flags = sc->flags; d.eps = sc->eps;
     d.n_lights_f = (R)sc->n_lights;

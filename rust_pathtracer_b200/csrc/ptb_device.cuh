@@ -249,7 +249,7 @@ template <class R> struct DMaterial {
 };
 template <class R> struct alignas(4 * sizeof(R)) DSphere { R cx, cy, cz, r; };   // one 16-byte (f32) / 32-byte (f64) vector load
 template <class R> struct DPlane { R px, py, pz, nx, ny, nz; };
-template <class R> struct DLight { R px, py, pz, radius, ex, ey, ez, area; uint32_t type, pad[3]; };
+template <class R> struct DLight { R px, py, pz, radius, ex, ey, ez, area; uint32_t type, pad; R ux, uy, uz, vx, vy, vz; };
 
 // One instruction of the signed-distance program, in postfix order (ptb_sdf_node_*, include/ptb200.h): primitives push
 // (distance, material), combinators pop two entries and push one.
@@ -292,6 +292,7 @@ template <class R> struct DScene {
     R n_lights_f;                       // number_of_lights() as F (tracer.rs:138,214)
     // signed-distance program (ptb_set_sdf_*): one more "primitive", tested after the planes.  The nodes live in the kernel
     // parameter (constant bank): every lane reads the same node at the same time, which is what that path is fast at.
+    uint32_t n_rect_lights;             // rectangular lights in the scene (tested by rays only with PTB_SCENE_EXTENDED_LIGHTS)
     uint32_t n_sdf, sdf_max_steps;
     R sdf_hit_eps, sdf_max_dist, sdf_normal_h;
     DSdfNode<R> sdf[PTB_SDF_MAX_NODES];
@@ -442,6 +443,23 @@ template <class R> PTB_DEV R isect_plane(V3<R> o, V3<R> d, V3<R> p, V3<R> n) {
         if (t >= R(0)) return t;
     }
     return R(-1);
+}
+
+// Ray against a rectangular light (extension, see PTB_LIGHT_RECTANGULAR): t >= 0 and the cosine at the quad, or -1.  The quad
+// emits from the side n = normalize(cross(u, v)) points to and is invisible from behind.
+template <class R> struct DLight;
+template <class R> PTB_DEV R isect_rect_light(const DLight<R>& L, V3<R> o, V3<R> d, R& cos_out) {
+    const V3<R> u(L.ux, L.uy, L.uz), v(L.vx, L.vy, L.vz), p(L.px, L.py, L.pz);
+    const V3<R> n = normalize(cross(u, v));
+    const R dn = dot(n, d);
+    if (!(dn < R(0))) return R(-1);
+    const R t = m_div(dot(n, p - o), dn);
+    if (!(t > R(0))) return R(-1);
+    const V3<R> w = (o + t * d) - p;
+    const R a1 = m_div(dot(u, w), dot(u, u)), a2 = m_div(dot(v, w), dot(v, v));
+    if (a1 < R(0) || a1 > R(1) || a2 < R(0) || a2 > R(1)) return R(-1);
+    cos_out = -dn;
+    return t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -736,11 +754,28 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
         R t = isect_sphere(o, d, V3<R>(L.px, L.py, L.pz), L.radius);
         if (t >= R(0) && t < ldist) { ldist = t; lbest = (int)i; }
     }
+    R rect_cos = 0;
+    if ((s.flags & PTB_SCENE_EXTENDED_LIGHTS) && s.n_rect_lights && ldist > R(0)) {
+        // quads (extension, PTB_LIGHT_RECTANGULAR in ptb200.h): hidden from behind, nearest wins like the spheres above; tested in
+        // light order AFTER the spherical lights, so a quad and a sphere at the same distance resolve to the sphere
+#pragma unroll 1
+        for (uint32_t i = 0; i < s.n_lights; ++i) {
+            DLight<R> L = sv.lights[i];
+            if (L.type != PTB_LIGHT_RECTANGULAR) continue;
+            R c;
+            R t = isect_rect_light(L, o, d, c);
+            if (t >= R(0) && t < ldist) { ldist = t; lbest = (int)i; rect_cos = c; }
+        }
+    }
     if (lbest >= 0) {
         DLight<R> L = sv.lights[lbest];
-        V3<R> hp = o + ldist * d;
-        R cos_theta = dot(-d, normalize(hp - V3<R>(L.px, L.py, L.pz)));
-        h.light_pdf = m_div(ldist * ldist, L.area * cos_theta * R(0.5));       // scene.rs:75
+        if (L.type == PTB_LIGHT_RECTANGULAR) {
+            h.light_pdf = m_div(ldist * ldist, L.area * rect_cos);
+        } else {
+            V3<R> hp = o + ldist * d;
+            R cos_theta = dot(-d, normalize(hp - V3<R>(L.px, L.py, L.pz)));
+            h.light_pdf = m_div(ldist * ldist, L.area * cos_theta * R(0.5));       // scene.rs:75
+        }
         h.light_emission = V3<R>(L.ex, L.ey, L.ez);
         h.is_emitter = true;
         h.hit_dist = ldist;
@@ -1229,6 +1264,28 @@ PTB_DEV V3<R> disney_sample(const Mat<R>& m, const ShadeCtx<R>& c, R r1, R r2, R
 
 // Tracer::sample_light, tracer.rs:173-220
 template <class R> struct LightSample { V3<R> normal, emission, direction; R dist, pdf; };
+// the two kinds the reference leaves unimplemented (tracer.rs:217 `_ => {}`), with the upstream GLSL project's semantics
+template <class R> PTB_DEV LightSample<R> sample_light_extended(const DLight<R>& L, R n_lights_f, V3<R> scatter_pos, R r1, R r2) {
+    LightSample<R> ls;
+    const V3<R> lp(L.px, L.py, L.pz);
+    ls.emission = n_lights_f * V3<R>(L.ex, L.ey, L.ez);
+    if (L.type == PTB_LIGHT_RECTANGULAR) {
+        const V3<R> u(L.ux, L.uy, L.uz), v(L.vx, L.vy, L.vz);
+        const V3<R> surf = (lp + r1 * u) + r2 * v;
+        ls.direction = surf - scatter_pos;
+        ls.dist = length(ls.direction);
+        const R dist_sq = ls.dist * ls.dist;
+        ls.direction = div_s(ls.direction, ls.dist);
+        ls.normal = normalize(cross(u, v));
+        ls.pdf = m_div(dist_sq, L.area * m_abs(dot(ls.normal, ls.direction)));
+    } else {                                            // PTB_LIGHT_DISTANT
+        ls.direction = normalize(lp);
+        ls.normal = normalize(scatter_pos - lp);
+        ls.dist = Const<R>::MAXV;
+        ls.pdf = R(1);
+    }
+    return ls;
+}
 template <class R> PTB_DEV LightSample<R> sample_light(const DLight<R>& L, R n_lights_f, V3<R> scatter_pos, R r1, R r2) {
     LightSample<R> ls;
     V3<R> lp(L.px, L.py, L.pz);
@@ -1330,9 +1387,12 @@ PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const 
         uint32_t li = (uint32_t)(u[SLOT_LIGHT_PICK] * s.n_lights_f);          // tracer.rs:137-139
         ns.scatter_pos = su.fhp + s.eps * su.ffn;
         const DLight<R> L = sv.lights[li];
-        ns.ls = sample_light(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
+        const bool extended = (s.flags & PTB_SCENE_EXTENDED_LIGHTS) != 0 && L.type != PTB_LIGHT_SPHERICAL;
+        if (extended) ns.ls = sample_light_extended(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
+        else ns.ls = sample_light(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
         ns.light_area = L.area;
-        ns.wants_shadow_ray = L.type == PTB_LIGHT_SPHERICAL && dot(ns.ls.direction, ns.ls.normal) < R(0);   // tracer.rs:148
+        // tracer.rs:148; a non-spherical light of the reference leaves direction and normal at zero: never a shadow ray
+        ns.wants_shadow_ray = (L.type == PTB_LIGHT_SPHERICAL || extended) && dot(ns.ls.direction, ns.ls.normal) < R(0);
     }
 }
 

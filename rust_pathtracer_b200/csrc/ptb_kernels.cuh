@@ -366,7 +366,11 @@ __global__ void k_test_sample_light(const __grid_constant__ DScene<R> s, size_t 
                                     R* nrm, R* em, R* dir, R* dist, R* pdf) {
     PTB_TEST_PROLOGUE
     if (i >= n) return;
-    LightSample<R> ls = sample_light(s.lights[li], s.n_lights_f, ld3(pos, n, i), r1[i], r2[i]);
+    const DLight<R> L = s.lights[li];
+    LightSample<R> ls;
+    if ((s.flags & PTB_SCENE_EXTENDED_LIGHTS) && L.type != PTB_LIGHT_SPHERICAL) ls = sample_light_extended(L, s.n_lights_f, ld3(pos, n, i), r1[i], r2[i]);
+    else if (L.type == PTB_LIGHT_SPHERICAL) ls = sample_light(L, s.n_lights_f, ld3(pos, n, i), r1[i], r2[i]);
+    else { ls.normal = ls.emission = ls.direction = V3<R>(R(0), R(0), R(0)); ls.dist = ls.pdf = R(0); }     // tracer.rs:217 `_ => {}`
     st3(nrm, n, i, ls.normal); st3(em, n, i, ls.emission); st3(dir, n, i, ls.direction);
     dist[i] = ls.dist; pdf[i] = ls.pdf;
 }

@@ -122,6 +122,8 @@ class Light:
     emission: F3
     radius: float
     area: float
+    u: F3 = field(default_factory=lambda: F3(0.0, 0.0, 0.0))
+    v: F3 = field(default_factory=lambda: F3(0.0, 0.0, 0.0))
 
 
 class AnalyticalLight:
@@ -135,6 +137,21 @@ class AnalyticalLight:
         import math
         return AnalyticalLight(Light(_abi.PTB_LIGHT_SPHERICAL, _f3(position), _f3(emission), float(radius),
                                      4.0 * math.pi * radius * radius))
+
+    # The reference has only `spherical` (light.rs:13-28) although Light carries u / v / area for the other two kinds
+    # (globals.rs:76-84); they take effect with PTB_SCENE_EXTENDED_LIGHTS (include/ptb200.h).
+    @staticmethod
+    def rectangular(position, u, v, emission) -> "AnalyticalLight":
+        """quad position + s*u + t*v, emitting from the side cross(u, v) points to"""
+        uu, vv = tuple(_f3(u)), tuple(_f3(v))
+        cx = (uu[1] * vv[2] - uu[2] * vv[1], uu[2] * vv[0] - uu[0] * vv[2], uu[0] * vv[1] - uu[1] * vv[0])
+        area = (cx[0] ** 2 + cx[1] ** 2 + cx[2] ** 2) ** 0.5
+        return AnalyticalLight(Light(_abi.PTB_LIGHT_RECTANGULAR, _f3(position), _f3(emission), 0.0, area, _f3(u), _f3(v)))
+
+    @staticmethod
+    def distant(direction, emission) -> "AnalyticalLight":
+        """light from infinitely far away in `direction` (stored as the position, like upstream)"""
+        return AnalyticalLight(Light(_abi.PTB_LIGHT_DISTANT, _f3(direction), _f3(emission), 0.0, 0.0))
 
 
 class Camera3D:
@@ -295,6 +312,7 @@ class DeviceScene:
         for i, l in enumerate(self.lights):
             li[i].position = v3(l.light.position); li[i].radius = l.light.radius
             li[i].emission = v3(l.light.emission); li[i].type = l.light.light_type
+            li[i].u = v3(l.light.u); li[i].v = v3(l.light.v)
         sc = T["Scene"]()
         sc.n_spheres, sc.n_planes, sc.n_materials, sc.n_lights = len(self.spheres), len(self.planes), len(self.materials), len(self.lights)
         sc.spheres = C.cast(sph, C.POINTER(T["Sphere"])); sc.planes = C.cast(pl, C.POINTER(T["Plane"]))

@@ -178,6 +178,33 @@ def test_sample_light(dev, oracle_demo):
     assert np.percentile(rel_err(got["pdf"][well], ref["pdf"][well]), 99) < TOL
 
 
+def test_sample_light_extended_kinds(rp, po):
+    """PTB_SCENE_EXTENDED_LIGHTS: uniform-by-area quad sampling and the distant light against the oracle's statement; without
+    the flag both kinds leave the record zeroed like the reference (tracer.rs:217)."""
+    from test_gpu_image import extended_light_export
+    rng = np.random.default_rng(17)
+    pos = rng.uniform(-3, 3, (3, N)).astype(np.float32); pos[1] = rng.uniform(-1, 2.5, N)
+    r1, r2 = rng.uniform(0, 1, N).astype(np.float32), rng.uniform(0, 1, N).astype(np.float32)
+    for on in (True, False):
+        e = extended_light_export(rp)
+        if not on:
+            e.flags &= ~rp._abi.PTB_SCENE_EXTENDED_LIGHTS
+        dev, orc = DeviceFns(rp, e), po.OracleScene(e)
+        for li in range(3):
+            ref, got = orc.sample_light(li, pos, r1, r2), dev.sample_light(li, pos, r1, r2)
+            if not on and li != 1:
+                for k in ("direction", "normal", "emission", "dist", "pdf"):
+                    assert not got[k].any() and not ref[k].any(), (li, k)
+                continue
+            assert np.array_equal(got["emission"], ref["emission"])
+            assert vec_rel_err(got["direction"], ref["direction"]).max() < TOL, li
+            assert vec_rel_err(got["normal"], ref["normal"]).max() < TOL, li
+            assert rel_err(got["dist"], ref["dist"]).max() < TOL, li
+            well = np.abs((ref["normal"].astype(np.float64) * ref["direction"]).sum(0)) > 0.02
+            assert rel_err(got["pdf"][well], ref["pdf"][well]).max() < 5e-5, li
+        dev.close(); orc.close()
+
+
 def test_finalize(dev, oracle_demo):
     rng = np.random.default_rng(8)
     n = 20000

@@ -665,6 +665,74 @@ def test_non_spherical_light_types_are_inert_like_the_reference(rp, po):
     assert oc["any_hit"] < 0.5 * oc1["any_hit"]
 
 
+def extended_light_export(rp, quad=True, distant=True, spherical=True):
+    """the demo scene lit by a downward-facing quad above the spheres and / or a distant light (PTB_SCENE_EXTENDED_LIGHTS)"""
+    e = rp.AnalyticalScene.new().device_export()
+    lights = []
+    if quad:       # cross(u, v) = (0, -2.4, 0): emits downwards
+        lights.append(rp.AnalyticalLight.rectangular(rp.F3(-1.0, 3.0, -0.6), rp.F3(2.0, 0.0, 0.0), rp.F3(0.0, 0.0, 1.2), rp.F3(9.0, 8.0, 7.0)))
+    if spherical:
+        lights.append(e.lights[0])
+    if distant:
+        lights.append(rp.AnalyticalLight.distant(rp.F3(0.4, 1.0, 0.3), rp.F3(0.5, 0.6, 0.9)))
+    e.lights = lights
+    e.flags |= rp._abi.PTB_SCENE_EXTENDED_LIGHTS
+    return e
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_extended_light_types_match_the_oracle(rp, po, precision):
+    """with PTB_SCENE_EXTENDED_LIGHTS rectangular and distant lights are sampled (and quads are hit by rays) with
+    the semantics the reference's hooks were written for (tracer.rs:148 single-sided cull, tracer.rs:158 no MIS when area == 0,
+    globals.rs:76-84 u / v / area).  The oracle states the same extension on the CPU; all integrators must agree with it."""
+    e = extended_light_export(rp)
+    W, H, S = 160, 100, 4
+    ref, _, _, oc = po.OracleScene(e, precision=precision).render(W, H, S, counters=True)
+    inert = extended_light_export(rp); inert.flags &= ~rp._abi.PTB_SCENE_EXTENDED_LIGHTS
+    ref_inert, _, _, oc_inert = po.OracleScene(inert, precision=precision).render(W, H, S, counters=True)
+    assert oc["any_hit"] > 2 * oc_inert["any_hit"]                 # all three lights cast shadow rays now
+    assert lum(ref).mean() > 1.2 * lum(ref_inert).mean()
+    integs = (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED) + ((rp._abi.PTB_INTEGRATOR_STREAM,) if precision == "f32" else ())
+    for integ in integs:
+        pt = rp.Tracer.new(rp.ExportedScene(e), integrator=integ, collect_counters=True, precision=precision)
+        buf = rp.ColorBuffer.new(W, H, precision=precision)
+        pt.render_spp(buf, S)
+        c = pt.counters()
+        pt.close()
+        rel = pix_rel(buf.pixels, ref)
+        bar = 1e-4 if precision == "f32" else 1e-9
+        assert (rel < bar).mean() >= 0.99, (integ, (rel < bar).mean())
+        for k in ("closest_hit", "any_hit", "shade", "nee_contrib", "end_sky", "end_emitter"):
+            assert abs(c[k] - oc[k]) <= max(5, 1e-3 * W * H * S), (integ, k, c[k], oc[k])
+
+
+def test_quad_light_is_single_sided_and_visible(rp, po):
+    """A quad in front of the left sphere, facing the camera.  Primary rays that hit it end there (tracer.rs:80-88) — with the
+    reference's MIS weight power_heuristic(0, pdf) = 0 for a path that has not scattered yet, i.e. BLACK, exactly like a directly
+    seen spherical light of the reference.  The same quad flipped (u and v swapped) is invisible from the camera and lights the
+    sphere behind it instead.  (Lights are only ever hit in front of geometry: against the sky the stale hit_dist hides them,
+    scene.rs:66-71.)"""
+    def render(flip):
+        e = rp.AnalyticalScene.new().device_export()
+        u, v = rp.F3(0.6, 0.0, 0.0), rp.F3(0.0, 0.6, 0.0)
+        if flip:
+            u, v = v, u
+        e.lights = [rp.AnalyticalLight.rectangular(rp.F3(-1.4, -0.3, 1.5), u, v, rp.F3(9.0, 8.0, 7.0))]
+        e.flags |= rp._abi.PTB_SCENE_EXTENDED_LIGHTS
+        pt = rp.Tracer.new(rp.ExportedScene(e))
+        buf = rp.ColorBuffer.new(96, 96)
+        pt.render_spp(buf, 8)
+        pt.close()
+        ref, _, _, _ = po.OracleScene(e).render(96, 96, 8)
+        assert (pix_rel(buf.pixels, ref) < 1e-4).mean() >= 0.99
+        return buf.pixels.reshape(-1, 4)[:, :3]
+    front, back = render(False), render(True)
+    black = (front == 0).all(1)
+    assert 300 <= black.sum() <= 700, black.sum()          # 0.6 / 1.5 * 48 / tan(40 deg) = 23 pixels on a side
+    assert not (back == 0).all(1).any()
+    assert back.mean() > 1.2 * front.mean()                # flipped, it faces the sphere and lights it
+
+
 @pytest.mark.parametrize("wh_spp", [(1920, 1080, 2), (3840, 2160, 2), (3840, 2160, 1)])
 @pytest.mark.parametrize("strict", [False, True])
 def test_benchmarked_kernel_full_frame_parity(rp, scene, oracle_demo, wh_spp, strict):

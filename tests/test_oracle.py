@@ -321,3 +321,64 @@ def test_chacha_render_converges_to_the_counter_rng_image(po, oracle_demo):
     # per-pixel: two independent 48-spp estimates of the same image
     d = (a - b).reshape(-1, 4)[:, :3]
     assert np.sqrt((d ** 2).mean()) < 0.08
+
+
+# ---- extended light kinds (PTB_SCENE_EXTENDED_LIGHTS): the library's extension, pinned by closed forms ------------------------
+def _quad_scene(rp, a=2.0, b=1.2, h=1.5):
+    """a quad of a x b, h above the origin, centred, facing down; plus a distant light"""
+    e = rp.AnalyticalScene.new().device_export()
+    e.lights = [rp.AnalyticalLight.rectangular(rp.F3(-a / 2, h, -b / 2), rp.F3(a, 0.0, 0.0), rp.F3(0.0, 0.0, b), rp.F3(2.0, 3.0, 4.0)),
+                rp.AnalyticalLight.distant(rp.F3(0.0, 2.0, 0.0), rp.F3(1.0, 1.0, 1.0))]
+    e.flags |= rp._abi.PTB_SCENE_EXTENDED_LIGHTS
+    return e
+
+
+def test_quad_light_sampling_integrates_to_the_form_factor(rp, po):
+    """Irradiance of a uniform quad on a parallel element under its centre has a closed form (four corner form factors):
+    F_corner = 1/(2 pi) [X/sqrt(1+X^2) atan(Y/sqrt(1+X^2)) + Y/sqrt(1+Y^2) atan(X/sqrt(1+Y^2))], X = a/h, Y = b/h.
+    The estimator the tracer uses, mean(L cos / pdf) over sample_light draws, must converge to pi L F."""
+    a, b, h = 2.0, 1.2, 1.5
+    orc = po.OracleScene(_quad_scene(rp, a, b, h), "f64")
+    n = 400_000
+    rng = np.random.default_rng(3)
+    r1, r2 = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    pos = np.zeros((3, n))
+    ls = orc.sample_light(0, pos, r1, r2)
+    assert np.allclose(ls["normal"], np.array([[0.0], [-1.0], [0.0]]))
+    assert np.allclose(ls["emission"], np.array([[4.0], [6.0], [8.0]]))      # number_of_lights() x emission (tracer.rs:214)
+    cos_surface = ls["direction"][1]                                        # element normal (0, 1, 0)
+    est = (cos_surface / ls["pdf"]).mean()
+
+    def corner(x, y):
+        X, Y = x / h, y / h
+        return (X / math.sqrt(1 + X * X) * math.atan(Y / math.sqrt(1 + X * X)) + Y / math.sqrt(1 + Y * Y) * math.atan(X / math.sqrt(1 + Y * Y))) / (2 * math.pi)
+    want = math.pi * 4 * corner(a / 2, b / 2)
+    assert abs(est / want - 1) < 5e-3, (est, want)
+    # the sampled points lie on the quad and dist is their distance
+    p = ls["direction"] * ls["dist"]
+    assert np.allclose(p[1], h) and p[0].min() >= -a / 2 - 1e-9 and p[0].max() <= a / 2 + 1e-9 and np.abs(p[2]).max() <= b / 2 + 1e-9
+    # the distant light: fixed direction, pdf 1, infinitely far
+    ds = orc.sample_light(1, pos[:, :8], r1[:8], r2[:8])
+    assert np.allclose(ds["direction"], np.array([[0.0], [1.0], [0.0]])) and np.all(ds["pdf"] == 1.0) and np.all(ds["dist"] > 1e300)
+
+
+def test_quad_light_hit_pdf_is_the_sampling_pdf(rp, po):
+    """A ray that hits the quad reports pdf = t^2 / (area cos), the density sample_light would have assigned to that direction —
+    what the MIS weight at tracer.rs:84 needs; from behind the quad does not exist."""
+    a, b, h = 2.0, 1.2, 1.5
+    e = _quad_scene(rp, a, b, h)
+    e.planes[0].point = rp.F3(0.0, 5.0, 0.0)               # the ground plane becomes a ceiling behind the quad: rays find a hit_dist
+    e.planes[0].normal = rp.F3(0.0, -1.0, 0.0)
+    e.spheres = []
+    orc = po.OracleScene(e, "f64")
+    o = np.array([[0.3, 0.3], [-2.0, 4.0], [0.1, 0.1]]); d = np.array([[0.0, 0.0], [1.0, -1.0], [0.0, 0.0]])
+    o[1, 0] = -2.0
+    tgt = np.array([0.5, h, -0.2])
+    d[:, 0] = (tgt - o[:, 0]) / np.linalg.norm(tgt - o[:, 0])
+    r = orc.closest_hit(o, d, np.array([-1.0, -1.0]))
+    t = np.linalg.norm(tgt - o[:, 0])
+    assert r["is_emitter"][0] == 1 and abs(r["hit_dist"][0] - t) < 1e-12
+    assert abs(r["light_pdf"][0] / (t * t / (a * b * d[1, 0])) - 1) < 1e-12
+    assert r["is_emitter"][1] == 0                          # from above: the back side
+    ls = orc.sample_light(0, o[:, :1], np.array([(0.5 + a / 2) / a]), np.array([(-0.2 + b / 2) / b]))
+    assert np.allclose(ls["direction"][:, 0], d[:, 0]) and abs(ls["pdf"][0] / r["light_pdf"][0] - 1) < 1e-12
