@@ -80,6 +80,20 @@ enum {
  *   DISTANT      direction normalize(position), emission constant, pdf 1, area 0 (no MIS), never hit by rays             */
 enum { PTB_LIGHT_RECTANGULAR = 0, PTB_LIGHT_SPHERICAL = 1, PTB_LIGHT_DISTANT = 2 };
 
+/* Medium kinds, rust-pathtracer/src/material.rs:7-13.  The reference declares the type, carries it in Material / State
+ * (material.rs:75, globals.rs:19) and clamps its anisotropy (material.rs:126) but its tracer never reads it ("Support of
+ * mediums / volumetric objects" is an open item, Readme.md:13; the hook is direct_light's unused `_is_surface`, tracer.rs:125).
+ * A material with medium_type == NONE (the default) behaves exactly like the reference.  Otherwise the body behind the surface
+ * is filled with the medium, with the semantics of the GLSL project the reference was ported from: a path is inside after it
+ * leaves a surface of such a material towards its back side (dot(new direction, geometry normal) < 0) and outside again after
+ * leaving one towards the front; no nesting.  While inside, at the next surface hit at distance t (before shading it):
+ *   ABSORB    throughput *= exp(-(1 - color) * t * density)
+ *   EMISSIVE  radiance   += color * t * density * throughput
+ *   SCATTER   free-flight distance s = -ln(u) / density; if s < t the bounce happens in the medium instead of at the surface:
+ *             throughput *= color, next-event estimation from the point with the Henyey-Greenstein phase function (value = pdf),
+ *             new direction sampled from it (its pdf feeds the MIS weight of a light hit like a BSDF pdf would)                */
+enum { PTB_MEDIUM_NONE = 0, PTB_MEDIUM_ABSORB = 1, PTB_MEDIUM_SCATTER = 2, PTB_MEDIUM_EMISSIVE = 3 };
+
 /* Background kinds. */
 enum {
     PTB_BG_CONSTANT = 0,     /* colour_a                                                           */
@@ -141,6 +155,11 @@ enum {
         uint32_t albedo_kind;            /* PTB_ALBEDO_*                                      */  \
         REAL checker_a, checker_b;       /* the two grey levels (0.25 / 0.1 in the demo)      */  \
         REAL checker_scale, checker_offset; /* 0.5 / 100 in the demo                          */  \
+        /* material.rs:5-34 `Medium` (PTB_MEDIUM_*): what fills the body behind this surface  */  \
+        uint32_t medium_type;                                                                     \
+        REAL medium_density;                                                                      \
+        REAL medium_color[3];                                                                     \
+        REAL medium_anisotropy;          /* clamped to [-0.9, 0.9] (material.rs:126)          */  \
     } ptb_material_##SFX;                                                                         \
     /* analytical.rs:41-99,166-190 */                                                             \
     typedef struct ptb_sphere_##SFX {                                                             \

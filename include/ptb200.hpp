@@ -45,6 +45,15 @@ struct F3 {
 };
 
 // material.rs:48-114 — defaults are Material::new()'s (rgb 1.5, roughness 0.5, ior 1.45)
+// material.rs:5-34 (semantics: PTB_MEDIUM_* in ptb200.h)
+struct Medium {
+    uint32_t medium_type = PTB_MEDIUM_NONE;
+    F density = 0;
+    F3 color{};
+    F anisotropy = 0;
+    static Medium new_() { return Medium(); }
+};
+
 struct Material {
     F3 rgb{F(1.5), F(1.5), F(1.5)};
     F3 emission{};
@@ -54,11 +63,12 @@ struct Material {
     uint32_t set_mask = PTB_MAT_ALL;
     uint32_t albedo_kind = PTB_ALBEDO_CONSTANT;
     F checker_a = F(0.25), checker_b = F(0.1), checker_scale = F(0.5), checker_offset = F(100);
+    Medium medium;                                                       // material.rs:75
     static Material new_() { return Material(); }
 };
 
 // globals.rs:76-84, light.rs:5-28
-struct Light { uint32_t light_type = PTB_LIGHT_SPHERICAL; F3 position, emission; F radius = 0, area = 0; };
+struct Light { uint32_t light_type = PTB_LIGHT_SPHERICAL; F3 position, emission; F3 u{}, v{}; F radius = 0, area = 0; };
 struct AnalyticalLight {
     Light light;
     static AnalyticalLight spherical(F3 position, F radius, F3 emission) {
@@ -66,6 +76,21 @@ struct AnalyticalLight {
         a.light.light_type = PTB_LIGHT_SPHERICAL;
         a.light.position = position; a.light.emission = emission; a.light.radius = radius;
         a.light.area = F(4) * F(3.14159265358979323846) * radius * radius;   // light.rs:22
+        return a;
+    }
+    // the two kinds the reference declares but does not implement; they take effect with PTB_SCENE_EXTENDED_LIGHTS (ptb200.h)
+    static AnalyticalLight rectangular(F3 position, F3 u, F3 v, F3 emission) {
+        AnalyticalLight a;
+        a.light.light_type = PTB_LIGHT_RECTANGULAR;
+        a.light.position = position; a.light.emission = emission; a.light.u = u; a.light.v = v;
+        const F cx = u.y * v.z - u.z * v.y, cy = u.z * v.x - u.x * v.z, cz = u.x * v.y - u.y * v.x;
+        a.light.area = std::sqrt(cx * cx + cy * cy + cz * cz);
+        return a;
+    }
+    static AnalyticalLight distant(F3 direction, F3 emission) {
+        AnalyticalLight a;
+        a.light.light_type = PTB_LIGHT_DISTANT;
+        a.light.position = direction; a.light.emission = emission;
         return a;
     }
 };
@@ -180,11 +205,12 @@ public:
             const Material& m = e.materials[i];
             ma[i] = MA{{m.rgb.x, m.rgb.y, m.rgb.z}, {m.emission.x, m.emission.y, m.emission.z}, m.anisotropic, m.metallic, m.roughness, m.subsurface,
                        m.specular_tint, m.sheen, m.sheen_tint, m.clearcoat, m.clearcoat_gloss, m.spec_trans, m.ior, m.set_mask, m.albedo_kind,
-                       m.checker_a, m.checker_b, m.checker_scale, m.checker_offset};
+                       m.checker_a, m.checker_b, m.checker_scale, m.checker_offset,
+                       m.medium.medium_type, m.medium.density, {m.medium.color.x, m.medium.color.y, m.medium.color.z}, m.medium.anisotropy};
         }
         for (size_t i = 0; i < li.size(); ++i) {
             const Light& l = e.lights[i].light;
-            li[i] = LI{{l.position.x, l.position.y, l.position.z}, l.radius, {l.emission.x, l.emission.y, l.emission.z}, l.light_type, {0, 0, 0}, {0, 0, 0}};
+            li[i] = LI{{l.position.x, l.position.y, l.position.z}, l.radius, {l.emission.x, l.emission.y, l.emission.z}, l.light_type, {l.u.x, l.u.y, l.u.z}, {l.v.x, l.v.y, l.v.z}};
         }
         S s{};
         s.n_spheres = (uint32_t)sp.size(); s.n_planes = (uint32_t)pl.size(); s.n_materials = (uint32_t)ma.size(); s.n_lights = (uint32_t)li.size();

@@ -339,6 +339,15 @@ void pto_chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream, 
     void pto_any_hit_##SFX(void* sb, size_t n, const R* o, const R* d, const R* md, uint32_t* hit) {                    \
         t_any_hit<R>(static_cast<SceneBox<R>*>(sb), n, o, d, md, hit);                                                  \
     }                                                                                                                   \
+    /* media extension: Henyey-Greenstein sample around v (3, n) and its phase value = pdf */                           \
+    void pto_sample_hg_##SFX(size_t n, const R* v, R g, const R* r1, const R* r2, R* dir, R* pdf) {                      \
+        for (size_t i = 0; i < n; ++i) {                                                                                \
+            const V3<R> vv = ld3(v, n, i);                                                                              \
+            const V3<R> d = Tracer<R>::sample_hg(vv, g, r1[i], r2[i]);                                                  \
+            st3(dir, n, i, d);                                                                                          \
+            pdf[i] = Tracer<R>::phase_hg(dot(vv, d), g);                                                                \
+        }                                                                                                               \
+    }                                                                                                                   \
     void pto_background_##SFX(void* sb, size_t n, const R* d, R* rgb) { t_background<R>(static_cast<SceneBox<R>*>(sb), n, d, rgb); } \
     void pto_sample_light_##SFX(void* sb, size_t n, uint32_t li, const R* pos, const R* r1, const R* r2, R* nrm, R* em, \
                                 R* dir, R* dist, R* pdf) {                                                              \

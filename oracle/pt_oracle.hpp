@@ -112,6 +112,14 @@ template <class R> struct Ray {
 };
 
 // material.rs:48-131 — only the fields the tracer reads
+// material.rs:7-34.  The reference's tracer never reads it; the semantics used here are the library's extension (PTB_MEDIUM_*
+// in include/ptb200.h), stated in Tracer::medium_step below.
+template <class R> struct Medium {
+    uint32_t type = PTB_MEDIUM_NONE;
+    R density = 0;
+    V3<R> color{0, 0, 0};
+    R anisotropy = 0;
+};
 template <class R> struct Material {
     V3<R> rgb{R(1.5), R(1.5), R(1.5)};     // material.rs:85
     V3<R> emission{0, 0, 0};
@@ -119,8 +127,10 @@ template <class R> struct Material {
     R sheen = 0, sheen_tint = 0, clearcoat = 0, clearcoat_gloss = 0, clearcoat_roughness = 0;
     R spec_trans = 0, ior = R(1.45);
     R ax = 0, ay = 0;
+    Medium<R> medium;                       // material.rs:75
     // material.rs:117-131
     void finalize() {
+        medium.anisotropy = medium.anisotropy < R(-0.9) ? R(-0.9) : (medium.anisotropy > R(0.9) ? R(0.9) : medium.anisotropy);   // material.rs:126
         roughness = fmax_(roughness, R(0.01));
         clearcoat_roughness = mix_f(R(0.1), R(0.001), clearcoat_gloss);
         R aspect = std::sqrt(R(1) - anisotropic * R(0.9));
@@ -696,6 +706,9 @@ template <class R> struct FlatScene : Scene<R> {
         if (k & PTB_MAT_CLEARCOAT_GLOSS) o.clearcoat_gloss = m.clearcoat_gloss;
         if (k & PTB_MAT_SPEC_TRANS) o.spec_trans = m.spec_trans;
         if (k & PTB_MAT_IOR) o.ior = m.ior;
+        // the medium belongs to the body: always the hit primitive's own (no set_mask bit)
+        o.medium.type = m.medium_type; o.medium.density = m.medium_density;
+        o.medium.color = V3<R>(m.medium_color[0], m.medium_color[1], m.medium_color[2]); o.medium.anisotropy = m.medium_anisotropy;
         state.material_index = (int)mi;
     }
     bool closest_hit(const Ray<R>& ray, State<R>& state, LightSampleRec<R>& light_sample) const override {
@@ -1197,6 +1210,76 @@ template <class R> struct Tracer {
         return ld;
     }
 
+    // ---- media (extension, PTB_MEDIUM_* in include/ptb200.h): Henyey-Greenstein, pbrt convention ----
+    static R phase_hg(R cos_theta, R g) {
+        const R denom = (R(1) + g * g) + (R(2) * g) * cos_theta;
+        return (R(1) / (R(4) * K<R>::PI)) * ((R(1) - g * g) / (denom * std::sqrt(denom)));
+    }
+    static V3<R> sample_hg(const V3<R>& v, R g, R r1, R r2) {
+        R cos_theta;
+        if (std::fabs(g) < R(0.001)) cos_theta = R(1) - R(2) * r2;
+        else {
+            const R sqr = (R(1) - g * g) / ((R(1) + g) - (R(2) * g) * r2);
+            cos_theta = -(((R(1) + g * g) - sqr * sqr) / (R(2) * g));
+        }
+        const R sin_theta = std::sqrt(fmax_(R(0), R(1) - cos_theta * cos_theta));
+        const R phi = K<R>::TWO_PI * r1;
+        V3<R> t, b;
+        onb(v, t, b);
+        return ((sin_theta * std::cos(phi)) * t + (sin_theta * std::sin(phi)) * b) + cos_theta * v;
+    }
+    // The medium's part of a bounce for a path inside `medium` that hit geometry at state.hit_dist.  Returns true when the bounce
+    // happened in the medium (ray, throughput, radiance and scatter_sample.pdf updated), false when the surface is shaded next.
+    template <class RNG>
+    bool medium_step(const Medium<R>& medium, Ray<R>& ray, const State<R>& state, V3<R>& radiance, V3<R>& throughput,
+                     ScatterSampleRec<R>& scatter_sample, const RNG& rng, uint32_t bounce, Counters* ctr) const {
+        const R t = state.hit_dist, density = medium.density;
+        const V3<R>& c = medium.color;
+        if (medium.type == PTB_MEDIUM_ABSORB) {
+            throughput = throughput * V3<R>(std::exp((-(R(1) - c.x) * t) * density), std::exp((-(R(1) - c.y) * t) * density),
+                                            std::exp((-(R(1) - c.z) * t) * density));
+            return false;
+        }
+        if (medium.type == PTB_MEDIUM_EMISSIVE) {
+            radiance += ((t * density) * c) * throughput;
+            return false;
+        }
+        const R u = rng.draw(bounce, SLOT_JITTER_Y);
+        const R ff = -std::log(u) / density;
+        const R sd = ff < t ? ff : t;
+        if (!(sd < t)) return false;
+        throughput = throughput * c;
+        ray.origin = ray.origin + sd * ray.direction;
+        // direct_light(ray, state, is_surface = false, rng): tracer.rs:125-170 with the phase function as f and pdf
+        const size_t number_lights = scene->number_of_lights();
+        const V3<R> back = -ray.direction;
+        if (number_lights > 0) {
+            R random = rng.draw(bounce, SLOT_LIGHT_PICK);
+            random *= (R)number_lights;
+            const Light<R>& light = scene->light_at((size_t)random);
+            LightSampleRec<R> ls;
+            const R r1 = rng.draw(bounce, SLOT_LIGHT_R1), r2 = rng.draw(bounce, SLOT_LIGHT_R2);
+            sample_light(light, ray.origin, ls, r1, r2);
+            if (dot(ls.direction, ls.normal) < R(0)) {
+                if (ctr) ctr->any_hit++;
+                if (!scene->any_hit(Ray<R>(ray.origin, ls.direction), ls.dist - eps)) {
+                    const R ph = phase_hg(dot(back, ls.direction), medium.anisotropy);
+                    R w = 1;
+                    if (light.area > R(0)) w = power_heuristic(ls.pdf, ph);
+                    if (ph > R(0)) {
+                        radiance += ((w * ls.emission) * V3<R>::new_x(ph / ls.pdf)) * throughput;
+                        if (ctr) ctr->nee_contrib++;
+                    }
+                } else if (ctr) ctr->nee_shadowed++;
+            } else if (ctr) ctr->nee_culled++;
+        }
+        const R h1 = rng.draw(bounce, SLOT_BSDF_R1), h2 = rng.draw(bounce, SLOT_BSDF_R2);
+        const V3<R> dir = sample_hg(back, medium.anisotropy, h1, h2);
+        scatter_sample.pdf = phase_hg(dot(back, dir), medium.anisotropy);
+        ray.direction = dir;
+        return true;
+    }
+
     // tracer.rs:44-103 — radiance of ONE sample of pixel (x, memory row r); W, H as F.
     // `pixel_id` keys the RNG (memory pixel index r*W + x), `sample` is the global sample index.
     V3<R> trace_sample(size_t x, size_t j, size_t width, R height, uint32_t pixel_id, uint64_t sample,
@@ -1221,6 +1304,8 @@ template <class R> struct Tracer {
         state.depth = scene->recursion_depth();
         if (ctr) ctr->samples++;
         bool ended = false;
+        bool in_medium = false;                                               // (extension) globals.rs:19 `State::medium`
+        Medium<R> medium;
         for (uint32_t bounce = 0; bounce < state.depth; ++bounce) {
             state.material = Material<R>();                                   // tracer.rs:63
             if (ctr) ctr->closest_hit++;
@@ -1233,6 +1318,8 @@ template <class R> struct Tracer {
             }
             state.finalize(ray);
             if (ctr) ctr->finalize++;
+            if (in_medium && !state.is_emitter &&
+                medium_step(medium, ray, state, radiance, throughput, scatter_sample, rng, bounce, ctr)) continue;   // (extension)
             radiance += state.material.emission * throughput;
             if (state.is_emitter) {
                 R mis_weight = 1;
@@ -1258,6 +1345,10 @@ template <class R> struct Tracer {
             }
             ray.direction = scatter_sample.l;
             ray.origin = state.fhp + eps * ray.direction;
+            if (state.material.medium.type != PTB_MEDIUM_NONE) {              // (extension) entering / leaving the body; no nesting
+                in_medium = dot(ray.direction, state.normal) < R(0);
+                medium = state.material.medium;
+            }
         }
         if (!ended && ctr) ctr->end_depth++;
         return radiance;

@@ -242,6 +242,17 @@ def chacha_block(key8, counter, stream, rounds):
     return [int(x) for x in o]
 
 
+def sample_hg(v, g, r1, r2, precision="f64"):
+    """media extension: Henyey-Greenstein direction around v (3, n) and its pdf"""
+    lib = load()
+    t = _NP[precision]
+    v, r1, r2 = (np.ascontiguousarray(x, t) for x in (v, r1, r2))
+    n = v.shape[1]
+    d, pdf = np.empty((3, n), t), np.empty(n, t)
+    getattr(lib, f"pto_sample_hg_{precision}")(C.c_size_t(n), _p(v), _CT[precision](g), _p(r1), _p(r2), _p(d), _p(pdf))
+    return d, pdf
+
+
 def sphere_hit(o, d, c, r, precision="f32"):
     lib = load(); dt = _NP[precision]
     o, d, c, r = (np.ascontiguousarray(x, dt) for x in (o, d, c, r))

@@ -82,6 +82,16 @@ impl DeviceScene {
         abi::Material { rgb: [1.5, 1.5, 1.5], roughness: 0.5, ior: 1.45, set_mask: sys::PTB_MAT_ALL, checker_a: 0.25, checker_b: 0.1,
                         checker_scale: 0.5, checker_offset: 100.0, ..Default::default() }
     }
+    /// all fields of a reference `Material` (material.rs:48-78), its `Medium` included (material.rs:15-22; PTB_MEDIUM_* in ptb200.h)
+    pub fn material(m: &Material) -> abi::Material {
+        abi::Material { rgb: [m.rgb.x, m.rgb.y, m.rgb.z], emission: [m.emission.x, m.emission.y, m.emission.z], anisotropic: m.anisotropic,
+                        metallic: m.metallic, roughness: m.roughness, subsurface: m.subsurface, specular_tint: m.specular_tint, sheen: m.sheen,
+                        sheen_tint: m.sheen_tint, clearcoat: m.clearcoat, clearcoat_gloss: m.clearcoat_gloss, spec_trans: m.spec_trans, ior: m.ior,
+                        medium_type: match m.medium.medium_type { MediumType::None => sys::PTB_MEDIUM_NONE, MediumType::Absorb => sys::PTB_MEDIUM_ABSORB,
+                                                                  MediumType::Scatter => sys::PTB_MEDIUM_SCATTER, MediumType::Emissive => sys::PTB_MEDIUM_EMISSIVE },
+                        medium_density: m.medium.density, medium_color: [m.medium.color.x, m.medium.color.y, m.medium.color.z],
+                        medium_anisotropy: m.medium.anisotropy, ..Self::material_default() }
+    }
     /// a spherical light; the library derives `area = 4 pi r^2` in `F` (light.rs:22)
     pub fn light(l: &AnalyticalLight) -> abi::Light {
         let p = l.light.position; let e = l.light.emission;

@@ -6,11 +6,11 @@ reference crate's prelude.  There is no CPU render path; importing works without
 a `Tracer` does not.
 """
 from . import _abi
-from .prelude import (F, I, F3, AnalyticalLight, Background, Camera3D, ColorBuffer, DeviceScene, Light, Material, Pinhole, Plane,
+from .prelude import (F, I, F3, AnalyticalLight, Background, Camera3D, ColorBuffer, DeviceScene, Light, Material, Medium, MediumType, Pinhole, Plane,
                       Scene, SdfNode, SdfProgram, Sphere, Tracer)
-from .scenes import AnalyticalScene, ExportedScene, divergence_stress_scene, sdf_demo_scene, sphere_field_scene
+from .scenes import AnalyticalScene, ExportedScene, divergence_stress_scene, lights_demo_scene, media_demo_scene, sdf_demo_scene, sphere_field_scene
 
-__all__ = ["F", "I", "F3", "AnalyticalLight", "Background", "Camera3D", "ColorBuffer", "DeviceScene", "Light", "Material", "Pinhole",
-           "Plane", "Scene", "SdfNode", "SdfProgram", "Sphere", "Tracer", "AnalyticalScene", "ExportedScene", "divergence_stress_scene", "sdf_demo_scene",
+__all__ = ["F", "I", "F3", "AnalyticalLight", "Background", "Camera3D", "ColorBuffer", "DeviceScene", "Light", "Material", "Medium", "MediumType", "Pinhole",
+           "Plane", "Scene", "SdfNode", "SdfProgram", "Sphere", "Tracer", "AnalyticalScene", "ExportedScene", "divergence_stress_scene", "lights_demo_scene", "media_demo_scene", "sdf_demo_scene",
            "sphere_field_scene",
            "_abi"]

@@ -21,6 +21,7 @@ PTB_INTEGRATOR_AUTO, PTB_INTEGRATOR_FUSED, PTB_INTEGRATOR_WAVEFRONT, PTB_INTEGRA
 PTB_PEER_HANDLE_BYTES = 64
 PTB_SCENE_EXTENDED_LIGHTS = 1 << 3
 PTB_FRAME_HOST_UNCHANGED = 1
+PTB_MEDIUM_NONE, PTB_MEDIUM_ABSORB, PTB_MEDIUM_SCATTER, PTB_MEDIUM_EMISSIVE = 0, 1, 2, 3
 PTB_SDF_SPHERE, PTB_SDF_BOX, PTB_SDF_TORUS, PTB_SDF_PLANE = 0, 1, 2, 3
 PTB_SDF_UNION, PTB_SDF_SMOOTH_UNION, PTB_SDF_SUBTRACT, PTB_SDF_INTERSECT = 16, 17, 18, 19
 PTB_SDF_MAX_NODES, PTB_SDF_MAX_STACK = 16, 8
@@ -39,7 +40,8 @@ def _declare(real):
                     ("specular_tint", real), ("sheen", real), ("sheen_tint", real), ("clearcoat", real),
                     ("clearcoat_gloss", real), ("spec_trans", real), ("ior", real),
                     ("set_mask", C.c_uint32), ("albedo_kind", C.c_uint32),
-                    ("checker_a", real), ("checker_b", real), ("checker_scale", real), ("checker_offset", real)]
+                    ("checker_a", real), ("checker_b", real), ("checker_scale", real), ("checker_offset", real),
+                    ("medium_type", C.c_uint32), ("medium_density", real), ("medium_color", real * 3), ("medium_anisotropy", real)]
 
     class Sphere(C.Structure):
         _fields_ = [("center", real * 3), ("radius", real), ("material", C.c_uint32)]

@@ -333,6 +333,11 @@ template <class R, class PodMaterial> static DMaterial<R> resolve_pod_material(c
     o.set_mask = k & PTB_MAT_ALL;
     o.albedo_kind = m.albedo_kind;
     o.checker_a = m.checker_a; o.checker_b = m.checker_b; o.checker_scale = m.checker_scale; o.checker_offset = m.checker_offset;
+    // material.rs:15-22; finalize clamps the anisotropy (material.rs:126)
+    o.med_type = m.medium_type;
+    o.med_density = m.medium_density;
+    for (int c = 0; c < 3; ++c) o.med_color[c] = m.medium_color[c];
+    o.med_g = m.medium_anisotropy < R(-0.9) ? R(-0.9) : (m.medium_anisotropy > R(0.9) ? R(0.9) : m.medium_anisotropy);
     return o;
 }
 
@@ -395,6 +400,16 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     }
     std::vector<DMaterial<R>> mats(sc->n_materials);
     for (uint32_t i = 0; i < sc->n_materials; ++i) mats[i] = resolve_pod_material<R>(sc->materials[i]);
+    bool has_media = false;
+    for (uint32_t i = 0; i < sc->n_materials; ++i) {
+        if (mats[i].med_type == PTB_MEDIUM_NONE) continue;
+        if (mats[i].med_type > PTB_MEDIUM_EMISSIVE) return fail(PTB_E_INVALID, "material %u: unknown medium type %u", i, mats[i].med_type);
+        if (i + 1u > PTB_MEDIUM_MAX_INDEX) return fail(PTB_E_UNSUPPORTED, "materials with a medium need an index below %u (the path state keeps 7 bits for it)", PTB_MEDIUM_MAX_INDEX);
+        has_media = true;
+    }
+    bool extended_lights = false;                   // scenes whose rectangular / distant lights are live: no resolved-material table
+    if (sc->flags & PTB_SCENE_EXTENDED_LIGHTS)
+        for (uint32_t i = 0; i < sc->n_lights; ++i) if (sc->lights[i].type != PTB_LIGHT_SPHERICAL) extended_lights = true;
     std::vector<DLight<R>> lights(sc->n_lights);
     const R PI_R = Const<R>::PI;
     for (uint32_t i = 0; i < sc->n_lights; ++i) {
@@ -479,7 +494,7 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     if constexpr (std::is_same<R, float>::value) {
         const uint32_t n_prims = sc->n_spheres + sc->n_planes;
         const char* off_env = getenv("PTB200_NO_RESOLVED_MATERIALS");     // A/B switch for profiling the generic shade path
-        if (!use_bvh && sc->n_materials > 0 && n_prims > 0 && (!patch || n_prims <= RM_MAX_PATCH_PRIMS) && !(off_env && off_env[0] == '1')) {
+        if (!use_bvh && !has_media && !extended_lights && sc->n_materials > 0 && n_prims > 0 && (!patch || n_prims <= RM_MAX_PATCH_PRIMS) && !(off_env && off_env[0] == '1')) {
             std::vector<uint32_t> keys;
             std::vector<RMat> table;
             auto add_key = [&](const std::vector<const DMaterial<float>*>& chain, const std::vector<uint32_t>& chain_index) {
@@ -557,6 +572,7 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     d.depth = sc->depth; d.flags = sc->flags; d.eps = sc->eps;
     d.n_lights_f = (R)sc->n_lights;
     d.has_emissive = 0;
+    d.has_media = has_media ? 1u : 0u;          // (the resolved-material kernel is not built for them: no table above)
     for (const auto& m : mats)
         if (m.emission[0] != R(0) || m.emission[1] != R(0) || m.emission[2] != R(0)) d.has_emissive = 1;
 
@@ -1030,6 +1046,11 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
         // signed-distance programs are compiled into the fused kernels and the generic (non-BVH) shared-memory wavefront kernel only
         if ((t->precision == 4 ? t->s32.d.n_sdf != 0 : t->s64.d.n_sdf != 0) &&
             (integ == PTB_INTEGRATOR_STREAM || (t->precision == 4 ? t->s32.d.use_bvh != 0 : t->s64.d.use_bvh != 0))) integ = PTB_INTEGRATOR_FUSED;
+    }
+    const bool has_media = t->precision == 4 ? t->s32.d.has_media != 0 : t->s64.d.has_media != 0;
+    if (has_media && integ == PTB_INTEGRATOR_STREAM) {
+        if (t->cfg.integrator == PTB_INTEGRATOR_AUTO) integ = PTB_INTEGRATOR_WAVEFRONT;
+        else return fail(PTB_E_UNSUPPORTED, "scenes with media run on the fused and the shared-memory wavefront integrators");
     }
     const bool has_sdf = t->precision == 4 ? t->s32.d.n_sdf != 0 : t->s64.d.n_sdf != 0;
     const bool bvh_scene = t->precision == 4 ? t->s32.d.use_bvh != 0 : t->s64.d.use_bvh != 0;

@@ -52,6 +52,16 @@ PTB_DEV float m_log2(float a) { return (float)log2((double)a); }
 PTB_DEV float m_log2(float a) { return log2f(a); }
 #endif
 PTB_DEV double m_log2(double a) { return log2(a); }
+// exp / ln of the medium code (PTB_MEDIUM_*): libm accuracy in both builds (media are not on the benchmarked path)
+#ifdef PTB_IEEE
+PTB_DEV float m_exp(float a) { return (float)exp((double)a); }
+PTB_DEV float m_ln(float a) { return (float)log((double)a); }
+#else
+PTB_DEV float m_exp(float a) { return expf(a); }
+PTB_DEV float m_ln(float a) { return logf(a); }
+#endif
+PTB_DEV double m_exp(double a) { return exp(a); }
+PTB_DEV double m_ln(double a) { return log(a); }
 PTB_DEV float m_floor(float a) { return floorf(a); }
 PTB_DEV double m_floor(double a) { return floor(a); }
 // IEEE division where a branch decision hangs on the last bit (checker cell, film coordinates)
@@ -94,12 +104,14 @@ template <> struct Const<float> {
     static constexpr float PI = 3.14159265358979323846f;
     static constexpr float INV_PI = 1.0f / 3.14159265358979323846f;      // lib.rs:9, evaluated in F
     static constexpr float TWO_PI = 3.14159265358979323846f * 2.0f;      // lib.rs:10
+    static constexpr float INV_4PI = 1.0f / (4.0f * 3.14159265358979323846f);
     static constexpr float MAXV = 3.402823466e+38f;
 };
 template <> struct Const<double> {
     static constexpr double PI = 3.14159265358979323846;
     static constexpr double INV_PI = 1.0 / 3.14159265358979323846;
     static constexpr double TWO_PI = 3.14159265358979323846 * 2.0;
+    static constexpr double INV_4PI = 1.0 / (4.0 * 3.14159265358979323846);
     static constexpr double MAXV = 1.7976931348623157e+308;
 };
 
@@ -246,7 +258,11 @@ template <class R> struct DMaterial {
     R anisotropic, metallic, roughness, subsurface, specular_tint, sheen, sheen_tint, clearcoat, clearcoat_gloss, spec_trans, ior;
     uint32_t set_mask, albedo_kind;
     R checker_a, checker_b, checker_scale, checker_offset;
+    // material.rs:15-22 (PTB_MEDIUM_*); med_g = anisotropy clamped to [-0.9, 0.9] (material.rs:126)
+    uint32_t med_type, med_pad;
+    R med_density, med_color[3], med_g;
 };
+constexpr uint32_t PTB_MEDIUM_MAX_INDEX = 127u;      // PathState::medium is kept in 7 bits of the wavefront slot's flag word
 template <class R> struct alignas(4 * sizeof(R)) DSphere { R cx, cy, cz, r; };   // one 16-byte (f32) / 32-byte (f64) vector load
 template <class R> struct DPlane { R px, py, pz, nx, ny, nz; };
 template <class R> struct DLight { R px, py, pz, radius, ex, ey, ez, area; uint32_t type, pad; R ux, uy, uz, vx, vy, vz; };
@@ -281,6 +297,7 @@ template <class R> struct DScene {
     const uint32_t* light_bvh_prim;
     uint32_t use_bvh;
     uint32_t has_emissive;              // 1 if any material has non-zero emission
+    uint32_t has_media;                 // 1 if any material carries a medium (PTB_MEDIUM_*): the path loop tracks inside / outside
     uint32_t patch_materials;           // 1 if any set_mask != PTB_MAT_ALL (order-dependent patching)
     uint32_t depth, flags;
     R eps;
@@ -706,8 +723,9 @@ PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o
 }
 
 // the rest of closest_hit given the sphere result: planes, then Scene::sample_lights
-// SDF = false compiles the signed-distance test out (instantiations whose scenes cannot carry a program)
-template <class R, bool BVH, bool SDF = true>
+// SDF = false compiles the signed-distance test out (instantiations whose scenes cannot carry a program); XL = false the
+// rectangular-light test (the resolved-material kernel: ptb_set_scene_* builds no table for scenes with extended lights)
+template <class R, bool BVH, bool SDF = true, bool XL = true>
 PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, int best, R dist,
                                       uint64_t accepted) {
     HitCore<R> h;
@@ -755,7 +773,7 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
         if (t >= R(0) && t < ldist) { ldist = t; lbest = (int)i; }
     }
     R rect_cos = 0;
-    if ((s.flags & PTB_SCENE_EXTENDED_LIGHTS) && s.n_rect_lights && ldist > R(0)) {
+    if (XL && (s.flags & PTB_SCENE_EXTENDED_LIGHTS) && s.n_rect_lights && ldist > R(0)) {
         // quads (extension, PTB_LIGHT_RECTANGULAR in ptb200.h): hidden from behind, nearest wins like the spheres above; tested in
         // light order AFTER the spherical lights, so a quad and a sphere at the same distance resolve to the sphere
 #pragma unroll 1
@@ -769,7 +787,7 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
     }
     if (lbest >= 0) {
         DLight<R> L = sv.lights[lbest];
-        if (L.type == PTB_LIGHT_RECTANGULAR) {
+        if (XL && L.type == PTB_LIGHT_RECTANGULAR) {
             h.light_pdf = m_div(ldist * ldist, L.area * rect_cos);
         } else {
             V3<R> hp = o + ldist * d;
@@ -785,13 +803,13 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
 }
 
 // normal of primitive `prim` at distance t along (o, d): analytical.rs:45-46 (sphere), :105 (plane)
-template <class R, bool BVH, bool SDF = true>
+template <class R, bool BVH, bool SDF = true, bool XL = true>
 PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, uint32_t* bvh_stats = nullptr) {
     int best;
     R dist;
     uint64_t accepted;
     closest_spheres<R, BVH>(s, sv, o, d, best, dist, accepted, bvh_stats);
-    return closest_hit_finish<R, BVH, SDF>(s, sv, o, d, hit_dist_in, best, dist, accepted);
+    return closest_hit_finish<R, BVH, SDF, XL>(s, sv, o, d, hit_dist_in, best, dist, accepted);
 }
 
 template <class R, bool BVH, bool SDF = true>
@@ -1328,6 +1346,7 @@ template <class R> struct PathState {
     R hit_dist;             // State::hit_dist, carried across bounces (A.1)
     R prev_pdf;             // scatter_sample.pdf of the previous bounce (0 on the first)
     uint32_t bounce;
+    uint32_t medium;        // 0 = outside; else 1 + index of the material whose medium the path is in (only maintained when s.has_media)
 };
 
 struct PathCounters {   // per-thread event counts (only when collect_counters)
@@ -1350,6 +1369,7 @@ template <class R> PTB_DEV void path_begin(const DScene<R>& s, PathState<R>& p, 
     p.hit_dist = R(-1);        // globals.rs:28
     p.prev_pdf = 0;
     p.bounce = 0;
+    p.medium = 0;
 }
 
 // Second half of a bounce, tracer.rs:72-101, for a path that hit geometry (not a light), in three pieces so that
@@ -1379,7 +1399,7 @@ PTB_DEV void shade_setup(const DScene<R>& s, PathState<R>& p, V3<R> normal, Mat<
     shade_ctx_init(su.c, mat, su.eta, su.ffn, -p.d);
 }
 
-template <class R>
+template <class R, bool XL = true>
 PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const ShadeSetup<R>& su, const R* u, NeeSample<R>& ns) {
     ns.wants_shadow_ray = false;
     ns.light_area = 0;
@@ -1387,7 +1407,7 @@ PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const 
         uint32_t li = (uint32_t)(u[SLOT_LIGHT_PICK] * s.n_lights_f);          // tracer.rs:137-139
         ns.scatter_pos = su.fhp + s.eps * su.ffn;
         const DLight<R> L = sv.lights[li];
-        const bool extended = (s.flags & PTB_SCENE_EXTENDED_LIGHTS) != 0 && L.type != PTB_LIGHT_SPHERICAL;
+        const bool extended = XL && (s.flags & PTB_SCENE_EXTENDED_LIGHTS) != 0 && L.type != PTB_LIGHT_SPHERICAL;
         if (extended) ns.ls = sample_light_extended(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
         else ns.ls = sample_light(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
         ns.light_area = L.area;
@@ -1540,7 +1560,7 @@ PTB_DEV bool path_shade_rm(const DScene<float>& s, const SceneView<float>& sv, P
     ShadeSetup<float> su;
     shade_setup_rm<COUNT, ADD_EMISSION>(p, normal, rm, su, pc);
     NeeSample<float> ns;
-    shade_nee_sample(s, sv, su, u, ns);
+    shade_nee_sample<float, false>(s, sv, su, u, ns);
     bool nee = false;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;
@@ -1606,6 +1626,88 @@ PTB_DEV int path_intersect(const DScene<R>& s, const SceneView<R>& sv, PathState
     return 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Media (PTB_MEDIUM_* in ptb200.h; material.rs:5-34, State::medium globals.rs:19, the `_is_surface` hook of direct_light,
+// tracer.rs:125).  The reference never reads its Medium: the semantics are the GLSL project's it was ported from, stated
+// identically by the oracle (Tracer::medium_step).  Henyey-Greenstein in the pbrt convention: cos is taken between the
+// direction back along the ray and the new direction, forward scattering (g > 0) peaks at cos = -1.
+template <class R> PTB_DEV R phase_hg(R cos_theta, R g) {
+    const R denom = (R(1) + g * g) + (R(2) * g) * cos_theta;
+    return Const<R>::INV_4PI * m_div(R(1) - g * g, denom * m_sqrt(denom));
+}
+template <class R> PTB_DEV V3<R> sample_hg(V3<R> v, R g, R r1, R r2) {
+    R cos_theta;
+    if (m_abs(g) < R(0.001)) cos_theta = R(1) - R(2) * r2;
+    else {
+        const R sqr = m_div(R(1) - g * g, (R(1) + g) - (R(2) * g) * r2);
+        cos_theta = -m_div((R(1) + g * g) - sqr * sqr, R(2) * g);
+    }
+    const R sin_theta = m_sqrt(m_max(R(0), R(1) - cos_theta * cos_theta));
+    R sn, cs;
+    m_sincos(Const<R>::TWO_PI * r1, &sn, &cs);
+    V3<R> t, b;
+    onb(v, t, b);
+    return ((sin_theta * cs) * t + (sin_theta * sn) * b) + cos_theta * v;
+}
+// The medium's part of a bounce, for a path that is inside one (p.medium != 0) and has just hit geometry at p.hit_dist.
+// Returns 0: go on with the surface (absorption / emission applied), 1: the bounce happened in the medium and the path
+// continues from there, 2: it happened in the medium and the path ended (depth).  Draws: slot 1 (free after bounce 0; a path
+// cannot be inside on bounce 0) for the free-flight distance, the light slots as at a surface, the two BSDF slots for the phase
+// function.
+enum : int { MED_SURFACE = 0, MED_SCATTERED = 1, MED_ENDED = 2 };
+template <class R, bool COUNT, bool BVH, bool SDF>
+PTB_DEV int path_medium(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, PathCounters* pc) {
+    const DMaterial<R>& mm = BVH ? s.materials[p.medium - 1u] : sv.materials[p.medium - 1u];
+    const R density = mm.med_density, t = p.hit_dist;
+    const V3<R> color(mm.med_color[0], mm.med_color[1], mm.med_color[2]);
+    if (mm.med_type == PTB_MEDIUM_ABSORB) {
+        p.thr = p.thr * V3<R>(m_exp((-(R(1) - color.x) * t) * density), m_exp((-(R(1) - color.y) * t) * density), m_exp((-(R(1) - color.z) * t) * density));
+        return MED_SURFACE;
+    }
+    if (mm.med_type == PTB_MEDIUM_EMISSIVE) {
+        p.rad = p.rad + ((t * density) * color) * p.thr;
+        return MED_SURFACE;
+    }
+    const R sd = m_min(m_div(-m_ln(u[SLOT_JITTER_Y]), density), t);
+    if (!(sd < t)) return MED_SURFACE;
+    p.thr = p.thr * color;
+    p.o = p.o + sd * p.d;
+    // direct_light(.., is_surface = false): the sample leaves from the point itself, the phase function is value and pdf
+    ShadeSetup<R> su;
+    su.fhp = p.o; su.ffn = V3<R>(R(0), R(0), R(0));
+    NeeSample<R> ns;
+    shade_nee_sample(s, sv, su, u, ns);
+    const V3<R> back = -p.d;
+    if (ns.wants_shadow_ray) {
+        if (COUNT) pc->any_hit++;
+        if (!any_hit<R, BVH, SDF>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT ? pc->bvh : nullptr)) {
+            const R ph = phase_hg(dot(back, ns.ls.direction), mm.med_g);
+            R w = R(1);
+            if (ns.light_area > R(0)) w = power_heuristic(ns.ls.pdf, ph);
+            if (ph > R(0)) {
+                p.rad = p.rad + ((w * ns.ls.emission) * V3<R>(m_div(ph, ns.ls.pdf), m_div(ph, ns.ls.pdf), m_div(ph, ns.ls.pdf))) * p.thr;
+                if (COUNT) pc->nee_contrib++;
+            }
+        }
+    }
+    const V3<R> dir = sample_hg(back, mm.med_g, u[SLOT_BSDF_R1], u[SLOT_BSDF_R2]);
+    p.prev_pdf = phase_hg(dot(back, dir), mm.med_g);
+    p.d = dir;
+    p.bounce++;
+    if (p.bounce >= s.depth) {
+        if (COUNT) pc->end_depth++;
+        return MED_ENDED;
+    }
+    return MED_SCATTERED;
+}
+// after a surface bounce: a path that leaves a surface with a medium towards its back side is inside it, towards the front
+// outside; surfaces without a medium change nothing (no nesting).  p.d is the new direction, `normal` the geometry normal.
+template <class R, bool BVH>
+PTB_DEV void path_medium_update(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, uint32_t mi) {
+    const DMaterial<R>& mm = BVH ? s.materials[mi] : sv.materials[mi];
+    if (mm.med_type != PTB_MEDIUM_NONE) p.medium = dot(p.d, normal) < R(0) ? mi + 1u : 0u;
+}
+
 // Runs ONE bounce (both halves); returns true while the path continues.  COUNT enables event counters.
 template <class R, bool COUNT, bool BVH>
 PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, uint32_t rr_start, PathCounters* pc) {
@@ -1617,10 +1719,16 @@ PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R
     }
     HitCore<R> h;
     if (!path_intersect<R, COUNT, BVH>(s, sv, p, h, pc)) return false;
+    if (s.has_media && p.medium) {
+        const int med = path_medium<R, COUNT, BVH, true>(s, sv, p, u, pc);
+        if (med != MED_SURFACE) return med == MED_SCATTERED;
+    }
     Mat<R> mat;
-    hit_material<R, BVH>(s, sv, h.prim, h.accepted, p.d, mat);
+    const uint32_t mi = hit_material<R, BVH>(s, sv, h.prim, h.accepted, p.d, mat);
     V3<R> normal = hit_normal<R, BVH>(s, sv, h.prim, p.o, p.d, h.hit_dist);
-    return path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, pc);
+    const bool alive = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, pc);
+    if (s.has_media) path_medium_update<R, BVH>(s, sv, p, normal, mi);
+    return alive;
 }
 
 }  // namespace ptb

@@ -248,8 +248,14 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_cons
 // while-while): the lane parks the leaf reference, pops the next node and keeps traversing; parked leaves are intersected
 // together once ST_LEAF_MIN lanes hold one, or no lane can advance otherwise.  Node references carry the leaf count in
 // their low 3 bits, so neither the stack pop nor the parked leaf needs to touch the node array again.
-constexpr int ST_REFILL = 8;
-constexpr int ST_LEAF_MIN = 12;
+#ifndef PTB_ST_REFILL
+#define PTB_ST_REFILL 8
+#endif
+#ifndef PTB_ST_LEAF_MIN
+#define PTB_ST_LEAF_MIN 12
+#endif
+constexpr int ST_REFILL = PTB_ST_REFILL;
+constexpr int ST_LEAF_MIN = PTB_ST_LEAF_MIN;
 constexpr int ST_STACK = 40;
 constexpr uint32_t ST_NONE = 0xffffffffu;
 
@@ -303,10 +309,41 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
     uint32_t stack_n[ST_STACK];
     float stack_t[ST_STACK];
 
+#ifdef PTB_ST_DEFER_FINISH
+    bool fin = false;                        // the lane's ray is done, its result not yet written (written with the next refill)
+#endif
     while (true) {
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(FULL, !active);
         if (idle) {
+#ifdef PTB_ST_DEFER_FINISH
+            // results are written by all idle lanes together, right before they are refilled (or at the very end): the write-back
+            // used to run for one or two lanes in almost every iteration
+            if ((!exhausted && __popc(idle) >= ST_REFILL) || idle == FULL) {
+                if (fin) {
+                    fin = false;
+                    if (ANY) {
+                        if (best < 0) {                                       // unoccluded: tracer.rs:162-164
+                            const float4 S1 = a.s1[slot], S2 = a.s2[slot];
+                            const uint32_t flags = __float_as_uint(S2.w);
+                            if (flags & 16u) {
+                                const uint32_t ps = __float_as_uint(S1.w);
+                                float4 A3 = a.a3[ps];
+                                A3.x += S2.x; A3.y += S2.y; A3.z += S2.z;
+                                a.a3[ps] = A3;
+                                if (COUNT) pc.nee_contrib++;
+                            }
+                            if (COUNT) {
+                                pc.eval_calls++;
+                                for (int k = 0; k < 4; ++k) pc.ev[k] += (flags >> k) & 1u;
+                            }
+                        }
+                    } else {
+                        a.hit[slot] = make_uint4((uint32_t)best, 0u, 0u, __float_as_uint(best_t));
+                    }
+                }
+            }
+#endif
             if (!exhausted && (__popc(idle) >= ST_REFILL || idle == FULL)) {
                 const uint32_t cnt = (uint32_t)__popc(idle);
                 uint32_t base = 0;
@@ -397,6 +434,9 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
             }
         }
         if (active && cur == ST_NONE && pend == 0u && sp == 0) finished = true;
+#ifdef PTB_ST_DEFER_FINISH
+        if (active && finished) { active = false; fin = true; }
+#else
         if (active && finished) {
             active = false;
             if (ANY) {
@@ -419,6 +459,7 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
                 a.hit[slot] = make_uint4((uint32_t)best, 0u, 0u, __float_as_uint(best_t));
             }
         }
+#endif
     }
     if (COUNT) pc_flush(pc, 0, a.counters);
 }

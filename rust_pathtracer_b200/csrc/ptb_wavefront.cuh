@@ -77,7 +77,8 @@ constexpr uint32_t WF_MISS = 8;             // the path left the scene: backgrou
 //   ro = (o.xyz, State::hit_dist)        rd = (d.xyz, pixel column | row << 16)
 //   tr = (throughput.xyz, flags)         ra = (radiance.xyz, sample index)
 //   ac = (pixel sum.xyz, hit primitive / accepted set of the pending shading event)
-// flags word: bit0 alive, bit1 have_pixel, bits 3..7 sample block (tail items), bits 8..23 bounce, bit 24 tail item
+// flags word: bit0 alive, bit1 have_pixel, bits 3..7 sample block (tail items), bits 8..23 bounce, bit 24 tail item,
+//             bits 25..31 PathState::medium (0 = outside, else 1 + material index; scenes with media only)
 constexpr uint32_t FL_ALIVE = 1u, FL_PIXEL = 2u, FL_BLOCK = 1u << 24, FL_BLOCK_BITS = FL_BLOCK | (31u << 3);
 #ifndef PTB_WF_TAIL_LOG2
 #define PTB_WF_TAIL_LOG2 3
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                 if constexpr (!RM) accepted = (uint64_t)sm.acc_lo[i] | ((uint64_t)sm.acc_hi[i] << 32);
             }
             p.bounce = (fl0 >> 8) & 0xffffu;
+            p.medium = RM ? 0u : fl0 >> 25;                             // (media: generic instantiations only)
             bool alive = valid && (fl0 & FL_ALIVE);
             const bool had_event = alive;
 
@@ -258,16 +260,23 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                     } else {
                         const int prim = (int)prim_bits;
                         Mat<R> mat;
-                        hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
-                        if (s.has_emissive) {
-                            const V4 t4 = sm.tr[i];
-                            V4 r4 = sm.ra[i];
-                            r4.x = r4.x + mat.emission.x * t4.x; r4.y = r4.y + mat.emission.y * t4.y; r4.z = r4.z + mat.emission.z * t4.z;
-                            sm.ra[i] = r4;
+                        const uint32_t mi = hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+                        shade_draws(rng, p.bounce, s.n_lights > 1u || p.medium != 0u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
+                        int med = MED_SURFACE;
+                        if (s.has_media && p.medium) med = path_medium<R, COUNT, BVH, !BVH>(s, sv, p, u, &pc);       // works on the unit throughput like the shading below
+                        if (med != MED_SURFACE) {
+                            alive = med == MED_SCATTERED;
+                        } else {
+                            if (s.has_emissive) {                       // tracer.rs:74 (behind a medium: on the attenuated throughput)
+                                const V4 t4 = sm.tr[i];
+                                V4 r4 = sm.ra[i];
+                                r4.x = r4.x + mat.emission.x * (t4.x * p.thr.x); r4.y = r4.y + mat.emission.y * (t4.y * p.thr.y); r4.z = r4.z + mat.emission.z * (t4.z * p.thr.z);
+                                sm.ra[i] = r4;
+                            }
+                            const V3<R> normal = hit_normal<R, BVH, !BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
+                            alive = path_shade<R, COUNT, BVH, false, !BVH>(s, sv, p, normal, mat, u, &pc);
+                            if (s.has_media) path_medium_update<R, BVH>(s, sv, p, normal, mi);
                         }
-                        shade_draws(rng, p.bounce, s.n_lights > 1u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
-                        const V3<R> normal = hit_normal<R, BVH, !BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-                        alive = path_shade<R, COUNT, BVH, false, !BVH>(s, sv, p, normal, mat, u, &pc);
                     }
                 }
             }
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                     if (COUNT) pc.end_depth++;
                 } else {
                     if (COUNT) pc.closest_hit++;
-                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc.bvh : nullptr);   // signed-distance programs: generic instantiation only
+                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH, !RM>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc.bvh : nullptr);   // signed-distance programs: generic instantiation only
                     p.hit_dist = h.hit_dist;
                     if (!h.hit) {
                         key = WF_MISS;                                 // background lookup next iteration, with full warps
@@ -410,7 +419,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                 sm.ac[i].w = wf_word(R(0), new_prim);
             }
             if (valid) {
-                fl = (p.bounce << 8) | blkbits | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u);
+                fl = (p.bounce << 8) | blkbits | (alive ? FL_ALIVE : 0u) | (have_pixel ? FL_PIXEL : 0u) | (p.medium << 25);
                 sm.tr[i] = mk4(p.thr.x, p.thr.y, p.thr.z, wf_word(R(0), fl));
                 sm.ra[i] = mk4(p.rad.x, p.rad.y, p.rad.z, wf_word(R(0), sidx));
                 uint32_t ticket = 0;

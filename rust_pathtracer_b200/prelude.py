@@ -59,6 +59,24 @@ def _f3(v) -> F3:
     return v if isinstance(v, F3) else F3(*v)
 
 
+class MediumType:
+    """material.rs:7-13"""
+    NONE, ABSORB, SCATTER, EMISSIVE = _abi.PTB_MEDIUM_NONE, _abi.PTB_MEDIUM_ABSORB, _abi.PTB_MEDIUM_SCATTER, _abi.PTB_MEDIUM_EMISSIVE
+
+
+@dataclass
+class Medium:
+    """material.rs:15-34 — the reference's tracer never reads it; semantics here: PTB_MEDIUM_* in include/ptb200.h"""
+    medium_type: int = _abi.PTB_MEDIUM_NONE
+    density: float = 0.0
+    color: F3 = field(default_factory=F3.zeros)
+    anisotropy: float = 0.0
+
+    @staticmethod
+    def new() -> "Medium":
+        return Medium()
+
+
 @dataclass
 class Material:
     """material.rs:48-114 — defaults are Material::new()'s (rgb 1.5!, roughness 0.5, ior 1.45).
@@ -86,6 +104,7 @@ class Material:
     checker_b: float = 0.1
     checker_scale: float = 0.5
     checker_offset: float = 100.0
+    medium: "Medium" = field(default_factory=lambda: Medium())
 
     _MASKS = {"rgb": _abi.PTB_MAT_RGB, "emission": _abi.PTB_MAT_EMISSION, "anisotropic": _abi.PTB_MAT_ANISOTROPIC,
               "metallic": _abi.PTB_MAT_METALLIC, "roughness": _abi.PTB_MAT_ROUGHNESS, "subsurface": _abi.PTB_MAT_SUBSURFACE,
@@ -308,6 +327,8 @@ class DeviceScene:
                       "clearcoat_gloss", "spec_trans", "ior", "checker_a", "checker_b", "checker_scale", "checker_offset"):
                 setattr(d, k, getattr(m, k))
             d.set_mask = m.set_mask; d.albedo_kind = m.albedo_kind
+            d.medium_type = m.medium.medium_type; d.medium_density = m.medium.density
+            d.medium_color = v3(m.medium.color); d.medium_anisotropy = m.medium.anisotropy
         li = (T["Light"] * max(1, len(self.lights)))()
         for i, l in enumerate(self.lights):
             li[i].position = v3(l.light.position); li[i].radius = l.light.radius

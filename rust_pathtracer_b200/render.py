@@ -14,9 +14,10 @@ import time
 
 import numpy as np
 
-from . import AnalyticalScene, ColorBuffer, Tracer, divergence_stress_scene, sdf_demo_scene, sphere_field_scene
+from . import AnalyticalScene, ColorBuffer, Tracer, divergence_stress_scene, lights_demo_scene, media_demo_scene, sdf_demo_scene, sphere_field_scene
 
-SCENES = {"demo": AnalyticalScene.new, "field": sphere_field_scene, "stress": divergence_stress_scene, "sdf": sdf_demo_scene}
+SCENES = {"demo": AnalyticalScene.new, "field": sphere_field_scene, "stress": divergence_stress_scene, "sdf": sdf_demo_scene,
+          "media": media_demo_scene, "lights": lights_demo_scene}
 
 
 def write_image(path: str, rgba8: np.ndarray, w: int, h: int) -> str:

@@ -180,3 +180,40 @@ def sdf_demo_scene(depth: int = 4) -> ExportedScene:
     return ExportedScene(DeviceScene(spheres=[], planes=[Plane(F3(0.0, -1.0, 0.0), F3(0.0, 1.0, 0.0), 0)], materials=mats,
                                      lights=[AnalyticalLight.spherical(F3(3.0, 2.0, 2.0), 1.0, F3(3.0, 3.0, 3.0))], camera=cam,
                                      depth=depth, flags=0, eps=0.005, sdf=prog))
+
+
+def media_demo_scene(depth: int = 12) -> ExportedScene:
+    """The reference's open item "Support of mediums / volumetric objects" (Readme.md:13) in device form, on the demo scene's checker
+    plane under the demo scene's light and sky: three glass balls filled with an absorbing (Beer-Lambert tint), a scattering
+    (Henyey-Greenstein fog) and an emissive medium (PTB_MEDIUM_* in include/ptb200.h), plus the demo scene's metal ball."""
+    from .prelude import Medium, MediumType
+
+    def glass(medium):
+        m = Material(); m.rgb = F3(1.0, 1.0, 1.0); m.spec_trans = 1.0; m.roughness = 0.02; m.ior = 1.3; m.medium = medium
+        return m
+    metal = Material(); metal.rgb = F3(1.0, 1.0, 1.0); metal.metallic = 1.0; metal.roughness = 0.05
+    mats = [_checker_plane_material(),
+            glass(Medium(MediumType.ABSORB, 1.5, F3(0.2, 0.8, 0.3), 0.0)),
+            glass(Medium(MediumType.SCATTER, 2.5, F3(0.9, 0.9, 0.95), 0.4)),
+            glass(Medium(MediumType.EMISSIVE, 0.4, F3(1.0, 0.5, 0.1), 0.0)),
+            metal]
+    return ExportedScene(DeviceScene(
+        spheres=[Sphere(F3(-2.1, 0.0, 0.0), 1.0, 1), Sphere(F3(0.0, 0.0, 0.0), 1.0, 2), Sphere(F3(2.1, 0.0, 0.0), 1.0, 3),
+                 Sphere(F3(0.9, -0.55, 1.5), 0.45, 4)],
+        planes=[Plane(F3(0.0, -1.0, 0.0), F3(0.0, 1.0, 0.0), 0)], materials=mats,
+        lights=[AnalyticalLight.spherical(F3(3.0, 2.0, 2.0), 1.0, F3(3.0, 3.0, 3.0))], camera=Pinhole.new(),
+        background=Background(_abi.PTB_BG_GRADIENT_Y, F3(1.0, 1.0, 1.0), F3(0.5, 0.7, 1.0), 0.5, 2.2),
+        depth=depth, flags=0, eps=0.005))
+
+
+def lights_demo_scene(depth: int = 4) -> ExportedScene:
+    """The demo scene lit by the two light kinds the reference enumerates but never implements (globals.rs:69-73, tracer.rs:217):
+    a downward-facing quad above the spheres and a faint bluish distant light, next to the reference's spherical light
+    (PTB_SCENE_EXTENDED_LIGHTS in include/ptb200.h)."""
+    e = AnalyticalScene.new().device_export()
+    e.lights = [AnalyticalLight.rectangular(F3(-1.0, 3.0, -0.6), F3(2.0, 0.0, 0.0), F3(0.0, 0.0, 1.2), F3(9.0, 8.0, 7.0)),
+                e.lights[0],
+                AnalyticalLight.distant(F3(0.4, 1.0, 0.3), F3(0.5, 0.6, 0.9))]
+    e.flags |= _abi.PTB_SCENE_EXTENDED_LIGHTS
+    e.depth = depth
+    return ExportedScene(e)

@@ -382,3 +382,70 @@ def test_quad_light_hit_pdf_is_the_sampling_pdf(rp, po):
     assert r["is_emitter"][1] == 0                          # from above: the back side
     ls = orc.sample_light(0, o[:, :1], np.array([(0.5 + a / 2) / a]), np.array([(-0.2 + b / 2) / b]))
     assert np.allclose(ls["direction"][:, 0], d[:, 0]) and abs(ls["pdf"][0] / r["light_pdf"][0] - 1) < 1e-12
+
+
+# ---- media (PTB_MEDIUM_*): the library's extension, pinned by closed forms ----------------------------------------------------
+def test_henyey_greenstein_sampling_matches_its_pdf(po):
+    """sample_hg draws from phase_hg: directions are unit, E[1 / pdf] = 4 pi (the pdf integrates to one over the sphere),
+    E[cos] = -g in the pbrt convention (v points back along the ray: forward scattering is cos = -1), and g = 0 is uniform."""
+    rng = np.random.default_rng(11)
+    n = 400_000
+    v = np.ascontiguousarray(np.tile(np.array([[0.3], [-0.5], [0.81]]) / np.linalg.norm([0.3, -0.5, 0.81]), (1, n)))
+    r1, r2 = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    for g in (-0.6, 0.0, 0.0005, 0.4, 0.9):
+        d, pdf = po.sample_hg(v, g, r1, r2)
+        assert np.allclose(np.linalg.norm(d, axis=0), 1.0, atol=1e-12)
+        cos = (d * v).sum(0)
+        assert abs(cos.mean() + g) < 4e-3, (g, cos.mean())
+        assert abs((1.0 / pdf).mean() / (4 * math.pi) - 1) < (2e-2 if abs(g) > 0.8 else 5e-3), (g, (1.0 / pdf).mean())
+        if g == 0.0:
+            assert np.allclose(pdf, 1 / (4 * math.pi))
+
+
+def _ball_in_white_sky(rp, medium, depth, ior=1.0002):
+    """one glass ball of radius 1 in a constant white sky, no lights, camera looking at its centre"""
+    e = rp.AnalyticalScene.new().device_export()
+    g = rp.Material(); g.rgb = rp.F3(1.0, 1.0, 1.0); g.spec_trans = 1.0; g.roughness = 0.01; g.ior = ior; g.medium = medium
+    e.materials = [g]
+    e.spheres = [rp.Sphere(rp.F3(0.0, 0.0, 0.0), 1.0, 0)]
+    e.planes = []; e.lights = []
+    e.background = rp.Background(rp._abi.PTB_BG_CONSTANT, rp.F3(1.0, 1.0, 1.0), rp.F3(1.0, 1.0, 1.0), 1.0, 1.0)
+    e.depth = depth; e.flags = 0
+    e.camera.set_fov(60.0)                 # half width 1.73 at the ball: the corners see the sky directly
+    return e
+
+
+def test_absorbing_medium_follows_beer_lambert(rp, po):
+    """straight through the centre of a ball with ior ~ 1: radiance = exp(-(1 - color) * 2 r * density) per channel"""
+    den, col = 0.8, (0.9, 0.5, 0.2)
+    e = _ball_in_white_sky(rp, rp.Medium(rp.MediumType.ABSORB, den, rp.F3(*col), 0.0), depth=6)
+    img, _, _, _ = po.OracleScene(e, "f64").render(65, 65, 64)
+    centre = img.reshape(65, 65, 4)[31:34, 31:34, :3].mean((0, 1))
+    want = np.exp(-(1 - np.array(col)) * 2.0 * den)
+    assert np.allclose(centre, want, rtol=0.02), (centre, want)
+    # outside the ball's silhouette nothing is attenuated
+    assert np.allclose(img.reshape(65, 65, 4)[0, 0, :3], 1.0)
+
+
+def test_emissive_medium_adds_density_times_length(rp, po):
+    den, col = 0.3, (1.0, 0.5, 0.25)
+    e = _ball_in_white_sky(rp, rp.Medium(rp.MediumType.EMISSIVE, den, rp.F3(*col), 0.0), depth=6)
+    img, _, _, _ = po.OracleScene(e, "f64").render(65, 65, 64)
+    centre = img.reshape(65, 65, 4)[31:34, 31:34, :3].mean((0, 1))
+    assert np.allclose(centre, 1.0 + np.array(col) * 2.0 * den, rtol=0.02), centre
+
+
+def test_scattering_medium_conserves_energy_in_a_white_furnace(rp, po):
+    """albedo 1, any anisotropy: every path ends in the white sky with throughput 1 unless the depth limit cuts it; with albedo a the
+    radiance is below 1 and above a^(expected number of collisions bound)"""
+    for g in (0.0, 0.6):
+        e = _ball_in_white_sky(rp, rp.Medium(rp.MediumType.SCATTER, 1.5, rp.F3(1.0, 1.0, 1.0), g), depth=200)
+        img, _, _, oc = po.OracleScene(e, "f64").render(65, 65, 16, counters=True)
+        centre = img.reshape(65, 65, 4)[28:37, 28:37, :3]
+        assert abs(centre.mean() - 1.0) < 0.01, (g, centre.mean())
+        assert oc["end_depth"] < 1e-3 * oc["samples"]
+    e = _ball_in_white_sky(rp, rp.Medium(rp.MediumType.SCATTER, 1.5, rp.F3(0.8, 0.8, 0.8), 0.0), depth=200)
+    img, _, _, _ = po.OracleScene(e, "f64").render(65, 65, 16)
+    c = img.reshape(65, 65, 4)[28:37, 28:37, :3].mean()
+    # unscattered share exp(-3) keeps 1; single scattering or more loses at least one factor 0.8
+    assert math.exp(-3.0) + 0.3 * (1 - math.exp(-3.0)) < c < math.exp(-3.0) + 0.8 * (1 - math.exp(-3.0)) + 0.01, c

@@ -21,7 +21,7 @@ def test_exr_writer_round_trip(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene_size", [("demo", 96, 54), ("sdf", 64, 36)])
+@pytest.mark.parametrize("scene_size", [("demo", 96, 54), ("sdf", 64, 36), ("media", 64, 36), ("lights", 64, 36)])
 def test_render_cli_writes_the_converted_frame(tmp_path, rp, po, scene_size):
     """CLI -> Tracer.render_spp -> convert_to_u8 -> PNG / EXR: the bytes on disk are the reference's encoding (buffer.rs:55-64) of
     the image the oracle renders with the same counter RNG."""
