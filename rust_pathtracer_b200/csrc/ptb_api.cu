@@ -1047,11 +1047,6 @@ int ptb_render(ptb_tracer* t, uint32_t spp, uint64_t sample_base) {
         if ((t->precision == 4 ? t->s32.d.n_sdf != 0 : t->s64.d.n_sdf != 0) &&
             (integ == PTB_INTEGRATOR_STREAM || (t->precision == 4 ? t->s32.d.use_bvh != 0 : t->s64.d.use_bvh != 0))) integ = PTB_INTEGRATOR_FUSED;
     }
-    const bool has_media = t->precision == 4 ? t->s32.d.has_media != 0 : t->s64.d.has_media != 0;
-    if (has_media && integ == PTB_INTEGRATOR_STREAM) {
-        if (t->cfg.integrator == PTB_INTEGRATOR_AUTO) integ = PTB_INTEGRATOR_WAVEFRONT;
-        else return fail(PTB_E_UNSUPPORTED, "scenes with media run on the fused and the shared-memory wavefront integrators");
-    }
     const bool has_sdf = t->precision == 4 ? t->s32.d.n_sdf != 0 : t->s64.d.n_sdf != 0;
     const bool bvh_scene = t->precision == 4 ? t->s32.d.use_bvh != 0 : t->s64.d.use_bvh != 0;
     if (has_sdf && (integ == PTB_INTEGRATOR_STREAM || (integ == PTB_INTEGRATOR_WAVEFRONT && bvh_scene)))

@@ -182,8 +182,11 @@ enum : uint32_t { SLOT_JITTER_X = 0, SLOT_JITTER_Y = 1, SLOT_LIGHT_PICK = 2, SLO
 struct Philox4 { uint32_t v[4]; };
 PTB_DEV Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#ifndef PTB_PHILOX_ROUNDS
+#define PTB_PHILOX_ROUNDS 10      /* A/B knob only (tools/ab_variants.py): the oracle and every parity test use the 10-round generator */
+#endif
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PTB_PHILOX_ROUNDS; ++r) {
         uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
         uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
         c0 = hi1 ^ c1 ^ k0;
@@ -1655,8 +1658,12 @@ template <class R> PTB_DEV V3<R> sample_hg(V3<R> v, R g, R r1, R r2) {
 // cannot be inside on bounce 0) for the free-flight distance, the light slots as at a surface, the two BSDF slots for the phase
 // function.
 enum : int { MED_SURFACE = 0, MED_SCATTERED = 1, MED_ENDED = 2 };
+// `defer` (global-memory wavefront): the shadow ray of the in-medium light sample is not traced here; the sample is handed back
+// (origin, direction, length, contribution already multiplied by the throughput) for the shadow-ray kernel to add if unoccluded
+template <class R> struct MediumNee { bool wants; V3<R> pos, dir, contrib; R max_dist; };
 template <class R, bool COUNT, bool BVH, bool SDF>
-PTB_DEV int path_medium(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, PathCounters* pc) {
+PTB_DEV int path_medium(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, PathCounters* pc, MediumNee<R>* defer = nullptr) {
+    if (defer) defer->wants = false;
     const DMaterial<R>& mm = BVH ? s.materials[p.medium - 1u] : sv.materials[p.medium - 1u];
     const R density = mm.med_density, t = p.hit_dist;
     const V3<R> color(mm.med_color[0], mm.med_color[1], mm.med_color[2]);
@@ -1680,13 +1687,18 @@ PTB_DEV int path_medium(const DScene<R>& s, const SceneView<R>& sv, PathState<R>
     const V3<R> back = -p.d;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;
-        if (!any_hit<R, BVH, SDF>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT ? pc->bvh : nullptr)) {
+        if (defer || !any_hit<R, BVH, SDF>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT ? pc->bvh : nullptr)) {
             const R ph = phase_hg(dot(back, ns.ls.direction), mm.med_g);
             R w = R(1);
             if (ns.light_area > R(0)) w = power_heuristic(ns.ls.pdf, ph);
             if (ph > R(0)) {
-                p.rad = p.rad + ((w * ns.ls.emission) * V3<R>(m_div(ph, ns.ls.pdf), m_div(ph, ns.ls.pdf), m_div(ph, ns.ls.pdf))) * p.thr;
-                if (COUNT) pc->nee_contrib++;
+                const V3<R> c = ((w * ns.ls.emission) * V3<R>(m_div(ph, ns.ls.pdf), m_div(ph, ns.ls.pdf), m_div(ph, ns.ls.pdf))) * p.thr;
+                if (defer) {
+                    defer->wants = true; defer->pos = ns.scatter_pos; defer->dir = ns.ls.direction; defer->max_dist = ns.ls.dist - s.eps; defer->contrib = c;
+                } else {
+                    p.rad = p.rad + c;
+                    if (COUNT) pc->nee_contrib++;
+                }
             }
         }
     }

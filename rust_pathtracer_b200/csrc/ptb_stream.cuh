@@ -46,7 +46,10 @@ constexpr int ST_THREADS = 256;
 constexpr uint32_t ST_KEYS = 9;          // 8 lobe classes (lobe_class_of) + ST_MISS
 constexpr uint32_t ST_MISS = 8;          // the path left the scene: background lookup (tracer.rs:66-69)
 constexpr uint32_t ST_DEFAULT_WAVE = 1u << 23;
-constexpr uint32_t ST_SPLIT_MIN_SPHERES = 16384u;   // BVH scenes above this use the persistent-lane traversal kernels from bounce 1 on
+#ifndef PTB_ST_SPLIT_MIN
+#define PTB_ST_SPLIT_MIN 16384u
+#endif
+constexpr uint32_t ST_SPLIT_MIN_SPHERES = PTB_ST_SPLIT_MIN;   // BVH scenes above this use the persistent-lane traversal kernels from bounce 1 on
 inline bool stream_uses_split(const DScene<float>& d) { return d.use_bvh && d.n_spheres > ST_SPLIT_MIN_SPHERES; }
 
 struct BounceCtr {                       // 128 bytes per bounce, zeroed at the start of a wave
@@ -249,10 +252,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_cons
 // together once ST_LEAF_MIN lanes hold one, or no lane can advance otherwise.  Node references carry the leaf count in
 // their low 3 bits, so neither the stack pop nor the parked leaf needs to touch the node array again.
 #ifndef PTB_ST_REFILL
-#define PTB_ST_REFILL 8
+#define PTB_ST_REFILL 12
 #endif
 #ifndef PTB_ST_LEAF_MIN
-#define PTB_ST_LEAF_MIN 12
+#define PTB_ST_LEAF_MIN 8
 #endif
 constexpr int ST_REFILL = PTB_ST_REFILL;
 constexpr int ST_LEAF_MIN = PTB_ST_LEAF_MIN;
@@ -274,11 +277,25 @@ PTB_DEV float box_entry_s(float4 lo, float4 hi, const RayS& r, float limit) {
     return (tn <= tf * 1.0001f && tn <= limit) ? tn : 3.0e38f;
 }
 
+#ifndef PTB_ST_INNER_REPS
+#define PTB_ST_INNER_REPS 4
+#endif
+// (an explicit minimum of 1 block makes nvcc budget 255 registers: the bounds below name a minimum only when a knob sets one)
+#ifdef PTB_ST_SHADE_MIN_BLOCKS
+#define PTB_ST_SHADE_BOUNDS __launch_bounds__(ST_THREADS, PTB_ST_SHADE_MIN_BLOCKS)
+#else
+#define PTB_ST_SHADE_BOUNDS __launch_bounds__(ST_THREADS)
+#endif
 #ifndef PTB_ST_TRACE_MIN_BLOCKS
-#define PTB_ST_TRACE_MIN_BLOCKS 1
+#define PTB_ST_TRACE_MIN_BLOCKS 5
+#endif
+#ifdef PTB_ST_TRACE_PLAIN
+#define PTB_ST_TRACE_BOUNDS __launch_bounds__(ST_THREADS)
+#else
+#define PTB_ST_TRACE_BOUNDS __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS)
 #endif
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_trace(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+__global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);       // planes (shadow rays test them first)
@@ -309,14 +326,14 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
     uint32_t stack_n[ST_STACK];
     float stack_t[ST_STACK];
 
-#ifdef PTB_ST_DEFER_FINISH
+#ifndef PTB_ST_EAGER_FINISH
     bool fin = false;                        // the lane's ray is done, its result not yet written (written with the next refill)
 #endif
     while (true) {
         // ---- refill idle lanes
         const unsigned idle = __ballot_sync(FULL, !active);
         if (idle) {
-#ifdef PTB_ST_DEFER_FINISH
+#ifndef PTB_ST_EAGER_FINISH
             // results are written by all idle lanes together, right before they are refilled (or at the very end): the write-back
             // used to run for one or two lanes in almost every iteration
             if ((!exhausted && __popc(idle) >= ST_REFILL) || idle == FULL) {
@@ -333,7 +350,7 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
                                 a.a3[ps] = A3;
                                 if (COUNT) pc.nee_contrib++;
                             }
-                            if (COUNT) {
+                            if (COUNT && !(flags & 32u)) {
                                 pc.eval_calls++;
                                 for (int k = 0; k < 4; ++k) pc.ev[k] += (flags >> k) & 1u;
                             }
@@ -381,7 +398,11 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
                 break;
             }
         }
-        // ---- one inner node: both children with one 64-byte read, nearer first
+        // ---- one inner node: both children with one 64-byte read, nearer first.  PTB_ST_INNER_REPS > 1: that many traversal steps
+        //      (node + park / pop) per iteration, so that the ballots, the leaf batch test, the write-back and the refill test
+        //      around them are paid once per several node visits
+#pragma unroll
+        for (int rep = 0; rep < PTB_ST_INNER_REPS; ++rep) {
         if (active && cur != ST_NONE && (cur & 7u) == 0u) {
             if (COUNT) pc.bvh[0]++;
             const float4* c = nodes + (size_t)(cur >> 3) * 2u;
@@ -411,6 +432,7 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
                 }
             }
         }
+        }
         // ---- parked leaves, together
         const unsigned m_pend = __ballot_sync(FULL, active && pend != 0u);
         const unsigned m_inner = __ballot_sync(FULL, active && cur != ST_NONE && (cur & 7u) == 0u);
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
             }
         }
         if (active && cur == ST_NONE && pend == 0u && sp == 0) finished = true;
-#ifdef PTB_ST_DEFER_FINISH
+#ifndef PTB_ST_EAGER_FINISH
         if (active && finished) { active = false; fin = true; }
 #else
         if (active && finished) {
@@ -450,7 +472,7 @@ __global__ void __launch_bounds__(ST_THREADS, PTB_ST_TRACE_MIN_BLOCKS) k_stream_
                         a.a3[ps] = A3;
                         if (COUNT) pc.nee_contrib++;
                     }
-                    if (COUNT) {
+                    if (COUNT && !(flags & 32u)) {
                         pc.eval_calls++;
                         for (int k = 0; k < 4; ++k) pc.ev[k] += (flags >> k) & 1u;
                     }
@@ -515,8 +537,10 @@ struct ShadowSink {
     }
 };
 
-template <bool COUNT, bool BVH>
-__global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
+// MEDIA: the scene has materials with a medium (PTB_MEDIUM_*); a separate instantiation because the in-medium bounce inlined next
+// to the surface shading would cost every scene 90 registers
+template <bool COUNT, bool BVH, bool MEDIA>
+__global__ void PTB_ST_SHADE_BOUNDS k_stream_shade(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
@@ -559,6 +583,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
         p.rad = V3<R>(A3.x, A3.y, A3.z);
         p.prev_pdf = 0;
         p.bounce = bounce;
+        const uint32_t w2 = __float_as_uint(A2.w);               // sample index within the wave | PathState::medium << 24 (scenes with media)
+        const uint32_t sidx = w2 & 0xffffffu;
+        p.medium = MEDIA ? w2 >> 24 : 0u;
         if (key == ST_MISS) {                                    // tracer.rs:66-69
             path_add_sky(s, p);
             if (COUNT) pc.end_sky++;
@@ -570,20 +597,36 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
         const int prim = (int)H.x;
         const uint64_t accepted = (uint64_t)H.y | ((uint64_t)H.z << 32);
         p.hit_dist = __uint_as_float(H.w);
-        Rng<R> rng(__float_as_uint(A3.w), a.sample0 + __float_as_uint(A2.w), a.seed);
+        Rng<R> rng(__float_as_uint(A3.w), a.sample0 + sidx, a.seed);
         R u[8];
-        shade_draws(rng, bounce, s.n_lights > 1u || (key & 4u) != 0u, u);      // the queue key is the lobe class: warp-uniform
-        Mat<R> mat;
-        hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
-        const V3<R> normal = hit_normal<R, BVH, false>(s, sv, prim, p.o, p.d, p.hit_dist);
-        ShadeSetup<R> su;
-        shade_setup<R, COUNT>(s, p, normal, mat, su, &pc);
-        if (s.has_emissive) { A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z; a.a3[slot] = A3; }     // tracer.rs:74
-        NeeSample<R> ns;
-        shade_nee_sample(s, sv, su, u, ns);
-        if (COUNT && ns.wants_shadow_ray) pc.any_hit++;
-        ShadowSink sink{&a, &ctr, slot, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT};
-        const bool cont0 = shade_finish<R, COUNT, true, ShadowSink>(s, p, mat, su, ns.wants_shadow_ray, ns.ls, ns.light_area, u, &pc, sink);
+        shade_draws(rng, bounce, s.n_lights > 1u || (MEDIA && p.medium != 0u) || (key & 4u) != 0u, u);      // the queue key is the lobe class: warp-uniform
+        bool cont0;
+        int med = MED_SURFACE;
+        if (MEDIA && p.medium) {                                 // media (PTB_MEDIUM_*): the in-medium light sample is deferred like a surface's
+            MediumNee<R> mn;
+            med = path_medium<R, COUNT, BVH, false>(s, sv, p, u, &pc, &mn);
+            if (mn.wants) {
+                ShadowSink sink{&a, &ctr, slot, mn.pos, mn.dir, mn.max_dist, COUNT};
+                sink(mn.contrib, 16u | 32u);                     // bit 5: not a Disney evaluation (event counters)
+            }
+            A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z; a.a3[slot] = A3;      // (an emissive medium has added to the radiance)
+        }
+        if (med != MED_SURFACE) {
+            cont0 = med == MED_SCATTERED;
+        } else {
+            Mat<R> mat;
+            const uint32_t mi = hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
+            const V3<R> normal = hit_normal<R, BVH, false>(s, sv, prim, p.o, p.d, p.hit_dist);
+            ShadeSetup<R> su;
+            shade_setup<R, COUNT>(s, p, normal, mat, su, &pc);
+            if (s.has_emissive) { A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z; a.a3[slot] = A3; }     // tracer.rs:74
+            NeeSample<R> ns;
+            shade_nee_sample(s, sv, su, u, ns);
+            if (COUNT && ns.wants_shadow_ray) pc.any_hit++;
+            ShadowSink sink{&a, &ctr, slot, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT};
+            cont0 = shade_finish<R, COUNT, true, ShadowSink>(s, p, mat, su, ns.wants_shadow_ray, ns.ls, ns.light_area, u, &pc, sink);
+            if (MEDIA) path_medium_update<R, BVH>(s, sv, p, normal, mi);
+        }
         bool cont = cont0;
         if (cont && a.rr_start != 0 && p.bounce >= a.rr_start) {     // RR extension at the start of bounce p.bounce (slot 0 of that bounce)
             R u4[4];
@@ -593,7 +636,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shade(const __grid_consta
         if (cont) {
             a.a0[slot] = make_float4(p.o.x, p.o.y, p.o.z, p.d.x);
             a.a1[slot] = make_float4(p.d.y, p.d.z, p.hit_dist, p.prev_pdf);
-            a.a2[slot] = make_float4(p.thr.x, p.thr.y, p.thr.z, A2.w);
+            a.a2[slot] = make_float4(p.thr.x, p.thr.y, p.thr.z, __uint_as_float(sidx | (p.medium << 24)));
             a.rayq[(bounce + 1u) & 1u][queue_reserve(&next.n_ray)] = slot;
         }
     }
@@ -631,7 +674,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_const
                 a.a3[slot] = A3;
                 if (COUNT) pc.nee_contrib++;
             }
-            if (COUNT) {
+            if (COUNT && !(flags & 32u)) {
                 pc.eval_calls++;
                 for (int k = 0; k < 4; ++k) pc.ev[k] += (flags >> k) & 1u;
             }
@@ -663,7 +706,7 @@ struct StreamState {
     uint32_t cap = 0;            // paths per wave the allocation was sized for
     BounceCtr* ctr = nullptr;
     uint32_t ctr_bounces = 0;
-    int grid[4][7] = {};         // persistent grid per [COUNT*2 + BVH][plain stage 0..2, split stage 0..3]
+    int grid[8][7] = {};         // persistent grid per [MEDIA*4 + COUNT*2 + BVH][plain stage 0..2, split stage 0..3]
     void release() {
         if (mem) cudaFree(mem);
         if (ctr) cudaFree(ctr);
@@ -717,7 +760,8 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, v
 
     const bool count = cfg.collect_counters != 0;
     const bool bvh = d.use_bvh != 0;
-    const int vi = (count ? 2 : 0) + (bvh ? 1 : 0);
+    const bool media = d.has_media != 0;
+    const int vi = (media ? 4 : 0) + (count ? 2 : 0) + (bvh ? 1 : 0);
     using StageKernel = void (*)(const DScene<float>, const StreamArgs, const uint32_t);
     // Stage kernels of a bounce, in launch order.  Plain form: closest, shade, shadow (one ray per lane per chunk).
     // Large BVH scenes from bounce 1 on (incoherent rays, deep tree): trace, finish, shade, trace<ANY> with persistent lanes —
@@ -726,11 +770,13 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, v
     StageKernel plain[3], split[4];
     if (bvh) {
         plain[0] = count ? k_stream_closest<true, true> : k_stream_closest<false, true>;
-        plain[1] = count ? k_stream_shade<true, true> : k_stream_shade<false, true>;
+        plain[1] = media ? (count ? k_stream_shade<true, true, true> : k_stream_shade<false, true, true>)
+                         : (count ? k_stream_shade<true, true, false> : k_stream_shade<false, true, false>);
         plain[2] = count ? k_stream_shadow<true, true> : k_stream_shadow<false, true>;
     } else {
         plain[0] = count ? k_stream_closest<true, false> : k_stream_closest<false, false>;
-        plain[1] = count ? k_stream_shade<true, false> : k_stream_shade<false, false>;
+        plain[1] = media ? (count ? k_stream_shade<true, false, true> : k_stream_shade<false, false, true>)
+                         : (count ? k_stream_shade<true, false, false> : k_stream_shade<false, false, false>);
         plain[2] = count ? k_stream_shadow<true, false> : k_stream_shadow<false, false>;
     }
     split[0] = count ? k_stream_trace<false, true> : k_stream_trace<false, false>;

@@ -30,6 +30,11 @@ static int test_cpu() {
     Pinhole p = Pinhole::new_();                                       // pinhole.rs:14-25
     CHECK(p.origin.z == 3 && p.fov == 80);
     CHECK(std::fabs(AnalyticalLight::spherical(F3(3, 2, 2), 1, F3(3, 3, 3)).light.area - F(12.566371)) < 1e-5);
+    // the two light kinds and the Medium the reference declares (globals.rs:69-84, material.rs:5-34): carried by the mirror
+    AnalyticalLight quad = AnalyticalLight::rectangular(F3(-1, 3, 0), F3(2, 0, 0), F3(0, 0, 1.5), F3(9, 8, 7));
+    CHECK(quad.light.light_type == PTB_LIGHT_RECTANGULAR && std::fabs(quad.light.area - F(3)) < 1e-6 && quad.light.u.x == 2);
+    CHECK(AnalyticalLight::distant(F3(0, 1, 0), F3(1, 1, 1)).light.area == 0);
+    CHECK(m.medium.medium_type == PTB_MEDIUM_NONE && m.medium.density == 0 && Medium::new_().anisotropy == 0);
     AnalyticalScene demo;
     auto e = demo.device_export();
     CHECK(e && e->spheres.size() == 2 && e->planes.size() == 1 && e->materials.size() == 3 && e->depth == 4);

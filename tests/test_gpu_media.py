@@ -24,14 +24,14 @@ def test_media_demo_scene_matches_the_oracle(rp, po, precision):
         m.medium = rp.Medium()
     ref_plain, _, _, _ = po.OracleScene(plain, precision=precision).render(W, H, S)
     assert (pix_rel(ref, ref_plain) > 1e-2).mean() > 0.05            # the media are visible
-    for integ in (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_AUTO):
+    for integ in (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED, rp._abi.PTB_INTEGRATOR_AUTO) + ((rp._abi.PTB_INTEGRATOR_STREAM,) if precision == "f32" else ()):
         pt = rp.Tracer.new(sc, integrator=integ, collect_counters=True, precision=precision)
         buf = rp.ColorBuffer.new(W, H, precision=precision)
         pt.render_spp(buf, S)
         c = pt.counters()
         used = pt.integrator_used()
         pt.close()
-        assert used.replace("_f64", "") in ("wavefront", "fused"), used   # never the resolved-material or the streaming kernels
+        assert used.replace("_f64", "") in ("wavefront", "fused", "stream"), used   # never the resolved-material kernel
         rel = pix_rel(buf.pixels, ref)
         bar = 1e-4 if precision == "f32" else 1e-9
         assert (rel < bar).mean() >= 0.99, (integ, (rel < bar).mean())
@@ -57,19 +57,48 @@ def test_single_medium_ball_closed_forms_on_the_device(rp, po, kind):
         assert np.allclose(centre, want, rtol=0.02), (kind, integ, centre, want)
 
 
-def test_media_are_refused_by_the_streaming_integrator_and_rerouted_by_auto(rp):
-    sc = rp.media_demo_scene(depth=4)
-    pt = rp.Tracer.new(sc, integrator=rp._abi.PTB_INTEGRATOR_STREAM)
-    buf = rp.ColorBuffer.new(64, 48)
-    with pytest.raises(Exception, match="media"):
-        pt.render_spp(buf, 1)
-    pt.close()
-    # a BVH scene large enough for AUTO to pick the streaming integrator: with a medium it runs on the shared-memory wavefront
+@pytest.mark.parametrize("strict", [True, False])
+def test_media_in_a_bvh_scene_on_the_streaming_integrator(rp, po, strict):
+    """a sphere field large enough for AUTO to pick the streaming integrator (split traversal kernels), every third ball glass with
+    an absorbing, scattering or emissive medium: the path's medium travels in the spare bits of its sample-index word, the
+    in-medium light sample goes through the shadow queue like a surface's.  Bars as for the medium-free sphere field
+    (test_config4_full_scene_parity): the strict build within 1e-4 on >= 98.5 % of the pixels; the shipped build's outliers are
+    paths through the field's glass / high-gloss clearcoat lobes (measured 91.6 % at depth 6, identical on all four integrators
+    and for every medium kind), bar 90 %."""
     big = rp.sphere_field_scene(n_spheres=5000, n_lights_side=2).device_export()
-    big.materials[2].spec_trans = 1.0
-    big.materials[2].medium = rp.Medium(rp.MediumType.ABSORB, 2.0, rp.F3(0.3, 0.6, 0.9), 0.0)
-    pt = rp.Tracer.new(rp.ExportedScene(big))
-    pt.render_spp(buf, 1)
-    assert pt.integrator_used().startswith("wavefront")
-    assert np.isfinite(buf.pixels).all()
-    pt.close()
+    kinds = (rp.MediumType.ABSORB, rp.MediumType.SCATTER, rp.MediumType.EMISSIVE)
+    n = 0
+    for i, m in enumerate(big.materials[:120]):
+        if m.spec_trans > 0.0:
+            m.medium = rp.Medium(kinds[n % 3], 1.0 + n % 4, rp.F3(0.3 + 0.2 * (n % 3), 0.6, 0.9 - 0.2 * (n % 3)), 0.3 * (n % 3))
+            n += 1
+    assert n >= 30
+    big.depth = 6
+    W, H, S = 128, 72, 2
+    ref, _, _, oc = po.OracleScene(big).render(W, H, S, counters=True)
+    imgs = {}
+    for integ in (rp._abi.PTB_INTEGRATOR_AUTO, rp._abi.PTB_INTEGRATOR_STREAM, rp._abi.PTB_INTEGRATOR_WAVEFRONT):
+        pt = rp.Tracer.new(rp.ExportedScene(big), integrator=integ, collect_counters=True, strict=strict)
+        buf = rp.ColorBuffer.new(W, H)
+        pt.render_spp(buf, S)
+        c = pt.counters()
+        used = pt.integrator_used()
+        pt.close()
+        assert used.startswith("stream") if integ != rp._abi.PTB_INTEGRATOR_WAVEFRONT else used.startswith("wavefront"), used
+        rel = pix_rel(buf.pixels, ref)
+        frac = (rel < 1e-4).mean()
+        print(f"[media in a BVH scene] strict={strict} {used}: within 1e-4: {frac:.4f}, median {np.median(rel):.2e}")
+        assert frac >= (0.985 if strict else 0.90), (integ, frac)
+        assert np.median(rel) < 1e-6
+        for k in ("closest_hit", "any_hit", "shade", "nee_contrib", "eval_calls", "end_sky", "end_emitter", "end_depth"):
+            assert abs(c[k] - oc[k]) <= max(5, (2e-3 if strict else 1e-2) * W * H * S), (integ, k, c[k], oc[k])
+        imgs[integ] = buf.pixels.copy()
+    # the two integrators trace the same paths with the same device functions
+    a, b = imgs[rp._abi.PTB_INTEGRATOR_STREAM], imgs[rp._abi.PTB_INTEGRATOR_WAVEFRONT]
+    assert (pix_rel(a, b) < 1e-4).mean() >= 0.99
+    # a medium-free copy differs visibly: the media are actually hit at this camera
+    plain = copy.deepcopy(big)
+    for m in plain.materials:
+        m.medium = rp.Medium()
+    ref_plain, _, _, _ = po.OracleScene(plain).render(W, H, S)
+    assert (pix_rel(ref, ref_plain) > 1e-2).mean() > 0.001

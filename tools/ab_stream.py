@@ -14,11 +14,14 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     ("default", []),
-    ("defer_finish", ["-DPTB_ST_DEFER_FINISH"]),
-    ("defer_refill4", ["-DPTB_ST_DEFER_FINISH", "-DPTB_ST_REFILL=4"]),
-    ("defer_refill12", ["-DPTB_ST_DEFER_FINISH", "-DPTB_ST_REFILL=12"]),
-    ("defer_leaf8", ["-DPTB_ST_DEFER_FINISH", "-DPTB_ST_LEAF_MIN=8"]),
-    ("defer_leaf16", ["-DPTB_ST_DEFER_FINISH", "-DPTB_ST_LEAF_MIN=16"]),
+    ("r4_defer_plain", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_PLAIN"]),
+    ("r4_defer_mb5", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5"]),
+    ("r4_defer_mb5_leaf8", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5", "-DPTB_ST_LEAF_MIN=8"]),
+    ("r6_defer_mb5", ["-DPTB_ST_INNER_REPS=6", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5"]),
+    ("r3_defer_mb5", ["-DPTB_ST_INNER_REPS=3", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5"]),
+    ("r4_defer_mb6", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=6"]),
+    ("r4_defer_mb5_split2048", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5", "-DPTB_ST_SPLIT_MIN=2048u"]),
+    ("r4_defer_mb5_refill12", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5", "-DPTB_ST_REFILL=12"]),
 ]
 
 

@@ -27,12 +27,7 @@ VARIANTS = [
     #   PTB_SAT_DROPS_NAN + PTB_CONTRACT_VIEW_COSINE                  round 1's NaN behaviour (saturate drops NaN, v.z contracted)
     #   PTB_WF_ASYNC                                                 barrier-free per-key rings (ptb_wavefront_async.cuh); PTB_WF_REGEN_DEN: in-place regeneration threshold
     ("default", [], {}),
-    ("t832_p2496", ["-DPTB_WF_THREADS_RM=832", "-DPTB_WF_POOL_RM=2496"], {}),
-    ("t576_p2304", ["-DPTB_WF_THREADS_RM=576", "-DPTB_WF_POOL_RM=2304"], {}),
-    ("t640_p2560", ["-DPTB_WF_THREADS_RM=640", "-DPTB_WF_POOL_RM=2560", "-DPTB_WF_SCENE_BYTES_RM=11264"], {}),
-    ("t704_p2112", ["-DPTB_WF_THREADS_RM=704", "-DPTB_WF_POOL_RM=2112"], {}),
-    ("t896_p1792", ["-DPTB_WF_THREADS_RM=896", "-DPTB_WF_POOL_RM=1792"], {}),
-    ("t512_p2048", ["-DPTB_WF_THREADS_RM=512", "-DPTB_WF_POOL_RM=2048"], {}),
+    ("philox7", ["-DPTB_PHILOX_ROUNDS=7"], {}),
 ]
 
 

@@ -41,4 +41,12 @@ pt = rp.Tracer.new(rp.ExportedScene(ex), integrator=WF)
 buf = rp.ColorBuffer.new(80, 45)
 pt.render_spp(buf, 3)
 pt.close()
+# round 2 (later): media (generic wavefront + fused, f32 and f64) and the extended light kinds
+for prec in ("f32", "f64"):
+    for integ in (WF, rp._abi.PTB_INTEGRATOR_FUSED):
+        for scene in (rp.media_demo_scene(depth=8), rp.lights_demo_scene()):
+            pt = rp.Tracer.new(scene, integrator=integ, precision=prec)
+            buf = rp.ColorBuffer.new(64, 36, prec)
+            pt.render_spp(buf, 2)
+            pt.close()
 print("ok")
