@@ -323,8 +323,7 @@ __global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScen
     uint32_t cur = ST_NONE;                  // node to visit next (inner or leaf reference)
     uint32_t pend = 0;                       // parked leaf reference (0 = none)
     int sp = 0;
-    uint32_t stack_n[ST_STACK];
-    float stack_t[ST_STACK];
+    uint2 stack[ST_STACK];                   // (node reference, entry distance bits): one 8-byte local load per pop
 
 #ifndef PTB_ST_EAGER_FINISH
     bool fin = false;                        // the lane's ray is done, its result not yet written (written with the next refill)
@@ -416,8 +415,7 @@ __global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScen
                 // (far child written as ra ^ rb ^ near and max(ta, tb): nvcc 12.9 compiled the mirrored select
                 //  `a_near ? rb : ra` next to `a_near ? ra : rb` into an unconditional store of rb — found with a per-ray
                 //  differential check against bvh_traverse)
-                stack_n[sp] = ra ^ rb ^ near_ref;
-                stack_t[sp] = fmaxf(ta, tb);
+                stack[sp] = make_uint2(ra ^ rb ^ near_ref, __float_as_uint(fmaxf(ta, tb)));
                 ++sp;
             }
             cur = (ha || hb) ? near_ref : ST_NONE;
@@ -428,7 +426,8 @@ __global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScen
             if (cur == ST_NONE) {
                 while (sp > 0) {
                     --sp;
-                    if (stack_t[sp] <= best_t) { cur = stack_n[sp]; break; }
+                    const uint2 e = stack[sp];
+                    if (__uint_as_float(e.y) <= best_t) { cur = e.x; break; }
                 }
             }
         }

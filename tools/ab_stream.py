@@ -13,15 +13,10 @@ VDIR = os.path.join(ROOT, "rust_pathtracer_b200", "variants")
 sys.path.insert(0, ROOT)
 
 VARIANTS = [
+    # knobs (ptb_stream.cuh): PTB_ST_INNER_REPS, PTB_ST_EAGER_FINISH, PTB_ST_REFILL, PTB_ST_LEAF_MIN, PTB_ST_TRACE_MIN_BLOCKS,
+    # PTB_ST_TRACE_PLAIN, PTB_ST_SHADE_MIN_BLOCKS, PTB_ST_SPLIT_MIN; results of round 2: profiles/r02_ab_stream.txt
     ("default", []),
-    ("r4_defer_plain", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_PLAIN"]),
-    ("r4_defer_mb5", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5"]),
-    ("r4_defer_mb5_leaf8", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5", "-DPTB_ST_LEAF_MIN=8"]),
-    ("r6_defer_mb5", ["-DPTB_ST_INNER_REPS=6", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5"]),
-    ("r3_defer_mb5", ["-DPTB_ST_INNER_REPS=3", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5"]),
-    ("r4_defer_mb6", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=6"]),
-    ("r4_defer_mb5_split2048", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5", "-DPTB_ST_SPLIT_MIN=2048u"]),
-    ("r4_defer_mb5_refill12", ["-DPTB_ST_INNER_REPS=4", "-DPTB_ST_DEFER_FINISH", "-DPTB_ST_TRACE_MIN_BLOCKS=5", "-DPTB_ST_REFILL=12"]),
+    ("reps1_eager", ["-DPTB_ST_INNER_REPS=1", "-DPTB_ST_EAGER_FINISH", "-DPTB_ST_REFILL=8", "-DPTB_ST_LEAF_MIN=12", "-DPTB_ST_TRACE_MIN_BLOCKS=1"]),
 ]
 
 
