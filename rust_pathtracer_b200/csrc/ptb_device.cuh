@@ -633,8 +633,10 @@ PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __
     r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
     r.idx = m_rcp((float)d.x); r.idy = m_rcp((float)d.y); r.idz = m_rcp((float)d.z);
     constexpr int STACK = BVH_STACK;
-    uint32_t stack_n[STACK];
-    float stack_t[STACK];
+    // an entry = (node reference, entry distance): the reference carries the child's link and leaf count (count <= 7, builder: <= 4),
+    // so a pop is ONE 8-byte local load and goes straight on to the children — the first version popped with two dependent local
+    // loads and then re-read the popped node from global memory just to learn its link and count
+    uint2 stack[STACK];
     int sp = 0;
     BvhNode root = load_node(nodes);
     if (box_entry(root.lo, root.hi, r, (float)best_t) >= 3.0e38f) return -1;
@@ -660,22 +662,23 @@ PTB_DEV int bvh_traverse(const BvhNode* __restrict__ nodes, const DSphere<R>* __
             const bool ha = ta < 3.0e38f, hb = tb < 3.0e38f;
             if (ha || hb) {
                 const bool a_near = ha && (!hb || ta <= tb);
+                const uint32_t ra = (a.left_or_first << 3) | a.count, rb = (b.left_or_first << 3) | b.count;
+                const uint32_t near_ref = a_near ? ra : rb;
                 if (ha && hb && sp < STACK) {
-                    stack_n[sp] = a_near ? cur_lf + 1 : cur_lf;
-                    stack_t[sp] = a_near ? tb : ta;
+                    // (far child as ra ^ rb ^ near: see the note on nvcc 12.9 and mirrored selects in ptb_stream.cuh)
+                    stack[sp] = make_uint2(ra ^ rb ^ near_ref, __float_as_uint(fmaxf(ta, tb)));
                     ++sp;
                 }
-                if (a_near) { cur_lf = a.left_or_first; cur_cnt = a.count; }
-                else { cur_lf = b.left_or_first; cur_cnt = b.count; }
+                cur_lf = near_ref >> 3; cur_cnt = near_ref & 7u;
                 continue;
             }
         }
         bool found = false;
         while (sp > 0) {
             --sp;
-            if (stack_t[sp] <= (float)best_t) {
-                const BvhNode n = load_node(nodes + stack_n[sp]);
-                cur_lf = n.left_or_first; cur_cnt = n.count;
+            const uint2 e = stack[sp];
+            if (__uint_as_float(e.y) <= (float)best_t) {
+                cur_lf = e.x >> 3; cur_cnt = e.x & 7u;
                 found = true;
                 break;
             }
