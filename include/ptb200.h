@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 3
+#define PTB_ABI_VERSION 4   /* 4: ptb_light_* gained u, v; ptb_material_* gained medium_* (struct sizes changed) */
 
 /* ---- status codes ------------------------------------------------------------------------ */
 enum {

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-PTB_ABI_VERSION = 3
+PTB_ABI_VERSION = 4
 
 # status codes
 PTB_OK, PTB_E_INVALID, PTB_E_NO_DEVICE, PTB_E_CUDA, PTB_E_NO_SCENE, PTB_E_PRECISION, PTB_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
