@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
         // ================================ sort: tickets -> key-ordered queue ================================
         // keys with more lobes cost more to process: queue them first so that the dynamic chunking ends on cheap chunks
         // (longest-processing-time-first); every thread derives the offsets itself from the ten counters
+#ifdef PTB_WF_SORT_SELECT
         uint32_t off[WF_NKEYS];
         {
             const int order_by_cost[WF_NKEYS] = {7, 3, 5, 6, 1, 2, 4, 0, (int)WF_MISS, (int)WF_REGEN};
@@ -451,6 +452,28 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                 sm.kt[i] = WF_NOKEY << 16;
             }
         }
+#else
+        // lane c of every warp holds the queue offset of key c; a slot fetches its key's offset with one shuffle (the first
+        // version selected it out of ten registers: 20 instructions per slot, 2 % of the kernel's)
+        uint32_t off_lane = 0;
+        {
+            const int order_by_cost[WF_NKEYS] = {7, 3, 5, 6, 1, 2, 4, 0, (int)WF_MISS, (int)WF_REGEN};
+            uint32_t run = 0;
+#pragma unroll
+            for (int k = 0; k < (int)WF_NKEYS; ++k) { const int c = order_by_cost[k]; off_lane = (uint32_t)c == lane ? run : off_lane; run += sm.cnt[par ^ 1u][c]; }
+            n_queue = run;
+        }
+        static_assert(WF_POOL % 32u == 0, "whole warps in the sort pass (the shuffle below needs all 32 lanes)");
+#pragma unroll 1
+        for (uint32_t i = tid; i < WF_POOL; i += WF_THREADS) {
+            const uint32_t kt = sm.kt[i], k = kt >> 16;
+            const uint32_t o = __shfl_sync(FULL, off_lane, (int)(k & 31u));
+            if (k != WF_NOKEY) {
+                sm.order[o + (kt & 0xffffu)] = (uint16_t)i;
+                sm.kt[i] = WF_NOKEY << 16;
+            }
+        }
+#endif
         if (tid < WF_NKEYS) sm.cnt[par][tid] = 0;       // this iteration's consumers are done with it; it collects the tickets of the next one
         if (tid == 0) sm.cursor[par] = 0;
         par ^= 1u;
