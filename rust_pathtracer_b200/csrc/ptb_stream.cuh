@@ -120,6 +120,15 @@ PTB_DEV uint32_t queue_reserve(uint32_t* counter) {
     return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
 }
 
+// A stage is launched with a persistent grid sized for a full queue; deep bounces leave it a few hundred rays.  CTAs that the
+// queue cannot feed leave before they copy the scene into shared memory (the floor of a nearly empty stage was 30 us — 740 CTAs
+// staging 12 KB each — against 5 us for the launch itself; config 5 runs 39 such stages per wave).
+#ifdef PTB_ST_NO_EARLY_EXIT
+#define PTB_ST_LEAVE_IF_IDLE(n_entries) do {} while (0)
+#else
+#define PTB_ST_LEAVE_IF_IDLE(n_entries) do { if ((uint64_t)blockIdx.x * (32u * (ST_THREADS / 32u)) >= (uint64_t)(n_entries)) return; } while (0)
+#endif
+
 // tiled pixel index -> pixel coordinates (16x16 tiles, as the other integrators hand pixels out)
 PTB_DEV bool tiled_pixel(const StreamArgs& a, uint32_t ip, uint32_t& px, uint32_t& prow) {
     const uint32_t tile = ip >> 8, within = ip & 255u;
@@ -207,6 +216,7 @@ PTB_DEV void push_by_key(const StreamArgs& a, BounceCtr& ctr, uint32_t key, uint
 template <bool COUNT, bool BVH>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
+    PTB_ST_LEAVE_IF_IDLE(a.ctr[bounce].n_ray);
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
     BounceCtr& ctr = a.ctr[bounce];
@@ -297,6 +307,7 @@ PTB_DEV float box_entry_s(float4 lo, float4 hi, const RayS& r, float limit) {
 template <bool ANY, bool COUNT>
 __global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
+    PTB_ST_LEAVE_IF_IDLE(ANY ? a.ctr[bounce].n_shadow : a.ctr[bounce].n_ray);
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);       // planes (shadow rays test them first)
     BounceCtr& ctr = a.ctr[bounce];
@@ -490,6 +501,7 @@ __global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScen
 template <bool COUNT>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_finish(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
+    PTB_ST_LEAVE_IF_IDLE(a.ctr[bounce].n_ray);
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
     BounceCtr& ctr = a.ctr[bounce];
@@ -541,6 +553,12 @@ struct ShadowSink {
 template <bool COUNT, bool BVH, bool MEDIA>
 __global__ void PTB_ST_SHADE_BOUNDS k_stream_shade(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
+    {
+        uint32_t chunks = 0;                                 // chunks of this stage: every key's queue rounded up to whole chunks
+#pragma unroll
+        for (int k = 0; k < (int)ST_KEYS; ++k) chunks += (a.ctr[bounce].n_shade[k] + 31u) >> 5;
+        PTB_ST_LEAVE_IF_IDLE((uint64_t)chunks * 32u);
+    }
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
     BounceCtr& ctr = a.ctr[bounce];
@@ -647,6 +665,7 @@ __global__ void PTB_ST_SHADE_BOUNDS k_stream_shade(const __grid_constant__ DScen
 template <bool COUNT, bool BVH>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_shadow(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
+    PTB_ST_LEAVE_IF_IDLE(a.ctr[bounce].n_shadow);
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
     BounceCtr& ctr = a.ctr[bounce];
