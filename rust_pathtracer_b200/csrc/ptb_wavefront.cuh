@@ -99,6 +99,10 @@ template <class R, uint32_t WF_POOL, uint32_t SCENE_BYTES, bool GENERIC> struct 
     uint16_t order[WF_POOL];        // the queue: slot indices, key-ordered
     uint32_t cnt[2][WF_NKEYS + 2];  // tickets handed out per key for the NEXT queue (double-buffered by iteration parity)
     uint32_t cursor[2];             // next 32-entry chunk of the current queue (double-buffered like cnt)
+    // PTB_WF_HALVES: the pool as two halves with a queue each (cnt[h], cursor[h] belong to half h); see the kernel
+    uint32_t arrive[2];             // warps that have left the current queue of half h
+    uint32_t epoch[2];              // sorts completed for half h (visit k may start once epoch >= k)
+    uint32_t nq[2];                 // length of the current queue of half h
 };
 
 // a 32-bit word kept in the .w lane of a vector of reals (bit pattern only: the lane is never used arithmetically)
@@ -190,10 +194,12 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
         sm.kt[i] = WF_NOKEY << 16;
     }
     if (tid < 2u * (WF_NKEYS + 2u)) (&sm.cnt[0][0])[tid] = 0;
-    if (tid < 2u) sm.cursor[tid] = 0;
+    if (tid < 2u) { sm.cursor[tid] = 0; sm.arrive[tid] = 0; sm.epoch[tid] = 0; sm.nq[tid] = WF_POOL / 2u; }
     __syncthreads();
 
+#ifndef PTB_WF_HALVES
     uint32_t n_queue = WF_POOL, par = 0;      // par: which cnt / cursor buffer the CURRENT iteration's consumers use
+#endif
     PathCounters pc;
     uint32_t n_samples = 0;
     if (COUNT) {
@@ -204,16 +210,42 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
         pc.bvh[0] = pc.bvh[1] = 0;
     }
 
+#ifdef PTB_WF_HALVES
+    // Two half-pools with a queue each, and no CTA barrier: a warp that runs out of chunks in half A goes on to half B's queue
+    // instead of waiting for the slowest chunk of A; the LAST warp to leave a queue sorts that half's tickets into its next queue
+    // (alone: 39 steps of a warp) and publishes it.  All warps visit (half, round) in the same order, so "the queue of my k-th
+    // visit of half h is ready" is `epoch[h] >= k`.
+    static_assert((WF_POOL / 2u) % 32u == 0, "half pools of whole chunks");
+    constexpr uint32_t HALF = WF_POOL / 2u, NWARPS = WF_THREADS / 32;
+    uint32_t visit0 = 0, visit1 = 0;
+    bool done0 = false, done1 = false;
+    for (uint32_t turn = 0; !(done0 && done1); ++turn) {
+        const uint32_t h = turn & 1u;
+        if (h ? done1 : done0) continue;
+        const uint32_t my_visit = h ? visit1 : visit0;
+        if (lane == 0) { while (*(volatile uint32_t*)&sm.epoch[h] < my_visit) __nanosleep(40); }
+        __syncwarp();
+        __threadfence_block();
+        const uint32_t n_queue = *(volatile uint32_t*)&sm.nq[h];
+        if (n_queue == 0) { if (h) done1 = true; else done0 = true; continue; }
+        const uint32_t WF_QBASE = h * HALF;
+        uint32_t* const WF_NEXT_CNT = sm.cnt[h];
+        uint32_t* const WF_CURSOR = &sm.cursor[h];
+#else
     while (n_queue) {
+        constexpr uint32_t WF_QBASE = 0;
+        uint32_t* const WF_NEXT_CNT = sm.cnt[par ^ 1u];
+        uint32_t* const WF_CURSOR = &sm.cursor[par];
+#endif
 #pragma unroll 1
         while (true) {
             uint32_t chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&sm.cursor[par], 1u);
+            if (lane == 0) chunk = atomicAdd(WF_CURSOR, 1u);
             chunk = __shfl_sync(FULL, chunk, 0);
             if (chunk * 32u >= n_queue) break;
             const uint32_t j = chunk * 32u + lane;
             const bool valid = j < n_queue;
-            const uint32_t i = valid ? sm.order[j] : 0u;
+            const uint32_t i = valid ? sm.order[WF_QBASE + j] : 0u;
             // ---- load what the pending event needs: the ray, the hit, the flags ----
             // Radiance, throughput, pixel and sample index stay in shared memory while the event is evaluated: A works on a unit
             // throughput and a zero radiance, and what it returns is applied to the slot's values afterwards — `rad + x * thr` and
@@ -423,10 +455,43 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                 sm.tr[i] = mk4(p.thr.x, p.thr.y, p.thr.z, wf_word(R(0), fl));
                 sm.ra[i] = mk4(p.rad.x, p.rad.y, p.rad.z, wf_word(R(0), sidx));
                 uint32_t ticket = 0;
-                if (key != WF_NOKEY) ticket = atomicAdd(&sm.cnt[par ^ 1u][key], 1u);
+                if (key != WF_NOKEY) ticket = atomicAdd(&WF_NEXT_CNT[key], 1u);
                 sm.kt[i] = (key << 16) | ticket;
             }
         }
+#ifdef PTB_WF_HALVES
+        // ---- leave the queue; the last warp out sorts the half ----
+        __syncwarp();
+        uint32_t last = 0;
+        if (lane == 0) { __threadfence_block(); last = atomicAdd(&sm.arrive[h], 1u) == NWARPS - 1u ? 1u : 0u; }
+        last = __shfl_sync(FULL, last, 0);
+        if (last) {
+            __threadfence_block();
+            uint32_t off_lane = 0, run = 0;
+            {
+                const int order_by_cost[WF_NKEYS] = {7, 3, 5, 6, 1, 2, 4, 0, (int)WF_MISS, (int)WF_REGEN};
+#pragma unroll
+                for (int k = 0; k < (int)WF_NKEYS; ++k) { const int c = order_by_cost[k]; off_lane = (uint32_t)c == lane ? run : off_lane; run += *(volatile uint32_t*)&sm.cnt[h][c]; }
+            }
+#pragma unroll 1
+            for (uint32_t i = WF_QBASE + lane; i < WF_QBASE + HALF; i += 32u) {
+                const uint32_t kt = *(volatile uint32_t*)&sm.kt[i], k = kt >> 16;
+                const uint32_t o = __shfl_sync(FULL, off_lane, (int)(k & 31u));
+                if (k != WF_NOKEY) {
+                    sm.order[WF_QBASE + o + (kt & 0xffffu)] = (uint16_t)i;
+                    sm.kt[i] = WF_NOKEY << 16;
+                }
+            }
+            __syncwarp();
+            if (lane < WF_NKEYS) sm.cnt[h][lane] = 0;
+            if (lane == 0) { sm.cursor[h] = 0; sm.arrive[h] = 0; sm.nq[h] = run; }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) *(volatile uint32_t*)&sm.epoch[h] = my_visit + 1u;
+        }
+        if (h) ++visit1; else ++visit0;
+    }
+#else
         __syncthreads();
 
         // ================================ sort: tickets -> key-ordered queue ================================
@@ -479,6 +544,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
         par ^= 1u;
         __syncthreads();
     }
+#endif
 
     if (COUNT) {
         DeviceCounters* c = a.counters;
