@@ -384,6 +384,8 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     if (patch && use_bvh) return fail(PTB_E_INVALID, "BVH scenes need PTB_MAT_ALL on every material (order-independent)");
     if (patch && sc->n_spheres + sc->n_planes > 64u)
         return fail(PTB_E_INVALID, "partial material masks support at most 64 primitives");
+    if (use_bvh && sc->n_spheres >= (1u << 27))         // node references pack (link << 3 | leaf count) into 32 bits; 2n - 1 nodes
+        return fail(PTB_E_UNSUPPORTED, "sphere BVH: at most 2^27 - 1 spheres (%u given)", sc->n_spheres);
 
     std::vector<DSphere<R>> spheres(sc->n_spheres);
     std::vector<uint32_t> smat(sc->n_spheres);
