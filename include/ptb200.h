@@ -109,7 +109,8 @@ enum {
     /* Build / use the sphere BVH even for small sphere counts (otherwise: count >= bvh_threshold) */
     PTB_SCENE_FORCE_BVH               = 1u << 1,
     PTB_SCENE_NO_BVH                  = 1u << 2,
-    /* Rectangular and distant lights are sampled / hit (see PTB_LIGHT_*) instead of being inert like in the reference */
+    /* Rectangular and distant lights are sampled / hit (see PTB_LIGHT_*) instead of being inert like in the reference.  A scene
+     * that has such lights (or a material with a medium) runs on the generic kernels: no resolved-material table is built. */
     PTB_SCENE_EXTENDED_LIGHTS         = 1u << 3
 };
 
