@@ -102,3 +102,23 @@ def test_media_in_a_bvh_scene_on_the_streaming_integrator(rp, po, strict):
         m.medium = rp.Medium()
     ref_plain, _, _, _ = po.OracleScene(plain).render(W, H, S)
     assert (pix_rel(ref, ref_plain) > 1e-2).mean() > 0.001
+
+
+def test_medium_error_paths(rp):
+    """a medium needs a material index below 127 (the path state keeps seven bits for it) and a known kind"""
+    e = rp.AnalyticalScene.new().device_export()
+    for _ in range(130):
+        e.materials.append(rp.Material())
+    e.materials[129].medium = rp.Medium(rp.MediumType.ABSORB, 1.0, rp.F3(0.5, 0.5, 0.5), 0.0)
+    with pytest.raises(Exception, match="index below"):
+        rp.Tracer.new(rp.ExportedScene(e))
+    e.materials[129].medium = rp.Medium()
+    e.materials[5].medium = rp.Medium(7, 1.0, rp.F3(0.5, 0.5, 0.5), 0.0)
+    with pytest.raises(Exception, match="unknown medium type"):
+        rp.Tracer.new(rp.ExportedScene(e))
+    e.materials[5].medium = rp.Medium(rp.MediumType.SCATTER, 1.0, rp.F3(0.5, 0.5, 0.5), 5.0)     # anisotropy is clamped to 0.9 (material.rs:126)
+    pt = rp.Tracer.new(rp.ExportedScene(e))
+    buf = rp.ColorBuffer.new(32, 24)
+    pt.render_spp(buf, 1)
+    assert np.isfinite(buf.pixels).all()
+    pt.close()
