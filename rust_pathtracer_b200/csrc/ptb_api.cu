@@ -574,6 +574,17 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
     d.depth = sc->depth; d.flags = sc->flags; d.eps = sc->eps;
     d.n_lights_f = (R)sc->n_lights;
     d.has_emissive = 0;
+    // small scenes: the primitives also go into the kernel parameter (the resolved-material kernel's EMB instantiation reads them there)
+    d.emb = (sc->n_spheres <= PTB_EMB_SPHERES && sc->n_planes <= PTB_EMB_PLANES && sc->n_lights <= PTB_EMB_LIGHTS && !use_bvh) ? 1u : 0u;
+#ifdef PTB_NO_EMB
+    d.emb = 0u;
+#endif
+    std::memset(d.emb_spheres, 0, sizeof(d.emb_spheres)); std::memset(d.emb_planes, 0, sizeof(d.emb_planes)); std::memset(d.emb_lights, 0, sizeof(d.emb_lights));
+    if (d.emb) {
+        for (uint32_t i = 0; i < sc->n_spheres; ++i) d.emb_spheres[i] = spheres[i];
+        for (uint32_t i = 0; i < sc->n_planes; ++i) d.emb_planes[i] = planes[i];
+        for (uint32_t i = 0; i < sc->n_lights; ++i) d.emb_lights[i] = lights[i];
+    }
     d.has_media = has_media ? 1u : 0u;          // (the resolved-material kernel is not built for them: no table above)
     for (const auto& m : mats)
         if (m.emission[0] != R(0) || m.emission[1] != R(0) || m.emission[2] != R(0)) d.has_emissive = 1;

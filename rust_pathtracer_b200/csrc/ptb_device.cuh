@@ -254,6 +254,9 @@ PTB_DEV void shade_draws(const Rng<float>& rng, uint32_t bounce, bool need_first
 }
 
 // ------------------------------------------------------------------------------------------------
+#define PTB_EMB_SPHERES 8
+#define PTB_EMB_PLANES 4
+#define PTB_EMB_LIGHTS 4
 // Device scene (what ptb_set_scene_* builds from the POD export)
 template <class R> struct DMaterial {
     // resolved values: Material::new() defaults (material.rs:82-114) patched by this material
@@ -301,6 +304,11 @@ template <class R> struct DScene {
     uint32_t use_bvh;
     uint32_t has_emissive;              // 1 if any material has non-zero emission
     uint32_t has_media;                 // 1 if any material carries a medium (PTB_MEDIUM_*): the path loop tracks inside / outside
+    // small scenes: the primitives themselves in the kernel parameter (constant bank, uniform loads) — see PTB_EMB_SCENE
+    uint32_t emb;                       // 1 if the three arrays below hold the whole scene
+    DSphere<R> emb_spheres[PTB_EMB_SPHERES];
+    DPlane<R> emb_planes[PTB_EMB_PLANES];
+    DLight<R> emb_lights[PTB_EMB_LIGHTS];
     uint32_t patch_materials;           // 1 if any set_mask != PTB_MAT_ALL (order-dependent patching)
     uint32_t depth, flags;
     R eps;
@@ -709,7 +717,15 @@ template <class R> struct HitCore {
 };
 
 // sphere part of closest_hit: the closest sphere (index, distance) — the part a dedicated traversal kernel can run
-template <class R, bool BVH>
+// EMB (the resolved-material kernel on scenes of a few primitives): spheres / planes / lights are read from the copies in the
+// kernel parameter (DScene::emb_*) instead of through the scene view.  The view's pointers are generic (a scene that does not fit
+// is read from global memory through the same code), and under that kernel's 72-register cap ptxas rematerialised them at every
+// use — S2UR SR_CgaCtaId, UMOV, ULEA, LDC, IADD3: 3 % of its instructions (capture r02-d); the parameter copies are read with
+// uniform constant-bank loads and need no pointer at all.
+#define SV_SPHERE(i) (EMB ? s.emb_spheres[i] : sv.spheres[i])
+#define SV_PLANE(i) (EMB ? s.emb_planes[i] : sv.planes[i])
+#define SV_LIGHT(i) (EMB ? s.emb_lights[i] : sv.lights[i])
+template <class R, bool BVH, bool EMB = false>
 PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, int& best, R& dist, uint64_t& accepted, uint32_t* bvh_stats = nullptr) {
     dist = Const<R>::MAXV;
     best = -1;
@@ -719,7 +735,7 @@ PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o
     } else {
 #pragma unroll 1
         for (uint32_t i = 0; i < s.n_spheres; ++i) {
-            DSphere<R> sp = sv.spheres[i];
+            DSphere<R> sp = SV_SPHERE(i);
             R t = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
             if (t >= R(0) && (i == 0 || t < dist)) {   // analytical.rs:43 (unconditional), :74 (d < dist)
                 dist = t; best = (int)i; accepted |= (1ull << (i & 63u));
@@ -731,7 +747,7 @@ PTB_DEV void closest_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o
 // the rest of closest_hit given the sphere result: planes, then Scene::sample_lights
 // SDF = false compiles the signed-distance test out (instantiations whose scenes cannot carry a program); XL = false the
 // rectangular-light test (the resolved-material kernel: ptb_set_scene_* builds no table for scenes with extended lights)
-template <class R, bool BVH, bool SDF = true, bool XL = true>
+template <class R, bool BVH, bool SDF = true, bool XL = true, bool EMB = false>
 PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, int best, R dist,
                                       uint64_t accepted) {
     HitCore<R> h;
@@ -739,7 +755,7 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
     h.light_pdf = 0; h.light_emission = V3<R>(0, 0, 0);
 #pragma unroll 1
     for (uint32_t i = 0; i < s.n_planes; ++i) {
-        DPlane<R> pl = sv.planes[i];
+        DPlane<R> pl = SV_PLANE(i);
         R t = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
         if (t >= R(0) && t < dist) {                   // analytical.rs:101-103
             dist = t; best = (int)(s.n_spheres + i); accepted |= (1ull << ((s.n_spheres + i) & 63u));
@@ -773,7 +789,7 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
     }
 #pragma unroll 1
     for (uint32_t i = 0; i < n_test; ++i) {
-        DLight<R> L = sv.lights[i];
+        DLight<R> L = SV_LIGHT(i);
         if (L.type != PTB_LIGHT_SPHERICAL) continue;
         R t = isect_sphere(o, d, V3<R>(L.px, L.py, L.pz), L.radius);
         if (t >= R(0) && t < ldist) { ldist = t; lbest = (int)i; }
@@ -792,7 +808,7 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
         }
     }
     if (lbest >= 0) {
-        DLight<R> L = sv.lights[lbest];
+        DLight<R> L = SV_LIGHT(lbest);
         if (XL && L.type == PTB_LIGHT_RECTANGULAR) {
             h.light_pdf = m_div(ldist * ldist, L.area * rect_cos);
         } else {
@@ -809,24 +825,24 @@ PTB_DEV HitCore<R> closest_hit_finish(const DScene<R>& s, const SceneView<R>& sv
 }
 
 // normal of primitive `prim` at distance t along (o, d): analytical.rs:45-46 (sphere), :105 (plane)
-template <class R, bool BVH, bool SDF = true, bool XL = true>
+template <class R, bool BVH, bool SDF = true, bool XL = true, bool EMB = false>
 PTB_DEV HitCore<R> closest_hit_core(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R hit_dist_in, uint32_t* bvh_stats = nullptr) {
     int best;
     R dist;
     uint64_t accepted;
-    closest_spheres<R, BVH>(s, sv, o, d, best, dist, accepted, bvh_stats);
-    return closest_hit_finish<R, BVH, SDF, XL>(s, sv, o, d, hit_dist_in, best, dist, accepted);
+    closest_spheres<R, BVH, EMB>(s, sv, o, d, best, dist, accepted, bvh_stats);
+    return closest_hit_finish<R, BVH, SDF, XL, EMB>(s, sv, o, d, hit_dist_in, best, dist, accepted);
 }
 
-template <class R, bool BVH, bool SDF = true>
+template <class R, bool BVH, bool SDF = true, bool EMB = false>
 PTB_DEV V3<R> hit_normal(const DScene<R>& s, const SceneView<R>& sv, int prim, V3<R> o, V3<R> d, R t) {
     if ((uint32_t)prim < s.n_spheres) {
-        DSphere<R> sp = BVH ? s.spheres[prim] : sv.spheres[prim];
+        DSphere<R> sp = BVH ? s.spheres[prim] : SV_SPHERE(prim);
         V3<R> hp = o + t * d;
         return normalize(hp - V3<R>(sp.cx, sp.cy, sp.cz));
     }
     if (SDF && (uint32_t)prim == sdf_prim(s)) return sdf_normal(s, o + t * d);
-    DPlane<R> pl = sv.planes[prim - s.n_spheres];
+    DPlane<R> pl = SV_PLANE(prim - s.n_spheres);
     return V3<R>(pl.nx, pl.ny, pl.nz);
 }
 
@@ -928,25 +944,25 @@ PTB_DEV HitRec<R> closest_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> 
 
 // Scene::any_hit, analytical.rs:130-145 (+ max_dist unless the scene flag says the impl ignores it), in two parts
 // so that a dedicated traversal kernel can run the sphere part
-template <class R, bool BVH> PTB_DEV bool any_hit_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist, uint32_t* bvh_stats = nullptr) {
+template <class R, bool BVH, bool EMB = false> PTB_DEV bool any_hit_spheres(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist, uint32_t* bvh_stats = nullptr) {
     const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
     if constexpr (BVH) {
         return bvh_any(s, o, d, max_dist, ignore, bvh_stats);
     } else {
 #pragma unroll 1
         for (uint32_t i = 0; i < s.n_spheres; ++i) {
-            DSphere<R> sp = sv.spheres[i];
+            DSphere<R> sp = SV_SPHERE(i);
             R t = isect_sphere(o, d, V3<R>(sp.cx, sp.cy, sp.cz), sp.r);
             if (t >= R(0) && (ignore || t < max_dist)) return true;
         }
         return false;
     }
 }
-template <class R, bool SDF = true> PTB_DEV bool any_hit_planes(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
+template <class R, bool SDF = true, bool EMB = false> PTB_DEV bool any_hit_planes(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist) {
     const bool ignore = (s.flags & PTB_SCENE_ANYHIT_IGNORES_MAX_DIST) != 0;
 #pragma unroll 1
     for (uint32_t i = 0; i < s.n_planes; ++i) {
-        DPlane<R> pl = sv.planes[i];
+        DPlane<R> pl = SV_PLANE(i);
         R t = isect_plane(o, d, V3<R>(pl.px, pl.py, pl.pz), V3<R>(pl.nx, pl.ny, pl.nz));
         if (t >= R(0) && (ignore || t < max_dist)) return true;
     }
@@ -956,8 +972,8 @@ template <class R, bool SDF = true> PTB_DEV bool any_hit_planes(const DScene<R>&
     }
     return false;
 }
-template <class R, bool BVH, bool SDF = true> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist, uint32_t* bvh_stats = nullptr) {
-    return any_hit_spheres<R, BVH>(s, sv, o, d, max_dist, bvh_stats) || any_hit_planes<R, SDF>(s, sv, o, d, max_dist);
+template <class R, bool BVH, bool SDF = true, bool EMB = false> PTB_DEV bool any_hit(const DScene<R>& s, const SceneView<R>& sv, V3<R> o, V3<R> d, R max_dist, uint32_t* bvh_stats = nullptr) {
+    return any_hit_spheres<R, BVH, EMB>(s, sv, o, d, max_dist, bvh_stats) || any_hit_planes<R, SDF, EMB>(s, sv, o, d, max_dist);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1405,14 +1421,14 @@ PTB_DEV void shade_setup(const DScene<R>& s, PathState<R>& p, V3<R> normal, Mat<
     shade_ctx_init(su.c, mat, su.eta, su.ffn, -p.d);
 }
 
-template <class R, bool XL = true>
+template <class R, bool XL = true, bool EMB = false>
 PTB_DEV void shade_nee_sample(const DScene<R>& s, const SceneView<R>& sv, const ShadeSetup<R>& su, const R* u, NeeSample<R>& ns) {
     ns.wants_shadow_ray = false;
     ns.light_area = 0;
     if (s.n_lights > 0) {
         uint32_t li = (uint32_t)(u[SLOT_LIGHT_PICK] * s.n_lights_f);          // tracer.rs:137-139
         ns.scatter_pos = su.fhp + s.eps * su.ffn;
-        const DLight<R> L = sv.lights[li];
+        const DLight<R> L = SV_LIGHT(li);
         const bool extended = XL && (s.flags & PTB_SCENE_EXTENDED_LIGHTS) != 0 && L.type != PTB_LIGHT_SPHERICAL;
         if (extended) ns.ls = sample_light_extended(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
         else ns.ls = sample_light(L, s.n_lights_f, ns.scatter_pos, u[SLOT_LIGHT_R1], u[SLOT_LIGHT_R2]);
@@ -1560,17 +1576,17 @@ PTB_DEV void shade_setup_rm(PathState<float>& p, V3<float> normal, const RMat& r
     c.sheen_col = V3<float>(rm.sheen_col[0], rm.sheen_col[1], rm.sheen_col[2]);
     c.lum = rm.lum; c.wd0 = rm.wd0; c.wc0 = rm.wc0;
 }
-template <bool COUNT, bool ADD_EMISSION = true>
+template <bool COUNT, bool ADD_EMISSION = true, bool EMB = false>
 PTB_DEV bool path_shade_rm(const DScene<float>& s, const SceneView<float>& sv, PathState<float>& p, V3<float> normal, const RMat& rm, const float* u,
                            PathCounters* pc) {
     ShadeSetup<float> su;
     shade_setup_rm<COUNT, ADD_EMISSION>(p, normal, rm, su, pc);
     NeeSample<float> ns;
-    shade_nee_sample<float, false>(s, sv, su, u, ns);
+    shade_nee_sample<float, false, EMB>(s, sv, su, u, ns);
     bool nee = false;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;
-        nee = !any_hit<float, false, false>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
+        nee = !any_hit<float, false, false, EMB>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps);   // tracer.rs:150-154
     }
 #ifdef PTB_RM_SINGLE_COPY
     return shade_finish<float, COUNT, false, NoSink, false>(s, p, rm.m, su, nee, ns.ls, ns.light_area, u, pc);

@@ -148,7 +148,8 @@ PTB_DEV uint32_t lds32_late(const uint32_t* p) {
 // shared-memory copy, so every scene read of this instantiation is a shared-memory load (LDS, not a generic LD).
 template <class R> __host__ __device__ constexpr int wf_threads(bool rm) { return sizeof(R) == 8 ? WF_THREADS_F64 : (rm ? WF_THREADS_RM : WF_THREADS_GENERIC); }
 template <class R> __host__ __device__ constexpr uint32_t wf_pool(bool rm) { return sizeof(R) == 8 ? WF_POOL_F64 : (rm ? WF_POOL_RM : WF_POOL_GENERIC); }
-template <class R, bool COUNT, bool BVH, bool RM>
+// EMB: resolved-material instantiation for scenes whose primitives fit DScene::emb_* (see SV_SPHERE in ptb_device.cuh)
+template <class R, bool COUNT, bool BVH, bool RM, bool EMB = false>
 __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const __grid_constant__ DScene<R> s, const RenderArgs a) {
     constexpr int WF_THREADS = wf_threads<R>(RM);
     static_assert(!(RM && BVH), "the resolved-material table is for scenes that live in shared memory");
@@ -287,8 +288,8 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                             sm.ra[i] = r4;
                         }
                         shade_draws(rng, p.bounce, s.n_lights > 1u || (rm.lobe_class & 4u) != 0u, u);
-                        const V3<R> normal = hit_normal<R, BVH, false>(s, sv, prim, p.o, p.d, p.hit_dist);
-                        alive = path_shade_rm<COUNT, false>(s, sv, p, normal, rm, u, &pc);
+                        const V3<R> normal = hit_normal<R, BVH, false, EMB>(s, sv, prim, p.o, p.d, p.hit_dist);
+                        alive = path_shade_rm<COUNT, false, EMB>(s, sv, p, normal, rm, u, &pc);
                     } else {
                         const int prim = (int)prim_bits;
                         Mat<R> mat;
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                     if (COUNT) pc.end_depth++;
                 } else {
                     if (COUNT) pc.closest_hit++;
-                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH, !RM>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc.bvh : nullptr);   // signed-distance programs: generic instantiation only
+                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH, !RM, EMB>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc.bvh : nullptr);   // signed-distance programs: generic instantiation only
                     p.hit_dist = h.hit_dist;
                     if (!h.hit) {
                         key = WF_MISS;                                 // background lookup next iteration, with full warps
@@ -639,7 +640,8 @@ inline int wavefront_render(WavefrontState& wf, const DScene<R>& d, void* accum,
     if constexpr (F32) {
         rm = d.rm_entries != 0 && !d.use_bvh;
         kern = d.use_bvh ? (count ? k_render_wavefront<float, true, true, false> : k_render_wavefront<float, false, true, false>)
-               : rm      ? (count ? k_render_wavefront<float, true, false, true> : k_render_wavefront<float, false, false, true>)
+               : rm      ? (d.emb ? (count ? k_render_wavefront<float, true, false, true, true> : k_render_wavefront<float, false, false, true, true>)
+                                  : (count ? k_render_wavefront<float, true, false, true, false> : k_render_wavefront<float, false, false, true, false>))
                          : (count ? k_render_wavefront<float, true, false, false> : k_render_wavefront<float, false, false, false>);
         smem_bytes = rm ? sizeof(WfSmemT<float, WF_POOL_RM, WF_SCENE_BYTES_RM, false>) : sizeof(WfSmemT<float, WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, true>);
     } else {

@@ -862,3 +862,32 @@ def test_bvh_work_counters(rp):
     pt.close()
     assert abs(c["closest_hit"] - f["closest_hit"]) <= 1e-2 * f["closest_hit"]      # (a few paths flip a branch between the two instantiations)
     assert 0.5 < c["bvh_nodes"] / f["bvh_nodes"] < 2.0 and 0.5 < c["bvh_leaf_tests"] / f["bvh_leaf_tests"] < 2.0
+
+
+def test_resolved_material_kernel_with_and_without_embedded_primitives(rp, po):
+    """The resolved-material wavefront kernel has two instantiations: scenes of up to 8 spheres / 4 planes / 4 lights read their
+    primitives from the copies in the kernel parameter (constant bank), larger small scenes through the shared-memory scene view.
+    Both against the oracle and against the fused integrator: the demo scene (embedded), a 16-sphere field without BVH (view),
+    and a 9-sphere scene right above the limit."""
+    def field(n):
+        e = rp.sphere_field_scene(n_spheres=n, n_lights_side=2).device_export()
+        e.flags |= rp._abi.PTB_SCENE_NO_BVH
+        e.camera.set(rp.F3(0.0, 2.0, 6.0), rp.F3(0.0, 0.0, -20.0))
+        return e
+    W, H, S = 128, 72, 3
+    for name, e in (("demo", rp.AnalyticalScene.new().device_export()), ("field16", field(16)), ("field9", field(9)), ("field8", field(8))):
+        ref, _, _, _ = po.OracleScene(e).render(W, H, S)
+        imgs = {}
+        for integ in (rp._abi.PTB_INTEGRATOR_WAVEFRONT, rp._abi.PTB_INTEGRATOR_FUSED):
+            pt = rp.Tracer.new(rp.ExportedScene(e), integrator=integ)
+            buf = rp.ColorBuffer.new(W, H)
+            pt.render_spp(buf, S)
+            used = pt.integrator_used()
+            pt.close()
+            imgs[integ] = buf.pixels.copy()
+            if integ == rp._abi.PTB_INTEGRATOR_WAVEFRONT:
+                assert used == "wavefront_rm", (name, used)
+            rel = pix_rel(buf.pixels, ref)
+            assert (rel < 1e-4).mean() >= 0.97, (name, used, (rel < 1e-4).mean())
+            assert np.median(rel) < 1e-6
+        assert (pix_rel(imgs[rp._abi.PTB_INTEGRATOR_WAVEFRONT], imgs[rp._abi.PTB_INTEGRATOR_FUSED]) < 1e-4).mean() >= 0.99

@@ -27,7 +27,7 @@ VARIANTS = [
     #   PTB_SAT_DROPS_NAN + PTB_CONTRACT_VIEW_COSINE                  round 1's NaN behaviour (saturate drops NaN, v.z contracted)
     #   PTB_WF_ASYNC                                                 barrier-free per-key rings (ptb_wavefront_async.cuh); PTB_WF_REGEN_DEN: in-place regeneration threshold
     ("default", [], {}),
-    ("halves", ["-DPTB_WF_HALVES"], {}),
+    ("no_emb", ["-DPTB_NO_EMB"], {}),
 ]
 
 
