@@ -123,11 +123,6 @@ PTB_DEV float4 lds128_late(const float4* p) {
     asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
-PTB_DEV uint32_t lds32_late(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-    return v;
-}
 
 // One stage per iteration.  Every slot that still has work is in the queue exactly once, ordered by key; warps take 32-entry
 // chunks and run, for their 32 slots,
@@ -230,18 +225,19 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
         const uint32_t n_queue = *(volatile uint32_t*)&sm.nq[h];
         if (n_queue == 0) { if (h) done1 = true; else done0 = true; continue; }
         const uint32_t WF_QBASE = h * HALF;
-        uint32_t* const WF_NEXT_CNT = sm.cnt[h];
-        uint32_t* const WF_CURSOR = &sm.cursor[h];
+#define WF_CNT_IDX h
+#define WF_CUR_IDX h
 #else
     while (n_queue) {
         constexpr uint32_t WF_QBASE = 0;
-        uint32_t* const WF_NEXT_CNT = sm.cnt[par ^ 1u];
-        uint32_t* const WF_CURSOR = &sm.cursor[par];
+        // (indices, not pointers: a pointer to a shared-memory member is a generic pointer, and forming one costs an S2R)
+#define WF_CNT_IDX (par ^ 1u)
+#define WF_CUR_IDX par
 #endif
 #pragma unroll 1
         while (true) {
             uint32_t chunk = 0;
-            if (lane == 0) chunk = atomicAdd(WF_CURSOR, 1u);
+            if (lane == 0) chunk = atomicAdd(&sm.cursor[WF_CUR_IDX], 1u);
             chunk = __shfl_sync(FULL, chunk, 0);
             if (chunk * 32u >= n_queue) break;
             const uint32_t j = chunk * 32u + lane;
@@ -456,7 +452,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                 sm.tr[i] = mk4(p.thr.x, p.thr.y, p.thr.z, wf_word(R(0), fl));
                 sm.ra[i] = mk4(p.rad.x, p.rad.y, p.rad.z, wf_word(R(0), sidx));
                 uint32_t ticket = 0;
-                if (key != WF_NOKEY) ticket = atomicAdd(&WF_NEXT_CNT[key], 1u);
+                if (key != WF_NOKEY) ticket = atomicAdd(&sm.cnt[WF_CNT_IDX][key], 1u);
                 sm.kt[i] = (key << 16) | ticket;
             }
         }
