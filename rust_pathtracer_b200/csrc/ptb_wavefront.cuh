@@ -123,6 +123,11 @@ PTB_DEV float4 lds128_late(const float4* p) {
     asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
+PTB_DEV uint32_t lds32_late(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
 
 // One stage per iteration.  Every slot that still has work is in the queue exactly once, ordered by key; warps take 32-entry
 // chunks and run, for their 32 slots,
