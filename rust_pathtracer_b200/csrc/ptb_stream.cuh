@@ -287,6 +287,17 @@ PTB_DEV float box_entry_s(float4 lo, float4 hi, const RayS& r, float limit) {
     return (tn <= tf * 1.0001f && tn <= limit) ? tn : 3.0e38f;
 }
 
+PTB_DEV bool box_test_s(float4 lo, float4 hi, const RayS& r, float limit, float& tn_out) {
+    const float tx0 = fmaf(lo.x, r.idx, r.nox), tx1 = fmaf(hi.x, r.idx, r.nox);
+    const float ty0 = fmaf(lo.y, r.idy, r.noy), ty1 = fmaf(hi.y, r.idy, r.noy);
+    const float tz0 = fmaf(lo.z, r.idz, r.noz), tz1 = fmaf(hi.z, r.idz, r.noz);
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    tn *= 0.9999f;
+    tn_out = tn;
+    return tn <= tf * 1.0001f && tn <= limit;
+}
+
 #ifndef PTB_ST_INNER_REPS
 #define PTB_ST_INNER_REPS 4
 #endif
@@ -417,8 +428,15 @@ __global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScen
             if (COUNT) pc.bvh[0]++;
             const float4* c = nodes + (size_t)(cur >> 3) * 2u;
             const float4 alo = __ldg(c), ahi = __ldg(c + 1), blo = __ldg(c + 2), bhi = __ldg(c + 3);
+#ifdef PTB_ST_BOX_SENTINEL
             const float ta = box_entry_s(alo, ahi, r, best_t), tb = box_entry_s(blo, bhi, r, best_t);
             const bool ha = ta < 3.0e38f, hb = tb < 3.0e38f;
+#else
+            // (hit flag and entry distance separately: the 3e38 sentinel cost four selects and two compares per visit on the ALU
+            //  pipe, which is what this kernel is short of)
+            float ta, tb;
+            const bool ha = box_test_s(alo, ahi, r, best_t, ta), hb = box_test_s(blo, bhi, r, best_t, tb);
+#endif
             const uint32_t ra = node_ref(__float_as_uint(alo.w), __float_as_uint(ahi.w)), rb = node_ref(__float_as_uint(blo.w), __float_as_uint(bhi.w));
             const bool a_near = ha && (!hb || ta <= tb);
             const uint32_t near_ref = a_near ? ra : rb;

@@ -16,7 +16,7 @@ VARIANTS = [
     # knobs (ptb_stream.cuh): PTB_ST_INNER_REPS, PTB_ST_EAGER_FINISH, PTB_ST_REFILL, PTB_ST_LEAF_MIN, PTB_ST_TRACE_MIN_BLOCKS,
     # PTB_ST_TRACE_PLAIN, PTB_ST_SHADE_MIN_BLOCKS, PTB_ST_SPLIT_MIN; results of round 2: profiles/r02_ab_stream.txt
     ("default", []),
-    ("no_early_exit", ["-DPTB_ST_NO_EARLY_EXIT"]),
+    ("box_sentinel", ["-DPTB_ST_BOX_SENTINEL"]),
     ("reps1_eager", ["-DPTB_ST_INNER_REPS=1", "-DPTB_ST_EAGER_FINISH", "-DPTB_ST_REFILL=8", "-DPTB_ST_LEAF_MIN=12", "-DPTB_ST_TRACE_MIN_BLOCKS=1"]),
 ]
 
