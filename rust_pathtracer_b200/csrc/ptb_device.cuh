@@ -1507,16 +1507,16 @@ PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat
 }
 
 // the three pieces in one go (fused integrator, shared-memory wavefront)
-template <class R, bool COUNT, bool BVH, bool ADD_EMISSION = true, bool SDF = true>
+template <class R, bool COUNT, bool BVH, bool ADD_EMISSION = true, bool SDF = true, bool EMB = false>
 PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, Mat<R>& mat, const R* u, PathCounters* pc) {
     ShadeSetup<R> su;
     shade_setup<R, COUNT, ADD_EMISSION>(s, p, normal, mat, su, pc);
     NeeSample<R> ns;
-    shade_nee_sample(s, sv, su, u, ns);
+    shade_nee_sample<R, true, EMB>(s, sv, su, u, ns);
     bool nee = false;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;
-        nee = !any_hit<R, BVH, SDF>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT ? pc->bvh : nullptr);   // tracer.rs:150-154
+        nee = !any_hit<R, BVH, SDF, EMB>(s, sv, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT ? pc->bvh : nullptr);   // tracer.rs:150-154
     }
     return shade_finish<R, COUNT, false, NoSink, true>(s, p, mat, su, nee, ns.ls, ns.light_area, u, pc);
 }

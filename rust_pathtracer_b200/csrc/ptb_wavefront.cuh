@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                                 r4.x = r4.x + mat.emission.x * (t4.x * p.thr.x); r4.y = r4.y + mat.emission.y * (t4.y * p.thr.y); r4.z = r4.z + mat.emission.z * (t4.z * p.thr.z);
                                 sm.ra[i] = r4;
                             }
-                            const V3<R> normal = hit_normal<R, BVH, !BVH>(s, sv, prim, p.o, p.d, p.hit_dist);
-                            alive = path_shade<R, COUNT, BVH, false, !BVH>(s, sv, p, normal, mat, u, &pc);
+                            const V3<R> normal = hit_normal<R, BVH, !BVH, EMB>(s, sv, prim, p.o, p.d, p.hit_dist);
+                            alive = path_shade<R, COUNT, BVH, false, !BVH, EMB>(s, sv, p, normal, mat, u, &pc);
                             if (s.has_media) path_medium_update<R, BVH>(s, sv, p, normal, mi);
                         }
                     }
@@ -643,11 +643,13 @@ inline int wavefront_render(WavefrontState& wf, const DScene<R>& d, void* accum,
         kern = d.use_bvh ? (count ? k_render_wavefront<float, true, true, false> : k_render_wavefront<float, false, true, false>)
                : rm      ? (d.emb ? (count ? k_render_wavefront<float, true, false, true, true> : k_render_wavefront<float, false, false, true, true>)
                                   : (count ? k_render_wavefront<float, true, false, true, false> : k_render_wavefront<float, false, false, true, false>))
-                         : (count ? k_render_wavefront<float, true, false, false> : k_render_wavefront<float, false, false, false>);
+                         : (d.emb ? (count ? k_render_wavefront<float, true, false, false, true> : k_render_wavefront<float, false, false, false, true>)
+                                  : (count ? k_render_wavefront<float, true, false, false, false> : k_render_wavefront<float, false, false, false, false>));
         smem_bytes = rm ? sizeof(WfSmemT<float, WF_POOL_RM, WF_SCENE_BYTES_RM, false>) : sizeof(WfSmemT<float, WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, true>);
     } else {
         kern = d.use_bvh ? (count ? k_render_wavefront<double, true, true, false> : k_render_wavefront<double, false, true, false>)
-                         : (count ? k_render_wavefront<double, true, false, false> : k_render_wavefront<double, false, false, false>);
+                         : (d.emb ? (count ? k_render_wavefront<double, true, false, false, true> : k_render_wavefront<double, false, false, false, true>)
+                                  : (count ? k_render_wavefront<double, true, false, false, false> : k_render_wavefront<double, false, false, false, false>));
         smem_bytes = sizeof(WfSmemT<double, WF_POOL_F64, PTB_SMEM_SCENE_BYTES, true>);
     }
     const uint32_t WF_POOL = wf_pool<R>(rm);
