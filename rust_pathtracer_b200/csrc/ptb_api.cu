@@ -585,7 +585,8 @@ template <class R> static int set_scene_impl(ptb_tracer* t, SceneBuffers<R>& sb,
         for (uint32_t i = 0; i < sc->n_planes; ++i) d.emb_planes[i] = planes[i];
         for (uint32_t i = 0; i < sc->n_lights; ++i) d.emb_lights[i] = lights[i];
     }
-    d.has_media = has_media ? 1u : 0u;          // (the resolved-material kernel is not built for them: no table above)
+    d.has_media = has_media ? 1u : 0u;
+    d.has_fx = (has_media || extended_lights) ? 1u : 0u;          // (the resolved-material kernel is not built for them: no table above)
     for (const auto& m : mats)
         if (m.emission[0] != R(0) || m.emission[1] != R(0) || m.emission[2] != R(0)) d.has_emissive = 1;
 

@@ -304,6 +304,7 @@ template <class R> struct DScene {
     uint32_t use_bvh;
     uint32_t has_emissive;              // 1 if any material has non-zero emission
     uint32_t has_media;                 // 1 if any material carries a medium (PTB_MEDIUM_*): the path loop tracks inside / outside
+    uint32_t has_fx;                    // has_media, or rectangular / distant lights that PTB_SCENE_EXTENDED_LIGHTS switches on
     // small scenes: the primitives themselves in the kernel parameter (constant bank, uniform loads) — see PTB_EMB_SCENE
     uint32_t emb;                       // 1 if the three arrays below hold the whole scene
     DSphere<R> emb_spheres[PTB_EMB_SPHERES];
@@ -1507,12 +1508,12 @@ PTB_DEV bool shade_finish(const DScene<R>& s, PathState<R>& p, const Mat<R>& mat
 }
 
 // the three pieces in one go (fused integrator, shared-memory wavefront)
-template <class R, bool COUNT, bool BVH, bool ADD_EMISSION = true, bool SDF = true, bool EMB = false>
+template <class R, bool COUNT, bool BVH, bool ADD_EMISSION = true, bool SDF = true, bool EMB = false, bool XL = true>
 PTB_DEV bool path_shade(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, V3<R> normal, Mat<R>& mat, const R* u, PathCounters* pc) {
     ShadeSetup<R> su;
     shade_setup<R, COUNT, ADD_EMISSION>(s, p, normal, mat, su, pc);
     NeeSample<R> ns;
-    shade_nee_sample<R, true, EMB>(s, sv, su, u, ns);
+    shade_nee_sample<R, XL, EMB>(s, sv, su, u, ns);
     bool nee = false;
     if (ns.wants_shadow_ray) {
         if (COUNT) pc->any_hit++;

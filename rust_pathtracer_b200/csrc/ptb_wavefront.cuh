@@ -148,8 +148,11 @@ PTB_DEV uint32_t lds32_late(const uint32_t* p) {
 // shared-memory copy, so every scene read of this instantiation is a shared-memory load (LDS, not a generic LD).
 template <class R> __host__ __device__ constexpr int wf_threads(bool rm) { return sizeof(R) == 8 ? WF_THREADS_F64 : (rm ? WF_THREADS_RM : WF_THREADS_GENERIC); }
 template <class R> __host__ __device__ constexpr uint32_t wf_pool(bool rm) { return sizeof(R) == 8 ? WF_POOL_F64 : (rm ? WF_POOL_RM : WF_POOL_GENERIC); }
-// EMB: resolved-material instantiation for scenes whose primitives fit DScene::emb_* (see SV_SPHERE in ptb_device.cuh)
-template <class R, bool COUNT, bool BVH, bool RM, bool EMB = false>
+// EMB: instantiation for scenes whose primitives fit DScene::emb_* (see SV_SPHERE in ptb_device.cuh)
+// FX:  the scene has media or live rectangular / distant lights (PTB_MEDIUM_*, PTB_SCENE_EXTENDED_LIGHTS).  A separate
+//      instantiation: the in-medium bounce and the quad tests inlined into the shading stage cost the f64 kernel 7 % on scenes
+//      that have neither.
+template <class R, bool COUNT, bool BVH, bool RM, bool EMB = false, bool FX = false>
 __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const __grid_constant__ DScene<R> s, const RenderArgs a) {
     constexpr int WF_THREADS = wf_threads<R>(RM);
     static_assert(!(RM && BVH), "the resolved-material table is for scenes that live in shared memory");
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                 if constexpr (!RM) accepted = (uint64_t)sm.acc_lo[i] | ((uint64_t)sm.acc_hi[i] << 32);
             }
             p.bounce = (fl0 >> 8) & 0xffffu;
-            p.medium = RM ? 0u : fl0 >> 25;                             // (media: generic instantiations only)
+            p.medium = (RM || !FX) ? 0u : fl0 >> 25;                    // (media: the FX instantiations only)
             bool alive = valid && (fl0 & FL_ALIVE);
             const bool had_event = alive;
 
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                         const uint32_t mi = hit_material<R, BVH>(s, sv, prim, accepted, p.d, mat);
                         shade_draws(rng, p.bounce, s.n_lights > 1u || p.medium != 0u || (lobe_class_of(mat.metallic, mat.spec_trans, mat.clearcoat) & 4u) != 0u, u);
                         int med = MED_SURFACE;
-                        if (s.has_media && p.medium) med = path_medium<R, COUNT, BVH, !BVH>(s, sv, p, u, &pc);       // works on the unit throughput like the shading below
+                        if (FX && s.has_media && p.medium) med = path_medium<R, COUNT, BVH, !BVH>(s, sv, p, u, &pc);       // works on the unit throughput like the shading below
                         if (med != MED_SURFACE) {
                             alive = med == MED_SCATTERED;
                         } else {
@@ -308,8 +311,8 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                                 sm.ra[i] = r4;
                             }
                             const V3<R> normal = hit_normal<R, BVH, !BVH, EMB>(s, sv, prim, p.o, p.d, p.hit_dist);
-                            alive = path_shade<R, COUNT, BVH, false, !BVH, EMB>(s, sv, p, normal, mat, u, &pc);
-                            if (s.has_media) path_medium_update<R, BVH>(s, sv, p, normal, mi);
+                            alive = path_shade<R, COUNT, BVH, false, !BVH, EMB, FX>(s, sv, p, normal, mat, u, &pc);
+                            if (FX && s.has_media) path_medium_update<R, BVH>(s, sv, p, normal, mi);
                         }
                     }
                 }
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(wf_threads<R>(RM), 1) k_render_wavefront(const
                     if (COUNT) pc.end_depth++;
                 } else {
                     if (COUNT) pc.closest_hit++;
-                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH, !RM, EMB>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc.bvh : nullptr);   // signed-distance programs: generic instantiation only
+                    const HitCore<R> h = closest_hit_core<R, BVH, !RM && !BVH, !RM && FX, EMB>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc.bvh : nullptr);   // signed-distance programs: generic instantiation only
                     p.hit_dist = h.hit_dist;
                     if (!h.hit) {
                         key = WF_MISS;                                 // background lookup next iteration, with full warps
@@ -638,20 +641,22 @@ inline int wavefront_render(WavefrontState& wf, const DScene<R>& d, void* accum,
     bool rm = false;
     void (*kern)(const DScene<R>, const RenderArgs);
     size_t smem_bytes;
+#define WF_K(RR, B, RMv, E, F) (count ? k_render_wavefront<RR, true, B, RMv, E, F> : k_render_wavefront<RR, false, B, RMv, E, F>)
+    const bool fx = d.has_fx != 0;          // media or live rectangular / distant lights: the FX instantiations (never with RM)
     if constexpr (F32) {
         rm = d.rm_entries != 0 && !d.use_bvh;
-        kern = d.use_bvh ? (count ? k_render_wavefront<float, true, true, false> : k_render_wavefront<float, false, true, false>)
-               : rm      ? (d.emb ? (count ? k_render_wavefront<float, true, false, true, true> : k_render_wavefront<float, false, false, true, true>)
-                                  : (count ? k_render_wavefront<float, true, false, true, false> : k_render_wavefront<float, false, false, true, false>))
-                         : (d.emb ? (count ? k_render_wavefront<float, true, false, false, true> : k_render_wavefront<float, false, false, false, true>)
-                                  : (count ? k_render_wavefront<float, true, false, false, false> : k_render_wavefront<float, false, false, false, false>));
+        kern = d.use_bvh ? (fx ? WF_K(float, true, false, false, true) : WF_K(float, true, false, false, false))
+               : rm      ? (d.emb ? WF_K(float, false, true, true, false) : WF_K(float, false, true, false, false))
+               : fx      ? WF_K(float, false, false, false, true)
+               : d.emb   ? WF_K(float, false, false, true, false) : WF_K(float, false, false, false, false);
         smem_bytes = rm ? sizeof(WfSmemT<float, WF_POOL_RM, WF_SCENE_BYTES_RM, false>) : sizeof(WfSmemT<float, WF_POOL_GENERIC, PTB_SMEM_SCENE_BYTES, true>);
     } else {
-        kern = d.use_bvh ? (count ? k_render_wavefront<double, true, true, false> : k_render_wavefront<double, false, true, false>)
-                         : (d.emb ? (count ? k_render_wavefront<double, true, false, false, true> : k_render_wavefront<double, false, false, false, true>)
-                                  : (count ? k_render_wavefront<double, true, false, false, false> : k_render_wavefront<double, false, false, false, false>));
+        kern = d.use_bvh ? (fx ? WF_K(double, true, false, false, true) : WF_K(double, true, false, false, false))
+               : fx      ? WF_K(double, false, false, false, true)
+               : d.emb   ? WF_K(double, false, false, true, false) : WF_K(double, false, false, false, false);
         smem_bytes = sizeof(WfSmemT<double, WF_POOL_F64, PTB_SMEM_SCENE_BYTES, true>);
     }
+#undef WF_K
     const uint32_t WF_POOL = wf_pool<R>(rm);
     const int threads = wf_threads<R>(rm);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
