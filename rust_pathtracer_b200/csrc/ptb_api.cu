@@ -1013,9 +1013,14 @@ template <class R> static int render_fused(ptb_tracer* t, DScene<R>& d, uint32_t
     a.counters = t->counters;
     int& blocks = sizeof(R) == 4 ? t->fused_blocks_f32 : t->fused_blocks_f64;
     const bool count = t->cfg.collect_counters != 0;
+    const bool fx = d.has_fx != 0 || d.n_sdf != 0;
     void (*kern)(const DScene<R>, const RenderArgs) =
-        d.use_bvh ? (count ? k_render_fused<R, true, true> : k_render_fused<R, false, true>)
-                  : (count ? k_render_fused<R, true, false> : k_render_fused<R, false, false>);
+        fx ? (d.use_bvh ? (count ? k_render_fused<R, true, true, true> : k_render_fused<R, false, true, true>)
+                        : (count ? k_render_fused<R, true, false, true> : k_render_fused<R, false, false, true>))
+           : (d.use_bvh ? (count ? k_render_fused<R, true, true, false> : k_render_fused<R, false, true, false>)
+                        : (count ? k_render_fused<R, true, false, false> : k_render_fused<R, false, false, false>));
+    static thread_local const void* last_kern = nullptr;            // (the cached grid belongs to one instantiation)
+    if (last_kern != (const void*)kern) { blocks = 0; last_kern = (const void*)kern; }
     if (blocks == 0) {
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, 0));

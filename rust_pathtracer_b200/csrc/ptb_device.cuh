@@ -1627,14 +1627,15 @@ PTB_DEV void path_add_emitter(const DScene<R>& s, const SceneView<R>& sv, PathSt
 
 // First half of a bounce, tracer.rs:63-87: closest_hit, background on a miss, MIS-weighted emission
 // on a light hit.  Returns 0 = path ended, 1 = geometry hit (continue with path_shade).
-template <class R, bool COUNT, bool BVH>
+// FX = false (fused integrator on scenes without a signed-distance program, media or live extended lights): none of that code
+template <class R, bool COUNT, bool BVH, bool FX = true>
 PTB_DEV int path_intersect(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, HitCore<R>& h, PathCounters* pc) {
     if (p.bounce >= s.depth) {                                  // recursion_depth() == 0: `for _ in 0..0` never runs (tracer.rs:61)
         if (COUNT) pc->end_depth++;
         return 0;
     }
     if (COUNT) pc->closest_hit++;
-    h = closest_hit_core<R, BVH>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc->bvh : nullptr);
+    h = closest_hit_core<R, BVH, FX, FX>(s, sv, p.o, p.d, p.hit_dist, COUNT ? pc->bvh : nullptr);
     p.hit_dist = h.hit_dist;
     if (!h.hit) {
         path_add_sky(s, p);
@@ -1741,7 +1742,7 @@ PTB_DEV void path_medium_update(const DScene<R>& s, const SceneView<R>& sv, Path
 }
 
 // Runs ONE bounce (both halves); returns true while the path continues.  COUNT enables event counters.
-template <class R, bool COUNT, bool BVH>
+template <class R, bool COUNT, bool BVH, bool FX = true>
 PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R>& p, const R* u, uint32_t rr_start, PathCounters* pc) {
     if (rr_start != 0 && p.bounce >= rr_start && p.bounce > 0) {
         if (!russian_roulette_survives(p, u[0])) {
@@ -1750,16 +1751,16 @@ PTB_DEV bool path_bounce(const DScene<R>& s, const SceneView<R>& sv, PathState<R
         }
     }
     HitCore<R> h;
-    if (!path_intersect<R, COUNT, BVH>(s, sv, p, h, pc)) return false;
-    if (s.has_media && p.medium) {
+    if (!path_intersect<R, COUNT, BVH, FX>(s, sv, p, h, pc)) return false;
+    if (FX && s.has_media && p.medium) {
         const int med = path_medium<R, COUNT, BVH, true>(s, sv, p, u, pc);
         if (med != MED_SURFACE) return med == MED_SCATTERED;
     }
     Mat<R> mat;
     const uint32_t mi = hit_material<R, BVH>(s, sv, h.prim, h.accepted, p.d, mat);
-    V3<R> normal = hit_normal<R, BVH>(s, sv, h.prim, p.o, p.d, h.hit_dist);
-    const bool alive = path_shade<R, COUNT, BVH>(s, sv, p, normal, mat, u, pc);
-    if (s.has_media) path_medium_update<R, BVH>(s, sv, p, normal, mi);
+    V3<R> normal = hit_normal<R, BVH, FX>(s, sv, h.prim, p.o, p.d, h.hit_dist);
+    const bool alive = path_shade<R, COUNT, BVH, true, FX, false, FX>(s, sv, p, normal, mat, u, pc);
+    if (FX && s.has_media) path_medium_update<R, BVH>(s, sv, p, normal, mi);
     return alive;
 }
 

@@ -60,7 +60,8 @@ constexpr uint32_t FUSED_CHUNK = PTB_CHUNK;
 // HBM at all.  Pixels are handed out in 16x16-tile order, FUSED_CHUNK (two tile rows) per global atomic;
 // within a warp they are distributed with ballot/popc prefix ranks.  Every pixel's samples are
 // summed in sample order by one lane, so the image is bit-reproducible run to run.
-template <class R, bool COUNT, bool BVH>
+// FX: scenes with a signed-distance program, media or live extended lights (their code inlined cost every other scene a CTA per SM)
+template <class R, bool COUNT, bool BVH, bool FX>
 __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_constant__ DScene<R> s, const RenderArgs a) {
     __shared__ SceneSmem<R> sm;
     const SceneView<R> sv = stage_scene(s, sm.words, PTB_SMEM_SCENE_BYTES);
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_render_fused(const __grid_con
                 alive = true;
                 if (COUNT) n_samples++;
             }
-            alive = path_bounce<R, COUNT, BVH>(s, sv, p, u, a.rr_start, &pc);
+            alive = path_bounce<R, COUNT, BVH, FX>(s, sv, p, u, a.rr_start, &pc);
             if (!alive) {
                 acc = acc + p.rad;
                 s_idx++;
