@@ -213,7 +213,8 @@ PTB_DEV void push_by_key(const StreamArgs& a, BounceCtr& ctr, uint32_t key, uint
 
 // The whole of Scene::closest_hit in one kernel, one ray per lane per 32-ray chunk: small scenes (no BVH), and BVH scenes
 // while the rays of a chunk are coherent (camera rays) or the tree is shallow.
-template <bool COUNT, bool BVH>
+// FX: scenes with media or live extended lights (the quad tests are compiled into the FX instantiations only)
+template <bool COUNT, bool BVH, bool FX>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     PTB_ST_LEAVE_IF_IDLE(a.ctr[bounce].n_ray);
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_closest(const __grid_cons
             const float4 A0 = a.a0[slot], A1 = a.a1[slot];
             const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
             if (COUNT) pc.closest_hit++;
-            const HitCore<R> h = closest_hit_core<R, BVH, false>(s, sv, o, d, A1.z, COUNT ? pc.bvh : nullptr);       // (no signed-distance programs in this integrator)
+            const HitCore<R> h = closest_hit_core<R, BVH, false, FX>(s, sv, o, d, A1.z, COUNT ? pc.bvh : nullptr);       // (no signed-distance programs in this integrator)
             key = stream_after_hit<COUNT, BVH>(s, sv, a, slot, d, A1.w, h, pc);
         }
         push_by_key(a, ctr, key, slot);
@@ -516,7 +517,7 @@ __global__ void PTB_ST_TRACE_BOUNDS k_stream_trace(const __grid_constant__ DScen
 
 // BVH scenes: the rest of Scene::closest_hit after the sphere traversal — planes, Scene::sample_lights (light BVH when
 // there are many lights), emitter hits, queue keys.  Full, coherent warps.
-template <bool COUNT>
+template <bool COUNT, bool FX>
 __global__ void __launch_bounds__(ST_THREADS) k_stream_finish(const __grid_constant__ DScene<float> s, const StreamArgs a, const uint32_t bounce) {
     using R = float;
     PTB_ST_LEAVE_IF_IDLE(a.ctr[bounce].n_ray);
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stream_finish(const __grid_const
             const float4 A0 = a.a0[slot], A1 = a.a1[slot];
             const uint4 H = a.hit[slot];
             const V3<R> o(A0.x, A0.y, A0.z), d(A0.w, A1.x, A1.y);
-            const HitCore<R> h = closest_hit_finish<R, true, false>(s, sv, o, d, A1.z, (int)H.x, __uint_as_float(H.w), 0ull);
+            const HitCore<R> h = closest_hit_finish<R, true, false, FX>(s, sv, o, d, A1.z, (int)H.x, __uint_as_float(H.w), 0ull);
             key = stream_after_hit<COUNT, true>(s, sv, a, slot, d, A1.w, h, pc);
         }
         push_by_key(a, ctr, key, slot);
@@ -656,7 +657,7 @@ __global__ void PTB_ST_SHADE_BOUNDS k_stream_shade(const __grid_constant__ DScen
             shade_setup<R, COUNT>(s, p, normal, mat, su, &pc);
             if (s.has_emissive) { A3.x = p.rad.x; A3.y = p.rad.y; A3.z = p.rad.z; a.a3[slot] = A3; }     // tracer.rs:74
             NeeSample<R> ns;
-            shade_nee_sample(s, sv, su, u, ns);
+            shade_nee_sample<R, MEDIA>(s, sv, su, u, ns);            // (MEDIA = the scene's FX flag: media or live extended lights)
             if (COUNT && ns.wants_shadow_ray) pc.any_hit++;
             ShadowSink sink{&a, &ctr, slot, ns.scatter_pos, ns.ls.direction, ns.ls.dist - s.eps, COUNT};
             cont0 = shade_finish<R, COUNT, true, ShadowSink>(s, p, mat, su, ns.wants_shadow_ray, ns.ls, ns.light_area, u, &pc, sink);
@@ -796,7 +797,7 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, v
 
     const bool count = cfg.collect_counters != 0;
     const bool bvh = d.use_bvh != 0;
-    const bool media = d.has_media != 0;
+    const bool media = d.has_fx != 0;           // media or live extended lights: the FX instantiations of closest / finish / shade
     const int vi = (media ? 4 : 0) + (count ? 2 : 0) + (bvh ? 1 : 0);
     using StageKernel = void (*)(const DScene<float>, const StreamArgs, const uint32_t);
     // Stage kernels of a bounce, in launch order.  Plain form: closest, shade, shadow (one ray per lane per chunk).
@@ -805,18 +806,20 @@ inline int stream_render(StreamState& st, const DScene<float>& d, void* accum, v
     // (wash) ... while 4096 spheres run 1.3x faster in the plain form on every bounce (profiles/r01_ncu_stream.md).
     StageKernel plain[3], split[4];
     if (bvh) {
-        plain[0] = count ? k_stream_closest<true, true> : k_stream_closest<false, true>;
+        plain[0] = media ? (count ? k_stream_closest<true, true, true> : k_stream_closest<false, true, true>)
+                         : (count ? k_stream_closest<true, true, false> : k_stream_closest<false, true, false>);
         plain[1] = media ? (count ? k_stream_shade<true, true, true> : k_stream_shade<false, true, true>)
                          : (count ? k_stream_shade<true, true, false> : k_stream_shade<false, true, false>);
         plain[2] = count ? k_stream_shadow<true, true> : k_stream_shadow<false, true>;
     } else {
-        plain[0] = count ? k_stream_closest<true, false> : k_stream_closest<false, false>;
+        plain[0] = media ? (count ? k_stream_closest<true, false, true> : k_stream_closest<false, false, true>)
+                         : (count ? k_stream_closest<true, false, false> : k_stream_closest<false, false, false>);
         plain[1] = media ? (count ? k_stream_shade<true, false, true> : k_stream_shade<false, false, true>)
                          : (count ? k_stream_shade<true, false, false> : k_stream_shade<false, false, false>);
         plain[2] = count ? k_stream_shadow<true, false> : k_stream_shadow<false, false>;
     }
     split[0] = count ? k_stream_trace<false, true> : k_stream_trace<false, false>;
-    split[1] = count ? k_stream_finish<true> : k_stream_finish<false>;
+    split[1] = media ? (count ? k_stream_finish<true, true> : k_stream_finish<false, true>) : (count ? k_stream_finish<true, false> : k_stream_finish<false, false>);
     split[2] = plain[1];
     split[3] = count ? k_stream_trace<true, true> : k_stream_trace<true, false>;
     const bool use_split = stream_uses_split(d);
